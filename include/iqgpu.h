@@ -1,0 +1,197 @@
+/*
+ * iqgpu.h — C ABI of libiqgpu.so: the B200 (sm_100a) implementation of iq_tool's per-block
+ * sample-processing chain.  Plain pointers and sizes only; no CUDA or torch types.
+ *
+ * The reference (pclov3r/iq_tool) has no FFI for this path: its boundary is the C function
+ * set declared in its stage/module headers, linked statically.  Each group
+ * of entry points below names the reference interface it replaces (file:line under
+ * /root/reference).  the files under iq_tool_b200/host/ provide drop-in translation units with the
+ * reference's exact prototypes that forward to these entry points; INTEGRATION.md shows how a
+ * maintainer links them.
+ *
+ * Conventions
+ *   - Every function returns IQGPU_OK (0) or a negative IQGPU_E* code; the message for the last
+ *     error on the calling thread is available from iqgpu_last_error().  There is NO CPU
+ *     fallback: without a usable CUDA device every compute entry point fails with
+ *     IQGPU_ENODEVICE.
+ *   - "frames" are complex I/Q pairs.  cf32 buffers are interleaved {re, im} floats.
+ *   - Host-pointer entry points copy H2D/D2H internally (pinned staging); *_device entry points
+ *     take device pointers valid on the chain's device and an optional CUDA stream handle
+ *     (cudaStream_t cast to void*, NULL = the chain's own stream).
+ *   - A chain processes a "train" of reference chunks per call.  Per-chunk semantics of the
+ *     reference (digital-AGC gain per chunk, FFT-filter output quantisation per chunk,
+ *     per-chunk frames_to_write) are preserved exactly; see DESIGN.md §Chunk trains.
+ */
+#ifndef IQGPU_H
+#define IQGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IQGPU_ABI_VERSION 1
+
+enum {
+    IQGPU_OK = 0,
+    IQGPU_EINVAL = -1,     /* bad argument / unsupported configuration (reference would log_fatal) */
+    IQGPU_ENODEVICE = -2,  /* no CUDA device / driver */
+    IQGPU_ECUDA = -3,      /* CUDA runtime error */
+    IQGPU_ENOMEM = -4,
+    IQGPU_ECAPACITY = -5   /* output buffer too small */
+};
+
+/* sample formats: numeric values of the reference's format_t (include/common_types.h:33-37) */
+enum {
+    IQGPU_FMT_UNKNOWN = 0, IQGPU_FMT_U8, IQGPU_FMT_S8, IQGPU_FMT_U16, IQGPU_FMT_S16, IQGPU_FMT_U32,
+    IQGPU_FMT_S32, IQGPU_FMT_F32, IQGPU_FMT_CU8, IQGPU_FMT_CS8, IQGPU_FMT_CU16, IQGPU_FMT_CS16,
+    IQGPU_FMT_CS24, IQGPU_FMT_CU32, IQGPU_FMT_CS32, IQGPU_FMT_CF32, IQGPU_FMT_SC16Q11
+};
+/* FilterType (common_types.h:45-51), FilterTypeRequest (:61-65), FilterImplementationType (:53-59),
+ * AgcProfile (:77-82) */
+enum { IQGPU_FILTER_NONE = 0, IQGPU_FILTER_LOWPASS, IQGPU_FILTER_HIGHPASS, IQGPU_FILTER_PASSBAND, IQGPU_FILTER_STOPBAND };
+enum { IQGPU_FILTER_REQ_AUTO = 0, IQGPU_FILTER_REQ_FIR, IQGPU_FILTER_REQ_FFT };
+enum { IQGPU_FILTER_IMPL_NONE = 0, IQGPU_FILTER_IMPL_FIR_SYM, IQGPU_FILTER_IMPL_FIR_ASYM, IQGPU_FILTER_IMPL_FFT_SYM, IQGPU_FILTER_IMPL_FFT_ASYM };
+enum { IQGPU_AGC_OFF = 0, IQGPU_AGC_DX, IQGPU_AGC_LOCAL, IQGPU_AGC_DIGITAL };
+
+#define IQGPU_MAX_FILTER_CHAIN 5      /* MAX_FILTER_CHAIN, include/constants.h:249 */
+#define IQGPU_CHUNK_SAMPLES    16384  /* PIPELINE_CHUNK_BASE_SAMPLES, include/constants.h:123 */
+
+typedef struct {
+    int32_t type;      /* IQGPU_FILTER_* */
+    float   freq1_hz;  /* cutoff, or centre for pass/stop band (src/config.c:192-216) */
+    float   freq2_hz;  /* bandwidth for pass/stop band */
+} iqgpu_filter_request;
+
+/* The fields of AppConfig / AppResources (include/app_context.h:66-138, 205-283) that the
+ * chain reads, resolved the way src/config.c and src/setup.c resolve them. */
+typedef struct {
+    int32_t input_format;           /* AppResources.input_format */
+    int32_t output_format;          /* AppConfig.output_format */
+    double  input_rate_hz;          /* source_info.samplerate (integer Hz) */
+    double  target_rate_hz;         /* AppConfig.target_rate */
+    float   gain;                   /* AppConfig.gain */
+    int32_t dc_block_enable;        /* AppConfig.dc_block.enable */
+    int32_t iq_correction_enable;   /* AppConfig.iq_correction.enable */
+    float   iq_mag;                 /* initial IqCorrectionFactors.mag */
+    float   iq_phase;               /* initial IqCorrectionFactors.phase */
+    int32_t shift_after_resample;   /* AppConfig.shift_after_resample */
+    double  freq_shift_hz;          /* AppResources.nco_shift_hz */
+    int32_t no_resample;            /* AppConfig.no_resample (native-rate processing) */
+    int32_t num_filter_requests;
+    iqgpu_filter_request filter_requests[IQGPU_MAX_FILTER_CHAIN];
+    float   transition_width_hz;    /* --transition-width, 0 = auto */
+    int32_t filter_taps;            /* --filter-taps, 0 = auto */
+    float   attenuation_db;         /* --attenuation, 0 = 60 dB */
+    int32_t filter_type_request;    /* IQGPU_FILTER_REQ_* (AUTO == option not given) */
+    int32_t filter_fft_size;        /* --filter-fft-size, 0 = auto */
+    int32_t agc_enable;             /* AppConfig.output_agc.enable */
+    int32_t agc_profile;            /* IQGPU_AGC_* */
+    float   agc_target_level_arg;   /* --agc-target, 0 = profile default */
+    int32_t reserved;
+} iqgpu_chain_config;
+
+typedef struct {
+    float    ratio;                 /* float r = (float)(target/input), src/setup.c:107 */
+    int32_t  is_interp;
+    uint32_t num_halfband;          /* S */
+    uint32_t halfband_m[16];        /* semi-length per design index (index 0 = lowest rate) */
+    float    rate_arbitrary;
+    uint32_t arb_step;              /* 24-bit fixed-point phase step */
+    int32_t  filter_impl;           /* IQGPU_FILTER_IMPL_* */
+    int32_t  filter_post_resample;  /* AppConfig.apply_user_filter_post_resample */
+    uint32_t filter_block_size;     /* AppResources.user_filter_block_size */
+    uint32_t filter_num_taps;
+    uint32_t nco_dtheta;            /* 32-bit NCO phase increment, 0 if no shift */
+    int32_t  nco_is_post;
+    uint32_t agc_locked;            /* AppResources.agc_is_locked */
+    float    agc_gain;              /* AppResources.agc_current_gain */
+    float    agc_peak_memory;       /* AppResources.agc_peak_memory */
+    uint64_t agc_samples_seen;      /* AppResources.agc_samples_seen */
+    uint64_t frames_in_total;       /* input frames consumed since create/reset */
+    uint64_t frames_out_total;      /* output frames produced since create/reset */
+    uint32_t fused_front;           /* 1 when the fused convert+mix+resample kernel is in use */
+    uint32_t kernel_launches;       /* kernels launched by the last process call */
+    uint32_t halo_frames;           /* raw-input halo the fused front re-reads per train */
+    uint32_t reserved;
+} iqgpu_chain_info;
+
+typedef struct iqgpu_chain iqgpu_chain;
+
+/* ---- library ---------------------------------------------------------------------- */
+int         iqgpu_abi_version(void);
+const char *iqgpu_last_error(void);
+int         iqgpu_device_count(void);
+/* pinned host memory for chunk pools (replaces the malloc slab of src/pipeline.c:277) */
+void       *iqgpu_host_alloc(size_t bytes);
+void        iqgpu_host_free(void *p);
+
+/* ---- whole chain: pre_processor_apply_chain + resampler_execute + post_processor_apply_chain
+ *      (include/pre_processor.h:24, include/resampler.h:48, include/post_processor.h:24;
+ *       object creation order of src/pipeline.c:138-147) --------------------------------- */
+int  iqgpu_chain_create(const iqgpu_chain_config *cfg, int device, iqgpu_chain **out);
+void iqgpu_chain_destroy(iqgpu_chain *c);
+/* stream discontinuity: pre_processor_reset + resampler_reset + post_processor_reset
+ * (include/pre_processor.h:34, include/resampler.h:43, include/post_processor.h:34) */
+int  iqgpu_chain_reset(iqgpu_chain *c);
+int  iqgpu_chain_get_info(iqgpu_chain *c, iqgpu_chain_info *info);
+/* runtime knobs: "fused" (0/1), "subtrain_frames", "chunk_frames" */
+int  iqgpu_chain_set_option(iqgpu_chain *c, const char *key, int64_t value);
+/* live update of the I/Q correction factors (iq_correct.c:206-216 double-buffer swap) */
+int  iqgpu_chain_set_iq_factors(iqgpu_chain *c, float mag, float phase);
+
+/* Process a train of n_frames input frames held in HOST memory.  The train is cut into
+ * reference chunks of IQGPU_CHUNK_SAMPLES frames (last one short) unless chunk_frames/n_chunks
+ * give explicit chunk lengths (SDR-style irregular chunks; sum must equal n_frames).
+ * out receives the converted output frames; per_chunk_out (optional, one entry per chunk)
+ * receives each chunk's frames_to_write (src/pipeline.c:523). */
+int  iqgpu_chain_process(iqgpu_chain *c, const void *raw_in, size_t n_frames,
+                         const uint32_t *chunk_frames, size_t n_chunks,
+                         void *out, size_t out_capacity_bytes, size_t *out_frames,
+                         uint32_t *per_chunk_out);
+/* Same, with raw_in / out resident in device memory; runs asynchronously on `cuda_stream`
+ * except for the final output-frame count, which is closed-form and returned immediately. */
+int  iqgpu_chain_process_device(iqgpu_chain *c, const void *dev_raw_in, size_t n_frames,
+                                const uint32_t *chunk_frames, size_t n_chunks,
+                                void *dev_out, size_t out_capacity_bytes, size_t *out_frames,
+                                uint32_t *per_chunk_out, void *cuda_stream);
+/* closed-form output frame count for the NEXT n_frames (no data touched) */
+int  iqgpu_chain_predict_output(iqgpu_chain *c, size_t n_frames, size_t *out_frames);
+/* copy the cf32 stream observed at an internal tap of the LAST process call to host:
+ * tap 0 = after the pre-processor chain, 1 = after the resampler, 2 = before output conversion.
+ * Taps 0 is only materialised when the chain runs unfused. */
+int  iqgpu_chain_read_tap(iqgpu_chain *c, int tap, float *host_cf32, size_t capacity_frames, size_t *frames);
+/* design introspection (filter.c master taps; msresamp design) */
+int  iqgpu_chain_get_filter_taps(iqgpu_chain *c, float *cf32_taps, uint32_t capacity, uint32_t *num_taps);
+int  iqgpu_chain_get_halfband_taps(iqgpu_chain *c, uint32_t design_index, float *taps, uint32_t capacity, uint32_t *num_taps);
+int  iqgpu_chain_get_arb_taps(iqgpu_chain *c, float *taps, uint32_t capacity, uint32_t *num_taps);
+
+/* ---- time-sharding (multi-GPU): position this chain at absolute input
+ *      frame `first_frame` of a longer capture with EMPTY filter histories.  NCO phase, halfband
+ *      alignment, arbitrary-resampler phase and output index are set in closed form;
+ *      `out_first_frame` receives the absolute output-frame index of the first output the chain
+ *      will emit.  To reproduce the single-stream result a shard seeks to
+ *      (shard_start - halo), processes from there and drops the outputs that precede
+ *      shard_start (their count is closed form too); halo from iqgpu_chain_halo_frames. ------ */
+int  iqgpu_chain_seek(iqgpu_chain *c, uint64_t first_frame, uint64_t *out_first_frame);
+int  iqgpu_chain_halo_frames(iqgpu_chain *c, size_t *halo_frames);
+
+/* ---- sample_convert.h (include/sample_convert.h:19,35,50) — host buffers ------------- */
+size_t iqgpu_get_bytes_per_sample(int format);
+int    iqgpu_convert_block_to_cf32(const void *in, float *out_cf32, size_t n_frames, int format, float gain);
+int    iqgpu_convert_cf32_to_block(const float *in_cf32, void *out, size_t n_frames, int format);
+
+/* ---- I/Q optimiser metric (include/iq_correct.h:56; src/iq_correct.c:154-235,315-393) -
+ * One optimisation pass on a 1024-sample cf32 block: power estimate, 1+25 metric evaluations
+ * with caller-supplied +-1 directions (2*25 floats; the reference draws them from rand()),
+ * 5 % smoothing.  in/out: mag, phase.  Returns average_power / power_range as the reference
+ * stores them. */
+int  iqgpu_iq_optimize(const float *block1024_cf32, const float *directions50,
+                       float *mag, float *phase, float *avg_power, float *power_range);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IQGPU_H */

@@ -1,0 +1,993 @@
+// chain.cu — the chain engine and the C ABI (include/iqgpu.h).
+//
+// One iqgpu_chain owns the DSP state of a full reference pipeline
+// (src/pipeline.c:138-147: dc_block, iq_correct, freq_shift, resampler, filter, agc) and runs
+// "trains" of reference chunks through it.  Everything that is not data dependent — NCO phase,
+// halfband alignment, arbitrary-resampler phase, per-chunk output counts, FFT-filter block
+// bookkeeping — is closed-form integer arithmetic on the absolute stream position and is
+// evaluated on the host; the device only carries data-dependent state (DC-blocker carry, filter
+// histories, AGC state).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/iqgpu.h"
+#include "design.hpp"
+#include "kernels.hpp"
+
+using namespace iqgpu;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e_);                                \
+            return IQGPU_ECUDA;                                                                        \
+        }                                                                                              \
+    } while (0)
+
+namespace {
+
+size_t bytes_per_sample(int fmt)
+{
+    switch (fmt) {  // reference src/sample_convert.c:102-123
+        case IQGPU_FMT_S8: case IQGPU_FMT_U8: return 1;
+        case IQGPU_FMT_S16: case IQGPU_FMT_U16: return 2;
+        case IQGPU_FMT_S32: case IQGPU_FMT_U32: case IQGPU_FMT_F32: return 4;
+        case IQGPU_FMT_CS8: case IQGPU_FMT_CU8: return 2;
+        case IQGPU_FMT_CS16: case IQGPU_FMT_CU16: case IQGPU_FMT_SC16Q11: return 4;
+        case IQGPU_FMT_CS24: return 6;
+        case IQGPU_FMT_CS32: case IQGPU_FMT_CU32: case IQGPU_FMT_CF32: return 8;
+        default: return 0;
+    }
+}
+bool is_complex_format(int fmt) { return fmt >= IQGPU_FMT_CU8 && fmt <= IQGPU_FMT_SC16Q11; }
+
+// cf32 stream segment with history head-room.  New data of a call is written at base+pos; the
+// previous `hist` samples sit right below it.
+struct DevStream {
+    float2* base = nullptr;
+    size_t cap = 0, hist = 0, pos = 0, max_n = 0;
+    int alloc(size_t hist_, size_t max_n_)
+    {
+        hist = (hist_ + 3) & ~(size_t)3;
+        max_n = std::max(max_n_, hist) + 4;
+        cap = hist + 2 * max_n;
+        cudaError_t e = cudaMalloc(&base, cap * sizeof(float2));
+        if (e != cudaSuccess) return -1;
+        return 0;
+    }
+    void release() { if (base) cudaFree(base); base = nullptr; }
+    cudaError_t reset(cudaStream_t st)
+    {
+        pos = hist;
+        return hist ? cudaMemsetAsync(base, 0, hist * sizeof(float2), st) : cudaSuccess;
+    }
+    // make room for n new samples; returns pointer to the first new sample
+    cudaError_t begin(size_t n, cudaStream_t st, float2** p)
+    {
+        if (n > max_n) return cudaErrorInvalidValue;
+        if (pos + n > cap) {
+            // move the history to the front (ranges cannot overlap: pos - hist >= hist)
+            cudaError_t e = cudaMemcpyAsync(base, base + pos - hist, hist * sizeof(float2), cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) return e;
+            pos = hist;
+        }
+        *p = base + pos;
+        return cudaSuccess;
+    }
+    void commit(size_t n) { pos += n; }
+    float2* cur() const { return base + pos; }
+};
+
+struct TapBuf {
+    float2* p = nullptr;
+    size_t cap = 0, len = 0;
+    cudaError_t append(const float2* src, size_t n, cudaStream_t st)
+    {
+        if (len + n > cap) {
+            size_t ncap = std::max(cap * 2, len + n + 1024);
+            float2* np = nullptr;
+            cudaError_t e = cudaMalloc(&np, ncap * sizeof(float2));
+            if (e != cudaSuccess) return e;
+            if (len) {
+                e = cudaMemcpyAsync(np, p, len * sizeof(float2), cudaMemcpyDeviceToDevice, st);
+                if (e != cudaSuccess) return e;
+                cudaStreamSynchronize(st);
+            }
+            if (p) cudaFree(p);
+            p = np; cap = ncap;
+        }
+        cudaError_t e = cudaMemcpyAsync(p + len, src, n * sizeof(float2), cudaMemcpyDeviceToDevice, st);
+        len += n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = len = 0; }
+};
+
+}  // namespace
+
+struct iqgpu_chain {
+    iqgpu_chain_config cfg{};
+    int device = -1;
+    bool plan_only = false;
+    int in_rate = 0;
+    double target_rate = 0;
+    float ratio = 1.f;
+    size_t in_bps = 0, out_bps = 0;
+
+    DcPlan dc;
+    ResamplerPlan rs;
+    FilterPlan filt;
+    bool nco_pre = false, nco_post = false;
+    uint32_t nco_dtheta = 0;
+    float nco_sign = 1.f;
+    float iq_mag = 0.f, iq_phase = 0.f;
+    int agc_mode = 0;  // 0 none, 1 digital, 2 rms
+    float agc_target = 0.f, agc_alpha = 0.f;
+
+    // options
+    size_t subtrain_frames = (size_t)1 << 22;
+    uint32_t chunk_frames = IQGPU_CHUNK_SAMPLES;
+    bool want_fused = true;
+    bool record_taps = false;
+
+    // ---- stream position (host, closed form) ----
+    uint64_t n_in = 0;        // input frames since reset
+    uint64_t n_nco_post = 0;  // samples that went through the post NCO
+    uint64_t n_out = 0;
+    uint32_t fft_rem = 0;     // FFT filter remainder length (frames waiting for a full block)
+    uint32_t launches = 0;
+
+    // ---- device state ----
+    cudaStream_t stream = nullptr, h2d = nullptr, d2h = nullptr;
+    float* d_lut = nullptr;
+    double2* d_dc_carry = nullptr;
+    double2 *d_run_sums = nullptr, *d_run_start = nullptr;
+    size_t max_runs = 0;
+    std::vector<float*> d_hb_taps;  // per design index
+    float* d_bank = nullptr;
+    float* d_fir_taps = nullptr;
+    unsigned fir_taps_padded = 0;
+    float2 *d_fft_H = nullptr, *d_fft_tw = nullptr;
+    AgcState* d_agc = nullptr;
+    uint32_t* d_seg_start = nullptr;
+    float *d_seg_peak = nullptr, *d_seg_gain = nullptr;
+    size_t max_segs = 0;
+    float2* d_agc_scratch = nullptr;
+    size_t agc_scratch_cap = 0;
+    // streams: s_in = pre output; s_stage[d] = output of executed halfband stage d; s_rs = resampler
+    // output; s_f = post-filter output (or pre-filter output when the filter is pre-resample)
+    DevStream s_in, s_pref, s_arb_in, s_rs, s_f;
+    std::vector<DevStream> s_stage;
+    TapBuf tap[3];
+    // host-path staging
+    void* d_raw[2] = {nullptr, nullptr};
+    void* d_out[2] = {nullptr, nullptr};
+    size_t d_raw_bytes = 0, d_out_bytes = 0;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+    bool buffers_ready = false;
+
+    ~iqgpu_chain();
+    int init_device();
+    int ensure_buffers();
+    int reset_state();
+    size_t max_out_for(size_t n_frames) const;
+    // closed-form per-chunk output frame counts from the current position (no state change)
+    size_t count_outputs(const uint32_t* chunks, size_t n_chunks, uint32_t* per_chunk) const;
+    int run_subtrain(const void* d_rawp, size_t n, const uint32_t* chunks, size_t n_chunks, void* d_outp,
+                     size_t* out_frames, uint32_t* per_chunk, cudaStream_t st);
+};
+
+iqgpu_chain::~iqgpu_chain()
+{
+    if (plan_only) return;
+    cudaSetDevice(device);
+    if (stream) cudaStreamSynchronize(stream);
+    for (auto* t : d_hb_taps) cudaFree(t);
+    cudaFree(d_lut); cudaFree(d_dc_carry); cudaFree(d_run_sums); cudaFree(d_run_start); cudaFree(d_bank);
+    cudaFree(d_fir_taps); cudaFree(d_fft_H); cudaFree(d_fft_tw); cudaFree(d_agc); cudaFree(d_seg_start);
+    cudaFree(d_seg_peak); cudaFree(d_seg_gain); cudaFree(d_agc_scratch);
+    s_in.release(); s_pref.release(); s_arb_in.release(); s_rs.release(); s_f.release();
+    for (auto& s : s_stage) s.release();
+    for (auto& t : tap) t.release();
+    for (int i = 0; i < 2; i++) {
+        cudaFree(d_raw[i]); cudaFree(d_out[i]);
+        if (ev_h2d[i]) cudaEventDestroy(ev_h2d[i]);
+        if (ev_done[i]) cudaEventDestroy(ev_done[i]);
+        if (ev_d2h[i]) cudaEventDestroy(ev_d2h[i]);
+    }
+    if (stream) cudaStreamDestroy(stream);
+    if (h2d) cudaStreamDestroy(h2d);
+    if (d2h) cudaStreamDestroy(d2h);
+}
+
+static bool filter_is_fft(const FilterPlan& f)
+{
+    return f.impl == IQGPU_FILTER_IMPL_FFT_SYM || f.impl == IQGPU_FILTER_IMPL_FFT_ASYM;
+}
+static bool filter_is_fir(const FilterPlan& f)
+{
+    return f.impl == IQGPU_FILTER_IMPL_FIR_SYM || f.impl == IQGPU_FILTER_IMPL_FIR_ASYM;
+}
+
+size_t iqgpu_chain::max_out_for(size_t n) const
+{
+    double r = rs.passthrough ? 1.0 : (double)ratio;
+    size_t m = (size_t)std::ceil((double)n * std::max(r, 0.0)) + 4096;
+    if (rs.is_interp) m += ((size_t)2 << rs.num_halfband);
+    if (filter_is_fft(filt)) m += filt.block;
+    return m;
+}
+
+size_t iqgpu_chain::count_outputs(const uint32_t* chunks, size_t n_chunks, uint32_t* per_chunk) const
+{
+    // mirrors the reference's per-chunk bookkeeping: resampler frames_to_write (pipeline.c:523),
+    // FFT-filter block quantisation (filter.c:491-526), empty chunks skipped (post_processor.c:12)
+    const bool fft = filter_is_fft(filt);
+    const bool pre_fft = fft && !filt.post_resample, post_fft = fft && filt.post_resample;
+    uint32_t rem = fft_rem;
+    uint64_t pos = pre_fft ? n_in - fft_rem : n_in;
+    uint64_t before = resampler_outputs_after(rs, pos), total = 0;
+    for (size_t c = 0; c < n_chunks; c++) {
+        uint32_t f = chunks[c];
+        if (pre_fft) { const uint32_t tot = rem + f, b = tot / filt.block; f = b * filt.block; rem = tot - f; }
+        pos += f;
+        const uint64_t after = resampler_outputs_after(rs, pos);
+        uint32_t r = (uint32_t)(after - before);
+        before = after;
+        if (post_fft && r) { const uint32_t tot = rem + r, b = tot / filt.block; r = b * filt.block; rem = tot - r; }
+        if (per_chunk) per_chunk[c] = r;
+        total += r;
+    }
+    return (size_t)total;
+}
+
+int iqgpu_chain::init_device()
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(IQGPU_ENODEVICE, "no CUDA device available");
+    if (device >= ndev) return fail(IQGPU_EINVAL, "device index out of range");
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CK(cudaEventCreateWithFlags(&ev_h2d[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_d2h[i], cudaEventDisableTiming));
+    }
+    // constant tables
+    float lut[1024];
+    nco_sine_table(lut);
+    CK(cudaMalloc(&d_lut, sizeof(lut)));
+    CK(cudaMemcpy(d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d_dc_carry, sizeof(double2)));
+    CK(cudaMalloc(&d_agc, sizeof(AgcState)));
+    if (!rs.passthrough) {
+        d_hb_taps.resize(rs.num_halfband, nullptr);
+        for (unsigned i = 0; i < rs.num_halfband; i++) {
+            CK(cudaMalloc(&d_hb_taps[i], rs.stages[i].h1.size() * sizeof(float)));
+            CK(cudaMemcpy(d_hb_taps[i], rs.stages[i].h1.data(), rs.stages[i].h1.size() * sizeof(float), cudaMemcpyHostToDevice));
+        }
+        CK(cudaMalloc(&d_bank, rs.bank.size() * sizeof(float)));
+        CK(cudaMemcpy(d_bank, rs.bank.data(), rs.bank.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    if (filter_is_fir(filt)) {
+        const unsigned N = (unsigned)filt.taps.size();
+        fir_taps_padded = (N + 7) & ~7u;
+        const unsigned pad = fir_taps_padded - N;
+        const bool cplx = filt.impl == IQGPU_FILTER_IMPL_FIR_ASYM;
+        std::vector<float> h((size_t)fir_taps_padded * (cplx ? 2 : 1), 0.f);
+        for (unsigned i = 0; i < N; i++) {  // oldest-first order: hrev[i] = h[N-1-i]
+            const cfloat t = filt.taps[N - 1 - i];
+            if (cplx) { h[2 * (pad + i)] = t.real(); h[2 * (pad + i) + 1] = t.imag(); }
+            else h[pad + i] = t.real();
+        }
+        CK(cudaMalloc(&d_fir_taps, h.size() * sizeof(float)));
+        CK(cudaMemcpy(d_fir_taps, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    if (filter_is_fft(filt)) {
+        if (!fftfilt_supported(filt.block)) return fail(IQGPU_EINVAL, "FFT filter block size not supported by the GPU FFT kernel");
+        const unsigned nfft = 2 * filt.block;
+        std::vector<float2> tw(nfft), hpad(nfft, make_float2(0.f, 0.f));
+        for (unsigned k = 0; k < nfft; k++) {
+            double a = -2.0 * M_PI * (double)k / (double)nfft;
+            tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+        for (size_t i = 0; i < filt.taps.size(); i++) hpad[i] = make_float2(filt.taps[i].real(), filt.taps[i].imag());
+        float2* d_h = nullptr;
+        CK(cudaMalloc(&d_fft_tw, nfft * sizeof(float2)));
+        CK(cudaMalloc(&d_fft_H, nfft * sizeof(float2)));
+        CK(cudaMalloc(&d_h, nfft * sizeof(float2)));
+        CK(cudaMemcpy(d_fft_tw, tw.data(), nfft * sizeof(float2), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_h, hpad.data(), nfft * sizeof(float2), cudaMemcpyHostToDevice));
+        CK(launch_fft_forward(d_h, nfft, d_fft_tw, d_fft_H, stream));
+        CK(cudaStreamSynchronize(stream));
+        cudaFree(d_h);
+    }
+    return IQGPU_OK;
+}
+
+int iqgpu_chain::ensure_buffers()
+{
+    if (buffers_ready) return IQGPU_OK;
+    CK(cudaSetDevice(device));
+    const size_t n = subtrain_frames + chunk_frames;  // a sub-train never exceeds this
+    const bool pre_filter = filt.impl != IQGPU_FILTER_IMPL_NONE && !filt.post_resample;
+    const bool post_filter = filt.impl != IQGPU_FILTER_IMPL_NONE && filt.post_resample;
+    const size_t filt_hist = filter_is_fir(filt) ? fir_taps_padded : (filter_is_fft(filt) ? 2 * (size_t)filt.block : 0);
+
+    // s_in: consumer is the pre-filter, else the first resampler stage, else nothing
+    size_t in_hist = 0;
+    if (pre_filter) in_hist = filt_hist;
+    else if (!rs.passthrough && !rs.is_interp) in_hist = rs.num_halfband ? 4 * rs.stages[rs.num_halfband - 1].m : 16;
+    else if (!rs.passthrough) in_hist = 16;
+    if (s_in.alloc(in_hist, n) != 0) return fail(IQGPU_ENOMEM, "device allocation failed (s_in)");
+    if (pre_filter) {
+        size_t h = 16;
+        if (!rs.passthrough && !rs.is_interp && rs.num_halfband) h = 4 * rs.stages[rs.num_halfband - 1].m;
+        if (s_pref.alloc(h, n + filt.block) != 0) return fail(IQGPU_ENOMEM, "device allocation failed (s_pref)");
+    }
+    size_t rs_max = n;
+    if (!rs.passthrough) {
+        const unsigned S = rs.num_halfband;
+        s_stage.resize(S);
+        if (!rs.is_interp) {
+            // executed stage d (design index S-1-d) halves the rate; its output feeds stage d+1 or the arb stage
+            for (unsigned d = 0; d < S; d++) {
+                const size_t cnt = (n >> (d + 1)) + 2;
+                const size_t h = (d + 1 < S) ? 4 * rs.stages[S - 2 - d].m : 16;
+                if (s_stage[d].alloc(h, cnt) != 0) return fail(IQGPU_ENOMEM, "device allocation failed (stage)");
+            }
+            rs_max = (size_t)std::ceil((double)(n >> S) * (double)rs.rate_arbitrary) + 16;
+        } else {
+            // arbitrary first (on s_in), then interpolators by design index 0..S-1
+            const size_t arb_cnt = (size_t)std::ceil((double)n * (double)rs.rate_arbitrary) + 16;
+            if (s_arb_in.alloc(S ? 2 * rs.stages[0].m : 0, arb_cnt) != 0) return fail(IQGPU_ENOMEM, "device allocation failed (arb)");
+            for (unsigned s = 0; s < S; s++) {
+                const size_t cnt = (arb_cnt << (s + 1));
+                const size_t h = (s + 1 < S) ? 2 * rs.stages[s + 1].m : 0;
+                if (s + 1 < S && s_stage[s].alloc(h, cnt) != 0) return fail(IQGPU_ENOMEM, "device allocation failed (stage)");
+            }
+            rs_max = arb_cnt << S;
+        }
+    }
+    if (s_rs.alloc(post_filter ? filt_hist : 0, rs_max + (post_filter ? filt.block : 0)) != 0)
+        return fail(IQGPU_ENOMEM, "device allocation failed (s_rs)");
+    if (post_filter && s_f.alloc(0, rs_max + 2 * (size_t)filt.block) != 0)
+        return fail(IQGPU_ENOMEM, "device allocation failed (s_f)");
+
+    max_runs = n / 128 + 2;
+    CK(cudaMalloc(&d_run_sums, max_runs * sizeof(double2)));
+    CK(cudaMalloc(&d_run_start, max_runs * sizeof(double2)));
+    max_segs = n / std::max<uint32_t>(1, std::min<uint32_t>(chunk_frames, 1024)) + 8;
+    CK(cudaMalloc(&d_seg_start, (max_segs + 1) * sizeof(uint32_t)));
+    CK(cudaMalloc(&d_seg_peak, max_segs * sizeof(float)));
+    CK(cudaMalloc(&d_seg_gain, max_segs * sizeof(float)));
+    buffers_ready = true;
+    return reset_state();
+}
+
+int iqgpu_chain::reset_state()
+{
+    n_in = 0; n_nco_post = 0; n_out = 0; fft_rem = 0;
+    if (plan_only || !buffers_ready) return IQGPU_OK;
+    CK(cudaSetDevice(device));
+    CK(cudaMemsetAsync(d_dc_carry, 0, sizeof(double2), stream));
+    AgcState a{};
+    a.locked = 0; a.gain = 1.0f; a.seen = 0; a.last_strong = 0.0;
+    a.peak_mem = (agc_mode == 1) ? 0.05f : 0.001f;   // agc.c:66,78
+    a.rms_g = 1.0f; a.rms_y2 = 1.0f;                  // agc.c:58-62 (set_signal_level then set_gain(1))
+    CK(cudaMemcpyAsync(d_agc, &a, sizeof(a), cudaMemcpyHostToDevice, stream));
+    CK(s_in.reset(stream));
+    if (s_pref.base) CK(s_pref.reset(stream));
+    if (s_arb_in.base) CK(s_arb_in.reset(stream));
+    for (auto& s : s_stage) if (s.base) CK(s.reset(stream));
+    CK(s_rs.reset(stream));
+    if (s_f.base) CK(s_f.reset(stream));
+    CK(cudaStreamSynchronize(stream));
+    return IQGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// one sub-train on the device
+// ---------------------------------------------------------------------------------------------
+int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chunks, size_t n_chunks, void* d_outp,
+                              size_t* out_frames, uint32_t* per_chunk, cudaStream_t st)
+{
+    const bool pre_filter = filt.impl != IQGPU_FILTER_IMPL_NONE && !filt.post_resample;
+    const bool post_filter = filt.impl != IQGPU_FILTER_IMPL_NONE && filt.post_resample;
+    const uint64_t N0 = n_in, N1 = n_in + n;
+
+    // ---------------- closed-form bookkeeping: per-chunk frame counts ----------------
+    std::vector<uint32_t> seg(n_chunks + 1, 0), counts(n_chunks, 0);
+    count_outputs(chunks, n_chunks, counts.data());
+    for (size_t c = 0; c < n_chunks; c++) {
+        seg[c + 1] = seg[c] + counts[c];
+        if (per_chunk) per_chunk[c] = counts[c];
+    }
+    const size_t total_out = seg[n_chunks];
+    launches = 0;
+
+    // ---------------- K1: pre-processor ----------------
+    PreParams pp{};
+    pp.format = cfg.input_format; pp.gain = cfg.gain;
+    pp.dc_enable = dc.enable; pp.dc_c = dc.c; pp.dc_a = dc.one_minus_c;
+    pp.iq_enable = cfg.iq_correction_enable; pp.iq_magp1 = 1.0f + iq_mag; pp.iq_phase = iq_phase;
+    pp.nco_enable = nco_pre; pp.nco_dtheta = nco_dtheta; pp.nco_sign = nco_sign; pp.nco_table = d_lut;
+    pp.nco_theta0 = (uint32_t)((uint64_t)(uint32_t)N0 * nco_dtheta);
+    float2* x_in = nullptr;
+    CK(s_in.begin(n, st, &x_in));
+    uint32_t rows = (uint32_t)((n + 127) / 128), rpr = 1;
+    while (rpr < 32 && rows / rpr > 16384) rpr <<= 1;
+    const uint32_t run_len = 128 * rpr;
+    if (dc.enable) {
+        const size_t n_runs = (n + run_len - 1) / run_len;
+        if (n_runs > max_runs) return fail(IQGPU_EINVAL, "internal: run table too small");
+        CK(launch_dc_run_sums(d_rawp, n, pp, run_len, d_run_sums, st));
+        CK(launch_dc_scan(d_run_sums, n_runs, run_len, n, dc.c, d_dc_carry, d_run_start, st));
+        launches += 2;
+    }
+    CK(launch_pre(d_rawp, n, pp, run_len, d_run_start, x_in, st));
+    launches++;
+    s_in.commit(n);
+    if (record_taps) CK(tap[0].append(x_in, n, st));
+
+    // ---------------- optional pre-resample filter ----------------
+    const float2* rs_src = x_in;     // stream feeding the resampler (first new sample)
+    size_t rs_n = n;                 // new samples in it
+    uint64_t rs_pos0 = N0;           // absolute index of rs_src[0] in the resampler input stream
+    if (pre_filter) {
+        if (filter_is_fir(filt)) {
+            float2* y = nullptr;
+            CK(s_pref.begin(n, st, &y));
+            CK(launch_fir(x_in, n, d_fir_taps, fir_taps_padded, filt.impl == IQGPU_FILTER_IMPL_FIR_ASYM, y, st));
+            launches++;
+            s_pref.commit(n);
+            rs_src = y;
+        } else {
+            const uint32_t tot = fft_rem + (uint32_t)n, blocks = tot / filt.block;
+            float2* y = nullptr;
+            CK(s_pref.begin((size_t)blocks * filt.block, st, &y));
+            if (blocks) {
+                CK(launch_fftfilt(x_in - fft_rem, blocks, filt.block, d_fft_H, d_fft_tw, y, st));
+                launches++;
+            }
+            s_pref.commit((size_t)blocks * filt.block);
+            rs_pos0 = N0 - fft_rem;
+            fft_rem = tot - blocks * filt.block;
+            rs_src = y; rs_n = (size_t)blocks * filt.block;
+        }
+    }
+
+    // ---------------- K2: resampler ----------------
+    const float2* post_src = rs_src;
+    size_t post_n = rs_n;
+    if (!rs.passthrough) {
+        const unsigned S = rs.num_halfband;
+        const uint64_t P0 = rs_pos0, P1 = rs_pos0 + rs_n;
+        float2* y_rs = nullptr;
+        if (!rs.is_interp) {
+            const float2* src = rs_src;
+            uint64_t a0 = P0;  // absolute index (in the current stage's input stream) of src[0]
+            for (unsigned d = 0; d < S; d++) {
+                const unsigned g = S - 1 - d;
+                const uint64_t k0 = P0 >> (d + 1), k1 = P1 >> (d + 1);
+                float2* y = nullptr;
+                CK(s_stage[d].begin((size_t)(k1 - k0), st, &y));
+                CK(launch_halfband_decim(src, (int64_t)a0, d_hb_taps[g], rs.stages[g].m, (int64_t)k0, (size_t)(k1 - k0),
+                                         (d + 1 == S) ? rs.zeta : 1.0f, y, st));
+                launches++;
+                s_stage[d].commit((size_t)(k1 - k0));
+                src = y; a0 = k0;
+            }
+            const uint64_t K0 = P0 >> S, K1 = P1 >> S;
+            const uint64_t O0 = arb_outputs_after(K0, rs.step), O1 = arb_outputs_after(K1, rs.step);
+            const unsigned __int128 Pph = (unsigned __int128)O0 * rs.step;
+            CK(s_rs.begin((size_t)(O1 - O0), st, &y_rs));
+            CK(launch_arb(src, (int64_t)K0, d_bank, rs.step, (int64_t)(uint64_t)(Pph >> 24), (uint32_t)(Pph & 0xffffffu),
+                          (size_t)(O1 - O0), y_rs, st));
+            launches++;
+            post_n = (size_t)(O1 - O0);
+        } else {
+            const uint64_t O0 = arb_outputs_after(P0, rs.step), O1 = arb_outputs_after(P1, rs.step);
+            const unsigned __int128 Pph = (unsigned __int128)O0 * rs.step;
+            float2* y = nullptr;
+            size_t cnt = (size_t)(O1 - O0);
+            if (S == 0) CK(s_rs.begin(cnt, st, &y)); else CK(s_arb_in.begin(cnt, st, &y));
+            CK(launch_arb(rs_src, (int64_t)P0, d_bank, rs.step, (int64_t)(uint64_t)(Pph >> 24), (uint32_t)(Pph & 0xffffffu), cnt, y, st));
+            launches++;
+            if (S == 0) y_rs = y; else s_arb_in.commit(cnt);
+            const float2* src = y;
+            uint64_t a0 = O0;
+            for (unsigned s = 0; s < S; s++) {
+                float2* yo = nullptr;
+                if (s + 1 == S) CK(s_rs.begin(2 * cnt, st, &yo)); else CK(s_stage[s].begin(2 * cnt, st, &yo));
+                CK(launch_halfband_interp(src, (int64_t)a0, d_hb_taps[s], rs.stages[s].m, (int64_t)a0, cnt, yo, st));
+                launches++;
+                if (s + 1 == S) y_rs = yo; else s_stage[s].commit(2 * cnt);
+                src = yo; a0 *= 2; cnt *= 2;
+            }
+            post_n = cnt;
+        }
+        s_rs.commit(post_n);
+        post_src = y_rs;
+    } else if (post_filter) {
+        // passthrough + post filter never happens (no_resample keeps the filter pre-resample), but keep the
+        // stream contract: copy into s_rs so the filter finds its history.
+        float2* y = nullptr;
+        CK(s_rs.begin(rs_n, st, &y));
+        CK(cudaMemcpyAsync(y, rs_src, rs_n * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+        s_rs.commit(rs_n);
+        post_src = y;
+    }
+    if (record_taps) CK(tap[1].append(post_src, post_n, st));
+
+    // ---------------- optional post-resample filter ----------------
+    if (post_filter) {
+        if (filter_is_fir(filt)) {
+            float2* y = nullptr;
+            CK(s_f.begin(post_n, st, &y));
+            CK(launch_fir(post_src, post_n, d_fir_taps, fir_taps_padded, filt.impl == IQGPU_FILTER_IMPL_FIR_ASYM, y, st));
+            launches++;
+            s_f.commit(post_n);
+            post_src = y;
+        } else {
+            const uint32_t tot = fft_rem + (uint32_t)post_n, blocks = tot / filt.block;
+            float2* y = nullptr;
+            CK(s_f.begin((size_t)blocks * filt.block, st, &y));
+            if (blocks) {
+                CK(launch_fftfilt(post_src - fft_rem, blocks, filt.block, d_fft_H, d_fft_tw, y, st));
+                launches++;
+            }
+            s_f.commit((size_t)blocks * filt.block);
+            fft_rem = tot - blocks * filt.block;
+            post_src = y; post_n = (size_t)blocks * filt.block;
+        }
+    }
+    if (post_n != total_out) return fail(IQGPU_EINVAL, "internal: closed-form output count disagrees with the kernels' count");
+
+    // ---------------- K5: post NCO + AGC + convert ----------------
+    PostParams qp{};
+    qp.format = cfg.output_format;
+    qp.nco_enable = nco_post; qp.nco_dtheta = nco_dtheta; qp.nco_sign = nco_sign; qp.nco_table = d_lut;
+    qp.nco_theta0 = (uint32_t)((uint64_t)(uint32_t)n_nco_post * nco_dtheta);
+    qp.agc_mode = agc_mode; qp.agc_target = agc_target; qp.agc_alpha = agc_alpha; qp.target_rate = target_rate;
+    float2* tap2 = nullptr;
+    if (record_taps && post_n) {
+        // reserve room in the tap buffer and let the post kernel write straight into it
+        CK(tap[2].append(post_src, post_n, st));
+        tap2 = tap[2].p + tap[2].len - post_n;
+    }
+    if (post_n) {
+        if (agc_mode == 1) {
+            if (n_chunks > max_segs) {
+                CK(cudaStreamSynchronize(st));
+                cudaFree(d_seg_start); cudaFree(d_seg_peak); cudaFree(d_seg_gain);
+                max_segs = n_chunks * 2;
+                CK(cudaMalloc(&d_seg_start, (max_segs + 1) * sizeof(uint32_t)));
+                CK(cudaMalloc(&d_seg_peak, max_segs * sizeof(float)));
+                CK(cudaMalloc(&d_seg_gain, max_segs * sizeof(float)));
+            }
+            CK(cudaMemcpyAsync(d_seg_start, seg.data(), (n_chunks + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+            CK(launch_agc_peaks(post_src, post_n, qp, d_seg_start, n_chunks, d_seg_peak, st));
+            CK(launch_agc_digital_scan(d_seg_start, n_chunks, d_seg_peak, qp, d_agc, d_seg_gain, st));
+            CK(launch_post(post_src, post_n, qp, d_seg_start, n_chunks, d_seg_gain, 0, tap2, d_outp, st));
+            launches += 3;
+        } else if (agc_mode == 2) {
+            if (post_n > agc_scratch_cap) {
+                CK(cudaStreamSynchronize(st));
+                cudaFree(d_agc_scratch);
+                agc_scratch_cap = post_n + post_n / 2 + 1024;
+                CK(cudaMalloc(&d_agc_scratch, agc_scratch_cap * sizeof(float2)));
+            }
+            float2* y = d_agc_scratch;
+            CK(launch_agc_rms(post_src, post_n, qp, d_agc, y, st));
+            CK(launch_post(y, post_n, qp, nullptr, 0, nullptr, 1, tap2, d_outp, st));
+            launches += 2;
+        } else {
+            CK(launch_post(post_src, post_n, qp, nullptr, 0, nullptr, 0, tap2, d_outp, st));
+            launches++;
+        }
+    }
+    if (nco_post) n_nco_post += post_n;
+    n_in = N1;
+    n_out += post_n;
+    *out_frames = post_n;
+    return IQGPU_OK;
+}
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int iqgpu_abi_version(void) { return IQGPU_ABI_VERSION; }
+const char* iqgpu_last_error(void) { return g_err.c_str(); }
+int iqgpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+void* iqgpu_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void iqgpu_host_free(void* p) { if (p) cudaFreeHost(p); }
+size_t iqgpu_get_bytes_per_sample(int format) { return bytes_per_sample(format); }
+
+int iqgpu_chain_create(const iqgpu_chain_config* cfgp, int device, iqgpu_chain** out)
+{
+    if (!cfgp || !out) return fail(IQGPU_EINVAL, "null argument");
+    *out = nullptr;
+    const iqgpu_chain_config& g = *cfgp;
+    if (!is_complex_format(g.input_format) || !bytes_per_sample(g.input_format))
+        return fail(IQGPU_EINVAL, "unhandled input format");       // sample_convert.c:207
+    if (!is_complex_format(g.output_format) || !bytes_per_sample(g.output_format))
+        return fail(IQGPU_EINVAL, "unhandled output format");      // sample_convert.c:304
+    iqgpu_chain* c = new iqgpu_chain();
+    c->cfg = g;
+    c->device = device;
+    c->plan_only = device < 0;
+    c->in_rate = (int)g.input_rate_hz;
+    c->target_rate = g.target_rate_hz;
+    c->in_bps = bytes_per_sample(g.input_format);
+    c->out_bps = bytes_per_sample(g.output_format);
+    std::string err;
+    auto bail = [&](int code, const std::string& m) { delete c; return fail(code, m); };
+    if (c->in_rate <= 0) return bail(IQGPU_EINVAL, "input sample rate must be positive");
+    // setup.c:91-113
+    if (g.no_resample) c->target_rate = (double)c->in_rate;
+    c->ratio = (float)(c->target_rate / (double)c->in_rate);
+    if (!std::isfinite(c->ratio) || c->ratio < 0.001f || c->ratio > 1000.0f)
+        return bail(IQGPU_EINVAL, "resampling ratio invalid or outside the acceptable range");
+    c->dc = design_dc(g.dc_block_enable != 0, c->in_rate);
+    if (g.dc_block_enable && c->dc.alpha <= 0.0f) return bail(IQGPU_EINVAL, "DC block alpha invalid");
+    c->iq_mag = g.iq_mag; c->iq_phase = g.iq_phase;
+    // frequency_shift.c:24-84
+    const double shift = (double)(float)g.freq_shift_hz;
+    if (g.shift_after_resample && std::fabs(shift) < 1e-9)
+        return bail(IQGPU_EINVAL, "--shift-after-resample used without an effective frequency shift");
+    if (std::fabs(shift) >= 1e-9) {
+        const double rate = g.shift_after_resample ? c->target_rate : (double)c->in_rate;
+        if (std::fabs(shift) > 5.0 * rate) return bail(IQGPU_EINVAL, "frequency shift exceeds the sanity limit");
+        c->nco_dtheta = nco_dtheta_for_shift(shift, rate);
+        c->nco_sign = shift >= 0 ? 1.0f : -1.0f;
+        c->nco_pre = !g.shift_after_resample;
+        c->nco_post = g.shift_after_resample != 0;
+    }
+    if (!design_resampler(c->ratio, 60.0f, g.no_resample != 0, c->rs, err)) return bail(IQGPU_EINVAL, err);
+    if (!design_filter(g, c->in_rate, c->target_rate, c->filt, err)) return bail(IQGPU_EINVAL, err);
+    // agc.c:21-84
+    if (g.agc_enable && g.agc_profile != IQGPU_AGC_OFF) {
+        if (g.agc_profile == IQGPU_AGC_DIGITAL) {
+            c->agc_mode = 1;
+            c->agc_target = (g.agc_target_level_arg > 0) ? g.agc_target_level_arg : 0.9f;
+        } else {
+            c->agc_mode = 2;
+            c->agc_alpha = (g.agc_profile == IQGPU_AGC_DX) ? 1e-4f : 1e-2f;
+        }
+    }
+    if (!c->plan_only) {
+        int rc = c->init_device();
+        if (rc != IQGPU_OK) { std::string m = g_err; delete c; return fail(rc, m); }
+    }
+    *out = c;
+    return IQGPU_OK;
+}
+
+void iqgpu_chain_destroy(iqgpu_chain* c) { delete c; }
+
+int iqgpu_chain_reset(iqgpu_chain* c)
+{
+    if (!c) return fail(IQGPU_EINVAL, "null chain");
+    return c->reset_state();
+}
+
+int iqgpu_chain_set_option(iqgpu_chain* c, const char* key, int64_t value)
+{
+    if (!c || !key) return fail(IQGPU_EINVAL, "null argument");
+    const std::string k(key);
+    if (k == "fused") { c->want_fused = value != 0; return IQGPU_OK; }
+    if (k == "record_taps") { c->record_taps = value != 0; return IQGPU_OK; }
+    if (k == "subtrain_frames" || k == "chunk_frames") {
+        if (c->buffers_ready) return fail(IQGPU_EINVAL, "option must be set before the first process call");
+        if (value <= 0) return fail(IQGPU_EINVAL, "value must be positive");
+        if (k == "chunk_frames") c->chunk_frames = (uint32_t)value;
+        else c->subtrain_frames = (size_t)value;
+        return IQGPU_OK;
+    }
+    return fail(IQGPU_EINVAL, "unknown option");
+}
+
+int iqgpu_chain_set_iq_factors(iqgpu_chain* c, float mag, float phase)
+{
+    if (!c) return fail(IQGPU_EINVAL, "null chain");
+    c->iq_mag = mag; c->iq_phase = phase;
+    return IQGPU_OK;
+}
+
+int iqgpu_chain_get_info(iqgpu_chain* c, iqgpu_chain_info* o)
+{
+    if (!c || !o) return fail(IQGPU_EINVAL, "null argument");
+    memset(o, 0, sizeof(*o));
+    o->ratio = c->ratio;
+    o->is_interp = c->rs.is_interp;
+    o->num_halfband = c->rs.num_halfband;
+    for (unsigned i = 0; i < c->rs.num_halfband && i < 16; i++) o->halfband_m[i] = c->rs.stages[i].m;
+    o->rate_arbitrary = c->rs.rate_arbitrary;
+    o->arb_step = c->rs.passthrough ? 0 : c->rs.step;
+    o->filter_impl = c->filt.impl;
+    o->filter_post_resample = c->filt.post_resample;
+    o->filter_block_size = c->filt.block;
+    o->filter_num_taps = (uint32_t)c->filt.taps.size();
+    o->nco_dtheta = c->nco_dtheta;
+    o->nco_is_post = c->nco_post;
+    o->frames_in_total = c->n_in;
+    o->frames_out_total = c->n_out;
+    o->fused_front = 0;
+    o->kernel_launches = c->launches;
+    o->halo_frames = (uint32_t)c->rs.halo_input_frames;
+    if (!c->plan_only && c->d_agc) {
+        AgcState a{};
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        if (cudaMemcpy(&a, c->d_agc, sizeof(a), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            o->agc_locked = a.locked; o->agc_gain = a.gain; o->agc_peak_memory = a.peak_mem; o->agc_samples_seen = a.seen;
+        }
+    }
+    return IQGPU_OK;
+}
+
+static int build_chunks(iqgpu_chain* c, size_t n_frames, const uint32_t* chunk_frames, size_t n_chunks,
+                        std::vector<uint32_t>& chunks)
+{
+    if (chunk_frames) {
+        size_t sum = 0;
+        chunks.assign(chunk_frames, chunk_frames + n_chunks);
+        for (auto f : chunks) sum += f;
+        if (sum != n_frames) return fail(IQGPU_EINVAL, "chunk lengths do not add up to n_frames");
+    } else {
+        chunks.clear();
+        size_t left = n_frames;
+        while (left) {
+            uint32_t f = (uint32_t)std::min<size_t>(left, c->chunk_frames);
+            chunks.push_back(f);
+            left -= f;
+        }
+    }
+    return IQGPU_OK;
+}
+
+int iqgpu_chain_predict_output(iqgpu_chain* c, size_t n_frames, size_t* out_frames)
+{
+    if (!c || !out_frames) return fail(IQGPU_EINVAL, "null argument");
+    std::vector<uint32_t> chunks;
+    int rc = build_chunks(c, n_frames, nullptr, 0, chunks);
+    if (rc) return rc;
+    *out_frames = c->count_outputs(chunks.data(), chunks.size(), nullptr);
+    return IQGPU_OK;
+}
+
+int iqgpu_chain_process_device(iqgpu_chain* c, const void* dev_raw_in, size_t n_frames, const uint32_t* chunk_frames,
+                               size_t n_chunks, void* dev_out, size_t out_capacity_bytes, size_t* out_frames,
+                               uint32_t* per_chunk_out, void* cuda_stream)
+{
+    if (!c || !out_frames) return fail(IQGPU_EINVAL, "null argument");
+    if (c->plan_only) return fail(IQGPU_ENODEVICE, "chain was created without a device (plan only)");
+    *out_frames = 0;
+    if (n_frames == 0) return IQGPU_OK;
+    if (!dev_raw_in || !dev_out) return fail(IQGPU_EINVAL, "null buffer");
+    CK(cudaSetDevice(c->device));
+    int rc = c->ensure_buffers();
+    if (rc) return rc;
+    std::vector<uint32_t> chunks;
+    rc = build_chunks(c, n_frames, chunk_frames, n_chunks, chunks);
+    if (rc) return rc;
+    for (auto f : chunks)
+        if (f > c->subtrain_frames) return fail(IQGPU_EINVAL, "a chunk exceeds subtrain_frames");
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+    if (c->count_outputs(chunks.data(), chunks.size(), nullptr) * c->out_bps > out_capacity_bytes)
+        return fail(IQGPU_ECAPACITY, "output buffer too small");
+    for (auto& t : c->tap) t.len = 0;
+    size_t ci = 0, in_off = 0, out_off = 0, total = 0;
+    uint32_t launches = 0;
+    while (ci < chunks.size()) {
+        size_t cj = ci, n = 0;
+        while (cj < chunks.size() && n + chunks[cj] <= c->subtrain_frames) { n += chunks[cj]; cj++; }
+        size_t produced = 0;
+        rc = c->run_subtrain((const char*)dev_raw_in + in_off * c->in_bps, n, chunks.data() + ci, cj - ci,
+                             (char*)dev_out + out_off, &produced, per_chunk_out ? per_chunk_out + ci : nullptr, st);
+        if (rc) return rc;
+        launches += c->launches;
+        in_off += n; out_off += produced * c->out_bps; total += produced;
+        ci = cj;
+    }
+    c->launches = launches;
+    *out_frames = total;
+    return IQGPU_OK;
+}
+
+int iqgpu_chain_process(iqgpu_chain* c, const void* raw_in, size_t n_frames, const uint32_t* chunk_frames, size_t n_chunks,
+                        void* out, size_t out_capacity_bytes, size_t* out_frames, uint32_t* per_chunk_out)
+{
+    if (!c || !out_frames) return fail(IQGPU_EINVAL, "null argument");
+    if (c->plan_only) return fail(IQGPU_ENODEVICE, "chain was created without a device (plan only)");
+    *out_frames = 0;
+    if (n_frames == 0) return IQGPU_OK;
+    if (!raw_in || !out) return fail(IQGPU_EINVAL, "null buffer");
+    CK(cudaSetDevice(c->device));
+    int rc = c->ensure_buffers();
+    if (rc) return rc;
+    std::vector<uint32_t> chunks;
+    rc = build_chunks(c, n_frames, chunk_frames, n_chunks, chunks);
+    if (rc) return rc;
+    for (auto f : chunks)
+        if (f > c->subtrain_frames) return fail(IQGPU_EINVAL, "a chunk exceeds subtrain_frames");
+    if (c->count_outputs(chunks.data(), chunks.size(), nullptr) * c->out_bps > out_capacity_bytes)
+        return fail(IQGPU_ECAPACITY, "output buffer too small");
+    // staging slots sized for one sub-train
+    const size_t raw_need = (c->subtrain_frames + 16) * c->in_bps, out_need = c->max_out_for(c->subtrain_frames) * c->out_bps;
+    if (c->d_raw_bytes < raw_need || c->d_out_bytes < out_need) {
+        for (int i = 0; i < 2; i++) {
+            cudaFree(c->d_raw[i]); cudaFree(c->d_out[i]);
+            CK(cudaMalloc(&c->d_raw[i], raw_need));
+            CK(cudaMalloc(&c->d_out[i], out_need));
+        }
+        c->d_raw_bytes = raw_need; c->d_out_bytes = out_need;
+    }
+    for (auto& t : c->tap) t.len = 0;
+    size_t ci = 0, in_off = 0, out_off = 0, total = 0;
+    uint32_t launches = 0;
+    int slot = 0;
+    bool used[2] = {false, false};
+    while (ci < chunks.size()) {
+        size_t cj = ci, n = 0;
+        while (cj < chunks.size() && n + chunks[cj] <= c->subtrain_frames) { n += chunks[cj]; cj++; }
+        // H2D of this sub-train (waits until the slot's previous D2H finished)
+        if (used[slot]) CK(cudaStreamWaitEvent(c->h2d, c->ev_d2h[slot], 0));
+        CK(cudaMemcpyAsync(c->d_raw[slot], (const char*)raw_in + in_off * c->in_bps, n * c->in_bps, cudaMemcpyHostToDevice, c->h2d));
+        CK(cudaEventRecord(c->ev_h2d[slot], c->h2d));
+        CK(cudaStreamWaitEvent(c->stream, c->ev_h2d[slot], 0));
+        size_t produced = 0;
+        rc = c->run_subtrain(c->d_raw[slot], n, chunks.data() + ci, cj - ci, c->d_out[slot], &produced,
+                             per_chunk_out ? per_chunk_out + ci : nullptr, c->stream);
+        if (rc) return rc;
+        launches += c->launches;
+        CK(cudaEventRecord(c->ev_done[slot], c->stream));
+        CK(cudaStreamWaitEvent(c->d2h, c->ev_done[slot], 0));
+        if (produced)
+            CK(cudaMemcpyAsync((char*)out + out_off, c->d_out[slot], produced * c->out_bps, cudaMemcpyDeviceToHost, c->d2h));
+        CK(cudaEventRecord(c->ev_d2h[slot], c->d2h));
+        used[slot] = true;
+        in_off += n; out_off += produced * c->out_bps; total += produced;
+        ci = cj; slot ^= 1;
+    }
+    CK(cudaStreamSynchronize(c->d2h));
+    CK(cudaStreamSynchronize(c->stream));
+    c->launches = launches;
+    *out_frames = total;
+    return IQGPU_OK;
+}
+
+int iqgpu_chain_read_tap(iqgpu_chain* c, int tapi, float* host_cf32, size_t capacity_frames, size_t* frames)
+{
+    if (!c || !frames || tapi < 0 || tapi > 2) return fail(IQGPU_EINVAL, "bad argument");
+    if (c->plan_only) return fail(IQGPU_ENODEVICE, "plan-only chain");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    const size_t n = c->tap[tapi].len;
+    *frames = n;
+    if (host_cf32) {
+        if (n > capacity_frames) return fail(IQGPU_ECAPACITY, "tap buffer too small");
+        if (n) CK(cudaMemcpy(host_cf32, c->tap[tapi].p, n * sizeof(float2), cudaMemcpyDeviceToHost));
+    }
+    return IQGPU_OK;
+}
+
+int iqgpu_chain_get_filter_taps(iqgpu_chain* c, float* taps, uint32_t capacity, uint32_t* num)
+{
+    if (!c || !num) return fail(IQGPU_EINVAL, "null argument");
+    *num = (uint32_t)c->filt.taps.size();
+    for (uint32_t i = 0; taps && i < *num && i < capacity; i++) { taps[2 * i] = c->filt.taps[i].real(); taps[2 * i + 1] = c->filt.taps[i].imag(); }
+    return IQGPU_OK;
+}
+int iqgpu_chain_get_halfband_taps(iqgpu_chain* c, uint32_t i, float* taps, uint32_t capacity, uint32_t* num)
+{
+    if (!c || !num) return fail(IQGPU_EINVAL, "null argument");
+    if (i >= c->rs.num_halfband) return fail(IQGPU_EINVAL, "stage index out of range");
+    *num = (uint32_t)c->rs.stages[i].h.size();
+    for (uint32_t k = 0; taps && k < *num && k < capacity; k++) taps[k] = c->rs.stages[i].h[k];
+    return IQGPU_OK;
+}
+int iqgpu_chain_get_arb_taps(iqgpu_chain* c, float* taps, uint32_t capacity, uint32_t* num)
+{
+    if (!c || !num) return fail(IQGPU_EINVAL, "null argument");
+    *num = (uint32_t)c->rs.arb_h.size();
+    for (uint32_t k = 0; taps && k < *num && k < capacity; k++) taps[k] = c->rs.arb_h[k];
+    return IQGPU_OK;
+}
+
+int iqgpu_chain_halo_frames(iqgpu_chain* c, size_t* halo)
+{
+    if (!c || !halo) return fail(IQGPU_EINVAL, "null argument");
+    size_t h = (size_t)c->rs.halo_input_frames;
+    // a post-resample FIR needs (ntaps-1) output-rate samples = (ntaps-1)/ratio input frames
+    if (filter_is_fir(c->filt) && c->filt.post_resample)
+        h += (size_t)std::ceil((double)c->filt.taps.size() / (double)c->ratio) + ((size_t)1 << c->rs.num_halfband);
+    else if (filter_is_fir(c->filt)) h += c->filt.taps.size();
+    *halo = h;
+    return IQGPU_OK;
+}
+
+int iqgpu_chain_seek(iqgpu_chain* c, uint64_t first_frame, uint64_t* out_first_frame)
+{
+    if (!c) return fail(IQGPU_EINVAL, "null chain");
+    if (filter_is_fft(c->filt)) return fail(IQGPU_EINVAL, "seek is not supported with an FFT filter (block alignment)");
+    if (c->agc_mode == 2) return fail(IQGPU_EINVAL, "seek is not supported with the RMS AGC (not shardable, SURVEY 8(e))");
+    int rc = c->plan_only ? IQGPU_OK : c->ensure_buffers();
+    if (rc) return rc;
+    rc = c->reset_state();
+    if (rc) return rc;
+    c->n_in = first_frame;
+    const uint64_t o = resampler_outputs_after(c->rs, first_frame);
+    c->n_out = o;
+    c->n_nco_post = o;
+    if (out_first_frame) *out_first_frame = o;
+    return IQGPU_OK;
+}
+
+// ---- sample_convert.h on host buffers -----------------------------------------------------------
+static int convert_common(const void* in, void* out, size_t n, int in_fmt, int out_fmt, float gain)
+{
+    if (!in || !out) return fail(IQGPU_EINVAL, "null buffer");
+    if (n == 0) return IQGPU_OK;
+    iqgpu_chain_config g{};
+    g.input_format = in_fmt; g.output_format = out_fmt;
+    g.input_rate_hz = 1e6; g.target_rate_hz = 1e6; g.gain = gain; g.no_resample = 1;
+    iqgpu_chain* c = nullptr;
+    int rc = iqgpu_chain_create(&g, 0, &c);
+    if (rc) return rc;
+    c->subtrain_frames = std::min<size_t>(std::max<size_t>(n, 1024), (size_t)1 << 22);
+    const uint32_t one = (uint32_t)std::min<size_t>(n, c->subtrain_frames);
+    std::vector<uint32_t> chunks;
+    for (size_t left = n; left;) { uint32_t f = (uint32_t)std::min<size_t>(left, one); chunks.push_back(f); left -= f; }
+    size_t produced = 0;
+    rc = iqgpu_chain_process(c, in, n, chunks.data(), chunks.size(), out, n * bytes_per_sample(out_fmt), &produced, nullptr);
+    std::string m = g_err;
+    delete c;
+    if (rc) return fail(rc, m);
+    return produced == n ? IQGPU_OK : fail(IQGPU_EINVAL, "internal: conversion produced a wrong frame count");
+}
+int iqgpu_convert_block_to_cf32(const void* in, float* out_cf32, size_t n, int format, float gain)
+{
+    if (!is_complex_format(format)) return fail(IQGPU_EINVAL, "Unhandled input format");
+    return convert_common(in, out_cf32, n, format, IQGPU_FMT_CF32, gain);
+}
+int iqgpu_convert_cf32_to_block(const float* in_cf32, void* out, size_t n, int format)
+{
+    if (!is_complex_format(format)) return fail(IQGPU_EINVAL, "Unhandled output format");
+    return convert_common(in_cf32, out, n, IQGPU_FMT_CF32, format, 1.0f);
+}
+
+int iqgpu_iq_optimize(const float*, const float*, float*, float*, float*, float*)
+{
+    return fail(IQGPU_EINVAL, "iqgpu_iq_optimize: not implemented yet");
+}
+
+}  // extern "C"

@@ -1,0 +1,821 @@
+// kernels.cu — stage kernels of the chain (sm_100a).  One kernel family per reference
+// primitive; each header comment names the reference function it replaces.
+//
+// Layout conventions: cf32 streams are interleaved float2 {re, im}; raw integer inputs are
+// interleaved I,Q.  "Stream" pointers address the first NEW sample of a call; older samples
+// (filter history) live at negative offsets in the same allocation (see chain.cu DevStream).
+#include "kernels.hpp"
+
+#include <cstdio>
+
+#include "../../include/iqgpu.h"
+
+namespace iqgpu {
+
+// =============================================================================================
+// raw sample loaders: reference src/sample_convert.c:127-211 (convert_block_to_cf32)
+//   (x * 2^-k) * gain  ==  x * (2^-k * gain) bit for bit: the power-of-two factor is exact, so
+//   both forms round once.  32-bit formats go through double like the reference (:174-196).
+// =============================================================================================
+template <int FMT> struct Fmt;
+template <> struct Fmt<IQGPU_FMT_CS16>    { static constexpr int bytes = 4; };
+template <> struct Fmt<IQGPU_FMT_SC16Q11> { static constexpr int bytes = 4; };
+template <> struct Fmt<IQGPU_FMT_CU16>    { static constexpr int bytes = 4; };
+template <> struct Fmt<IQGPU_FMT_CS8>     { static constexpr int bytes = 2; };
+template <> struct Fmt<IQGPU_FMT_CU8>     { static constexpr int bytes = 2; };
+template <> struct Fmt<IQGPU_FMT_CS24>    { static constexpr int bytes = 6; };
+template <> struct Fmt<IQGPU_FMT_CS32>    { static constexpr int bytes = 8; };
+template <> struct Fmt<IQGPU_FMT_CU32>    { static constexpr int bytes = 8; };
+template <> struct Fmt<IQGPU_FMT_CF32>    { static constexpr int bytes = 8; };
+
+template <int FMT>
+__device__ __forceinline__ float in_scale(float gain)
+{
+    if (FMT == IQGPU_FMT_CS16 || FMT == IQGPU_FMT_CU16) return gain * (1.0f / 32768.0f);
+    if (FMT == IQGPU_FMT_SC16Q11) return gain * (1.0f / 2048.0f);
+    if (FMT == IQGPU_FMT_CS8 || FMT == IQGPU_FMT_CU8) return gain * (1.0f / 128.0f);
+    if (FMT == IQGPU_FMT_CS24) return gain * (1.0f / 8388608.0f);
+    return gain;
+}
+
+// one frame -> cf32 (sc = in_scale<FMT>(gain))
+template <int FMT>
+__device__ __forceinline__ float2 load_frame(const void* __restrict__ raw, size_t i, float sc, float gain)
+{
+    float2 r;
+    if (FMT == IQGPU_FMT_CS16 || FMT == IQGPU_FMT_SC16Q11) {
+        const short2 v = __ldg(reinterpret_cast<const short2*>(raw) + i);
+        r.x = __fmul_rn((float)v.x, sc); r.y = __fmul_rn((float)v.y, sc);
+    } else if (FMT == IQGPU_FMT_CU16) {
+        const ushort2 v = __ldg(reinterpret_cast<const ushort2*>(raw) + i);
+        r.x = __fmul_rn((float)v.x - 32767.5f, sc); r.y = __fmul_rn((float)v.y - 32767.5f, sc);
+    } else if (FMT == IQGPU_FMT_CS8) {
+        const char2 v = __ldg(reinterpret_cast<const char2*>(raw) + i);
+        r.x = __fmul_rn((float)v.x, sc); r.y = __fmul_rn((float)v.y, sc);
+    } else if (FMT == IQGPU_FMT_CU8) {
+        const uchar2 v = __ldg(reinterpret_cast<const uchar2*>(raw) + i);
+        r.x = __fmul_rn((float)v.x - 127.5f, sc); r.y = __fmul_rn((float)v.y - 127.5f, sc);
+    } else if (FMT == IQGPU_FMT_CS24) {
+        const unsigned char* p = reinterpret_cast<const unsigned char*>(raw) + i * 6;
+        int a = (int)(((unsigned)p[0] << 8) | ((unsigned)p[1] << 16) | ((unsigned)p[2] << 24)) >> 8;
+        int b = (int)(((unsigned)p[3] << 8) | ((unsigned)p[4] << 16) | ((unsigned)p[5] << 24)) >> 8;
+        r.x = __fmul_rn((float)a, sc); r.y = __fmul_rn((float)b, sc);
+    } else if (FMT == IQGPU_FMT_CS32) {
+        const int2 v = __ldg(reinterpret_cast<const int2*>(raw) + i);
+        r.x = (float)(((double)v.x * (1.0 / 2147483648.0)) * (double)gain);
+        r.y = (float)(((double)v.y * (1.0 / 2147483648.0)) * (double)gain);
+    } else if (FMT == IQGPU_FMT_CU32) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(raw) + i);
+        r.x = (float)((((double)v.x - 2147483647.5) * (1.0 / 2147483648.0)) * (double)gain);
+        r.y = (float)((((double)v.y - 2147483647.5) * (1.0 / 2147483648.0)) * (double)gain);
+    } else {  // CF32
+        const float2 v = __ldg(reinterpret_cast<const float2*>(raw) + i);
+        r.x = __fmul_rn(v.x, gain); r.y = __fmul_rn(v.y, gain);
+    }
+    return r;
+}
+
+// four consecutive frames starting at i (i % 4 == 0 relative to a 16-byte aligned base); frames
+// at or beyond n read as zero.
+template <int FMT>
+__device__ __forceinline__ void load_quad(const void* __restrict__ raw, size_t i, size_t n, float sc, float gain,
+                                          bool aligned, float2 (&x)[4])
+{
+    if (aligned && i + 4 <= n) {
+        if (FMT == IQGPU_FMT_CS16 || FMT == IQGPU_FMT_SC16Q11) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(raw) + i * 4));
+            const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                x[k].x = __fmul_rn((float)(short)(w[k] & 0xffffu), sc);
+                x[k].y = __fmul_rn((float)(short)(w[k] >> 16), sc);
+            }
+            return;
+        }
+        if (FMT == IQGPU_FMT_CU8 || FMT == IQGPU_FMT_CS8) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(raw) + i * 2));
+            const unsigned w[2] = {v.x, v.y};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                unsigned b0 = (w[k >> 1] >> ((k & 1) * 16)) & 0xffu, b1 = (w[k >> 1] >> ((k & 1) * 16 + 8)) & 0xffu;
+                if (FMT == IQGPU_FMT_CU8) {
+                    x[k].x = __fmul_rn((float)b0 - 127.5f, sc); x[k].y = __fmul_rn((float)b1 - 127.5f, sc);
+                } else {
+                    x[k].x = __fmul_rn((float)(signed char)b0, sc); x[k].y = __fmul_rn((float)(signed char)b1, sc);
+                }
+            }
+            return;
+        }
+        if (FMT == IQGPU_FMT_CF32) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const char*>(raw) + i * 8));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const char*>(raw) + i * 8) + 1);
+            x[0] = make_float2(__fmul_rn(a.x, gain), __fmul_rn(a.y, gain));
+            x[1] = make_float2(__fmul_rn(a.z, gain), __fmul_rn(a.w, gain));
+            x[2] = make_float2(__fmul_rn(b.x, gain), __fmul_rn(b.y, gain));
+            x[3] = make_float2(__fmul_rn(b.z, gain), __fmul_rn(b.w, gain));
+            return;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        x[k] = (i + k < n) ? load_frame<FMT>(raw, i + k, sc, gain) : make_float2(0.f, 0.f);
+}
+
+// =============================================================================================
+// DC blocker as a blocked linear scan.
+//   reference src/dc_block.c:76 -> liquid iirfilt (direct form II):  v[n] = x[n] + c v[n-1],
+//   y[n] = v[n] - v[n-1]  ==  x[n] - (1-c) v[n-1].
+// A warp owns a contiguous "run"; each lane owns 4 consecutive samples of every 128-sample
+// row.  Row-local weighted prefix sums use shuffles; the run carry is kept in double.
+// =============================================================================================
+struct DcDev {
+    float c, a;        // pole, 1-pole
+    float w[5];        // c^(4*2^d), d = 0..4
+    float lanepow[32]; // c^(4*lane)
+    double c128;       // c^128
+};
+
+__host__ static DcDev make_dc_dev(float c, float a)
+{
+    DcDev d;
+    d.c = c; d.a = a;
+    for (int k = 0; k < 5; k++) d.w[k] = (float)pow((double)c, 4.0 * (double)(1 << k));
+    for (int l = 0; l < 32; l++) d.lanepow[l] = (float)pow((double)c, 4.0 * l);
+    d.c128 = pow((double)c, 128.0);
+    return d;
+}
+
+// returns the row's inclusive weighted total in lane 31 (all lanes get it via shfl) and, per lane,
+// E = v contribution of the lanes below (relative to a zero state at the row start)
+__device__ __forceinline__ void dc_row_scan(const float2 (&x)[4], const DcDev& d, int lane, float2& E, float2& T)
+{
+    // local weighted sum of the lane's 4 samples
+    float pr = x[0].x, pi = x[0].y;
+#pragma unroll
+    for (int k = 1; k < 4; k++) { pr = fmaf(pr, d.c, x[k].x); pi = fmaf(pi, d.c, x[k].y); }
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+        const int dist = 1 << s;
+        float qr = __shfl_up_sync(0xffffffffu, pr, dist);
+        float qi = __shfl_up_sync(0xffffffffu, pi, dist);
+        if (lane >= dist) { pr = fmaf(d.w[s], qr, pr); pi = fmaf(d.w[s], qi, pi); }
+    }
+    float er = __shfl_up_sync(0xffffffffu, pr, 1), ei = __shfl_up_sync(0xffffffffu, pi, 1);
+    E = (lane == 0) ? make_float2(0.f, 0.f) : make_float2(er, ei);
+    T.x = __shfl_sync(0xffffffffu, pr, 31);
+    T.y = __shfl_sync(0xffffffffu, pi, 31);
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(256) dc_run_sums_kernel(const void* __restrict__ raw, size_t n, float gain,
+                                                          DcDev d, uint32_t run_len, size_t n_runs, bool aligned,
+                                                          double2* __restrict__ run_sums)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const float sc = in_scale<FMT>(gain);
+    for (size_t run = warp; run < n_runs; run += nwarps) {
+        const size_t base = run * run_len;
+        const size_t end = (base + run_len < n) ? base + run_len : n;
+        double vr = 0.0, vi = 0.0;
+        for (size_t i0 = base; i0 < end; i0 += 128) {
+            float2 x[4], E, T;
+            load_quad<FMT>(raw, i0 + lane * 4, n, sc, gain, aligned, x);
+            dc_row_scan(x, d, lane, E, T);
+            vr = fma(d.c128, vr, (double)T.x);
+            vi = fma(d.c128, vi, (double)T.y);
+        }
+        if (lane == 0) run_sums[run] = make_double2(vr, vi);
+    }
+}
+
+// single block: exclusive scan of the affine maps v -> A v + S_r over the runs
+__global__ void __launch_bounds__(1024) dc_scan_kernel(const double2* __restrict__ run_sums, size_t n_runs,
+                                                       uint32_t run_len, size_t n, double c,
+                                                       double2* __restrict__ carry, double2* __restrict__ run_start)
+{
+    __shared__ double sa[1024], sbr[1024], sbi[1024];
+    const int t = threadIdx.x;
+    const size_t per = (n_runs + 1023) / 1024;
+    const size_t r0 = (size_t)t * per, r1 = (r0 + per < n_runs) ? r0 + per : n_runs;
+    const double A = pow(c, (double)run_len);
+    // padded length of the last run (rows are processed whole; the zeros only decay the state)
+    const size_t last_len = n - (n_runs - 1) * (size_t)run_len;
+    const size_t last_pad = ((last_len + 127) / 128) * 128;
+    const double A_last = pow(c, (double)last_pad);
+    double a = 1.0, br = 0.0, bi = 0.0;
+    for (size_t r = r0; r < r1; r++) {
+        const double Ar = (r == n_runs - 1) ? A_last : A;
+        const double2 s = run_sums[r];
+        a *= Ar; br = Ar * br + s.x; bi = Ar * bi + s.y;
+    }
+    sa[t] = a; sbr[t] = br; sbi[t] = bi;
+    __syncthreads();
+    for (int dist = 1; dist < 1024; dist <<= 1) {
+        double pa = 1.0, pbr = 0.0, pbi = 0.0;
+        if (t >= dist) { pa = sa[t - dist]; pbr = sbr[t - dist]; pbi = sbi[t - dist]; }
+        __syncthreads();
+        if (t >= dist) {  // compose: (a,b) after (pa,pb)
+            sbr[t] = sa[t] * pbr + sbr[t];
+            sbi[t] = sa[t] * pbi + sbi[t];
+            sa[t] = sa[t] * pa;
+        }
+        __syncthreads();
+    }
+    const double2 v0 = *carry;
+    double ea = 1.0, ebr = 0.0, ebi = 0.0;  // exclusive prefix of this thread
+    if (t > 0) { ea = sa[t - 1]; ebr = sbr[t - 1]; ebi = sbi[t - 1]; }
+    double vr = ea * v0.x + ebr, vi = ea * v0.y + ebi;
+    for (size_t r = r0; r < r1; r++) {
+        run_start[r] = make_double2(vr, vi);
+        const double Ar = (r == n_runs - 1) ? A_last : A;
+        const double2 s = run_sums[r];
+        vr = Ar * vr + s.x; vi = Ar * vi + s.y;
+    }
+    __syncthreads();
+    if (t == 1023) {
+        // state after ALL runs, with the zero padding of the last row undone
+        double fr = sa[1023] * v0.x + sbr[1023], fi = sa[1023] * v0.y + sbi[1023];
+        const double undo = pow(c, -(double)(last_pad - last_len));
+        *carry = make_double2(fr * undo, fi * undo);
+    }
+}
+
+// =============================================================================================
+// K1: pre-processor chain on one call: convert -> DC -> I/Q apply -> NCO mix
+//   reference src/pre_processor.c:10-55 (order), sample_convert.c:127, dc_block.c:76,
+//   iq_correct.c:307-313, frequency_shift.c:86-96 (liquid nco_crcf_mix_block_up/down).
+// Element-wise stages use unfused multiplies/adds so they reproduce the C arithmetic exactly.
+// =============================================================================================
+__device__ __forceinline__ float2 nco_mix(float2 x, uint32_t theta, float sign, const float* __restrict__ lut)
+{
+    const unsigned idx = ((theta + (1u << 21)) >> 22) & 0x3ffu;
+    const float s = lut[idx] * sign;
+    const float c = lut[(idx + 256u) & 0x3ffu];
+    float2 y;
+    y.x = __fsub_rn(__fmul_rn(x.x, c), __fmul_rn(x.y, s));
+    y.y = __fadd_rn(__fmul_rn(x.x, s), __fmul_rn(x.y, c));
+    return y;
+}
+
+template <int FMT, bool DC>
+__global__ void __launch_bounds__(256) pre_kernel(const void* __restrict__ raw, size_t n, PreParams p, DcDev d,
+                                                  uint32_t run_len, size_t n_runs, bool aligned,
+                                                  const double2* __restrict__ run_start, float2* __restrict__ out)
+{
+    __shared__ float lut[1024];
+    if (p.nco_enable) {
+        for (int i = threadIdx.x; i < 1024; i += blockDim.x) lut[i] = p.nco_table[i];
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const float sc = in_scale<FMT>(p.gain);
+    const float lanepow = DC ? d.lanepow[lane] : 0.f;
+    const bool out_aligned = ((reinterpret_cast<size_t>(out) & 15) == 0);
+    for (size_t run = warp; run < n_runs; run += nwarps) {
+        const size_t base = run * run_len;
+        const size_t end = (base + run_len < n) ? base + run_len : n;
+        double vr = 0.0, vi = 0.0;
+        if (DC) { const double2 v = run_start[run]; vr = v.x; vi = v.y; }
+        for (size_t i0 = base; i0 < end; i0 += 128) {
+            const size_t i = i0 + lane * 4;
+            float2 x[4];
+            load_quad<FMT>(raw, i, n, sc, p.gain, aligned, x);
+            if (DC) {
+                float2 E, T;
+                dc_row_scan(x, d, lane, E, T);
+                // v just before the lane's first sample
+                float wr = fmaf(lanepow, (float)vr, E.x), wi = fmaf(lanepow, (float)vi, E.y);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float xr = x[k].x, xi = x[k].y;
+                    x[k].x = fmaf(-d.a, wr, xr);
+                    x[k].y = fmaf(-d.a, wi, xi);
+                    wr = fmaf(d.c, wr, xr);
+                    wi = fmaf(d.c, wi, xi);
+                }
+                vr = fma(d.c128, vr, (double)T.x);
+                vi = fma(d.c128, vi, (double)T.y);
+            }
+            if (p.iq_enable) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const float re = x[k].x;
+                    x[k].x = __fmul_rn(re, p.iq_magp1);
+                    x[k].y = __fadd_rn(x[k].y, __fmul_rn(p.iq_phase, re));
+                }
+            }
+            if (p.nco_enable) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t th = p.nco_theta0 + (uint32_t)(i + k) * p.nco_dtheta;
+                    x[k] = nco_mix(x[k], th, p.nco_sign, lut);
+                }
+            }
+            if (out_aligned && i + 4 <= n) {
+                float4* o = reinterpret_cast<float4*>(out + i);
+                o[0] = make_float4(x[0].x, x[0].y, x[1].x, x[1].y);
+                o[1] = make_float4(x[2].x, x[2].y, x[3].x, x[3].y);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (i + k < n) out[i + k] = x[k];
+            }
+        }
+    }
+}
+
+static inline int grid_for_warps(size_t warps_needed, int threads)
+{
+    size_t blocks = (warps_needed * 32 + threads - 1) / threads;
+    const size_t cap = 148 * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+#define DISPATCH_FMT(fmt, CALL)                                          \
+    switch (fmt) {                                                        \
+        case IQGPU_FMT_CS16:    { CALL(IQGPU_FMT_CS16); break; }          \
+        case IQGPU_FMT_SC16Q11: { CALL(IQGPU_FMT_SC16Q11); break; }       \
+        case IQGPU_FMT_CU16:    { CALL(IQGPU_FMT_CU16); break; }          \
+        case IQGPU_FMT_CS8:     { CALL(IQGPU_FMT_CS8); break; }           \
+        case IQGPU_FMT_CU8:     { CALL(IQGPU_FMT_CU8); break; }           \
+        case IQGPU_FMT_CS24:    { CALL(IQGPU_FMT_CS24); break; }          \
+        case IQGPU_FMT_CS32:    { CALL(IQGPU_FMT_CS32); break; }          \
+        case IQGPU_FMT_CU32:    { CALL(IQGPU_FMT_CU32); break; }          \
+        case IQGPU_FMT_CF32:    { CALL(IQGPU_FMT_CF32); break; }          \
+        default: return cudaErrorInvalidValue;                            \
+    }
+
+cudaError_t launch_dc_run_sums(const void* raw, size_t n, const PreParams& p, uint32_t run_len,
+                               double2* run_sums, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    const size_t n_runs = (n + run_len - 1) / run_len;
+    const DcDev d = make_dc_dev(p.dc_c, p.dc_a);
+    const bool aligned = (reinterpret_cast<size_t>(raw) & 15) == 0;
+    const int grid = grid_for_warps(n_runs, 256);
+#define CALL(F) dc_run_sums_kernel<F><<<grid, 256, 0, st>>>(raw, n, p.gain, d, run_len, n_runs, aligned, run_sums)
+    DISPATCH_FMT(p.format, CALL)
+#undef CALL
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dc_scan(const double2* run_sums, size_t n_runs, uint32_t run_len, size_t n,
+                           float dc_c, double2* carry_inout, double2* run_start, cudaStream_t st)
+{
+    if (n_runs == 0) return cudaSuccess;
+    dc_scan_kernel<<<1, 1024, 0, st>>>(run_sums, n_runs, run_len, n, (double)dc_c, carry_inout, run_start);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pre(const void* raw, size_t n, const PreParams& p, uint32_t run_len,
+                       const double2* run_start, float2* out, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    const size_t n_runs = (n + run_len - 1) / run_len;
+    const DcDev d = make_dc_dev(p.dc_enable ? p.dc_c : 0.f, p.dc_a);
+    const bool aligned = (reinterpret_cast<size_t>(raw) & 15) == 0;
+    const int grid = grid_for_warps(n_runs, 256);
+#define CALL(F)                                                                                             \
+    if (p.dc_enable) pre_kernel<F, true><<<grid, 256, 0, st>>>(raw, n, p, d, run_len, n_runs, aligned, run_start, out); \
+    else pre_kernel<F, false><<<grid, 256, 0, st>>>(raw, n, p, d, run_len, n_runs, aligned, run_start, out)
+    DISPATCH_FMT(p.format, CALL)
+#undef CALL
+    return cudaGetLastError();
+}
+
+// =============================================================================================
+// K2 (unfused building blocks): liquid msresamp_crcf pieces, reference src/resampler.c:49
+// =============================================================================================
+// halfband decimator (liquid resamp2_crcf_decim_execute):
+//   y[k] = sum_{j<2m} h1[j] x[2(k-2m+1+j)] + x[2(k-m)+1]      (x by absolute stage-input index)
+__global__ void __launch_bounds__(256) halfband_decim_kernel(const float2* __restrict__ x, long long a0,
+                                                             const float* __restrict__ h1, unsigned m,
+                                                             long long k0, size_t count, float scale,
+                                                             float2* __restrict__ y)
+{
+    extern __shared__ float sh1[];
+    for (unsigned i = threadIdx.x; i < 2 * m; i += blockDim.x) sh1[i] = h1[i];
+    __syncthreads();
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += (size_t)gridDim.x * blockDim.x) {
+        const long long k = k0 + (long long)t;
+        const float2* xe = x + (2 * (k - 2 * (long long)m + 1) - a0);
+        float sr = 0.f, si = 0.f;
+        for (unsigned j = 0; j < 2 * m; j++) {
+            const float2 v = xe[2 * j];
+            sr = fmaf(sh1[j], v.x, sr);
+            si = fmaf(sh1[j], v.y, si);
+        }
+        const float2 c = x[2 * (k - (long long)m) + 1 - a0];
+        y[t] = make_float2((c.x + sr) * scale, (c.y + si) * scale);
+    }
+}
+
+// halfband interpolator (liquid resamp2_crcf_interp_execute):
+//   y[2k] = x[k-m] ;  y[2k+1] = sum_{j<2m} h1[j] x[k-2m+1+j]
+__global__ void __launch_bounds__(256) halfband_interp_kernel(const float2* __restrict__ x, long long a0,
+                                                              const float* __restrict__ h1, unsigned m,
+                                                              long long k0, size_t count, float2* __restrict__ y)
+{
+    extern __shared__ float sh1[];
+    for (unsigned i = threadIdx.x; i < 2 * m; i += blockDim.x) sh1[i] = h1[i];
+    __syncthreads();
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += (size_t)gridDim.x * blockDim.x) {
+        const long long k = k0 + (long long)t;
+        const float2* xw = x + (k - 2 * (long long)m + 1 - a0);
+        float sr = 0.f, si = 0.f;
+        for (unsigned j = 0; j < 2 * m; j++) {
+            const float2 v = xw[j];
+            sr = fmaf(sh1[j], v.x, sr);
+            si = fmaf(sh1[j], v.y, si);
+        }
+        y[2 * t] = x[k - (long long)m - a0];
+        y[2 * t + 1] = make_float2(sr, si);
+    }
+}
+
+// arbitrary-rate polyphase stage (liquid resamp_crcf, fixed-point phase; firpfb bank of 256):
+//   output o: P = phase0 + o*step, k = kbase + (P >> 24), idx = (P & (2^24-1)) >> 16,
+//   y = sum_{i<14} bank[idx][i] * x[k-13+i]
+__global__ void __launch_bounds__(256) arb_kernel(const float2* __restrict__ x, long long a0,
+                                                  const float* __restrict__ bank, uint32_t step, long long kbase,
+                                                  uint32_t phase0, size_t count, float2* __restrict__ y)
+{
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += (size_t)gridDim.x * blockDim.x) {
+        const unsigned long long P = (unsigned long long)phase0 + (unsigned long long)t * step;
+        const long long k = kbase + (long long)(P >> 24);
+        const unsigned idx = (unsigned)((P & 0xffffffull) >> 16);
+        const float* __restrict__ b = bank + idx * 14;
+        const float2* xw = x + (k - 13 - a0);
+        float sr = 0.f, si = 0.f;
+#pragma unroll
+        for (int i = 0; i < 14; i++) {
+            const float2 v = xw[i];
+            const float h = __ldg(b + i);
+            sr = fmaf(h, v.x, sr);
+            si = fmaf(h, v.y, si);
+        }
+        y[t] = make_float2(sr, si);
+    }
+}
+
+static inline int grid_1d(size_t count, int threads)
+{
+    size_t blocks = (count + threads - 1) / threads;
+    const size_t cap = 148 * 32;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+cudaError_t launch_halfband_decim(const float2* x, int64_t a0, const float* h1, unsigned m, int64_t k0,
+                                  size_t count, float scale, float2* y, cudaStream_t st)
+{
+    if (count == 0) return cudaSuccess;
+    halfband_decim_kernel<<<grid_1d(count, 256), 256, 2 * m * sizeof(float), st>>>(x, a0, h1, m, k0, count, scale, y);
+    return cudaGetLastError();
+}
+cudaError_t launch_halfband_interp(const float2* x, int64_t a0, const float* h1, unsigned m, int64_t k0,
+                                   size_t count, float2* y, cudaStream_t st)
+{
+    if (count == 0) return cudaSuccess;
+    halfband_interp_kernel<<<grid_1d(count, 256), 256, 2 * m * sizeof(float), st>>>(x, a0, h1, m, k0, count, y);
+    return cudaGetLastError();
+}
+cudaError_t launch_arb(const float2* x, int64_t a0, const float* bank, uint32_t step, int64_t kbase,
+                       uint32_t phase0, size_t count, float2* y, cudaStream_t st)
+{
+    if (count == 0) return cudaSuccess;
+    arb_kernel<<<grid_1d(count, 256), 256, 0, st>>>(x, a0, bank, step, kbase, phase0, count, y);
+    return cudaGetLastError();
+}
+
+// =============================================================================================
+// K3: tiled time-domain FIR.  reference src/filter.c:449-462 -> liquid firfilt_crcf/cccf
+//   y[n] = sum_{i<N} hrev[i] x[n-(N-1)+i]   (oldest sample first, like liquid's dot product)
+// Block: 128 threads x 8 consecutive outputs = 1024 outputs.  Taps are consumed in chunks of
+// FIR_TC; the input window of a chunk is staged in shared memory with one pad slot per 8
+// samples so that lane-strided reads (stride 8 float2) are bank-conflict free.  Each thread
+// keeps an 8-sample sliding register window: one LDS.64 + 16 (real) / 32 (complex) FFMA per tap.
+// =============================================================================================
+constexpr int FIR_R = 8;
+constexpr int FIR_THREADS = 128;
+constexpr int FIR_TILE = FIR_R * FIR_THREADS;   // outputs per block
+constexpr int FIR_TC = 256;                     // taps per chunk (multiple of FIR_R)
+__device__ __forceinline__ int fir_pad(int j) { return j + (j >> 3); }
+
+template <bool CPLX>
+__global__ void __launch_bounds__(FIR_THREADS) fir_kernel(const float2* __restrict__ x, size_t n,
+                                                          const float* __restrict__ hrev, unsigned ntaps,
+                                                          float2* __restrict__ y)
+{
+    constexpr int WIN = FIR_TILE + FIR_TC;  // samples staged per chunk (one spare group)
+    __shared__ float2 sx[WIN + WIN / 8 + 8];
+    __shared__ float2 sh[FIR_TC];           // (re, im) or (re, 0)
+    const int t = threadIdx.x;
+    const long long tile0 = (long long)blockIdx.x * FIR_TILE;  // first output of this block
+    float2 acc[FIR_R];
+#pragma unroll
+    for (int r = 0; r < FIR_R; r++) acc[r] = make_float2(0.f, 0.f);
+
+    for (unsigned c0 = 0; c0 < ntaps; c0 += FIR_TC) {
+        const int tc = (ntaps - c0 < (unsigned)FIR_TC) ? (int)(ntaps - c0) : FIR_TC;
+        // sample needed by output o (block-relative) and tap i: x[tile0 + o - (ntaps-1) + i]
+        const long long wbase = tile0 - (long long)(ntaps - 1) + c0;
+        __syncthreads();
+        for (int j = t; j < FIR_TILE + tc - 1; j += FIR_THREADS) {
+            const long long g = wbase + j;
+            sx[fir_pad(j)] = (g < (long long)n) ? x[g] : make_float2(0.f, 0.f);
+        }
+        for (int j = t; j < tc; j += FIR_THREADS)
+            sh[j] = CPLX ? make_float2(hrev[2 * (c0 + j)], hrev[2 * (c0 + j) + 1]) : make_float2(hrev[c0 + j], 0.f);
+        __syncthreads();
+
+        float2 win[FIR_R];
+        const int o0 = t * FIR_R;
+#pragma unroll
+        for (int r = 0; r < FIR_R; r++) win[r] = sx[fir_pad(o0 + r)];
+        for (int i0 = 0; i0 < tc; i0 += FIR_R) {
+#pragma unroll
+            for (int u = 0; u < FIR_R; u++) {
+                const float2 h = sh[i0 + u];
+#pragma unroll
+                for (int r = 0; r < FIR_R; r++) {
+                    const float2 v = win[(r + u) % FIR_R];
+                    if (CPLX) {
+                        // (hr + j hi)(vr + j vi)
+                        acc[r].x = fmaf(h.x, v.x, acc[r].x);
+                        acc[r].x = fmaf(-h.y, v.y, acc[r].x);
+                        acc[r].y = fmaf(h.x, v.y, acc[r].y);
+                        acc[r].y = fmaf(h.y, v.x, acc[r].y);
+                    } else {
+                        acc[r].x = fmaf(h.x, v.x, acc[r].x);
+                        acc[r].y = fmaf(h.x, v.y, acc[r].y);
+                    }
+                }
+                win[u % FIR_R] = sx[fir_pad(o0 + i0 + u + FIR_R)];
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < FIR_R; r++) {
+        const long long o = tile0 + t * FIR_R + r;
+        if (o < (long long)n) y[o] = acc[r];
+    }
+}
+
+cudaError_t launch_fir(const float2* x, size_t n, const float* hrev, unsigned ntaps_padded, int complex_taps,
+                       float2* y, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    const int grid = (int)((n + FIR_TILE - 1) / FIR_TILE);
+    if (complex_taps) fir_kernel<true><<<grid, FIR_THREADS, 0, st>>>(x, n, hrev, ntaps_padded, y);
+    else fir_kernel<false><<<grid, FIR_THREADS, 0, st>>>(x, n, hrev, ntaps_padded, y);
+    return cudaGetLastError();
+}
+
+// =============================================================================================
+// K5: post-processor.  reference src/post_processor.c:9-70 (order), frequency_shift.c:86-96,
+//     agc.c:86-222, sample_convert.c:213-306.
+// =============================================================================================
+__device__ __forceinline__ unsigned find_segment(const uint32_t* __restrict__ seg_start, unsigned nseg, uint32_t i)
+{
+    // largest s with seg_start[s] <= i  (seg_start[nseg] == n)
+    unsigned lo = 0, hi = nseg;
+    while (hi - lo > 1) {
+        const unsigned mid = (lo + hi) >> 1;
+        if (__ldg(seg_start + mid) <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// per-segment peak |x| after the (optional) post NCO.  reference agc.c:117-124 / 168-173 uses
+// cabsf (hypotf, correctly rounded): each thread tracks its largest |x|^2 and evaluates the
+// magnitude of that one sample in double.
+__global__ void __launch_bounds__(256) agc_peaks_kernel(const float2* __restrict__ x, size_t n, PostParams p,
+                                                        const uint32_t* __restrict__ seg_start, unsigned nseg,
+                                                        float* __restrict__ seg_peak)
+{
+    __shared__ float lut[1024];
+    if (p.nco_enable) {
+        for (int i = threadIdx.x; i < 1024; i += blockDim.x) lut[i] = p.nco_table[i];
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    for (size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < n; i0 += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = i0 + lane;
+        float mag = 0.f;
+        unsigned seg = 0xffffffffu;
+        if (i < n) {
+            float2 v = x[i];
+            if (p.nco_enable) v = nco_mix(v, p.nco_theta0 + (uint32_t)i * p.nco_dtheta, p.nco_sign, lut);
+            mag = (float)sqrt((double)v.x * (double)v.x + (double)v.y * (double)v.y);
+            seg = find_segment(seg_start, nseg, (uint32_t)i);
+        }
+        const unsigned seg0 = __shfl_sync(0xffffffffu, seg, 0);
+        const bool uniform = __all_sync(0xffffffffu, seg == seg0);
+        if (uniform) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) mag = fmaxf(mag, __shfl_xor_sync(0xffffffffu, mag, d));
+            if (lane == 0 && seg0 != 0xffffffffu) atomicMax(reinterpret_cast<unsigned*>(seg_peak) + seg0, __float_as_uint(mag));
+        } else if (seg != 0xffffffffu) {
+            atomicMax(reinterpret_cast<unsigned*>(seg_peak) + seg, __float_as_uint(mag));
+        }
+    }
+}
+
+// digital AGC state machine, one step per reference chunk (agc.c:105-222).  Wall-clock reads in
+// the reference (agc.c:176,202-207) are replaced by the sample clock seen/target_rate.
+__global__ void agc_digital_scan_kernel(const uint32_t* __restrict__ seg_start, unsigned nseg,
+                                        const float* __restrict__ seg_peak, PostParams p,
+                                        AgcState* __restrict__ st, float* __restrict__ seg_gain)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    AgcState s = *st;
+    const float target = p.agc_target;
+    for (unsigned c = 0; c < nseg; c++) {
+        const unsigned cnt = seg_start[c + 1] - seg_start[c];
+        if (cnt == 0) { seg_gain[c] = 1.0f; continue; }          // agc_apply returns on num_samples == 0
+        const float pk = seg_peak[c];
+        float g;
+        if (!s.locked) {
+            if (pk > s.peak_mem) s.peak_mem = pk;
+            const float safe = (s.peak_mem < 1e-4f) ? 1e-4f : s.peak_mem;
+            g = __fdiv_rn(target, safe);
+            const double elapsed = (double)s.seen / p.target_rate;
+            if (elapsed > (double)2.0f) {
+                s.locked = 1; s.gain = g;
+                s.last_strong = elapsed;
+            }
+        } else {
+            g = s.gain;
+            const float opk = __fmul_rn(pk, g);
+            const double now = (double)s.seen / p.target_rate;
+            if (opk > 1.0f) {
+                g = __fdiv_rn(0.99f, pk);
+                s.last_strong = now;
+            } else if (opk > __fmul_rn(target, 0.75f)) {
+                s.last_strong = now;
+            } else if (now - s.last_strong > (double)4.0f) {
+                g = __fmul_rn(g, 1.0005f);
+            }
+            s.gain = g;
+        }
+        seg_gain[c] = g;
+        s.seen += cnt;
+    }
+    *st = s;
+}
+
+// liquid agc_crcf_execute_block (agc.c:92-100): nonlinear per-sample recurrence; serial.
+__global__ void agc_rms_kernel(const float2* __restrict__ x, size_t n, PostParams p, AgcState* __restrict__ st,
+                               float2* __restrict__ y)
+{
+    __shared__ float lut[1024];
+    if (p.nco_enable) {
+        for (int i = threadIdx.x; i < 1024; i += blockDim.x) lut[i] = p.nco_table[i];
+    }
+    __syncthreads();
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float g = st->rms_g, y2p = st->rms_y2;
+    const float alpha = p.agc_alpha;
+    const double oma = 1.0 - (double)alpha;
+    for (size_t i = 0; i < n; i++) {
+        float2 v = x[i];
+        if (p.nco_enable) v = nco_mix(v, p.nco_theta0 + (uint32_t)i * p.nco_dtheta, p.nco_sign, lut);
+        const float yr = __fmul_rn(v.x, g), yi = __fmul_rn(v.y, g);
+        const float y2 = __fadd_rn(__fmul_rn(yr, yr), __fmul_rn(yi, yi));
+        y2p = (float)(oma * (double)y2p + (double)__fmul_rn(alpha, y2));
+        if (y2p > 1e-6f) {
+            // logf/expf evaluated in double and rounded once: matches a correctly rounded libm
+            const float lf = (float)log((double)y2p);
+            const float ex = (float)exp((double)__fmul_rn(__fmul_rn(-0.5f, alpha), lf));
+            g = __fmul_rn(g, ex);
+        }
+        if (g > 1e6f) g = 1e6f;
+        y[i] = make_float2(yr, yi);
+    }
+    st->rms_g = g; st->rms_y2 = y2p;
+}
+
+// cf32 -> output sample formats, reference sample_convert.c:40-73, 213-306
+template <int FMT>
+__device__ __forceinline__ void store_out(void* __restrict__ out, size_t i, float2 v)
+{
+    if (FMT == IQGPU_FMT_CF32) {
+        reinterpret_cast<float2*>(out)[i] = v;
+    } else if (FMT == IQGPU_FMT_CS16 || FMT == IQGPU_FMT_SC16Q11 || FMT == IQGPU_FMT_CS8) {
+        const float S = (FMT == IQGPU_FMT_CS16) ? 32767.0f : (FMT == IQGPU_FMT_SC16Q11 ? 2048.0f : 127.0f);
+        const float hi = (FMT == IQGPU_FMT_CS8) ? 127.0f : 32767.0f;
+        const float lo = (FMT == IQGPU_FMT_CS8) ? -128.0f : -32768.0f;
+        float a = __fmul_rn(v.x, S), b = __fmul_rn(v.y, S);
+        a = (a > 0.0f) ? __fadd_rn(a, 0.5f) : __fsub_rn(a, 0.5f);
+        b = (b > 0.0f) ? __fadd_rn(b, 0.5f) : __fsub_rn(b, 0.5f);
+        a = (a > hi) ? hi : a; a = (a < lo) ? lo : a;
+        b = (b > hi) ? hi : b; b = (b < lo) ? lo : b;
+        const int ia = __float2int_rz(a), ib = __float2int_rz(b);
+        if (FMT == IQGPU_FMT_CS8) reinterpret_cast<char2*>(out)[i] = make_char2((signed char)ia, (signed char)ib);
+        else reinterpret_cast<short2*>(out)[i] = make_short2((short)ia, (short)ib);
+    } else if (FMT == IQGPU_FMT_CU8 || FMT == IQGPU_FMT_CU16) {
+        const float S = (FMT == IQGPU_FMT_CU8) ? 127.0f : 32767.0f;
+        const float OFF = (FMT == IQGPU_FMT_CU8) ? 127.5f : 32767.5f;
+        const float hi = (FMT == IQGPU_FMT_CU8) ? 255.0f : 65535.0f;
+        float a = __fadd_rn(__fmul_rn(v.x, S), OFF), b = __fadd_rn(__fmul_rn(v.y, S), OFF);
+        a = (a > hi) ? hi : a; a = (a < 0.0f) ? 0.0f : a;
+        b = (b > hi) ? hi : b; b = (b < 0.0f) ? 0.0f : b;
+        const unsigned ua = __float2uint_rz(__fadd_rn(a, 0.5f)), ub = __float2uint_rz(__fadd_rn(b, 0.5f));
+        if (FMT == IQGPU_FMT_CU8) reinterpret_cast<uchar2*>(out)[i] = make_uchar2((unsigned char)ua, (unsigned char)ub);
+        else reinterpret_cast<ushort2*>(out)[i] = make_ushort2((unsigned short)ua, (unsigned short)ub);
+    } else if (FMT == IQGPU_FMT_CS24) {
+        float a = __fmul_rn(v.x, 8388607.0f), b = __fmul_rn(v.y, 8388607.0f);
+        int ia = __float2int_rz((a > 0.0f) ? __fadd_rn(a, 0.5f) : __fsub_rn(a, 0.5f));
+        int ib = __float2int_rz((b > 0.0f) ? __fadd_rn(b, 0.5f) : __fsub_rn(b, 0.5f));
+        ia = min(max(ia, -8388608), 8388607); ib = min(max(ib, -8388608), 8388607);
+        unsigned char* o = reinterpret_cast<unsigned char*>(out) + i * 6;
+        o[0] = ia & 0xff; o[1] = (ia >> 8) & 0xff; o[2] = (ia >> 16) & 0xff;
+        o[3] = ib & 0xff; o[4] = (ib >> 8) & 0xff; o[5] = (ib >> 16) & 0xff;
+    } else if (FMT == IQGPU_FMT_CS32) {
+        const double hi = 2147483647.0, lo = -2147483648.0;
+        double a = (double)v.x * hi, b = (double)v.y * hi;
+        a = (a > 0.0) ? a + 0.5 : a - 0.5; b = (b > 0.0) ? b + 0.5 : b - 0.5;
+        a = (a > hi) ? hi : a; a = (a < lo) ? lo : a;
+        b = (b > hi) ? hi : b; b = (b < lo) ? lo : b;
+        reinterpret_cast<int2*>(out)[i] = make_int2(__double2int_rz(a), __double2int_rz(b));
+    } else if (FMT == IQGPU_FMT_CU32) {
+        const double hi = 4294967295.0;
+        double a = (double)v.x * 2147483647.0 + 2147483647.5, b = (double)v.y * 2147483647.0 + 2147483647.5;
+        a = (a > hi) ? hi : a; a = (a < 0.0) ? 0.0 : a;
+        b = (b > hi) ? hi : b; b = (b < 0.0) ? 0.0 : b;
+        reinterpret_cast<uint2*>(out)[i] = make_uint2(__double2uint_rz(a + 0.5), __double2uint_rz(b + 0.5));
+    }
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(256) post_kernel(const float2* __restrict__ x, size_t n, PostParams p,
+                                                   const uint32_t* __restrict__ seg_start, unsigned nseg,
+                                                   const float* __restrict__ seg_gain, int nco_done,
+                                                   float2* __restrict__ tap, void* __restrict__ out)
+{
+    __shared__ float lut[1024];
+    const bool do_nco = p.nco_enable && !nco_done;
+    if (do_nco) {
+        for (int i = threadIdx.x; i < 1024; i += blockDim.x) lut[i] = p.nco_table[i];
+        __syncthreads();
+    }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float2 v = x[i];
+        if (do_nco) v = nco_mix(v, p.nco_theta0 + (uint32_t)i * p.nco_dtheta, p.nco_sign, lut);
+        if (seg_gain) {
+            const float g = __ldg(seg_gain + find_segment(seg_start, nseg, (uint32_t)i));
+            v.x = __fmul_rn(v.x, g); v.y = __fmul_rn(v.y, g);
+        }
+        if (tap) tap[i] = v;
+        store_out<FMT>(out, i, v);
+    }
+}
+
+cudaError_t launch_agc_peaks(const float2* x, size_t n, const PostParams& p, const uint32_t* seg_start,
+                             size_t nseg, float* seg_peak, cudaStream_t st)
+{
+    cudaError_t e = cudaMemsetAsync(seg_peak, 0, nseg * sizeof(float), st);
+    if (e != cudaSuccess || n == 0) return e;
+    agc_peaks_kernel<<<grid_1d(n, 256), 256, 0, st>>>(x, n, p, seg_start, (unsigned)nseg, seg_peak);
+    return cudaGetLastError();
+}
+cudaError_t launch_agc_digital_scan(const uint32_t* seg_start, size_t nseg, const float* seg_peak,
+                                    const PostParams& p, AgcState* state, float* seg_gain, cudaStream_t st)
+{
+    if (nseg == 0) return cudaSuccess;
+    agc_digital_scan_kernel<<<1, 32, 0, st>>>(seg_start, (unsigned)nseg, seg_peak, p, state, seg_gain);
+    return cudaGetLastError();
+}
+cudaError_t launch_agc_rms(const float2* x, size_t n, const PostParams& p, AgcState* state, float2* y,
+                           cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    agc_rms_kernel<<<1, 256, 0, st>>>(x, n, p, state, y);
+    return cudaGetLastError();
+}
+cudaError_t launch_post(const float2* x, size_t n, const PostParams& p, const uint32_t* seg_start, size_t nseg,
+                        const float* seg_gain, int nco_done, float2* tap, void* out, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    const int grid = grid_1d(n, 256);
+#define CALL(F) post_kernel<F><<<grid, 256, 0, st>>>(x, n, p, seg_start, (unsigned)nseg, seg_gain, nco_done, tap, out)
+    DISPATCH_FMT(p.format, CALL)
+#undef CALL
+    return cudaGetLastError();
+}
+cudaError_t launch_convert_out(const float2* x, size_t n, int format, void* out, cudaStream_t st)
+{
+    PostParams p{};
+    p.format = format;
+    return launch_post(x, n, p, nullptr, 0, nullptr, 1, nullptr, out, st);
+}
+
+}  // namespace iqgpu

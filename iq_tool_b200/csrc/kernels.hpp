@@ -1,0 +1,103 @@
+// kernels.hpp — launch interface of the sm_100a kernels (kernels.cu / fused_front.cu).
+// All pointers are device pointers unless noted; every launcher enqueues on `st` and
+// returns the cudaError_t of the launch.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace iqgpu {
+
+// ---- K1: pre-processor (convert [+DC] [+I/Q apply] [+NCO]) ---------------------------------
+struct PreParams {
+    int      format;        // IQGPU_FMT_*
+    float    gain;
+    int      dc_enable;
+    float    dc_c;          // pole
+    float    dc_a;          // 1 - pole
+    int      iq_enable;
+    float    iq_magp1;      // 1 + mag
+    float    iq_phase;
+    int      nco_enable;
+    uint32_t nco_theta0;    // phase of the first sample of this call
+    uint32_t nco_dtheta;
+    float    nco_sign;      // +1 mix up, -1 mix down
+    const float* nco_table; // 1024-entry sine table (device)
+};
+// DC pass 1: per-run weighted sums S_r = sum_k c^(len-1-k) x[k] (converted samples)
+cudaError_t launch_dc_run_sums(const void* raw, size_t n, const PreParams& p, uint32_t run_len,
+                               double2* run_sums, cudaStream_t st);
+// DC pass 2: v at the start of every run from the carried state; updates the carry in place
+cudaError_t launch_dc_scan(const double2* run_sums, size_t n_runs, uint32_t run_len, size_t n,
+                           float dc_c, double2* carry_inout, double2* run_start, cudaStream_t st);
+// convert + (DC apply) + I/Q + NCO -> cf32
+cudaError_t launch_pre(const void* raw, size_t n, const PreParams& p, uint32_t run_len,
+                       const double2* run_start, float2* out, cudaStream_t st);
+
+// ---- K2: resampler building blocks (unfused) -------------------------------------------------
+// x points at the stream sample with absolute index a0 (history lies at negative offsets).
+// Produces outputs k in [k0, k0+count): y[k-k0].  h1: 2m taps, oldest first.
+cudaError_t launch_halfband_decim(const float2* x, int64_t a0, const float* h1, unsigned m,
+                                  int64_t k0, size_t count, float scale, float2* y, cudaStream_t st);
+// interpolator: inputs k in [k0,k0+count) -> outputs 2k, 2k+1 written at y[2(k-k0)], y[2(k-k0)+1]
+cudaError_t launch_halfband_interp(const float2* x, int64_t a0, const float* h1, unsigned m,
+                                   int64_t k0, size_t count, float2* y, cudaStream_t st);
+// arbitrary polyphase stage: outputs o in [0,count): P = phase0 + o*step; k = kbase + (P>>24)
+// (k is an absolute input index, x points at absolute index a0); bank [256][14] oldest first.
+cudaError_t launch_arb(const float2* x, int64_t a0, const float* bank, uint32_t step, int64_t kbase,
+                       uint32_t phase0, size_t count, float2* y, cudaStream_t st);
+
+// ---- K3: time-domain FIR ---------------------------------------------------------------------
+// y[n] = sum_{i<ntaps} hrev[i] * x[n - (ntaps-1) + i]; x points at the first NEW sample.
+// hrev: ntaps_padded complex or real taps, oldest first, zero-padded at the FRONT to a multiple of 8.
+cudaError_t launch_fir(const float2* x, size_t n, const float* hrev, unsigned ntaps_padded,
+                       int complex_taps, float2* y, cudaStream_t st);
+
+// ---- K4: FFT block filter (overlap-save form of liquid's fftfilt) --------------------------
+// For each block b in [0,nblocks): window = x[(b-1)*B .. (b+1)*B), y[b*B .. (b+1)*B) =
+// last B samples of IFFT(FFT(window) .* H) / (2B).  x points at block 0's first sample.
+cudaError_t launch_fftfilt(const float2* x, size_t nblocks, unsigned B, const float2* H,
+                           const float2* twiddle, float2* y, cudaStream_t st);
+// H = FFT(h || 0) of size 2B (forward, un-normalised); twiddle: exp(-j 2 pi k / 2B), k < 2B
+cudaError_t launch_fft_forward(const float2* in, unsigned nfft, const float2* twiddle, float2* out,
+                               cudaStream_t st);
+bool fftfilt_supported(unsigned B);
+
+// ---- K5: post-processor ([NCO] + AGC + convert) ---------------------------------------------
+struct AgcState {           // lives in device memory
+    int      locked;
+    float    gain;
+    float    peak_mem;
+    unsigned long long seen;
+    double   last_strong;   // sample-clock seconds
+    float    rms_g;         // liquid agc_crcf state
+    float    rms_y2;
+};
+struct PostParams {
+    int      format;        // output IQGPU_FMT_*
+    int      nco_enable;
+    uint32_t nco_theta0;
+    uint32_t nco_dtheta;
+    float    nco_sign;
+    const float* nco_table;
+    int      agc_mode;      // 0 none, 1 digital, 2 rms
+    float    agc_target;
+    float    agc_alpha;     // rms bandwidth
+    double   target_rate;
+};
+// segment table: seg_start[0..nseg] (prefix offsets into the n samples of this call)
+cudaError_t launch_agc_peaks(const float2* x, size_t n, const PostParams& p, const uint32_t* seg_start,
+                             size_t nseg, float* seg_peak, cudaStream_t st);
+cudaError_t launch_agc_digital_scan(const uint32_t* seg_start, size_t nseg, const float* seg_peak,
+                                    const PostParams& p, AgcState* state, float* seg_gain, cudaStream_t st);
+// rms AGC: sequential recurrence, in place on x (after NCO if enabled -> writes mixed+scaled cf32 to y)
+cudaError_t launch_agc_rms(const float2* x, size_t n, const PostParams& p, AgcState* state, float2* y,
+                           cudaStream_t st);
+// y_cf32 (optional tap) and converted out
+cudaError_t launch_post(const float2* x, size_t n, const PostParams& p, const uint32_t* seg_start,
+                        size_t nseg, const float* seg_gain, int nco_already_applied, float2* tap_cf32,
+                        void* out, cudaStream_t st);
+
+// ---- conversions for the module-level API ---------------------------------------------------
+cudaError_t launch_convert_out(const float2* x, size_t n, int format, void* out, cudaStream_t st);
+
+}  // namespace iqgpu

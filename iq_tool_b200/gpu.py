@@ -1,0 +1,233 @@
+"""ctypes binding of libiqgpu.so (include/iqgpu.h) — the host-side entry to the CUDA chain.
+
+There is no CPU fallback: importing this module fails loudly when the shared library has not
+been built (run `python -c "import __graft_entry__ as g; g.build()"` or `make -C
+iq_tool_b200/csrc`), and every compute call raises IqGpuError when CUDA is unavailable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .configs import NUMPY_DTYPE, ChainConfig, ChainConfigC
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libiqgpu.so")
+
+
+class IqGpuError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"iqgpu error {code}: {msg}")
+        self.code = code
+
+
+class ChainInfoC(C.Structure):
+    _fields_ = [
+        ("ratio", C.c_float), ("is_interp", C.c_int32), ("num_halfband", C.c_uint32),
+        ("halfband_m", C.c_uint32 * 16), ("rate_arbitrary", C.c_float), ("arb_step", C.c_uint32),
+        ("filter_impl", C.c_int32), ("filter_post_resample", C.c_int32),
+        ("filter_block_size", C.c_uint32), ("filter_num_taps", C.c_uint32),
+        ("nco_dtheta", C.c_uint32), ("nco_is_post", C.c_int32), ("agc_locked", C.c_uint32),
+        ("agc_gain", C.c_float), ("agc_peak_memory", C.c_float), ("agc_samples_seen", C.c_uint64),
+        ("frames_in_total", C.c_uint64), ("frames_out_total", C.c_uint64),
+        ("fused_front", C.c_uint32), ("kernel_launches", C.c_uint32), ("halo_frames", C.c_uint32),
+        ("reserved", C.c_uint32),
+    ]
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built. "
+            "Run `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). "
+            "iq_tool_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, sz, u32p = C.c_void_p, C.c_size_t, C.POINTER(C.c_uint32)
+    lib.iqgpu_abi_version.restype = C.c_int
+    lib.iqgpu_last_error.restype = C.c_char_p
+    lib.iqgpu_device_count.restype = C.c_int
+    lib.iqgpu_host_alloc.restype = vp
+    lib.iqgpu_host_alloc.argtypes = [sz]
+    lib.iqgpu_host_free.argtypes = [vp]
+    lib.iqgpu_chain_create.restype = C.c_int
+    lib.iqgpu_chain_create.argtypes = [C.POINTER(ChainConfigC), C.c_int, C.POINTER(vp)]
+    lib.iqgpu_chain_destroy.argtypes = [vp]
+    lib.iqgpu_chain_reset.argtypes = [vp]
+    lib.iqgpu_chain_get_info.argtypes = [vp, C.POINTER(ChainInfoC)]
+    lib.iqgpu_chain_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    lib.iqgpu_chain_set_iq_factors.argtypes = [vp, C.c_float, C.c_float]
+    lib.iqgpu_chain_process.argtypes = [vp, vp, sz, u32p, sz, vp, sz, C.POINTER(sz), u32p]
+    lib.iqgpu_chain_process_device.argtypes = [vp, vp, sz, u32p, sz, vp, sz, C.POINTER(sz), u32p, vp]
+    lib.iqgpu_chain_predict_output.argtypes = [vp, sz, C.POINTER(sz)]
+    lib.iqgpu_chain_read_tap.argtypes = [vp, C.c_int, vp, sz, C.POINTER(sz)]
+    lib.iqgpu_chain_get_filter_taps.argtypes = [vp, vp, C.c_uint32, u32p]
+    lib.iqgpu_chain_get_halfband_taps.argtypes = [vp, C.c_uint32, vp, C.c_uint32, u32p]
+    lib.iqgpu_chain_get_arb_taps.argtypes = [vp, vp, C.c_uint32, u32p]
+    lib.iqgpu_chain_seek.argtypes = [vp, C.c_uint64, C.POINTER(C.c_uint64)]
+    lib.iqgpu_chain_halo_frames.argtypes = [vp, C.POINTER(sz)]
+    lib.iqgpu_get_bytes_per_sample.restype = sz
+    lib.iqgpu_get_bytes_per_sample.argtypes = [C.c_int]
+    lib.iqgpu_convert_block_to_cf32.argtypes = [vp, vp, sz, C.c_int, C.c_float]
+    lib.iqgpu_convert_cf32_to_block.argtypes = [vp, vp, sz, C.c_int]
+    lib.iqgpu_iq_optimize.argtypes = [vp, vp, C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                      C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    for name in ("iqgpu_chain_reset", "iqgpu_chain_get_info", "iqgpu_chain_set_option",
+                 "iqgpu_chain_set_iq_factors", "iqgpu_chain_process", "iqgpu_chain_process_device",
+                 "iqgpu_chain_predict_output", "iqgpu_chain_read_tap", "iqgpu_chain_get_filter_taps",
+                 "iqgpu_chain_get_halfband_taps", "iqgpu_chain_get_arb_taps", "iqgpu_chain_seek",
+                 "iqgpu_chain_halo_frames", "iqgpu_convert_block_to_cf32",
+                 "iqgpu_convert_cf32_to_block", "iqgpu_iq_optimize"):
+        getattr(lib, name).restype = C.c_int
+    return lib
+
+
+lib = _load()
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise IqGpuError(rc, lib.iqgpu_last_error().decode("utf-8", "replace"))
+
+
+def device_count() -> int:
+    return lib.iqgpu_device_count()
+
+
+class Chain:
+    """One configured chain (pre-processor + resampler + post-processor) on one GPU.
+
+    device=-1 builds a plan-only chain: design and closed-form bookkeeping work, compute fails.
+    """
+
+    def __init__(self, cfg: ChainConfig, device: int = 0, **options):
+        self.cfg = cfg
+        self._c = cfg.to_c()
+        self._h = C.c_void_p()
+        _check(lib.iqgpu_chain_create(C.byref(self._c), device, C.byref(self._h)))
+        for k, v in options.items():
+            self.set_option(k, v)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            lib.iqgpu_chain_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, key: str, value: int) -> None:
+        _check(lib.iqgpu_chain_set_option(self._h, key.encode(), int(value)))
+
+    def set_iq_factors(self, mag: float, phase: float) -> None:
+        _check(lib.iqgpu_chain_set_iq_factors(self._h, mag, phase))
+
+    def reset(self) -> None:
+        _check(lib.iqgpu_chain_reset(self._h))
+
+    def info(self) -> ChainInfoC:
+        o = ChainInfoC()
+        _check(lib.iqgpu_chain_get_info(self._h, C.byref(o)))
+        return o
+
+    def predict_output(self, n_frames: int) -> int:
+        o = C.c_size_t(0)
+        _check(lib.iqgpu_chain_predict_output(self._h, n_frames, C.byref(o)))
+        return o.value
+
+    def halo_frames(self) -> int:
+        o = C.c_size_t(0)
+        _check(lib.iqgpu_chain_halo_frames(self._h, C.byref(o)))
+        return o.value
+
+    def seek(self, first_frame: int) -> int:
+        o = C.c_uint64(0)
+        _check(lib.iqgpu_chain_seek(self._h, first_frame, C.byref(o)))
+        return o.value
+
+    # ---- design introspection ----
+    def filter_taps(self) -> np.ndarray:
+        n = C.c_uint32(0)
+        _check(lib.iqgpu_chain_get_filter_taps(self._h, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=np.complex64)
+        if n.value:
+            _check(lib.iqgpu_chain_get_filter_taps(self._h, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def halfband_taps(self, i: int) -> np.ndarray:
+        n = C.c_uint32(0)
+        _check(lib.iqgpu_chain_get_halfband_taps(self._h, i, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=np.float32)
+        _check(lib.iqgpu_chain_get_halfband_taps(self._h, i, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def arb_taps(self) -> np.ndarray:
+        n = C.c_uint32(0)
+        _check(lib.iqgpu_chain_get_arb_taps(self._h, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=np.float32)
+        if n.value:
+            _check(lib.iqgpu_chain_get_arb_taps(self._h, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    # ---- compute ----
+    def _chunks(self, chunk_frames: Optional[Sequence[int]]):
+        if chunk_frames is None:
+            return None, 0, None
+        arr = np.ascontiguousarray(chunk_frames, dtype=np.uint32)
+        return arr.ctypes.data_as(C.POINTER(C.c_uint32)), arr.size, arr
+
+    def out_capacity_frames(self, n_frames: int) -> int:
+        return int(n_frames * max(1.0, self.cfg.ratio)) + 4 * 16384 + 4096
+
+    def process(self, raw: np.ndarray, chunk_frames: Optional[Sequence[int]] = None,
+                return_chunk_counts: bool = False):
+        """Host-buffer path (H2D/D2H inside).  raw: interleaved input samples."""
+        raw = np.ascontiguousarray(raw)
+        n_frames = raw.nbytes // self.cfg.in_bytes
+        out = np.zeros(self.out_capacity_frames(n_frames) * self.cfg.out_bytes, dtype=np.uint8)
+        nout = C.c_size_t(0)
+        cptr, ncz, keep = self._chunks(chunk_frames)
+        nchunks = ncz if chunk_frames is not None else (n_frames + 16383) // 16384
+        counts = np.zeros(max(1, nchunks), dtype=np.uint32)
+        _check(lib.iqgpu_chain_process(self._h, raw.ctypes.data, n_frames, cptr, ncz, out.ctypes.data,
+                                       out.nbytes, C.byref(nout),
+                                       counts.ctypes.data_as(C.POINTER(C.c_uint32))))
+        res = out[: nout.value * self.cfg.out_bytes].view(NUMPY_DTYPE[self.cfg.output_format])
+        return (res, counts[:nchunks]) if return_chunk_counts else res
+
+    def process_device(self, dev_in_ptr: int, n_frames: int, dev_out_ptr: int, out_capacity_bytes: int,
+                       stream: int = 0, chunk_frames: Optional[Sequence[int]] = None) -> int:
+        """Device-resident path; pointers are raw device addresses (e.g. torch data_ptr())."""
+        nout = C.c_size_t(0)
+        cptr, ncz, keep = self._chunks(chunk_frames)
+        _check(lib.iqgpu_chain_process_device(self._h, dev_in_ptr, n_frames, cptr, ncz, dev_out_ptr,
+                                              out_capacity_bytes, C.byref(nout), None,
+                                              C.c_void_p(stream) if stream else None))
+        return nout.value
+
+    def read_tap(self, tap: int) -> np.ndarray:
+        n = C.c_size_t(0)
+        _check(lib.iqgpu_chain_read_tap(self._h, tap, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=np.complex64)
+        if n.value:
+            _check(lib.iqgpu_chain_read_tap(self._h, tap, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+
+def convert_block_to_cf32(raw: np.ndarray, fmt_code: int, n_frames: int, gain: float) -> np.ndarray:
+    raw = np.ascontiguousarray(raw)
+    out = np.zeros(n_frames, dtype=np.complex64)
+    _check(lib.iqgpu_convert_block_to_cf32(raw.ctypes.data, out.ctypes.data, n_frames, fmt_code, gain))
+    return out
+
+
+def convert_cf32_to_block(x: np.ndarray, fmt_code: int, out_dtype, bytes_per_sample: int) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.complex64)
+    out = np.zeros(x.shape[0] * bytes_per_sample, dtype=np.uint8)
+    _check(lib.iqgpu_convert_cf32_to_block(x.ctypes.data, out.ctypes.data, x.shape[0], fmt_code))
+    return out.view(out_dtype)

@@ -343,8 +343,10 @@ int firfilt_cccf_freqresponse(firfilt_cccf q, float fc, cf *H)
     unsigned int i;
     cf acc = 0.0f;
     for (i = 0; i < q->n; i++) {
-        double ang = 2 * M_PI * fc * i;
-        cf e = cf_make((float)cos(ang), (float)sin(ang));
+        /* liquid: cexpf(_Complex_I*2*M_PI*fc*i) -- the angle is formed in double but cexpf()
+         * receives it as a FLOAT complex, so cos/sin see the float-rounded angle */
+        float ang = (float)(2 * M_PI * fc * i);
+        cf e = cf_make(cosf(ang), sinf(ang));
         acc += cf_mul(q->hrev[i], e);
     }
     *H = cf_mul(acc, q->scale);

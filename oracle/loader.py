@@ -103,13 +103,12 @@ def get_lib(kind: str):
     """kind: 'ref' | 'ref_fast' | 'oracle'"""
     if kind not in _LIBS:
         if kind == "oracle":
-            if not os.path.exists(oracle_path()):
-                build("oracle")
+            build("oracle")  # incremental; plain C, builds anywhere gcc exists
             _LIBS[kind] = (_load(oracle_path(), "iqo_"), "iqo_")
         else:
             fast = kind == "ref_fast"
-            if not have_ref(fast) and os.path.isdir(REF_ROOT):
-                build("ref")
+            if os.path.isdir(REF_ROOT):
+                build("ref")  # incremental; only possible where the reference sources exist
             if not have_ref(fast):
                 raise FileNotFoundError(ref_path(fast))
             _LIBS[kind] = (_load(ref_path(fast), "iqref_"), "iqref_")
