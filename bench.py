@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py — Msamples/s through iq_tool's resample+shift+filter chain on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
+
+A "step" is one pass of the whole hot path (convert -> DC block -> multi-stage resample -> FIR ->
+convert) over one HBM-resident synthetic capture of the workload BASELINE.json's metric is
+quoted on (configs[1] = cfg2: cs16 @ 20 Msps -> 744187.5 sps, 255-tap low-pass FIR + DC block).
+With N > 1 (torchrun, one rank per GPU) the capture is time-sharded: rank r owns input frames
+[r*n, (r+1)*n) of an N*n-frame capture, re-computes a filter/DC halo in front of its shard and
+no collective touches the data path (weak scaling).
+
+Prints ONE JSON line (see the task contract): value = whole-job Msamples/s with inputs resident
+in HBM, e2e = the same metric through the host-buffer C-ABI call (pinned host memory, H2D + D2H
+inside the timed region), roofline = the dominant kernel against the measured HBM peak, and
+cpu_baseline = the reference's stage code (oracle/_ref, on the restated liquid layer) timed on
+the host cores for a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Msamples/s through resample+shift+filter chain"
+UNIT = "Msamples/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", d
+    return 6650.0, "fallback (B200_PROFILING.md)", {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.lines = []
+        self.proc = None
+        self.t = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def rd():
+            for ln in self.proc.stdout:
+                self.lines.append((time.time(), ln.strip()))
+        self.t = threading.Thread(target=rd, daemon=True)
+        self.t.start()
+
+    def stop(self, t0: float, t1: float):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], None, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clk, mx = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            smax = mx
+            if t0 - 0.05 <= ts <= t1 + 0.1:
+                sm.append(clk)
+                try:
+                    power.append(float(f[3]))
+                except ValueError:
+                    pass
+                for k, nm in enumerate(names):
+                    if f[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+        if not sm:  # region shorter than the sampling period: use the nearest samples
+            sm = [float(l.split(",")[1]) for _, l in self.lines[-3:] if len(l.split(",")) > 2] or [0.0]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+# algorithmic bytes per INPUT sample for each kernel class of a workload
+def class_bytes_per_sample(cfg, info):
+    r = info.ratio
+    inb, outb = cfg.in_bytes, cfg.out_bytes
+    return {
+        "fused_front": inb + 8.0 * r,          # raw in, resampled cf32 out
+        "pre": inb + 8.0,                      # raw in, cf32 out
+        "dc_scan": float(inb),                 # raw in
+        "resampler": 8.0 + 8.0 * r,            # cf32 in, cf32 out (ideal, no inter-stage traffic)
+        "filter": 16.0 * r,                    # cf32 in/out at the output rate
+        "post": (8.0 + outb) * r,
+    }
+
+
+def chain_flops_per_sample(cfg, info):
+    """FP32 FLOPs (FMA = 2) per input sample actually required by the chain."""
+    fl = 2.0  # convert
+    if cfg.dc_block:
+        fl += 6.0
+    if cfg.freq_shift_hz and not cfg.shift_after_resample:
+        fl += 6.0
+    S = info.num_halfband
+    rate = 1.0
+    for d in range(S):
+        m = info.halfband_m[S - 1 - d]
+        rate *= 0.5
+        fl += rate * (8.0 * m + 2.0)
+    fl += info.ratio * 56.0
+    if info.filter_num_taps:
+        fl += info.ratio * info.filter_num_taps * (8.0 if info.filter_impl == 2 else 4.0)
+    fl += info.ratio * 4.0
+    return fl
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (its stage sources
+    compiled in place, oracle/_ref) with the reference's thread model (one thread per stage),
+    on a bounded sample of the same workload per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import numpy as np
+    from iq_tool_b200 import baseline_workloads
+    from iq_tool_b200.synth import synth_numpy
+    from oracle.loader import CpuChain, have_ref
+    wl = baseline_workloads()[args.workload]
+    kind = "ref_fast" if have_ref(fast=True) else "oracle"
+    n = args.cpu_samples
+    raw = synth_numpy(wl, n)
+    ch = CpuChain(wl.config, kind)
+    threaded = kind != "oracle"
+    for _ in range(args.warmup):
+        ch.process(raw[: 2 * min(n, 1 << 20)], threaded=threaded)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ch.process(raw, threaded=threaded)
+    dt = time.perf_counter() - t0
+    val = n * args.steps / dt / 1e6
+    cores = 3 if threaded else 1
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{wl.name}: {wl.description}", "frames_per_step": n},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores,
+                         "kind": "reference" if kind != "oracle" else "port",
+                         "sample": f"{n} input frames per step; reference stage sources (-O3 -ffast-math) on the "
+                                   f"restated liquid layer, pre/resampler/post stage threads as in pipeline.c:99-116"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "host_cpus": os.cpu_count(),
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--samples", type=int, default=0, help="input frames per GPU per step (default: workload's)")
+    ap.add_argument("--cpu-samples", type=int, default=1 << 26)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fused", type=int, default=1)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from iq_tool_b200 import baseline_workloads, gpu
+    from iq_tool_b200.synth import synth_torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if gpu.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; iq_tool_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    wl = baseline_workloads()[args.workload]
+    cfg = wl.config
+    n = args.samples or wl.throughput_samples
+    n -= n % 16384
+
+    chain = gpu.Chain(cfg, local_rank, time_kernels=1, fused=args.fused, subtrain_frames=1 << 26)
+    info = chain.info()
+    halo = chain.halo_frames() if rank > 0 else 0
+    halo += (-halo) % 16384                       # keep chunk boundaries aligned with the single-stream cut
+    shard_start = rank * n
+    raw = synth_torch(wl, n + halo, dev, start=shard_start - halo)
+    out_frames_max = chain.out_capacity_frames(n + halo)
+    out = torch.empty(out_frames_max * cfg.out_bytes, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        chain.seek(shard_start - halo)
+        return chain.process_device(raw.data_ptr(), n + halo, out.data_ptr(), out.numel(), stream.cuda_stream)
+
+    for _ in range(args.warmup):
+        produced = step()
+    chain.kernel_times(reset=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.15)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    e0.record(stream)
+    for _ in range(args.steps):
+        produced = step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    t1 = time.time()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop(t0, t1)
+    ms = e0.elapsed_time(e1)
+    ktimes = chain.kernel_times(reset=True)
+    launches_per_step = chain.info().kernel_launches
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * n * args.steps / (ms / 1e3) / 1e6
+
+    # ---- end-to-end: host buffers through the C ABI (pinned host memory, H2D + D2H inside) ----
+    e2e = None
+    if args.e2e_steps > 0:
+        import ctypes as C
+        nbytes = (n + halo) * cfg.in_bytes
+        hin = gpu.lib.iqgpu_host_alloc(nbytes)
+        hout = gpu.lib.iqgpu_host_alloc(out.numel())
+        if hin and hout:
+            torch.cuda.synchronize()
+            # fill the pinned input from the device capture (outside the timed region)
+            host_in = torch.frombuffer((C.c_uint8 * nbytes).from_address(hin), dtype=torch.uint8)
+            host_in.copy_(raw.view(torch.uint8))
+            nout = C.c_size_t(0)
+            def e2e_step():
+                chain.seek(shard_start - halo)
+                gpu._check(gpu.lib.iqgpu_chain_process(chain._h, hin, n + halo, None, 0, hout, out.numel(),
+                                                       C.byref(nout), None))
+            e2e_step()
+            if world > 1:
+                dist.barrier()
+            tt0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                e2e_step()
+            dt = time.perf_counter() - tt0
+            if world > 1:
+                t = torch.tensor([dt], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            e2e = {"value": world * n * args.e2e_steps / dt / 1e6, "unit": UNIT,
+                   "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(nout.value * cfg.out_bytes),
+                   "steps": args.e2e_steps, "host_memory": "pinned (iqgpu_host_alloc)"}
+            gpu.lib.iqgpu_host_free(hin)
+            gpu.lib.iqgpu_host_free(hout)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel class ----
+    hbm_peak, peak_src, peaks = load_peaks()
+    bps = class_bytes_per_sample(cfg, info)
+    dom = max(ktimes.items(), key=lambda kv: kv[1][0])[0] if ktimes else None
+    roofline = None
+    if dom:
+        dom_ms, dom_groups = ktimes[dom]
+        per_launch_ms = dom_ms / max(1, dom_groups)
+        frames_per_launch = (n + halo) * args.steps / max(1, dom_groups)
+        alg_bytes = bps.get(dom, 0.0) * frames_per_launch
+        achieved = alg_bytes / (per_launch_ms / 1e3) / 1e9 if per_launch_ms > 0 else 0.0
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                tj = json.load(f)
+            if tj.get(dom, {}).get("bytes_per_input_frame"):
+                traffic = tj[dom]["bytes_per_input_frame"] * frames_per_launch
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                    "launch_ms": per_launch_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                    "share_of_step": dom_ms / (ms if world == 1 else sum(v[0] for v in ktimes.values()))}
+    flops = chain_flops_per_sample(cfg, info)
+    sm_mhz = clocks.get("sm_mhz") or 1965.0
+    fp32_peak_nominal = 148 * 128 * 2 * 1.965e9 / 1e12
+    fp32 = {"achieved_tflops": flops * value * 1e6 / world / 1e12, "peak_tflops_nominal": fp32_peak_nominal,
+            "frac_of_nominal": flops * value * 1e6 / world / 1e12 / fp32_peak_nominal,
+            "flops_per_input_sample": flops, "peak_tflops_at_observed_clock": 148 * 128 * 2 * sm_mhz * 1e6 / 1e12}
+
+    # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle.loader import CpuChain, have_ref
+        kind = "ref_fast" if have_ref(fast=True) else "oracle"
+        m = min(n, args.cpu_samples)
+        sample = raw[: 2 * m].cpu().numpy()
+        ch = CpuChain(cfg, kind)
+        ch.process(sample[: 2 * (1 << 20)], threaded=(kind != "oracle"))
+        ch = CpuChain(cfg, kind)
+        tt0 = time.perf_counter()
+        ch.process(sample, threaded=(kind != "oracle"))
+        dt = time.perf_counter() - tt0
+        cpu = {"value": m / dt / 1e6, "unit": UNIT, "cores": 3 if kind != "oracle" else 1,
+               "kind": "reference" if kind != "oracle" else "port",
+               "sample": f"first {m} frames of the same capture; reference stage sources on the restated liquid "
+                         f"layer, one thread per stage (pre/resampler/post) as pipeline.c:99-116; host has "
+                         f"{os.cpu_count()} cpus"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{wl.name}: {wl.description}", "frames_per_gpu_per_step": n, "halo_frames": halo,
+                   "output_frames_per_step": int(produced), "l2_policy": "inputs larger than L2 (no flush needed)",
+                   "sharding": "time shards, no collective" if world > 1 else "single stream",
+                   "fused_front": int(chain.info().fused_front),
+                   "chunk_frames": 16384},
+        "roofline": roofline, "fp32": fp32, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": int(launches_per_step) * args.steps, "clocks": clocks,
+        "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items()},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -137,8 +137,22 @@ void iqgpu_chain_destroy(iqgpu_chain *c);
  * (include/pre_processor.h:34, include/resampler.h:43, include/post_processor.h:34) */
 int  iqgpu_chain_reset(iqgpu_chain *c);
 int  iqgpu_chain_get_info(iqgpu_chain *c, iqgpu_chain_info *info);
-/* runtime knobs: "fused" (0/1), "subtrain_frames", "chunk_frames" */
+/* runtime knobs: "fused" (0/1), "subtrain_frames", "chunk_frames", "record_taps" (0/1),
+ * "time_kernels" (0/1: bracket every kernel class with CUDA events on the launch stream) */
 int  iqgpu_chain_set_option(iqgpu_chain *c, const char *key, int64_t value);
+/* kernel classes for iqgpu_chain_get_kernel_times */
+enum {
+    IQGPU_KCLASS_PRE = 0,       /* K1 convert [+DC apply] [+I/Q] [+NCO]        */
+    IQGPU_KCLASS_DC_SCAN,       /* DC-blocker run sums + carry scan             */
+    IQGPU_KCLASS_RESAMPLER,     /* K2 halfband stages + arbitrary stage (unfused) */
+    IQGPU_KCLASS_FILTER,        /* K3 FIR / K4 FFT filter                       */
+    IQGPU_KCLASS_POST,          /* K5 [NCO] + AGC + convert                     */
+    IQGPU_KCLASS_FUSED_FRONT,   /* fused K1+K2                                  */
+    IQGPU_KCLASS_COUNT = 8
+};
+/* accumulated device time (ms) and launch-group counts per kernel class since the last reset
+ * of the counters; arrays of IQGPU_KCLASS_COUNT entries (either may be NULL) */
+int  iqgpu_chain_get_kernel_times(iqgpu_chain *c, double *ms, uint32_t *launches, int reset);
 /* live update of the I/Q correction factors (iq_correct.c:206-216 double-buffer swap) */
 int  iqgpu_chain_set_iq_factors(iqgpu_chain *c, float mag, float phase);
 

@@ -179,6 +179,44 @@ struct iqgpu_chain {
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
     bool buffers_ready = false;
 
+    // optional per-kernel-class device timing (CUDA events on the launch stream)
+    bool time_kernels = false;
+    struct TimedSpan { int cls; cudaEvent_t a, b; };
+    std::vector<TimedSpan> spans;
+    std::vector<cudaEvent_t> ev_pool;
+    double class_ms[IQGPU_KCLASS_COUNT] = {0};
+    uint32_t class_launches[IQGPU_KCLASS_COUNT] = {0};
+    cudaEvent_t get_event()
+    {
+        cudaEvent_t e = nullptr;
+        if (!ev_pool.empty()) { e = ev_pool.back(); ev_pool.pop_back(); }
+        else cudaEventCreate(&e);
+        return e;
+    }
+    void span_begin(int cls, cudaStream_t st)
+    {
+        class_launches[cls]++;
+        if (!time_kernels) return;
+        TimedSpan sp{cls, get_event(), get_event()};
+        cudaEventRecord(sp.a, st);
+        spans.push_back(sp);
+    }
+    void span_end(cudaStream_t st)
+    {
+        if (!time_kernels || spans.empty()) return;
+        cudaEventRecord(spans.back().b, st);
+    }
+    void collect_spans()
+    {
+        for (auto& sp : spans) {
+            float ms = 0.f;
+            if (cudaEventSynchronize(sp.b) == cudaSuccess && cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess)
+                class_ms[sp.cls] += ms;
+            ev_pool.push_back(sp.a); ev_pool.push_back(sp.b);
+        }
+        spans.clear();
+    }
+
     ~iqgpu_chain();
     int init_device();
     int ensure_buffers();
@@ -195,6 +233,8 @@ iqgpu_chain::~iqgpu_chain()
     if (plan_only) return;
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
+    collect_spans();
+    for (auto e : ev_pool) cudaEventDestroy(e);
     for (auto* t : d_hb_taps) cudaFree(t);
     cudaFree(d_lut); cudaFree(d_dc_carry); cudaFree(d_run_sums); cudaFree(d_run_start); cudaFree(d_bank);
     cudaFree(d_fir_taps); cudaFree(d_fft_H); cudaFree(d_fft_tw); cudaFree(d_agc); cudaFree(d_seg_start);
@@ -436,11 +476,15 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
     if (dc.enable) {
         const size_t n_runs = (n + run_len - 1) / run_len;
         if (n_runs > max_runs) return fail(IQGPU_EINVAL, "internal: run table too small");
+        span_begin(IQGPU_KCLASS_DC_SCAN, st);
         CK(launch_dc_run_sums(d_rawp, n, pp, run_len, d_run_sums, st));
         CK(launch_dc_scan(d_run_sums, n_runs, run_len, n, dc.c, d_dc_carry, d_run_start, st));
+        span_end(st);
         launches += 2;
     }
+    span_begin(IQGPU_KCLASS_PRE, st);
     CK(launch_pre(d_rawp, n, pp, run_len, d_run_start, x_in, st));
+    span_end(st);
     launches++;
     s_in.commit(n);
     if (record_taps) CK(tap[0].append(x_in, n, st));
@@ -476,6 +520,7 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
     const float2* post_src = rs_src;
     size_t post_n = rs_n;
     if (!rs.passthrough) {
+        span_begin(IQGPU_KCLASS_RESAMPLER, st);
         const unsigned S = rs.num_halfband;
         const uint64_t P0 = rs_pos0, P1 = rs_pos0 + rs_n;
         float2* y_rs = nullptr;
@@ -524,6 +569,7 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
         }
         s_rs.commit(post_n);
         post_src = y_rs;
+        span_end(st);
     } else if (post_filter) {
         // passthrough + post filter never happens (no_resample keeps the filter pre-resample), but keep the
         // stream contract: copy into s_rs so the filter finds its history.
@@ -537,6 +583,7 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
 
     // ---------------- optional post-resample filter ----------------
     if (post_filter) {
+        span_begin(IQGPU_KCLASS_FILTER, st);
         if (filter_is_fir(filt)) {
             float2* y = nullptr;
             CK(s_f.begin(post_n, st, &y));
@@ -556,6 +603,7 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
             fft_rem = tot - blocks * filt.block;
             post_src = y; post_n = (size_t)blocks * filt.block;
         }
+        span_end(st);
     }
     if (post_n != total_out) return fail(IQGPU_EINVAL, "internal: closed-form output count disagrees with the kernels' count");
 
@@ -572,6 +620,7 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
         tap2 = tap[2].p + tap[2].len - post_n;
     }
     if (post_n) {
+        span_begin(IQGPU_KCLASS_POST, st);
         if (agc_mode == 1) {
             if (n_chunks > max_segs) {
                 CK(cudaStreamSynchronize(st));
@@ -601,6 +650,7 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
             CK(launch_post(post_src, post_n, qp, nullptr, 0, nullptr, 0, tap2, d_outp, st));
             launches++;
         }
+        span_end(st);
     }
     if (nco_post) n_nco_post += post_n;
     n_in = N1;
@@ -705,6 +755,7 @@ int iqgpu_chain_set_option(iqgpu_chain* c, const char* key, int64_t value)
     const std::string k(key);
     if (k == "fused") { c->want_fused = value != 0; return IQGPU_OK; }
     if (k == "record_taps") { c->record_taps = value != 0; return IQGPU_OK; }
+    if (k == "time_kernels") { c->time_kernels = value != 0; return IQGPU_OK; }
     if (k == "subtrain_frames" || k == "chunk_frames") {
         if (c->buffers_ready) return fail(IQGPU_EINVAL, "option must be set before the first process call");
         if (value <= 0) return fail(IQGPU_EINVAL, "value must be positive");
@@ -713,6 +764,18 @@ int iqgpu_chain_set_option(iqgpu_chain* c, const char* key, int64_t value)
         return IQGPU_OK;
     }
     return fail(IQGPU_EINVAL, "unknown option");
+}
+
+int iqgpu_chain_get_kernel_times(iqgpu_chain* c, double* ms, uint32_t* launches, int reset)
+{
+    if (!c) return fail(IQGPU_EINVAL, "null chain");
+    if (!c->plan_only) { cudaSetDevice(c->device); c->collect_spans(); }
+    for (int i = 0; i < IQGPU_KCLASS_COUNT; i++) {
+        if (ms) ms[i] = c->class_ms[i];
+        if (launches) launches[i] = c->class_launches[i];
+        if (reset) { c->class_ms[i] = 0; c->class_launches[i] = 0; }
+    }
+    return IQGPU_OK;
 }
 
 int iqgpu_chain_set_iq_factors(iqgpu_chain* c, float mag, float phase)
@@ -931,6 +994,8 @@ int iqgpu_chain_halo_frames(iqgpu_chain* c, size_t* halo)
     if (filter_is_fir(c->filt) && c->filt.post_resample)
         h += (size_t)std::ceil((double)c->filt.taps.size() / (double)c->ratio) + ((size_t)1 << c->rs.num_halfband);
     else if (filter_is_fir(c->filt)) h += c->filt.taps.size();
+    // DC blocker: infinite memory; 16 time constants leave e^-16 ~ 1e-7 of the integrator state
+    if (c->dc.enable) h += (size_t)std::ceil(16.0 / (double)c->dc.alpha);
     *halo = h;
     return IQGPU_OK;
 }

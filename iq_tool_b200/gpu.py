@@ -59,6 +59,8 @@ def _load() -> C.CDLL:
     lib.iqgpu_chain_get_info.argtypes = [vp, C.POINTER(ChainInfoC)]
     lib.iqgpu_chain_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     lib.iqgpu_chain_set_iq_factors.argtypes = [vp, C.c_float, C.c_float]
+    lib.iqgpu_chain_get_kernel_times.restype = C.c_int
+    lib.iqgpu_chain_get_kernel_times.argtypes = [vp, C.POINTER(C.c_double), u32p, C.c_int]
     lib.iqgpu_chain_process.argtypes = [vp, vp, sz, u32p, sz, vp, sz, C.POINTER(sz), u32p]
     lib.iqgpu_chain_process_device.argtypes = [vp, vp, sz, u32p, sz, vp, sz, C.POINTER(sz), u32p, vp]
     lib.iqgpu_chain_predict_output.argtypes = [vp, sz, C.POINTER(sz)]
@@ -134,6 +136,15 @@ class Chain:
         o = ChainInfoC()
         _check(lib.iqgpu_chain_get_info(self._h, C.byref(o)))
         return o
+
+    KERNEL_CLASSES = ("pre", "dc_scan", "resampler", "filter", "post", "fused_front", "_6", "_7")
+
+    def kernel_times(self, reset: bool = True) -> dict:
+        """Accumulated device ms / launch groups per kernel class (needs time_kernels=1)."""
+        ms = (C.c_double * 8)()
+        cnt = (C.c_uint32 * 8)()
+        _check(lib.iqgpu_chain_get_kernel_times(self._h, ms, cnt, int(reset)))
+        return {k: (ms[i], cnt[i]) for i, k in enumerate(self.KERNEL_CLASSES) if cnt[i]}
 
     def predict_output(self, n_frames: int) -> int:
         o = C.c_size_t(0)
