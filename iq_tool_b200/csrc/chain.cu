@@ -142,6 +142,9 @@ struct iqgpu_chain {
     uint32_t chunk_frames = IQGPU_CHUNK_SAMPLES;
     bool want_fused = true;
     bool record_taps = false;
+    bool record_tap0 = false;   // tap 0 (pre-processor output) only exists on the unfused path
+    bool fused_used = false;
+    bool fused_active = false;  // decided when the work buffers are created; fixed for the chain's life
 
     // ---- stream position (host, closed form) ----
     uint64_t n_in = 0;        // input frames since reset
@@ -172,6 +175,8 @@ struct iqgpu_chain {
     DevStream s_in, s_pref, s_arb_in, s_rs, s_f;
     std::vector<DevStream> s_stage;
     TapBuf tap[3];
+    FusedFront* fused = nullptr;
+    int num_sms = 148;
     // host-path staging
     void* d_raw[2] = {nullptr, nullptr};
     void* d_out[2] = {nullptr, nullptr};
@@ -233,6 +238,7 @@ iqgpu_chain::~iqgpu_chain()
     if (plan_only) return;
     cudaSetDevice(device);
     if (stream) cudaStreamSynchronize(stream);
+    fused_destroy(fused);
     collect_spans();
     for (auto e : ev_pool) cudaEventDestroy(e);
     for (auto* t : d_hb_taps) cudaFree(t);
@@ -324,6 +330,26 @@ int iqgpu_chain::init_device()
         CK(cudaMalloc(&d_bank, rs.bank.size() * sizeof(float)));
         CK(cudaMemcpy(d_bank, rs.bank.data(), rs.bank.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
+    {
+        cudaDeviceProp prop{};
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) num_sms = prop.multiProcessorCount;
+    }
+    const bool pre_filter0 = filt.impl != IQGPU_FILTER_IMPL_NONE && !filt.post_resample;
+    if (!rs.passthrough && !rs.is_interp && !pre_filter0) {
+        ResamplerDesc rd{};
+        rd.S = rs.num_halfband; rd.zeta = rs.zeta; rd.step = rs.step;
+        bool ok = rs.num_halfband <= (unsigned)FUSED_MAX_STAGES;
+        for (unsigned d = 0; ok && d < rs.num_halfband; d++) {
+            const unsigned g = rs.num_halfband - 1 - d;
+            rd.m_exec[d] = rs.stages[g].m;
+            rd.h1_exec[d] = rs.stages[g].h1.data();
+        }
+        if (ok && fused_supported(cfg.input_format, rd)) {
+            std::string ferr;
+            fused = fused_create(cfg.input_format, rd, nco_pre, d_bank, num_sms, ferr);
+            if (!fused) return fail(IQGPU_ECUDA, ferr);
+        }
+    }
     if (filter_is_fir(filt)) {
         const unsigned N = (unsigned)filt.taps.size();
         fir_taps_padded = (N + 7) & ~7u;
@@ -369,19 +395,22 @@ int iqgpu_chain::ensure_buffers()
     const bool post_filter = filt.impl != IQGPU_FILTER_IMPL_NONE && filt.post_resample;
     const size_t filt_hist = filter_is_fir(filt) ? fir_taps_padded : (filter_is_fft(filt) ? 2 * (size_t)filt.block : 0);
 
+    fused_active = fused && want_fused && !record_tap0;
     // s_in: consumer is the pre-filter, else the first resampler stage, else nothing
     size_t in_hist = 0;
     if (pre_filter) in_hist = filt_hist;
     else if (!rs.passthrough && !rs.is_interp) in_hist = rs.num_halfband ? 4 * rs.stages[rs.num_halfband - 1].m : 16;
     else if (!rs.passthrough) in_hist = 16;
-    if (s_in.alloc(in_hist, n) != 0) return fail(IQGPU_ENOMEM, "device allocation failed (s_in)");
+    if (!fused_active && s_in.alloc(in_hist, n) != 0) return fail(IQGPU_ENOMEM, "device allocation failed (s_in)");
     if (pre_filter) {
         size_t h = 16;
         if (!rs.passthrough && !rs.is_interp && rs.num_halfband) h = 4 * rs.stages[rs.num_halfband - 1].m;
         if (s_pref.alloc(h, n + filt.block) != 0) return fail(IQGPU_ENOMEM, "device allocation failed (s_pref)");
     }
     size_t rs_max = n;
-    if (!rs.passthrough) {
+    if (fused_active) {
+        rs_max = (size_t)std::ceil((double)(n >> rs.num_halfband) * (double)rs.rate_arbitrary) + 16;
+    } else if (!rs.passthrough) {
         const unsigned S = rs.num_halfband;
         s_stage.resize(S);
         if (!rs.is_interp) {
@@ -431,7 +460,8 @@ int iqgpu_chain::reset_state()
     a.peak_mem = (agc_mode == 1) ? 0.05f : 0.001f;   // agc.c:66,78
     a.rms_g = 1.0f; a.rms_y2 = 1.0f;                  // agc.c:58-62 (set_signal_level then set_gain(1))
     CK(cudaMemcpyAsync(d_agc, &a, sizeof(a), cudaMemcpyHostToDevice, stream));
-    CK(s_in.reset(stream));
+    if (fused) CK(fused_reset(fused, stream));
+    if (s_in.base) CK(s_in.reset(stream));
     if (s_pref.base) CK(s_pref.reset(stream));
     if (s_arb_in.base) CK(s_arb_in.reset(stream));
     for (auto& s : s_stage) if (s.base) CK(s.reset(stream));
@@ -468,116 +498,132 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
     pp.iq_enable = cfg.iq_correction_enable; pp.iq_magp1 = 1.0f + iq_mag; pp.iq_phase = iq_phase;
     pp.nco_enable = nco_pre; pp.nco_dtheta = nco_dtheta; pp.nco_sign = nco_sign; pp.nco_table = d_lut;
     pp.nco_theta0 = (uint32_t)((uint64_t)(uint32_t)N0 * nco_dtheta);
-    float2* x_in = nullptr;
-    CK(s_in.begin(n, st, &x_in));
-    uint32_t rows = (uint32_t)((n + 127) / 128), rpr = 1;
-    while (rpr < 32 && rows / rpr > 16384) rpr <<= 1;
-    const uint32_t run_len = 128 * rpr;
-    if (dc.enable) {
-        const size_t n_runs = (n + run_len - 1) / run_len;
-        if (n_runs > max_runs) return fail(IQGPU_EINVAL, "internal: run table too small");
-        span_begin(IQGPU_KCLASS_DC_SCAN, st);
-        CK(launch_dc_run_sums(d_rawp, n, pp, run_len, d_run_sums, st));
-        CK(launch_dc_scan(d_run_sums, n_runs, run_len, n, dc.c, d_dc_carry, d_run_start, st));
-        span_end(st);
-        launches += 2;
-    }
-    span_begin(IQGPU_KCLASS_PRE, st);
-    CK(launch_pre(d_rawp, n, pp, run_len, d_run_start, x_in, st));
-    span_end(st);
-    launches++;
-    s_in.commit(n);
-    if (record_taps) CK(tap[0].append(x_in, n, st));
-
-    // ---------------- optional pre-resample filter ----------------
-    const float2* rs_src = x_in;     // stream feeding the resampler (first new sample)
-    size_t rs_n = n;                 // new samples in it
-    uint64_t rs_pos0 = N0;           // absolute index of rs_src[0] in the resampler input stream
-    if (pre_filter) {
-        if (filter_is_fir(filt)) {
-            float2* y = nullptr;
-            CK(s_pref.begin(n, st, &y));
-            CK(launch_fir(x_in, n, d_fir_taps, fir_taps_padded, filt.impl == IQGPU_FILTER_IMPL_FIR_ASYM, y, st));
-            launches++;
-            s_pref.commit(n);
-            rs_src = y;
-        } else {
-            const uint32_t tot = fft_rem + (uint32_t)n, blocks = tot / filt.block;
-            float2* y = nullptr;
-            CK(s_pref.begin((size_t)blocks * filt.block, st, &y));
-            if (blocks) {
-                CK(launch_fftfilt(x_in - fft_rem, blocks, filt.block, d_fft_H, d_fft_tw, y, st));
-                launches++;
-            }
-            s_pref.commit((size_t)blocks * filt.block);
-            rs_pos0 = N0 - fft_rem;
-            fft_rem = tot - blocks * filt.block;
-            rs_src = y; rs_n = (size_t)blocks * filt.block;
-        }
-    }
-
-    // ---------------- K2: resampler ----------------
-    const float2* post_src = rs_src;
-    size_t post_n = rs_n;
-    if (!rs.passthrough) {
-        span_begin(IQGPU_KCLASS_RESAMPLER, st);
-        const unsigned S = rs.num_halfband;
-        const uint64_t P0 = rs_pos0, P1 = rs_pos0 + rs_n;
+    const bool use_fused = fused_active;
+    const float2* post_src = nullptr;
+    size_t post_n = 0;
+    if (use_fused) {
+        // ---------------- fused K1+K2: one pass over HBM ----------------
+        const uint64_t O0 = resampler_outputs_after(rs, N0), O1 = resampler_outputs_after(rs, N1);
         float2* y_rs = nullptr;
-        if (!rs.is_interp) {
-            const float2* src = rs_src;
-            uint64_t a0 = P0;  // absolute index (in the current stage's input stream) of src[0]
-            for (unsigned d = 0; d < S; d++) {
-                const unsigned g = S - 1 - d;
-                const uint64_t k0 = P0 >> (d + 1), k1 = P1 >> (d + 1);
-                float2* y = nullptr;
-                CK(s_stage[d].begin((size_t)(k1 - k0), st, &y));
-                CK(launch_halfband_decim(src, (int64_t)a0, d_hb_taps[g], rs.stages[g].m, (int64_t)k0, (size_t)(k1 - k0),
-                                         (d + 1 == S) ? rs.zeta : 1.0f, y, st));
-                launches++;
-                s_stage[d].commit((size_t)(k1 - k0));
-                src = y; a0 = k0;
-            }
-            const uint64_t K0 = P0 >> S, K1 = P1 >> S;
-            const uint64_t O0 = arb_outputs_after(K0, rs.step), O1 = arb_outputs_after(K1, rs.step);
-            const unsigned __int128 Pph = (unsigned __int128)O0 * rs.step;
-            CK(s_rs.begin((size_t)(O1 - O0), st, &y_rs));
-            CK(launch_arb(src, (int64_t)K0, d_bank, rs.step, (int64_t)(uint64_t)(Pph >> 24), (uint32_t)(Pph & 0xffffffu),
-                          (size_t)(O1 - O0), y_rs, st));
-            launches++;
-            post_n = (size_t)(O1 - O0);
-        } else {
-            const uint64_t O0 = arb_outputs_after(P0, rs.step), O1 = arb_outputs_after(P1, rs.step);
-            const unsigned __int128 Pph = (unsigned __int128)O0 * rs.step;
-            float2* y = nullptr;
-            size_t cnt = (size_t)(O1 - O0);
-            if (S == 0) CK(s_rs.begin(cnt, st, &y)); else CK(s_arb_in.begin(cnt, st, &y));
-            CK(launch_arb(rs_src, (int64_t)P0, d_bank, rs.step, (int64_t)(uint64_t)(Pph >> 24), (uint32_t)(Pph & 0xffffffu), cnt, y, st));
-            launches++;
-            if (S == 0) y_rs = y; else s_arb_in.commit(cnt);
-            const float2* src = y;
-            uint64_t a0 = O0;
-            for (unsigned s = 0; s < S; s++) {
-                float2* yo = nullptr;
-                if (s + 1 == S) CK(s_rs.begin(2 * cnt, st, &yo)); else CK(s_stage[s].begin(2 * cnt, st, &yo));
-                CK(launch_halfband_interp(src, (int64_t)a0, d_hb_taps[s], rs.stages[s].m, (int64_t)a0, cnt, yo, st));
-                launches++;
-                if (s + 1 == S) y_rs = yo; else s_stage[s].commit(2 * cnt);
-                src = yo; a0 *= 2; cnt *= 2;
-            }
-            post_n = cnt;
-        }
-        s_rs.commit(post_n);
-        post_src = y_rs;
+        CK(s_rs.begin((size_t)(O1 - O0), st, &y_rs));
+        span_begin(IQGPU_KCLASS_FUSED_FRONT, st);
+        CK(fused_launch(fused, d_rawp, (int64_t)N0, n, pp, d_dc_carry, (int64_t)O0, (size_t)(O1 - O0), y_rs, &launches, st));
         span_end(st);
-    } else if (post_filter) {
-        // passthrough + post filter never happens (no_resample keeps the filter pre-resample), but keep the
-        // stream contract: copy into s_rs so the filter finds its history.
-        float2* y = nullptr;
-        CK(s_rs.begin(rs_n, st, &y));
-        CK(cudaMemcpyAsync(y, rs_src, rs_n * sizeof(float2), cudaMemcpyDeviceToDevice, st));
-        s_rs.commit(rs_n);
-        post_src = y;
+        s_rs.commit((size_t)(O1 - O0));
+        post_src = y_rs; post_n = (size_t)(O1 - O0);
+        fused_used = true;
+    } else {
+        float2* x_in = nullptr;
+        CK(s_in.begin(n, st, &x_in));
+        uint32_t rows = (uint32_t)((n + 127) / 128), rpr = 1;
+        while (rpr < 32 && rows / rpr > 16384) rpr <<= 1;
+        const uint32_t run_len = 128 * rpr;
+        if (dc.enable) {
+            const size_t n_runs = (n + run_len - 1) / run_len;
+            if (n_runs > max_runs) return fail(IQGPU_EINVAL, "internal: run table too small");
+            span_begin(IQGPU_KCLASS_DC_SCAN, st);
+            CK(launch_dc_run_sums(d_rawp, n, pp, run_len, d_run_sums, st));
+            CK(launch_dc_scan(d_run_sums, n_runs, run_len, n, dc.c, d_dc_carry, d_run_start, st));
+            span_end(st);
+            launches += 2;
+        }
+        span_begin(IQGPU_KCLASS_PRE, st);
+        CK(launch_pre(d_rawp, n, pp, run_len, d_run_start, x_in, st));
+        span_end(st);
+        launches++;
+        s_in.commit(n);
+        if (record_tap0) CK(tap[0].append(x_in, n, st));
+
+        // ---------------- optional pre-resample filter ----------------
+        const float2* rs_src = x_in;     // stream feeding the resampler (first new sample)
+        size_t rs_n = n;                 // new samples in it
+        uint64_t rs_pos0 = N0;           // absolute index of rs_src[0] in the resampler input stream
+        if (pre_filter) {
+            if (filter_is_fir(filt)) {
+                float2* y = nullptr;
+                CK(s_pref.begin(n, st, &y));
+                CK(launch_fir(x_in, n, d_fir_taps, fir_taps_padded, filt.impl == IQGPU_FILTER_IMPL_FIR_ASYM, y, st));
+                launches++;
+                s_pref.commit(n);
+                rs_src = y;
+            } else {
+                const uint32_t tot = fft_rem + (uint32_t)n, blocks = tot / filt.block;
+                float2* y = nullptr;
+                CK(s_pref.begin((size_t)blocks * filt.block, st, &y));
+                if (blocks) {
+                    CK(launch_fftfilt(x_in - fft_rem, blocks, filt.block, d_fft_H, d_fft_tw, y, st));
+                    launches++;
+                }
+                s_pref.commit((size_t)blocks * filt.block);
+                rs_pos0 = N0 - fft_rem;
+                fft_rem = tot - blocks * filt.block;
+                rs_src = y; rs_n = (size_t)blocks * filt.block;
+            }
+        }
+
+        // ---------------- K2: resampler ----------------
+        post_src = rs_src;
+        post_n = rs_n;
+        if (!rs.passthrough) {
+            span_begin(IQGPU_KCLASS_RESAMPLER, st);
+            const unsigned S = rs.num_halfband;
+            const uint64_t P0 = rs_pos0, P1 = rs_pos0 + rs_n;
+            float2* y_rs = nullptr;
+            if (!rs.is_interp) {
+                const float2* src = rs_src;
+                uint64_t a0 = P0;  // absolute index (in the current stage's input stream) of src[0]
+                for (unsigned d = 0; d < S; d++) {
+                    const unsigned g = S - 1 - d;
+                    const uint64_t k0 = P0 >> (d + 1), k1 = P1 >> (d + 1);
+                    float2* y = nullptr;
+                    CK(s_stage[d].begin((size_t)(k1 - k0), st, &y));
+                    CK(launch_halfband_decim(src, (int64_t)a0, d_hb_taps[g], rs.stages[g].m, (int64_t)k0, (size_t)(k1 - k0),
+                                             (d + 1 == S) ? rs.zeta : 1.0f, y, st));
+                    launches++;
+                    s_stage[d].commit((size_t)(k1 - k0));
+                    src = y; a0 = k0;
+                }
+                const uint64_t K0 = P0 >> S, K1 = P1 >> S;
+                const uint64_t O0 = arb_outputs_after(K0, rs.step), O1 = arb_outputs_after(K1, rs.step);
+                const unsigned __int128 Pph = (unsigned __int128)O0 * rs.step;
+                CK(s_rs.begin((size_t)(O1 - O0), st, &y_rs));
+                CK(launch_arb(src, (int64_t)K0, d_bank, rs.step, (int64_t)(uint64_t)(Pph >> 24), (uint32_t)(Pph & 0xffffffu),
+                              (size_t)(O1 - O0), y_rs, st));
+                launches++;
+                post_n = (size_t)(O1 - O0);
+            } else {
+                const uint64_t O0 = arb_outputs_after(P0, rs.step), O1 = arb_outputs_after(P1, rs.step);
+                const unsigned __int128 Pph = (unsigned __int128)O0 * rs.step;
+                float2* y = nullptr;
+                size_t cnt = (size_t)(O1 - O0);
+                if (S == 0) CK(s_rs.begin(cnt, st, &y)); else CK(s_arb_in.begin(cnt, st, &y));
+                CK(launch_arb(rs_src, (int64_t)P0, d_bank, rs.step, (int64_t)(uint64_t)(Pph >> 24), (uint32_t)(Pph & 0xffffffu), cnt, y, st));
+                launches++;
+                if (S == 0) y_rs = y; else s_arb_in.commit(cnt);
+                const float2* src = y;
+                uint64_t a0 = O0;
+                for (unsigned s = 0; s < S; s++) {
+                    float2* yo = nullptr;
+                    if (s + 1 == S) CK(s_rs.begin(2 * cnt, st, &yo)); else CK(s_stage[s].begin(2 * cnt, st, &yo));
+                    CK(launch_halfband_interp(src, (int64_t)a0, d_hb_taps[s], rs.stages[s].m, (int64_t)a0, cnt, yo, st));
+                    launches++;
+                    if (s + 1 == S) y_rs = yo; else s_stage[s].commit(2 * cnt);
+                    src = yo; a0 *= 2; cnt *= 2;
+                }
+                post_n = cnt;
+            }
+            s_rs.commit(post_n);
+            post_src = y_rs;
+            span_end(st);
+        } else if (post_filter) {
+            // passthrough + post filter never happens (no_resample keeps the filter pre-resample), but keep the
+            // stream contract: copy into s_rs so the filter finds its history.
+            float2* y = nullptr;
+            CK(s_rs.begin(rs_n, st, &y));
+            CK(cudaMemcpyAsync(y, rs_src, rs_n * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+            s_rs.commit(rs_n);
+            post_src = y;
+        }
     }
     if (record_taps) CK(tap[1].append(post_src, post_n, st));
 
@@ -753,8 +799,16 @@ int iqgpu_chain_set_option(iqgpu_chain* c, const char* key, int64_t value)
 {
     if (!c || !key) return fail(IQGPU_EINVAL, "null argument");
     const std::string k(key);
-    if (k == "fused") { c->want_fused = value != 0; return IQGPU_OK; }
-    if (k == "record_taps") { c->record_taps = value != 0; return IQGPU_OK; }
+    if (k == "fused") {
+        if (c->buffers_ready) return fail(IQGPU_EINVAL, "option must be set before the first process call");
+        c->want_fused = value != 0;
+        return IQGPU_OK;
+    }
+    if (k == "record_taps") {
+        if (c->buffers_ready && (value > 1) != c->record_tap0) return fail(IQGPU_EINVAL, "record_taps=2 must be set before the first process call");
+        c->record_taps = value != 0; c->record_tap0 = value > 1;
+        return IQGPU_OK;
+    }
     if (k == "time_kernels") { c->time_kernels = value != 0; return IQGPU_OK; }
     if (k == "subtrain_frames" || k == "chunk_frames") {
         if (c->buffers_ready) return fail(IQGPU_EINVAL, "option must be set before the first process call");
@@ -803,9 +857,9 @@ int iqgpu_chain_get_info(iqgpu_chain* c, iqgpu_chain_info* o)
     o->nco_is_post = c->nco_post;
     o->frames_in_total = c->n_in;
     o->frames_out_total = c->n_out;
-    o->fused_front = 0;
+    o->fused_front = c->fused_used ? 1 : 0;
     o->kernel_launches = c->launches;
-    o->halo_frames = (uint32_t)c->rs.halo_input_frames;
+    o->halo_frames = c->fused ? fused_halo_frames(c->fused) : (uint32_t)c->rs.halo_input_frames;
     if (!c->plan_only && c->d_agc) {
         AgcState a{};
         cudaSetDevice(c->device);

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <string>
 
 namespace iqgpu {
 
@@ -26,6 +27,9 @@ struct PreParams {
 // DC pass 1: per-run weighted sums S_r = sum_k c^(len-1-k) x[k] (converted samples)
 cudaError_t launch_dc_run_sums(const void* raw, size_t n, const PreParams& p, uint32_t run_len,
                                double2* run_sums, cudaStream_t st);
+// same, frames below `lo` read as zero (virtual, absolute-aligned ranges)
+cudaError_t launch_dc_run_sums_masked(const void* raw, size_t n, size_t lo, const PreParams& p, uint32_t run_len,
+                                      double2* run_sums, cudaStream_t st);
 // DC pass 2: v at the start of every run from the carried state; updates the carry in place
 cudaError_t launch_dc_scan(const double2* run_sums, size_t n_runs, uint32_t run_len, size_t n,
                            float dc_c, double2* carry_inout, double2* run_start, cudaStream_t st);
@@ -99,5 +103,25 @@ cudaError_t launch_post(const float2* x, size_t n, const PostParams& p, const ui
 
 // ---- conversions for the module-level API ---------------------------------------------------
 cudaError_t launch_convert_out(const float2* x, size_t n, int format, void* out, cudaStream_t st);
+
+// ---- fused front: raw -> [convert, DC, I/Q, NCO] -> halfband cascade -> polyphase stage -------
+constexpr int FUSED_MAX_STAGES = 10;
+struct ResamplerDesc {
+    unsigned S;                                // halfband stages
+    unsigned m_exec[FUSED_MAX_STAGES];         // semi-length by EXECUTION depth (depth 0 = full input rate)
+    const float* h1_exec[FUSED_MAX_STAGES];    // host pointers to the 2m dot-product taps per depth
+    float zeta;
+    uint32_t step;
+};
+struct FusedFront;
+bool fused_supported(int format, const ResamplerDesc& r);
+FusedFront* fused_create(int format, const ResamplerDesc& r, bool nco, const float* d_bank, int num_sms, std::string& err);
+void fused_destroy(FusedFront* f);
+cudaError_t fused_reset(FusedFront* f, cudaStream_t st);
+uint32_t fused_halo_frames(const FusedFront* f);
+// raw[0] has absolute index n0; produces outputs [O0, O0+n_out) into y; d_dc_carry is the DC state at n0
+// (updated to the state at n0+n).  *launches is incremented by the kernels launched.
+cudaError_t fused_launch(FusedFront* f, const void* raw, int64_t n0, size_t n, const PreParams& pre, double2* d_dc_carry,
+                         int64_t O0, size_t n_out, float2* y, uint32_t* launches, cudaStream_t st);
 
 }  // namespace iqgpu

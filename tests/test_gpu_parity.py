@@ -30,8 +30,10 @@ def _oracle_kind():
     return "ref" if have_ref() else "oracle"
 
 
-def _run_pair(gpu, cfg, raw, **opts):
-    g = gpu.Chain(cfg, 0, record_taps=1, **opts)
+def _run_pair(gpu, cfg, raw, taps=2, **opts):
+    """taps=2 records all taps (forces the unfused stage-by-stage path); taps=1 records taps 1-2
+    and lets the chain use the fused front kernel where it applies."""
+    g = gpu.Chain(cfg, 0, record_taps=taps, **opts)
     o = CpuChain(cfg, _oracle_kind())
     n = raw.nbytes // cfg.in_bytes
     o.capture(0, n + 16)
@@ -58,7 +60,7 @@ def test_golden_fixture_parity(name, gpu, workloads, golden):
     """CUDA chain vs the committed reference outputs (no DC block in these configs)."""
     meta, data = golden
     cfg = workloads[name].config
-    g = gpu.Chain(cfg, 0, record_taps=1)
+    g = gpu.Chain(cfg, 0, record_taps=2)
     out, counts = g.process(data[name]["raw"], return_chunk_counts=True)
     assert np.array_equal(counts, data[name]["counts"])
     assert np.array_equal(g.read_tap(0)[:8192].view(np.uint32), data[name]["pre_head"].view(np.uint32))
@@ -248,3 +250,79 @@ def test_all_input_formats_roundtrip_against_oracle(gpu):
         out = gpu.Chain(cfg, 0).process(raw)
         ref = CpuChain(cfg, "oracle").process(raw)
         assert np.array_equal(out.view(np.uint32), ref.view(np.uint32)), fmt
+
+
+# ---------------------------------------------------------------------------------------------
+# fused front kernel (convert + DC + I/Q + NCO + halfband cascade + polyphase in one HBM pass)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,n", [("cfg1", (1 << 22) + 4097), ("cfg5", (1 << 23) + 11), ("cfg2", (1 << 22) + 333)])
+def test_fused_front_equals_stage_by_stage_path(name, n, gpu, workloads):
+    wl = workloads[name]
+    raw = synth_numpy(wl, n)
+    a = gpu.Chain(wl.config, 0, record_taps=1, fused=1)
+    b = gpu.Chain(wl.config, 0, record_taps=1, fused=0)
+    ya, ca = a.process(raw, return_chunk_counts=True)
+    yb, cb = b.process(raw, return_chunk_counts=True)
+    assert a.info().fused_front == 1 and b.info().fused_front == 0
+    assert np.array_equal(ca, cb)
+    ta, tb = a.read_tap(1), b.read_tap(1)
+    assert ta.size == tb.size
+    if not wl.config.dc_block:
+        assert np.array_equal(ta.view(np.uint32), tb.view(np.uint32))    # same FMA order -> same bits
+        assert np.array_equal(ya, yb)
+    else:
+        assert rel_rms_fullscale(ta, tb) <= 1e-7
+        assert max_lsb(ya, yb) <= 1
+
+
+@pytest.mark.parametrize("name,n", [("cfg1", (1 << 22) + 4097), ("cfg5", (1 << 23) + 11)])
+def test_fused_front_parity_vs_oracle(name, n, gpu, workloads):
+    wl = workloads[name]
+    raw = synth_numpy(wl, n)
+    g, o, out, ref, counts = _run_pair(gpu, wl.config, raw, taps=1)
+    assert g.info().fused_front == 1
+    assert np.array_equal(counts, o.traced())
+    assert rel_rms_fullscale(g.read_tap(1), o.captured(1)) <= 1e-6
+    assert snr_db(g.read_tap(1), o.captured(1)) >= 120.0
+    _check_final(wl.config, out, ref)
+
+
+def test_fused_front_is_call_size_invariant(gpu, workloads):
+    """Ragged calls (1 frame, odd sizes, sizes straddling block and run boundaries) through the
+    fused kernel == one big call, bit for bit: tests the cf32 tail, absolute-index alignment,
+    warm-up blocks and the DC table rewind."""
+    import dataclasses
+    for name in ("cfg5", "cfg2"):
+        wl = workloads[name]
+        cfg = dataclasses.replace(wl.config, output_format="cf32", agc_enable=False, filters=[], filter_taps=0,
+                                  filter_type_request=0)
+        n = 300000
+        raw = synth_numpy(wl, n)
+        one = gpu.Chain(cfg, 0, fused=1).process(raw).view(np.complex64)
+        g = gpu.Chain(cfg, 0, fused=1)
+        parts, pos = [], 0
+        for m in (1, 3, 127, 2048, 5000, 4095, 16384, 100001, 50000, n):
+            m = min(m, n - pos)
+            if m <= 0:
+                break
+            parts.append(g.process(raw[2 * pos:2 * (pos + m)], chunk_frames=[m]))
+            pos += m
+        many = np.concatenate(parts).view(np.complex64)
+        assert many.size == one.size
+        if cfg.dc_block:
+            assert rel_rms_fullscale(many, one) <= 2e-8
+        else:
+            assert np.array_equal(many.view(np.uint32), one.view(np.uint32))
+
+
+def test_fused_cu8_and_cf32_inputs(gpu):
+    rng = np.random.Generator(np.random.PCG64(41))
+    n = 200000
+    for fmt, raw in (("cu8", rng.integers(0, 256, 2 * n, dtype=np.uint8)),
+                     ("cf32", (rng.standard_normal(2 * n) * 0.3).astype(np.float32)),
+                     ("cs8", rng.integers(-128, 128, 2 * n, dtype=np.int8))):
+        cfg = ChainConfig(input_format=fmt, output_format="cf32", input_rate_hz=2.4e6, target_rate_hz=250e3,
+                          freq_shift_hz=37e3, gain=0.8)
+        g, o, out, ref, counts = _run_pair(gpu, cfg, raw, taps=1)
+        assert g.info().fused_front == 1 and np.array_equal(counts, o.traced())
+        _check_final(cfg, out, ref)
