@@ -226,8 +226,15 @@ def main():
     out = torch.empty(out_frames_max * cfg.out_bytes, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
 
+    def rewind():
+        # single stream: plain reset (works for every chain); shards: closed-form seek to the shard start
+        if world == 1:
+            chain.reset()
+        else:
+            chain.seek(shard_start - halo)
+
     def step():
-        chain.seek(shard_start - halo)
+        rewind()
         return chain.process_device(raw.data_ptr(), n + halo, out.data_ptr(), out.numel(), stream.cuda_stream)
 
     for _ in range(args.warmup):
@@ -274,7 +281,7 @@ def main():
             host_in.copy_(raw.view(torch.uint8))
             nout = C.c_size_t(0)
             def e2e_step():
-                chain.seek(shard_start - halo)
+                rewind()
                 gpu._check(gpu.lib.iqgpu_chain_process(chain._h, hin, n + halo, None, 0, hout, out.numel(),
                                                        C.byref(nout), None))
             e2e_step()

@@ -155,15 +155,29 @@ struct iqgpu_chain {
 
     // ---- device state ----
     cudaStream_t stream = nullptr, h2d = nullptr, d2h = nullptr;
+    cudaStream_t last_stream = nullptr;   // stream of the most recent process call
     float* d_lut = nullptr;
     double2* d_dc_carry = nullptr;
     double2 *d_run_sums = nullptr, *d_run_start = nullptr;
+    double* d_scan_ws = nullptr;
     size_t max_runs = 0;
     std::vector<float*> d_hb_taps;  // per design index
     float* d_bank = nullptr;
     float* d_fir_taps = nullptr;
     unsigned fir_taps_padded = 0;
-    float2 *d_fft_H = nullptr, *d_fft_tw = nullptr;
+    float2 *d_fft_H = nullptr, *d_fft_tw = nullptr, *d_fft_scratch = nullptr;
+    size_t fft_scratch_bytes = 0;
+    cudaError_t ensure_fft_scratch(size_t blocks, cudaStream_t st)
+    {
+        const size_t need = fftfilt_scratch_bytes(blocks, filt.block);
+        if (need <= fft_scratch_bytes) return cudaSuccess;
+        cudaStreamSynchronize(st);
+        cudaFree(d_fft_scratch);
+        d_fft_scratch = nullptr; fft_scratch_bytes = 0;
+        cudaError_t e = cudaMalloc(&d_fft_scratch, need + need / 2);
+        if (e == cudaSuccess) fft_scratch_bytes = need + need / 2;
+        return e;
+    }
     AgcState* d_agc = nullptr;
     uint32_t* d_seg_start = nullptr;
     float *d_seg_peak = nullptr, *d_seg_gain = nullptr;
@@ -242,8 +256,8 @@ iqgpu_chain::~iqgpu_chain()
     collect_spans();
     for (auto e : ev_pool) cudaEventDestroy(e);
     for (auto* t : d_hb_taps) cudaFree(t);
-    cudaFree(d_lut); cudaFree(d_dc_carry); cudaFree(d_run_sums); cudaFree(d_run_start); cudaFree(d_bank);
-    cudaFree(d_fir_taps); cudaFree(d_fft_H); cudaFree(d_fft_tw); cudaFree(d_agc); cudaFree(d_seg_start);
+    cudaFree(d_lut); cudaFree(d_dc_carry); cudaFree(d_run_sums); cudaFree(d_run_start); cudaFree(d_scan_ws); cudaFree(d_bank);
+    cudaFree(d_fir_taps); cudaFree(d_fft_H); cudaFree(d_fft_tw); cudaFree(d_fft_scratch); cudaFree(d_agc); cudaFree(d_seg_start);
     cudaFree(d_seg_peak); cudaFree(d_seg_gain); cudaFree(d_agc_scratch);
     s_in.release(); s_pref.release(); s_arb_in.release(); s_rs.release(); s_f.release();
     for (auto& s : s_stage) s.release();
@@ -440,6 +454,7 @@ int iqgpu_chain::ensure_buffers()
 
     max_runs = n / 128 + 2;
     CK(cudaMalloc(&d_run_sums, max_runs * sizeof(double2)));
+    CK(cudaMalloc(&d_scan_ws, dc_scan_workspace_doubles(max_runs) * sizeof(double)));
     CK(cudaMalloc(&d_run_start, max_runs * sizeof(double2)));
     max_segs = n / std::max<uint32_t>(1, std::min<uint32_t>(chunk_frames, 1024)) + 8;
     CK(cudaMalloc(&d_seg_start, (max_segs + 1) * sizeof(uint32_t)));
@@ -454,6 +469,7 @@ int iqgpu_chain::reset_state()
     n_in = 0; n_nco_post = 0; n_out = 0; fft_rem = 0;
     if (plan_only || !buffers_ready) return IQGPU_OK;
     CK(cudaSetDevice(device));
+    if (last_stream && last_stream != stream) CK(cudaStreamSynchronize(last_stream));   // queued work still reads the state
     CK(cudaMemsetAsync(d_dc_carry, 0, sizeof(double2), stream));
     AgcState a{};
     a.locked = 0; a.gain = 1.0f; a.seen = 0; a.last_strong = 0.0;
@@ -523,7 +539,7 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
             if (n_runs > max_runs) return fail(IQGPU_EINVAL, "internal: run table too small");
             span_begin(IQGPU_KCLASS_DC_SCAN, st);
             CK(launch_dc_run_sums(d_rawp, n, pp, run_len, d_run_sums, st));
-            CK(launch_dc_scan(d_run_sums, n_runs, run_len, n, dc.c, d_dc_carry, d_run_start, st));
+            CK(launch_dc_scan(d_run_sums, n_runs, run_len, n, dc.c, d_dc_carry, d_run_start, d_scan_ws, st));
             span_end(st);
             launches += 2;
         }
@@ -551,8 +567,8 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
                 float2* y = nullptr;
                 CK(s_pref.begin((size_t)blocks * filt.block, st, &y));
                 if (blocks) {
-                    CK(launch_fftfilt(x_in - fft_rem, blocks, filt.block, d_fft_H, d_fft_tw, y, st));
-                    launches++;
+                    CK(ensure_fft_scratch(blocks, st));
+                    CK(launch_fftfilt(x_in - fft_rem, blocks, filt.block, d_fft_H, d_fft_tw, y, d_fft_scratch, &launches, st));
                 }
                 s_pref.commit((size_t)blocks * filt.block);
                 rs_pos0 = N0 - fft_rem;
@@ -642,8 +658,8 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
             float2* y = nullptr;
             CK(s_f.begin((size_t)blocks * filt.block, st, &y));
             if (blocks) {
-                CK(launch_fftfilt(post_src - fft_rem, blocks, filt.block, d_fft_H, d_fft_tw, y, st));
-                launches++;
+                CK(ensure_fft_scratch(blocks, st));
+                CK(launch_fftfilt(post_src - fft_rem, blocks, filt.block, d_fft_H, d_fft_tw, y, d_fft_scratch, &launches, st));
             }
             s_f.commit((size_t)blocks * filt.block);
             fft_rem = tot - blocks * filt.block;
@@ -919,6 +935,7 @@ int iqgpu_chain_process_device(iqgpu_chain* c, const void* dev_raw_in, size_t n_
     for (auto f : chunks)
         if (f > c->subtrain_frames) return fail(IQGPU_EINVAL, "a chunk exceeds subtrain_frames");
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+    c->last_stream = st;
     if (c->count_outputs(chunks.data(), chunks.size(), nullptr) * c->out_bps > out_capacity_bytes)
         return fail(IQGPU_ECAPACITY, "output buffer too small");
     for (auto& t : c->tap) t.len = 0;

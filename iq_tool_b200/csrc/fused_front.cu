@@ -345,6 +345,7 @@ struct FusedFront {
     int tail_cur = 0;
     double2* d_dc_table = nullptr;
     double2* d_dc_sums = nullptr;
+    double* d_dc_ws = nullptr;
     size_t dc_cap = 0;
     int num_sms = 148;
     int ctas_per_sm = 3;
@@ -430,7 +431,7 @@ void fused_destroy(FusedFront* f)
 {
     if (!f) return;
     cudaFree(f->d_taps); cudaFree(f->d_tail[0]); cudaFree(f->d_tail[1]);
-    cudaFree(f->d_dc_table); cudaFree(f->d_dc_sums);
+    cudaFree(f->d_dc_table); cudaFree(f->d_dc_sums); cudaFree(f->d_dc_ws);
     delete f;
 }
 
@@ -479,11 +480,14 @@ static cudaError_t fused_dc_prepass(FusedFront* f, const void* raw, long long n0
     const size_t n_runs = (nv + 255) / 256;
     if (n_runs + 2 > f->dc_cap) {
         cudaStreamSynchronize(st);
-        cudaFree(f->d_dc_table); cudaFree(f->d_dc_sums);
+        cudaFree(f->d_dc_table); cudaFree(f->d_dc_sums); cudaFree(f->d_dc_ws);
+        f->d_dc_table = nullptr; f->d_dc_sums = nullptr; f->d_dc_ws = nullptr;
         f->dc_cap = n_runs * 2 + 16;
         cudaError_t e = cudaMalloc(&f->d_dc_table, f->dc_cap * sizeof(double2));
         if (e != cudaSuccess) return e;
         e = cudaMalloc(&f->d_dc_sums, f->dc_cap * sizeof(double2));
+        if (e != cudaSuccess) return e;
+        e = cudaMalloc(&f->d_dc_ws, dc_scan_workspace_doubles(f->dc_cap) * sizeof(double));
         if (e != cudaSuccess) return e;
     }
     const size_t bps = (pre.format == IQGPU_FMT_CS8 || pre.format == IQGPU_FMT_CU8) ? 2 : (pre.format == IQGPU_FMT_CF32 ? 8 : 4);
@@ -492,7 +496,7 @@ static cudaError_t fused_dc_prepass(FusedFront* f, const void* raw, long long n0
     if (back) dc_rewind_kernel<<<1, 1, 0, st>>>(d_carry, (double)pre.dc_c, back);
     cudaError_t e = launch_dc_run_sums_masked(vraw, nv, (size_t)back, pre, 256, f->d_dc_sums, st);
     if (e != cudaSuccess) return e;
-    return launch_dc_scan(f->d_dc_sums, n_runs, 256, nv, pre.dc_c, d_carry, f->d_dc_table, st);
+    return launch_dc_scan(f->d_dc_sums, n_runs, 256, nv, pre.dc_c, d_carry, f->d_dc_table, f->d_dc_ws, st);
 }
 
 cudaError_t fused_launch(FusedFront* f, const void* raw, int64_t n0, size_t n, const PreParams& pre, double2* d_dc_carry,

@@ -43,55 +43,128 @@ __global__ void __launch_bounds__(256) dc_run_sums_kernel(const void* __restrict
     }
 }
 
-// single block: exclusive scan of the affine maps v -> A v + S_r over the runs
-__global__ void __launch_bounds__(1024) dc_scan_kernel(const double2* __restrict__ run_sums, size_t n_runs,
-                                                       uint32_t run_len, size_t n, double c,
-                                                       double2* __restrict__ carry, double2* __restrict__ run_start)
+// ---- DC carry scan over the runs: v_start[r+1] = A_r v_start[r] + S_r -------------------------------
+// Two small kernels.  (1) one warp per group of DC_GROUP runs folds the group into one affine map;
+// (2) every CTA folds the groups in front of it (a few thousand at most), then one warp per group
+// expands the per-run start states.  All in double.
+constexpr int DC_GROUP = 256;                 // runs per group (8 per lane)
+struct DcScanParams {
+    size_t n_runs, n_groups;
+    double A, A_last;                         // c^run_len, c^(padded length of the last run)
+    double undo;                              // c^-(padding of the last run)
+};
+struct Affine { double a, br, bi; };
+__device__ __forceinline__ Affine affine_then(const Affine& first, const Affine& second)
+{   // apply `first`, then `second`
+    Affine r;
+    r.a = second.a * first.a;
+    r.br = fma(second.a, first.br, second.br);
+    r.bi = fma(second.a, first.bi, second.bi);
+    return r;
+}
+__device__ __forceinline__ Affine affine_shfl_up(const Affine& v, int d)
 {
-    __shared__ double sa[1024], sbr[1024], sbi[1024];
-    const int t = threadIdx.x;
-    const size_t per = (n_runs + 1023) / 1024;
-    const size_t r0 = (size_t)t * per, r1 = (r0 + per < n_runs) ? r0 + per : n_runs;
-    const double A = pow(c, (double)run_len);
-    // padded length of the last run (rows are processed whole; the zeros only decay the state)
-    const size_t last_len = n - (n_runs - 1) * (size_t)run_len;
-    const size_t last_pad = ((last_len + 127) / 128) * 128;
-    const double A_last = pow(c, (double)last_pad);
-    double a = 1.0, br = 0.0, bi = 0.0;
-    for (size_t r = r0; r < r1; r++) {
-        const double Ar = (r == n_runs - 1) ? A_last : A;
-        const double2 s = run_sums[r];
-        a *= Ar; br = Ar * br + s.x; bi = Ar * bi + s.y;
+    Affine r;
+    r.a = __shfl_up_sync(0xffffffffu, v.a, d);
+    r.br = __shfl_up_sync(0xffffffffu, v.br, d);
+    r.bi = __shfl_up_sync(0xffffffffu, v.bi, d);
+    return r;
+}
+// lane-local fold of the lane's 8 runs of group g; returns the inclusive warp scan in `inc`
+__device__ __forceinline__ void dc_group_scan(const double2* __restrict__ run_sums, const DcScanParams& p, size_t g,
+                                              int lane, double2 (&s)[8], Affine& inc)
+{
+    const size_t r0 = g * DC_GROUP + (size_t)lane * 8;
+    Affine loc{1.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const size_t r = r0 + k;
+        if (r < p.n_runs) {
+            s[k] = run_sums[r];
+            const double Ar = (r == p.n_runs - 1) ? p.A_last : p.A;
+            loc.a *= Ar; loc.br = fma(Ar, loc.br, s[k].x); loc.bi = fma(Ar, loc.bi, s[k].y);
+        } else s[k] = make_double2(0.0, 0.0);
     }
-    sa[t] = a; sbr[t] = br; sbi[t] = bi;
+    inc = loc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const Affine prev = affine_shfl_up(inc, d);
+        if (lane >= d) inc = affine_then(prev, inc);
+    }
+}
+
+__global__ void __launch_bounds__(256) dc_group_agg_kernel(const double2* __restrict__ run_sums, DcScanParams p,
+                                                           const double2* __restrict__ carry, double2* __restrict__ carry_snapshot,
+                                                           double* __restrict__ grp)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *carry_snapshot = *carry;
+    if (warp >= p.n_groups) return;
+    double2 s[8];
+    Affine inc;
+    dc_group_scan(run_sums, p, warp, lane, s, inc);
+    if (lane == 31) { grp[3 * warp] = inc.a; grp[3 * warp + 1] = inc.br; grp[3 * warp + 2] = inc.bi; }
+}
+
+__global__ void __launch_bounds__(1024) dc_expand_kernel(const double2* __restrict__ run_sums, DcScanParams p,
+                                                         const double* __restrict__ grp, const double2* __restrict__ carry_snapshot,
+                                                         double2* __restrict__ carry, double2* __restrict__ run_start)
+{
+    __shared__ Affine sh[1024];
+    __shared__ double2 gstart[32];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const size_t g0 = (size_t)blockIdx.x * 32;          // first group of this CTA
+    // ordered fold of groups [0, g0): thread t folds a contiguous slice, then a tree over threads
+    {
+        const size_t per = (g0 + 1023) / 1024;
+        const size_t a0 = (size_t)t * per, a1 = (a0 + per < g0) ? a0 + per : g0;
+        Affine f{1.0, 0.0, 0.0};
+        for (size_t g = a0; g < a1; g++) f = affine_then(f, Affine{grp[3 * g], grp[3 * g + 1], grp[3 * g + 2]});
+        sh[t] = f;
+    }
     __syncthreads();
-    for (int dist = 1; dist < 1024; dist <<= 1) {
-        double pa = 1.0, pbr = 0.0, pbi = 0.0;
-        if (t >= dist) { pa = sa[t - dist]; pbr = sbr[t - dist]; pbi = sbi[t - dist]; }
+    for (int d = 1; d < 1024; d <<= 1) {
+        Affine f;
+        const bool act = (t & (2 * d - 1)) == (2 * d - 1);
+        if (act) f = affine_then(sh[t - d], sh[t]);
         __syncthreads();
-        if (t >= dist) {  // compose: (a,b) after (pa,pb)
-            sbr[t] = sa[t] * pbr + sbr[t];
-            sbi[t] = sa[t] * pbi + sbi[t];
-            sa[t] = sa[t] * pa;
+        if (act) sh[t] = f;
+        __syncthreads();
+    }
+    if (t == 0) {
+        const double2 v0 = *carry_snapshot;
+        const Affine pre = sh[1023];
+        double vr = fma(pre.a, v0.x, pre.br), vi = fma(pre.a, v0.y, pre.bi);
+        for (int k = 0; k < 32; k++) {
+            gstart[k] = make_double2(vr, vi);
+            const size_t g = g0 + k;
+            if (g < p.n_groups) {
+                const double a = grp[3 * g];
+                vr = fma(a, vr, grp[3 * g + 1]); vi = fma(a, vi, grp[3 * g + 2]);
+            }
         }
-        __syncthreads();
-    }
-    const double2 v0 = *carry;
-    double ea = 1.0, ebr = 0.0, ebi = 0.0;  // exclusive prefix of this thread
-    if (t > 0) { ea = sa[t - 1]; ebr = sbr[t - 1]; ebi = sbi[t - 1]; }
-    double vr = ea * v0.x + ebr, vi = ea * v0.y + ebi;
-    for (size_t r = r0; r < r1; r++) {
-        run_start[r] = make_double2(vr, vi);
-        const double Ar = (r == n_runs - 1) ? A_last : A;
-        const double2 s = run_sums[r];
-        vr = Ar * vr + s.x; vi = Ar * vi + s.y;
     }
     __syncthreads();
-    if (t == 1023) {
-        // state after ALL runs, with the zero padding of the last row undone
-        double fr = sa[1023] * v0.x + sbr[1023], fi = sa[1023] * v0.y + sbi[1023];
-        const double undo = pow(c, -(double)(last_pad - last_len));
-        *carry = make_double2(fr * undo, fi * undo);
+    const size_t g = g0 + w;
+    if (g >= p.n_groups) return;
+    double2 s[8];
+    Affine inc;
+    dc_group_scan(run_sums, p, g, lane, s, inc);
+    Affine exc = affine_shfl_up(inc, 1);
+    if (lane == 0) exc = Affine{1.0, 0.0, 0.0};
+    const double2 gs = gstart[w];
+    double vr = fma(exc.a, gs.x, exc.br), vi = fma(exc.a, gs.y, exc.bi);
+    const size_t r0 = g * DC_GROUP + (size_t)lane * 8;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const size_t r = r0 + k;
+        if (r < p.n_runs) {
+            run_start[r] = make_double2(vr, vi);
+            const double Ar = (r == p.n_runs - 1) ? p.A_last : p.A;
+            vr = fma(Ar, vr, s[k].x); vi = fma(Ar, vi, s[k].y);
+            if (r == p.n_runs - 1) *carry = make_double2(vr * p.undo, vi * p.undo);   // state after ALL runs, padding undone
+        }
     }
 }
 
@@ -214,12 +287,28 @@ cudaError_t launch_dc_run_sums_masked(const void* raw, size_t n, size_t lo, cons
 }
 
 cudaError_t launch_dc_scan(const double2* run_sums, size_t n_runs, uint32_t run_len, size_t n,
-                           float dc_c, double2* carry_inout, double2* run_start, cudaStream_t st)
+                           float dc_c, double2* carry_inout, double2* run_start, double* scan_ws, cudaStream_t st)
 {
     if (n_runs == 0) return cudaSuccess;
-    dc_scan_kernel<<<1, 1024, 0, st>>>(run_sums, n_runs, run_len, n, (double)dc_c, carry_inout, run_start);
+    DcScanParams p{};
+    p.n_runs = n_runs;
+    p.n_groups = (n_runs + DC_GROUP - 1) / DC_GROUP;
+    const double c = (double)dc_c;
+    // rows are processed whole (128 frames); the zero padding of the last run only decays the state
+    const size_t last_len = n - (n_runs - 1) * (size_t)run_len;
+    const size_t last_pad = ((last_len + 127) / 128) * 128;
+    p.A = pow(c, (double)run_len);
+    p.A_last = pow(c, (double)last_pad);
+    p.undo = pow(c, -(double)(last_pad - last_len));
+    double2* snapshot = reinterpret_cast<double2*>(scan_ws);
+    double* grp = scan_ws + 2;
+    const int g1 = (int)((p.n_groups * 32 + 255) / 256);
+    dc_group_agg_kernel<<<g1, 256, 0, st>>>(run_sums, p, carry_inout, snapshot, grp);
+    const int g2 = (int)((p.n_groups + 31) / 32);
+    dc_expand_kernel<<<g2, 1024, 0, st>>>(run_sums, p, grp, snapshot, carry_inout, run_start);
     return cudaGetLastError();
 }
+size_t dc_scan_workspace_doubles(size_t n_runs) { return 2 + 3 * ((n_runs + DC_GROUP - 1) / DC_GROUP) + 8; }
 
 cudaError_t launch_pre(const void* raw, size_t n, const PreParams& p, uint32_t run_len,
                        const double2* run_start, float2* out, cudaStream_t st)
@@ -442,12 +531,35 @@ __device__ __forceinline__ unsigned find_segment(const uint32_t* __restrict__ se
     return lo;
 }
 
+// ---- warp tiles -------------------------------------------------------------------------------
+// The post-processor kernels walk the output stream in tiles of POST_TILE consecutive frames per
+// warp; a lane owns 4 consecutive frames per step (2 x LDG.128 in, one vector store out) and keeps
+// its segment (= reference chunk) index in a register, advancing it monotonically.
+constexpr int POST_TILE = 2048;
+__device__ __forceinline__ void load4(const float2* __restrict__ x, size_t i, size_t n, bool vec, float2 (&v)[4])
+{
+    if (vec && i + 4 <= n) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x + i));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(x + i) + 1);
+        v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w);
+        v[2] = make_float2(b.x, b.y); v[3] = make_float2(b.z, b.w);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = (i + k < n) ? x[i + k] : make_float2(0.f, 0.f);
+    }
+}
+
 // per-segment peak |x| after the (optional) post NCO.  reference agc.c:117-124 / 168-173 uses
-// cabsf (hypotf, correctly rounded): each thread tracks its largest |x|^2 and evaluates the
-// magnitude of that one sample in double.
+// cabsf (hypotf, correctly rounded = sqrt of the double sum of squares, rounded once).  sqrt and
+// the float rounding are monotone, so a lane tracks max(re^2 + im^2) in double and takes one
+// square root when it leaves a segment.
+__device__ __forceinline__ void peak_flush(float* __restrict__ seg_peak, unsigned seg, double d)
+{
+    if (d > 0.0) atomicMax(reinterpret_cast<unsigned*>(seg_peak) + seg, __float_as_uint((float)sqrt(d)));
+}
 __global__ void __launch_bounds__(256) agc_peaks_kernel(const float2* __restrict__ x, size_t n, PostParams p,
                                                         const uint32_t* __restrict__ seg_start, unsigned nseg,
-                                                        float* __restrict__ seg_peak)
+                                                        float* __restrict__ seg_peak, bool vec)
 {
     __shared__ float lut[1024];
     if (p.nco_enable) {
@@ -455,69 +567,134 @@ __global__ void __launch_bounds__(256) agc_peaks_kernel(const float2* __restrict
         __syncthreads();
     }
     const int lane = threadIdx.x & 31;
-    for (size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < n; i0 += (size_t)gridDim.x * blockDim.x) {
-        const size_t i = i0 + lane;
-        float mag = 0.f;
-        unsigned seg = 0xffffffffu;
-        if (i < n) {
-            float2 v = x[i];
-            if (p.nco_enable) v = nco_mix(v, p.nco_theta0 + (uint32_t)i * p.nco_dtheta, p.nco_sign, lut);
-            mag = (float)sqrt((double)v.x * (double)v.x + (double)v.y * (double)v.y);
-            seg = find_segment(seg_start, nseg, (uint32_t)i);
-        }
-        const unsigned seg0 = __shfl_sync(0xffffffffu, seg, 0);
-        const bool uniform = __all_sync(0xffffffffu, seg == seg0);
-        if (uniform) {
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const size_t ntiles = (n + POST_TILE - 1) / POST_TILE;
+    for (size_t tile = warp; tile < ntiles; tile += nwarps) {
+        const size_t t0 = tile * POST_TILE;
+        size_t i = t0 + (size_t)lane * 4;
+        unsigned seg = (i < n) ? find_segment(seg_start, nseg, (uint32_t)i) : 0u;
+        uint32_t seg_end = (i < n) ? __ldg(seg_start + seg + 1) : 0u;
+        double d = 0.0;
+#pragma unroll 1
+        for (int it = 0; it < POST_TILE / 128; it++, i += 128) {
+            if (i >= n) break;
+            float2 v[4];
+            load4(x, i, n, vec, v);
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) mag = fmaxf(mag, __shfl_xor_sync(0xffffffffu, mag, d));
-            if (lane == 0 && seg0 != 0xffffffffu) atomicMax(reinterpret_cast<unsigned*>(seg_peak) + seg0, __float_as_uint(mag));
-        } else if (seg != 0xffffffffu) {
-            atomicMax(reinterpret_cast<unsigned*>(seg_peak) + seg, __float_as_uint(mag));
+            for (int k = 0; k < 4; k++) {
+                const size_t ik = i + k;
+                if (ik >= n) break;
+                while ((uint32_t)ik >= seg_end) {           // next non-empty segment
+                    peak_flush(seg_peak, seg, d); d = 0.0;
+                    seg++; seg_end = __ldg(seg_start + seg + 1);
+                }
+                float2 w = v[k];
+                if (p.nco_enable) w = nco_mix(w, p.nco_theta0 + (uint32_t)ik * p.nco_dtheta, p.nco_sign, lut);
+                d = fmax(d, fma((double)w.x, (double)w.x, (double)w.y * (double)w.y));
+            }
         }
+        // one atomic per warp when the whole tile sits in one segment
+        const unsigned seg0 = __shfl_sync(0xffffffffu, seg, 0);
+        if (__all_sync(0xffffffffu, seg == seg0)) {
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) d = fmax(d, __shfl_xor_sync(0xffffffffu, d, s));
+            if (lane == 0) peak_flush(seg_peak, seg0, d);
+        } else peak_flush(seg_peak, seg, d);
     }
 }
 
 // digital AGC state machine, one step per reference chunk (agc.c:105-222).  Wall-clock reads in
 // the reference (agc.c:176,202-207) are replaced by the sample clock seen/target_rate.
-__global__ void agc_digital_scan_kernel(const uint32_t* __restrict__ seg_start, unsigned nseg,
-                                        const float* __restrict__ seg_peak, PostParams p,
-                                        AgcState* __restrict__ st, float* __restrict__ seg_gain)
-{
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    AgcState s = *st;
-    const float target = p.agc_target;
-    for (unsigned c = 0; c < nseg; c++) {
-        const unsigned cnt = seg_start[c + 1] - seg_start[c];
-        if (cnt == 0) { seg_gain[c] = 1.0f; continue; }          // agc_apply returns on num_samples == 0
-        const float pk = seg_peak[c];
+// One warp walks the chunks 32 at a time.  While nothing data dependent happens inside a group
+// (no ratchet, no creep, no lock transition) all 32 gains are produced in one step; otherwise the
+// group is replayed chunk by chunk with warp-uniform state -- the results are those of the
+// sequential reference loop in every case.
+struct AgcStep {   // sequential reference step, shared by both paths
+    __device__ static __forceinline__ float run(AgcState& s, float pk, unsigned cnt, float target, double rate)
+    {
         float g;
         if (!s.locked) {
             if (pk > s.peak_mem) s.peak_mem = pk;
             const float safe = (s.peak_mem < 1e-4f) ? 1e-4f : s.peak_mem;
             g = __fdiv_rn(target, safe);
-            const double elapsed = (double)s.seen / p.target_rate;
-            if (elapsed > (double)2.0f) {
-                s.locked = 1; s.gain = g;
-                s.last_strong = elapsed;
-            }
+            const double elapsed = (double)s.seen / rate;
+            if (elapsed > (double)2.0f) { s.locked = 1; s.gain = g; s.last_strong = elapsed; }
         } else {
             g = s.gain;
             const float opk = __fmul_rn(pk, g);
-            const double now = (double)s.seen / p.target_rate;
-            if (opk > 1.0f) {
-                g = __fdiv_rn(0.99f, pk);
-                s.last_strong = now;
-            } else if (opk > __fmul_rn(target, 0.75f)) {
-                s.last_strong = now;
-            } else if (now - s.last_strong > (double)4.0f) {
-                g = __fmul_rn(g, 1.0005f);
-            }
+            const double now = (double)s.seen / rate;
+            if (opk > 1.0f) { g = __fdiv_rn(0.99f, pk); s.last_strong = now; }
+            else if (opk > __fmul_rn(target, 0.75f)) s.last_strong = now;
+            else if (now - s.last_strong > (double)4.0f) g = __fmul_rn(g, 1.0005f);
             s.gain = g;
         }
-        seg_gain[c] = g;
         s.seen += cnt;
+        return g;
     }
-    *st = s;
+};
+__global__ void __launch_bounds__(32) agc_digital_scan_kernel(const uint32_t* __restrict__ seg_start, unsigned nseg,
+                                                              const float* __restrict__ seg_peak, PostParams p,
+                                                              AgcState* __restrict__ st, float* __restrict__ seg_gain)
+{
+    const unsigned lane = threadIdx.x;
+    AgcState s = *st;
+    const float target = p.agc_target;
+    const float strong_thr = __fmul_rn(target, 0.75f);
+    for (unsigned base = 0; base < nseg; base += 32) {
+        const unsigned c = base + lane;
+        const bool valid = c < nseg;
+        const unsigned cnt = valid ? (__ldg(seg_start + c + 1) - __ldg(seg_start + c)) : 0u;
+        const float pk = valid ? __ldg(seg_peak + c) : 0.f;
+        const bool act = cnt != 0;                               // agc_apply returns on num_samples == 0
+        // exclusive prefix of the sample counter
+        unsigned long long pre = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long q = __shfl_up_sync(0xffffffffu, pre, d);
+            if (lane >= (unsigned)d) pre += q;
+        }
+        const unsigned long long total = __shfl_sync(0xffffffffu, pre, 31);
+        const unsigned long long seen_before = s.seen + pre - cnt;
+        bool fast = false;
+        float g = 1.0f;
+        if (s.locked) {
+            const float opk = __fmul_rn(pk, s.gain);
+            const double now = (double)seen_before / p.target_rate;
+            const bool ratchet = act && opk > 1.0f;
+            const bool strong = act && opk > strong_thr;
+            // time of the latest strong chunk strictly before this lane (now is non-decreasing)
+            double ls = strong ? now : -1.0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double q = __shfl_up_sync(0xffffffffu, ls, d);
+                if (lane >= (unsigned)d) ls = fmax(ls, q);
+            }
+            const double ls_incl = ls;
+            double ls_excl = __shfl_up_sync(0xffffffffu, ls, 1);
+            if (lane == 0) ls_excl = -1.0;
+            ls_excl = fmax(ls_excl, s.last_strong);
+            const bool creep = act && !strong && (now - ls_excl > (double)4.0f);
+            if (!__any_sync(0xffffffffu, ratchet || creep)) {
+                fast = true;
+                g = s.gain;
+                s.last_strong = fmax(s.last_strong, __shfl_sync(0xffffffffu, ls_incl, 31));
+                s.seen += total;
+            }
+        }
+        if (!fast) {
+            // replay: warp-uniform sequential walk over the group's chunks
+            for (unsigned k = 0; k < 32 && base + k < nseg; k++) {
+                const unsigned ck = __shfl_sync(0xffffffffu, cnt, k);
+                const float pkk = __shfl_sync(0xffffffffu, pk, k);
+                if (ck == 0) continue;
+                const float gk = AgcStep::run(s, pkk, ck, target, p.target_rate);
+                if (lane == k) g = gk;
+            }
+        }
+        if (valid) seg_gain[c] = act ? g : 1.0f;
+    }
+    if (lane == 0) *st = s;
 }
 
 // liquid agc_crcf_execute_block (agc.c:92-100): nonlinear per-sample recurrence; serial.
@@ -603,11 +780,42 @@ __device__ __forceinline__ void store_out(void* __restrict__ out, size_t i, floa
     }
 }
 
+// four consecutive frames -> output format; vector stores when the destination is 16-byte aligned
+template <int FMT>
+__device__ __forceinline__ void store_out4(void* __restrict__ out, size_t i, size_t n, const float2 (&v)[4], bool vec)
+{
+    if (vec && i + 4 <= n) {
+        if (FMT == IQGPU_FMT_CF32) {
+            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float2*>(out) + i);
+            o[0] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+            o[1] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
+            return;
+        }
+        if (FMT == IQGPU_FMT_CS16 || FMT == IQGPU_FMT_SC16Q11 || FMT == IQGPU_FMT_CU16) {
+            __align__(16) unsigned short tmp[8];
+#pragma unroll
+            for (int k = 0; k < 4; k++) store_out<FMT>(tmp, k, v[k]);
+            *reinterpret_cast<uint4*>(reinterpret_cast<char*>(out) + i * 4) = *reinterpret_cast<const uint4*>(tmp);
+            return;
+        }
+        if (FMT == IQGPU_FMT_CS8 || FMT == IQGPU_FMT_CU8) {
+            __align__(8) unsigned char tmp[8];
+#pragma unroll
+            for (int k = 0; k < 4; k++) store_out<FMT>(tmp, k, v[k]);
+            *reinterpret_cast<uint2*>(reinterpret_cast<char*>(out) + i * 2) = *reinterpret_cast<const uint2*>(tmp);
+            return;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (i + k < n) store_out<FMT>(out, i + k, v[k]);
+}
+
 template <int FMT>
 __global__ void __launch_bounds__(256) post_kernel(const float2* __restrict__ x, size_t n, PostParams p,
                                                    const uint32_t* __restrict__ seg_start, unsigned nseg,
                                                    const float* __restrict__ seg_gain, int nco_done,
-                                                   float2* __restrict__ tap, void* __restrict__ out)
+                                                   float2* __restrict__ tap, void* __restrict__ out, bool vec_in, bool vec_out)
 {
     __shared__ float lut[1024];
     const bool do_nco = p.nco_enable && !nco_done;
@@ -615,24 +823,56 @@ __global__ void __launch_bounds__(256) post_kernel(const float2* __restrict__ x,
         for (int i = threadIdx.x; i < 1024; i += blockDim.x) lut[i] = p.nco_table[i];
         __syncthreads();
     }
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        float2 v = x[i];
-        if (do_nco) v = nco_mix(v, p.nco_theta0 + (uint32_t)i * p.nco_dtheta, p.nco_sign, lut);
-        if (seg_gain) {
-            const float g = __ldg(seg_gain + find_segment(seg_start, nseg, (uint32_t)i));
-            v.x = __fmul_rn(v.x, g); v.y = __fmul_rn(v.y, g);
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const size_t ntiles = (n + POST_TILE - 1) / POST_TILE;
+    for (size_t tile = warp; tile < ntiles; tile += nwarps) {
+        size_t i = tile * POST_TILE + (size_t)lane * 4;
+        unsigned seg = 0;
+        uint32_t seg_end = 0xffffffffu;
+        float g = 1.0f;
+        if (seg_gain && i < n) {
+            seg = find_segment(seg_start, nseg, (uint32_t)i);
+            seg_end = __ldg(seg_start + seg + 1);
+            g = __ldg(seg_gain + seg);
         }
-        if (tap) tap[i] = v;
-        store_out<FMT>(out, i, v);
+#pragma unroll 1
+        for (int it = 0; it < POST_TILE / 128; it++, i += 128) {
+            if (i >= n) break;
+            float2 v[4];
+            load4(x, i, n, vec_in, v);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const size_t ik = i + k;
+                if (do_nco) v[k] = nco_mix(v[k], p.nco_theta0 + (uint32_t)ik * p.nco_dtheta, p.nco_sign, lut);
+                if (seg_gain && ik < n) {
+                    while ((uint32_t)ik >= seg_end) { seg++; seg_end = __ldg(seg_start + seg + 1); g = __ldg(seg_gain + seg); }
+                    v[k].x = __fmul_rn(v[k].x, g); v[k].y = __fmul_rn(v[k].y, g);
+                }
+                if (tap && ik < n) tap[ik] = v[k];
+            }
+            store_out4<FMT>(out, i, n, v, vec_out);
+        }
     }
 }
+
+static inline int grid_tiles(size_t n)
+{
+    const size_t tiles = (n + POST_TILE - 1) / POST_TILE;
+    size_t blocks = (tiles + 7) / 8;            // 8 warps per CTA
+    const size_t cap = 148 * 8;
+    if (blocks > cap) blocks = cap;
+    return (int)(blocks ? blocks : 1);
+}
+static inline bool aligned16(const void* p) { return (reinterpret_cast<size_t>(p) & 15) == 0; }
 
 cudaError_t launch_agc_peaks(const float2* x, size_t n, const PostParams& p, const uint32_t* seg_start,
                              size_t nseg, float* seg_peak, cudaStream_t st)
 {
     cudaError_t e = cudaMemsetAsync(seg_peak, 0, nseg * sizeof(float), st);
     if (e != cudaSuccess || n == 0) return e;
-    agc_peaks_kernel<<<grid_1d(n, 256), 256, 0, st>>>(x, n, p, seg_start, (unsigned)nseg, seg_peak);
+    agc_peaks_kernel<<<grid_tiles(n), 256, 0, st>>>(x, n, p, seg_start, (unsigned)nseg, seg_peak, aligned16(x));
     return cudaGetLastError();
 }
 cudaError_t launch_agc_digital_scan(const uint32_t* seg_start, size_t nseg, const float* seg_peak,
@@ -653,8 +893,9 @@ cudaError_t launch_post(const float2* x, size_t n, const PostParams& p, const ui
                         const float* seg_gain, int nco_done, float2* tap, void* out, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
-    const int grid = grid_1d(n, 256);
-#define CALL(F) post_kernel<F><<<grid, 256, 0, st>>>(x, n, p, seg_start, (unsigned)nseg, seg_gain, nco_done, tap, out)
+    const int grid = grid_tiles(n);
+    const bool vi = aligned16(x), vo = aligned16(out);
+#define CALL(F) post_kernel<F><<<grid, 256, 0, st>>>(x, n, p, seg_start, (unsigned)nseg, seg_gain, nco_done, tap, out, vi, vo)
     DISPATCH_FMT(p.format, CALL)
 #undef CALL
     return cudaGetLastError();

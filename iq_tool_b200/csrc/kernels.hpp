@@ -31,8 +31,10 @@ cudaError_t launch_dc_run_sums(const void* raw, size_t n, const PreParams& p, ui
 cudaError_t launch_dc_run_sums_masked(const void* raw, size_t n, size_t lo, const PreParams& p, uint32_t run_len,
                                       double2* run_sums, cudaStream_t st);
 // DC pass 2: v at the start of every run from the carried state; updates the carry in place
+// scan_ws: device workspace of dc_scan_workspace_doubles(n_runs) doubles
 cudaError_t launch_dc_scan(const double2* run_sums, size_t n_runs, uint32_t run_len, size_t n,
-                           float dc_c, double2* carry_inout, double2* run_start, cudaStream_t st);
+                           float dc_c, double2* carry_inout, double2* run_start, double* scan_ws, cudaStream_t st);
+size_t dc_scan_workspace_doubles(size_t n_runs);
 // convert + (DC apply) + I/Q + NCO -> cf32
 cudaError_t launch_pre(const void* raw, size_t n, const PreParams& p, uint32_t run_len,
                        const double2* run_start, float2* out, cudaStream_t st);
@@ -59,9 +61,12 @@ cudaError_t launch_fir(const float2* x, size_t n, const float* hrev, unsigned nt
 // ---- K4: FFT block filter (overlap-save form of liquid's fftfilt) --------------------------
 // For each block b in [0,nblocks): window = x[(b-1)*B .. (b+1)*B), y[b*B .. (b+1)*B) =
 // last B samples of IFFT(FFT(window) .* H) / (2B).  x points at block 0's first sample.
+// 2B > 16384 needs a global scratch of fftfilt_scratch_bytes(nblocks, B); *launches += kernels launched.
 cudaError_t launch_fftfilt(const float2* x, size_t nblocks, unsigned B, const float2* H,
-                           const float2* twiddle, float2* y, cudaStream_t st);
-// H = FFT(h || 0) of size 2B (forward, un-normalised); twiddle: exp(-j 2 pi k / 2B), k < 2B
+                           const float2* twiddle, float2* y, float2* scratch, uint32_t* launches, cudaStream_t st);
+size_t fftfilt_scratch_bytes(size_t nblocks, unsigned B);
+// H = FFT(h || 0) of size 2B (forward, un-normalised, in the network's digit-reversed order);
+// twiddle: exp(-j 2 pi k / 2B), k < 2B
 cudaError_t launch_fft_forward(const float2* in, unsigned nfft, const float2* twiddle, float2* out,
                                cudaStream_t st);
 bool fftfilt_supported(unsigned B);

@@ -326,3 +326,87 @@ def test_fused_cu8_and_cf32_inputs(gpu):
         g, o, out, ref, counts = _run_pair(gpu, cfg, raw, taps=1)
         assert g.info().fused_front == 1 and np.array_equal(counts, o.traced())
         _check_final(cfg, out, ref)
+
+
+# ---------------------------------------------------------------------------------------------
+# K4: FFT block filter (hand-written FFT, overlap-save evaluation of liquid's overlap-add fftfilt)
+# ---------------------------------------------------------------------------------------------
+def test_cfg3_golden_fixture_parity(gpu, workloads, golden):
+    """cfg3 vs the committed reference outputs: 4095 complex taps, block n = 8192 (FFT 16384),
+    outputs quantised to whole FFT blocks per chunk, post-resample LUT-NCO shift, cs16."""
+    meta, data = golden
+    cfg = workloads["cfg3"].config
+    g = gpu.Chain(cfg, 0, record_taps=1)
+    out, counts = g.process(data["cfg3"]["raw"], return_chunk_counts=True)
+    assert np.array_equal(counts, data["cfg3"]["counts"])
+    taps = g.filter_taps()
+    assert taps.size == 4095 and rel_rms_fullscale(taps, data["cfg3"]["filter_taps"]) <= 1e-9
+    rs = g.read_tap(1)
+    assert rs.size == data["cfg3"]["rs"].size
+    assert rel_rms_fullscale(rs, data["cfg3"]["rs"]) <= 1e-6
+    _check_final(cfg, out, data["cfg3"]["out"])
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+def test_cfg3_parity_vs_oracle(fused, gpu, workloads):
+    wl = workloads["cfg3"]
+    n = (1 << 21) + 4099
+    raw = synth_numpy(wl, n)
+    g, o, out, ref, counts = _run_pair(gpu, wl.config, raw, taps=1, fused=fused)
+    assert g.info().fused_front == fused
+    assert np.array_equal(counts, o.traced())           # 0 or 8192 frames per chunk
+    assert set(np.unique(counts)) <= {0, 8192}
+    assert snr_db(g.read_tap(1), o.captured(1)) >= 120.0
+    _check_final(wl.config, out, ref)
+
+
+def test_fft_filter_equals_fir_filter_and_oracle(gpu):
+    """Same master taps through K4 (FFT) and K3 (FIR): identical streams up to fp32 rounding; FFT
+    output length is the whole-block prefix.  Covers real (crcf) and complex (cccf) taps, small
+    and odd-log2 transform sizes, and ragged chunking of the FFT remainder."""
+    from iq_tool_b200.configs import FILTER_REQ_FFT, pass_range
+    rng = np.random.Generator(np.random.PCG64(51))
+    n = 5 * 16384 + 1234
+    x = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 0.2).astype(np.complex64)
+    for filt, taps, fftsize in (([lowpass(100e3)], 255, 0), ([pass_range(102e3, 215e3)], 301, 0),
+                                ([lowpass(200e3)], 21, 0), ([pass_range(50e3, 90e3)], 1025, 4096),
+                                ([lowpass(50e3)], 63, 128)):
+        base = dict(input_format="cf32", output_format="cf32", input_rate_hz=1e6, target_rate_hz=1e6,
+                    no_resample=True, filters=filt, filter_taps=taps)
+        cfg_fft = ChainConfig(filter_type_request=FILTER_REQ_FFT, filter_fft_size=fftsize, **base)
+        cfg_fir = ChainConfig(filter_type_request=FILTER_REQ_FIR, **base)
+        g, o, out, ref, counts = _run_pair(gpu, cfg_fft, x.view(np.float32), taps=1)
+        assert np.array_equal(counts, o.traced())
+        _check_final(cfg_fft, out, ref)
+        fir = gpu.Chain(cfg_fir, 0).process(x.view(np.float32)).view(np.complex64)
+        a = out.view(np.complex64)
+        assert a.size % g.info().filter_block_size == 0 and a.size <= fir.size
+        assert rel_rms_fullscale(a, fir[: a.size]) <= 2e-6
+        # ragged calls carry the remainder exactly like one call
+        g2 = gpu.Chain(cfg_fft, 0)
+        parts, pos = [], 0
+        for m in (1, 100, 16384, 5000, 40000, n):
+            m = min(m, n - pos)
+            if m <= 0:
+                break
+            parts.append(g2.process(x.view(np.float32)[2 * pos:2 * (pos + m)], chunk_frames=[m]))
+            pos += m
+        assert np.array_equal(np.concatenate(parts).view(np.uint32), out.view(np.uint32))
+
+
+def test_fft_filter_large_transform_split_path(gpu):
+    """2n = 65536 > the shared-memory transform: radix-2 global stages + 16384-point sub-blocks.
+    Post-resample placement (the reference's pre-resample FFT path corrupts its input when the
+    block exceeds the chunk)."""
+    from iq_tool_b200.configs import FILTER_REQ_FFT
+    rng = np.random.Generator(np.random.PCG64(52))
+    n = 20 * 16384
+    x = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * 0.2).astype(np.complex64)
+    cfg = ChainConfig(input_format="cf32", output_format="cf32", input_rate_hz=2e6, target_rate_hz=1e6,
+                      filters=[lowpass(20e3)], filter_taps=9001,
+                      filter_type_request=FILTER_REQ_FFT, filter_fft_size=65536)
+    g, o, out, ref, counts = _run_pair(gpu, cfg, x.view(np.float32), taps=1)
+    assert g.info().filter_block_size == 32768 and g.info().filter_post_resample == 1
+    assert out.size == 2 * 5 * 32768
+    assert np.array_equal(counts, o.traced())
+    _check_final(cfg, out, ref)
