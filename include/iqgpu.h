@@ -56,6 +56,9 @@ enum { IQGPU_FILTER_REQ_AUTO = 0, IQGPU_FILTER_REQ_FIR, IQGPU_FILTER_REQ_FFT };
 enum { IQGPU_FILTER_IMPL_NONE = 0, IQGPU_FILTER_IMPL_FIR_SYM, IQGPU_FILTER_IMPL_FIR_ASYM, IQGPU_FILTER_IMPL_FFT_SYM, IQGPU_FILTER_IMPL_FFT_ASYM };
 enum { IQGPU_AGC_OFF = 0, IQGPU_AGC_DX, IQGPU_AGC_LOCAL, IQGPU_AGC_DIGITAL };
 
+enum { IQGPU_STAGE_DC = 1, IQGPU_STAGE_IQ = 2, IQGPU_STAGE_NCO = 4, IQGPU_STAGE_FILTER = 8,
+       IQGPU_STAGE_RESAMPLER = 16, IQGPU_STAGE_AGC = 32 };
+
 #define IQGPU_MAX_FILTER_CHAIN 5      /* MAX_FILTER_CHAIN, include/constants.h:249 */
 #define IQGPU_CHUNK_SAMPLES    16384  /* PIPELINE_CHUNK_BASE_SAMPLES, include/constants.h:123 */
 
@@ -90,7 +93,12 @@ typedef struct {
     int32_t agc_enable;             /* AppConfig.output_agc.enable */
     int32_t agc_profile;            /* IQGPU_AGC_* */
     float   agc_target_level_arg;   /* --agc-target, 0 = profile default */
-    int32_t reserved;
+    int32_t stage_select;           /* 0 = the whole chain.  Otherwise a mask of IQGPU_STAGE_*: the chain
+                                     * is DESIGNED from the full configuration above (identical taps, NCO
+                                     * increment, ratio, AGC timing) but executes only the selected
+                                     * stage(s) on cf32 input -> cf32 output: the module-level entry
+                                     * points (dc_block_apply, freq_shift_apply, filter_apply,
+                                     * resampler_execute, agc_apply, iq_correct_apply). */
 } iqgpu_chain_config;
 
 typedef struct {
@@ -171,6 +179,9 @@ int  iqgpu_chain_process_device(iqgpu_chain *c, const void *dev_raw_in, size_t n
                                 const uint32_t *chunk_frames, size_t n_chunks,
                                 void *dev_out, size_t out_capacity_bytes, size_t *out_frames,
                                 uint32_t *per_chunk_out, void *cuda_stream);
+/* closed form: resampler output frames after `frames_in` input frames since reset
+ * (msresamp_crcf_execute's cumulative *num_written, src/resampler.c:49) */
+int  iqgpu_chain_resampler_outputs_after(iqgpu_chain *c, uint64_t frames_in, uint64_t *frames_out);
 /* closed-form output frame count for the NEXT n_frames (no data touched) */
 int  iqgpu_chain_predict_output(iqgpu_chain *c, size_t n_frames, size_t *out_frames);
 /* copy the cf32 stream observed at an internal tap of the LAST process call to host:

@@ -32,6 +32,7 @@ FILTER_NONE, FILTER_LOWPASS, FILTER_HIGHPASS, FILTER_PASSBAND, FILTER_STOPBAND =
 FILTER_REQ_AUTO, FILTER_REQ_FIR, FILTER_REQ_FFT = range(3)
 FILTER_IMPL_NONE, FILTER_IMPL_FIR_SYM, FILTER_IMPL_FIR_ASYM, FILTER_IMPL_FFT_SYM, FILTER_IMPL_FFT_ASYM = range(5)
 AGC_OFF, AGC_DX, AGC_LOCAL, AGC_DIGITAL = range(4)
+STAGE_DC, STAGE_IQ, STAGE_NCO, STAGE_FILTER, STAGE_RESAMPLER, STAGE_AGC = 1, 2, 4, 8, 16, 32
 CHUNK_SAMPLES = 16384  # PIPELINE_CHUNK_BASE_SAMPLES, reference include/constants.h:123
 MAX_FILTER_CHAIN = 5
 
@@ -53,7 +54,7 @@ class ChainConfigC(C.Structure):
         ("transition_width_hz", C.c_float), ("filter_taps", C.c_int32),
         ("attenuation_db", C.c_float), ("filter_type_request", C.c_int32),
         ("filter_fft_size", C.c_int32), ("agc_enable", C.c_int32), ("agc_profile", C.c_int32),
-        ("agc_target_level_arg", C.c_float), ("reserved", C.c_int32),
+        ("agc_target_level_arg", C.c_float), ("stage_select", C.c_int32),
     ]
 
 
@@ -88,6 +89,7 @@ class ChainConfig:
     agc_enable: bool = False
     agc_profile: int = AGC_OFF
     agc_target_level_arg: float = 0.0
+    stage_select: int = 0   # IQGPU_STAGE_* mask: module-level chain (cf32 in/out), 0 = whole chain
 
     @property
     def in_bytes(self) -> int:
@@ -128,6 +130,7 @@ class ChainConfig:
         c.agc_enable = int(self.agc_enable)
         c.agc_profile = self.agc_profile if self.agc_enable else AGC_OFF
         c.agc_target_level_arg = self.agc_target_level_arg
+        c.stage_select = self.stage_select
         return c
 
 

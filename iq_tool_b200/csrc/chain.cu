@@ -795,6 +795,21 @@ int iqgpu_chain_create(const iqgpu_chain_config* cfgp, int device, iqgpu_chain**
             c->agc_alpha = (g.agc_profile == IQGPU_AGC_DX) ? 1e-4f : 1e-2f;
         }
     }
+    if (g.stage_select) {
+        // module-level chain: designed from the full configuration, runs only the selected stages cf32 -> cf32
+        const int m = g.stage_select;
+        c->cfg.input_format = IQGPU_FMT_CF32; c->cfg.output_format = IQGPU_FMT_CF32; c->cfg.gain = 1.0f;
+        c->in_bps = c->out_bps = bytes_per_sample(IQGPU_FMT_CF32);
+        if (!(m & IQGPU_STAGE_DC)) { c->dc.enable = false; c->cfg.dc_block_enable = 0; }
+        if (!(m & IQGPU_STAGE_IQ)) c->cfg.iq_correction_enable = 0;
+        if (!(m & IQGPU_STAGE_NCO)) { c->nco_pre = c->nco_post = false; }
+        if (!(m & IQGPU_STAGE_FILTER)) c->filt = FilterPlan();
+        if (!(m & IQGPU_STAGE_AGC)) c->agc_mode = 0;
+        if (!(m & IQGPU_STAGE_RESAMPLER)) {
+            c->rs = ResamplerPlan();
+            if (!design_resampler(1.0f, 60.0f, true, c->rs, err)) return bail(IQGPU_EINVAL, err);
+        }
+    }
     if (!c->plan_only) {
         int rc = c->init_device();
         if (rc != IQGPU_OK) { std::string m = g_err; delete c; return fail(rc, m); }
@@ -904,6 +919,13 @@ static int build_chunks(iqgpu_chain* c, size_t n_frames, const uint32_t* chunk_f
             left -= f;
         }
     }
+    return IQGPU_OK;
+}
+
+int iqgpu_chain_resampler_outputs_after(iqgpu_chain* c, uint64_t frames_in, uint64_t* frames_out)
+{
+    if (!c || !frames_out) return fail(IQGPU_EINVAL, "null argument");
+    *frames_out = resampler_outputs_after(c->rs, frames_in);
     return IQGPU_OK;
 }
 
@@ -1121,9 +1143,14 @@ int iqgpu_convert_cf32_to_block(const float* in_cf32, void* out, size_t n, int f
     return convert_common(in_cf32, out, n, IQGPU_FMT_CF32, format, 1.0f);
 }
 
-int iqgpu_iq_optimize(const float*, const float*, float*, float*, float*, float*)
+int iqgpu_iq_optimize(const float* block1024_cf32, const float* directions50, float* mag, float* phase,
+                      float* avg_power, float* power_range)
 {
-    return fail(IQGPU_EINVAL, "iqgpu_iq_optimize: not implemented yet");
+    if (!block1024_cf32 || !directions50 || !mag || !phase) return fail(IQGPU_EINVAL, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(IQGPU_ENODEVICE, "no CUDA device available"); }
+    CK(iq_optimize_device(block1024_cf32, directions50, mag, phase, avg_power, power_range, nullptr));
+    return IQGPU_OK;
 }
 
 }  // extern "C"

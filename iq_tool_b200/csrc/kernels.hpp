@@ -109,6 +109,10 @@ cudaError_t launch_post(const float2* x, size_t n, const PostParams& p, const ui
 // ---- conversions for the module-level API ---------------------------------------------------
 cudaError_t launch_convert_out(const float2* x, size_t n, int format, void* out, cudaStream_t st);
 
+// ---- K6: I/Q optimiser pass on one 1024-frame block (host pointers; synchronous) ---------------
+cudaError_t iq_optimize_device(const float* host_block1024, const float* host_dirs50, float* mag, float* phase,
+                               float* avg_power, float* power_range, int* optimized);
+
 // ---- fused front: raw -> [convert, DC, I/Q, NCO] -> halfband cascade -> polyphase stage -------
 constexpr int FUSED_MAX_STAGES = 10;
 struct ResamplerDesc {

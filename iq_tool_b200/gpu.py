@@ -242,3 +242,14 @@ def convert_cf32_to_block(x: np.ndarray, fmt_code: int, out_dtype, bytes_per_sam
     out = np.zeros(x.shape[0] * bytes_per_sample, dtype=np.uint8)
     _check(lib.iqgpu_convert_cf32_to_block(x.ctypes.data, out.ctypes.data, x.shape[0], fmt_code))
     return out.view(out_dtype)
+
+
+def iq_optimize(block1024: np.ndarray, directions50: np.ndarray, mag: float, phase: float):
+    """K6: one I/Q optimiser pass on the GPU.  Returns (mag, phase, avg_power, power_range)."""
+    blk = np.ascontiguousarray(block1024, dtype=np.complex64)
+    d = np.ascontiguousarray(directions50, dtype=np.float32)
+    if blk.size != 1024 or d.size != 50:
+        raise ValueError("iq_optimize needs 1024 frames and 50 directions")
+    m, p, a, r = C.c_float(mag), C.c_float(phase), C.c_float(0), C.c_float(0)
+    _check(lib.iqgpu_iq_optimize(blk.ctypes.data, d.ctypes.data, C.byref(m), C.byref(p), C.byref(a), C.byref(r)))
+    return m.value, p.value, a.value, r.value

@@ -74,6 +74,8 @@ def _load(path: str, prefix: str):
     if hasattr(lib, prefix + "process_threaded"):
         f("process_threaded").restype = C.c_int
         f("process_threaded").argtypes = [vp, vp, i64, vp, i64, C.POINTER(i64)]
+    if not hasattr(lib, "liquid_compat_msresamp_get_info"):
+        return lib   # the GPU drop-in harness carries no liquid layer
     lib.liquid_compat_msresamp_get_info.argtypes = [vp, C.POINTER(MsresampInfo)]
     lib.liquid_compat_msresamp_get_halfband.restype = C.c_uint
     lib.liquid_compat_msresamp_get_halfband.argtypes = [vp, C.c_uint, vp, C.c_uint]
@@ -99,10 +101,21 @@ def have_ref(fast: bool = False) -> bool:
     return os.path.exists(ref_path(fast))
 
 
+def dropin_path() -> str:
+    return os.path.join(os.path.dirname(HERE), "tests", "native", "_build", "libiqdropin_harness.so")
+
+
 def get_lib(kind: str):
-    """kind: 'ref' | 'ref_fast' | 'oracle'"""
+    """kind: 'ref' | 'ref_fast' | 'oracle' | 'dropin' (ref_harness.c driving the GPU drop-in host layer)"""
     if kind not in _LIBS:
-        if kind == "oracle":
+        if kind == "dropin":
+            if os.path.isdir(REF_ROOT):
+                subprocess.run(["make", "-C", os.path.join(os.path.dirname(HERE), "iq_tool_b200", "host"), "harness"],
+                               check=True, stdout=subprocess.DEVNULL)
+            if not os.path.exists(dropin_path()):
+                raise FileNotFoundError(dropin_path())
+            _LIBS[kind] = (_load(dropin_path(), "iqref_"), "iqref_")
+        elif kind == "oracle":
             build("oracle")  # incremental; plain C, builds anywhere gcc exists
             _LIBS[kind] = (_load(oracle_path(), "iqo_"), "iqo_")
         else:
@@ -145,6 +158,17 @@ class CpuChain:
 
     def reset(self):
         self._f("reset")(self.h)
+
+    def iq_optimize(self, block1024: np.ndarray, seed: int):
+        """One optimiser pass (iq_correct.c:154-235) with rand() seeded by `seed`.
+        Returns (mag, phase, avg_power, power_range)."""
+        blk = np.ascontiguousarray(block1024, dtype=np.complex64)
+        assert blk.size == 1024
+        m, p, a, r = C.c_float(0), C.c_float(0), C.c_float(0), C.c_float(0)
+        rc = self._f("iq_optimize")(self.h, blk.ctypes.data, seed, C.byref(m), C.byref(p), C.byref(a), C.byref(r))
+        if rc != 0:
+            raise RuntimeError("iq_optimize failed")
+        return m.value, p.value, a.value, r.value
 
     def info(self) -> RefInfo:
         o = RefInfo()
@@ -212,6 +236,14 @@ class CpuChain:
             raise RuntimeError(f"{self.kind}: process failed rc={rc}")
         from iq_tool_b200.configs import NUMPY_DTYPE
         return out[: nout.value * self.cfg.out_bytes].view(NUMPY_DTYPE[self.cfg.output_format])
+
+
+def libc_rand_directions(seed: int, n: int = 50) -> np.ndarray:
+    """The +-1 sequence `_get_random_direction` (iq_correct.c:391) yields after srand(seed)."""
+    libc = C.CDLL(None)
+    libc.srand(C.c_uint(seed))
+    rand_max = 2147483647
+    return np.array([1.0 if libc.rand() > rand_max // 2 else -1.0 for _ in range(n)], dtype=np.float32)
 
 
 def convert_to_cf32(kind: str, raw: np.ndarray, fmt_code: int, n: int, gain: float) -> np.ndarray:

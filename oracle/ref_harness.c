@@ -39,7 +39,12 @@
 #include "memory_arena.h"
 #include "log.h"
 
+/* IQ_HARNESS_NO_LIQUID: the same harness linked against the GPU drop-in host layer
+ * (iq_tool_b200/host/ + libiqgpu.so) instead of the reference's stage sources; the DSP objects
+ * are then not liquid objects, so liquid introspection is compiled out. */
+#ifndef IQ_HARNESS_NO_LIQUID
 #include "liquid/liquid.h"
+#endif
 #include "iq_chain_cfg.h"
 
 /* ---------------------------------------------------------------------------------------
@@ -452,14 +457,17 @@ void iqref_get_info(void *hv, iqref_info *o)
     o->filter_impl = r->user_filter_type_actual;
     o->filter_post_resample = h->config.apply_user_filter_post_resample;
     o->filter_block_size = r->user_filter_block_size;
+#ifndef IQ_HARNESS_NO_LIQUID
     void *nco = r->pre_resample_nco ? r->pre_resample_nco : r->post_resample_nco;
     if (nco) o->nco_dtheta = liquid_compat_nco_get_dtheta((nco_crcf)nco);
+#endif
     o->nco_is_post = r->post_resample_nco != NULL;
     o->cap_samples = (uint32_t)h->cap;
     o->agc_locked = r->agc_is_locked;
     o->agc_gain = r->agc_current_gain;
     o->agc_peak_memory = r->agc_peak_memory;
     o->agc_samples_seen = r->agc_samples_seen;
+#ifndef IQ_HARNESS_NO_LIQUID
     if (r->user_filter_object) {
         switch (r->user_filter_type_actual) {
             case FILTER_IMPL_FIR_SYMMETRIC:  o->filter_num_taps = liquid_compat_firfilt_crcf_get_taps(r->user_filter_object, NULL, 0); break;
@@ -467,6 +475,7 @@ void iqref_get_info(void *hv, iqref_info *o)
             default: o->filter_num_taps = liquid_compat_fftfilt_get_taps(r->user_filter_object, NULL, 0); break;
         }
     }
+#endif
 }
 /* master taps as interleaved complex floats */
 uint32_t iqref_get_filter_taps(void *hv, float *out, uint32_t cap)
@@ -474,6 +483,10 @@ uint32_t iqref_get_filter_taps(void *hv, float *out, uint32_t cap)
     iqref_t *h = (iqref_t *)hv;
     AppResources *r = &h->res;
     if (!r->user_filter_object) return 0;
+#ifdef IQ_HARNESS_NO_LIQUID
+    (void)out; (void)cap;
+    return 0;
+#else
     liquid_float_complex *o = (liquid_float_complex *)out;
     if (r->user_filter_type_actual == FILTER_IMPL_FIR_SYMMETRIC) {
         uint32_t n = liquid_compat_firfilt_crcf_get_taps(r->user_filter_object, NULL, 0);
@@ -486,6 +499,7 @@ uint32_t iqref_get_filter_taps(void *hv, float *out, uint32_t cap)
     if (r->user_filter_type_actual == FILTER_IMPL_FIR_ASYMMETRIC)
         return liquid_compat_firfilt_cccf_get_taps(r->user_filter_object, o, cap);
     return liquid_compat_fftfilt_get_taps(r->user_filter_object, o, cap);
+#endif
 }
 void *iqref_get_msresamp(void *hv) { return ((iqref_t *)hv)->res.resampler; }
 
