@@ -216,26 +216,41 @@ def main():
     n = args.samples or wl.throughput_samples
     n -= n % 16384
 
-    chain = gpu.Chain(cfg, local_rank, time_kernels=1, fused=args.fused, subtrain_frames=1 << 26)
+    # N > 1: the capture of world*n frames is time-sharded (iq_tool_b200/shard.py): closed-form seek,
+    # halo in front of the shard, and — for digital-AGC chains — the per-chunk peak exchange inside
+    # every step (the only collective; no sample data crosses GPUs)
+    from iq_tool_b200.shard import ShardedChain
+    sc = ShardedChain(cfg, local_rank, shard_frames_hint=n if world > 1 else 0, time_kernels=1, fused=args.fused,
+                      subtrain_frames=1 << 26)
+    chain = sc.chain
     info = chain.info()
-    halo = chain.halo_frames() if rank > 0 else 0
-    halo += (-halo) % 16384                       # keep chunk boundaries aligned with the single-stream cut
-    shard_start = rank * n
-    raw = synth_torch(wl, n + halo, dev, start=shard_start - halo)
+    replicas = False
+    if world > 1:
+        try:
+            chain.seek(0)
+        except gpu.IqGpuError:
+            replicas = True       # FFT-filter / RMS-AGC chains are not exactly shardable: N independent replicas
+    shard = sc.plan(n, 1)[0] if (world == 1 or replicas) else sc.plan(world * n, world)[rank]
+    halo = shard.start - shard.lead
+    shard_start = shard.start
+    raw = synth_torch(wl, shard.read_frames, dev, start=shard.lead)
     out_frames_max = chain.out_capacity_frames(n + halo)
     out = torch.empty(out_frames_max * cfg.out_bytes, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
+    exchange = bool(sc.digital_agc and world > 1 and not replicas)
 
     def rewind():
-        # single stream: plain reset (works for every chain); shards: closed-form seek to the shard start
-        if world == 1:
+        # single stream: plain reset (works for every chain); shards: closed-form seek to the shard lead
+        if world == 1 or replicas:
             chain.reset()
         else:
-            chain.seek(shard_start - halo)
+            chain.seek(shard.lead)
 
     def step():
-        rewind()
-        return chain.process_device(raw.data_ptr(), n + halo, out.data_ptr(), out.numel(), stream.cuda_stream)
+        if world == 1 or replicas:
+            chain.reset()
+            return chain.process_device(raw.data_ptr(), n, out.data_ptr(), out.numel(), stream.cuda_stream)
+        return sc.process_device(shard, raw.data_ptr(), out.data_ptr(), out.numel(), stream.cuda_stream, None, dev)[0]
 
     for _ in range(args.warmup):
         produced = step()
@@ -280,7 +295,16 @@ def main():
             host_in = torch.frombuffer((C.c_uint8 * nbytes).from_address(hin), dtype=torch.uint8)
             host_in.copy_(raw.view(torch.uint8))
             nout = C.c_size_t(0)
+            host_out = torch.frombuffer((C.c_uint8 * out.numel()).from_address(hout), dtype=torch.uint8)
             def e2e_step():
+                if exchange:
+                    # sharded digital AGC: the peak exchange sits between the two halves of the device call
+                    raw.view(torch.uint8).copy_(host_in, non_blocking=True)
+                    k = sc.process_device(shard, raw.data_ptr(), out.data_ptr(), out.numel(), stream.cuda_stream, None, dev)[0]
+                    host_out[: k * cfg.out_bytes].copy_(out[: k * cfg.out_bytes], non_blocking=True)
+                    torch.cuda.synchronize()
+                    nout.value = k
+                    return
                 rewind()
                 gpu._check(gpu.lib.iqgpu_chain_process(chain._h, hin, n + halo, None, 0, hout, out.numel(),
                                                        C.byref(nout), None))
@@ -360,7 +384,9 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{wl.name}: {wl.description}", "frames_per_gpu_per_step": n, "halo_frames": halo,
                    "output_frames_per_step": int(produced), "l2_policy": "inputs larger than L2 (no flush needed)",
-                   "sharding": "time shards, no collective" if world > 1 else "single stream",
+                   "sharding": ("single stream" if world == 1 else "replicas only (chain not exactly shardable)" if replicas else
+                                "time shards; all-gather of per-chunk AGC peaks (4 B / 16384 frames), no sample data exchanged"
+                                if exchange else "time shards, no collective"),
                    "fused_front": int(chain.info().fused_front),
                    "chunk_frames": 16384},
         "roofline": roofline, "fp32": fp32, "cpu_baseline": cpu, "e2e": e2e,

@@ -203,6 +203,37 @@ int  iqgpu_chain_get_arb_taps(iqgpu_chain *c, float *taps, uint32_t capacity, ui
 int  iqgpu_chain_seek(iqgpu_chain *c, uint64_t first_frame, uint64_t *out_first_frame);
 int  iqgpu_chain_halo_frames(iqgpu_chain *c, size_t *halo_frames);
 
+/* ---- sharded digital AGC: the one exchange step of a time-sharded run.
+ *      The digital AGC (src/agc.c:105-222) is a scalar state machine over per-chunk peaks, so a
+ *      shard needs the state left by every earlier chunk of the capture.  process_device is
+ *      split at that point:
+ *        begin   runs everything up to the per-chunk peaks of this call (one sub-train),
+ *        pending_chunk_peaks hands the peaks (and per-chunk frame counts) to the host,
+ *        -- the ranks all-gather their peaks; each advances the initial state over the chunks
+ *           of all earlier shards with iqgpu_agc_digital_advance and installs it with
+ *           iqgpu_chain_set_agc_state --
+ *        finish  runs the state machine over this call's chunks, scales and converts.
+ *      `skip_chunks` leading chunks (the shard's halo) get unit gain and leave the state alone.
+ *      Works for every chain (without a digital AGC the peaks read as zero). ------------------ */
+typedef struct {
+    uint32_t locked;          /* AppResources.agc_is_locked            (include/app_context.h:226-231) */
+    float    gain;            /* AppResources.agc_current_gain */
+    float    peak_memory;     /* AppResources.agc_peak_memory */
+    uint64_t samples_seen;    /* AppResources.agc_samples_seen */
+    double   last_strong_s;   /* agc_last_strong_peak_time on the sample clock (seconds) */
+} iqgpu_agc_state;
+int  iqgpu_chain_process_device_begin(iqgpu_chain *c, const void *dev_raw_in, size_t n_frames,
+                                      const uint32_t *chunk_frames, size_t n_chunks, void *cuda_stream);
+int  iqgpu_chain_pending_chunk_peaks(iqgpu_chain *c, float *peaks, uint32_t *counts, size_t capacity, size_t *n_chunks);
+int  iqgpu_chain_process_device_finish(iqgpu_chain *c, size_t skip_chunks, void *dev_out, size_t out_capacity_bytes,
+                                       size_t *out_frames, uint32_t *per_chunk_out, void *cuda_stream);
+int  iqgpu_chain_get_agc_state(iqgpu_chain *c, iqgpu_agc_state *s);
+int  iqgpu_chain_set_agc_state(iqgpu_chain *c, const iqgpu_agc_state *s);
+/* host-only (no device): agc_create's initial state (agc.c:66-80) and the per-chunk state machine */
+void iqgpu_agc_digital_initial_state(iqgpu_agc_state *s);
+int  iqgpu_agc_digital_advance(iqgpu_agc_state *s, float target, double target_rate_hz, const float *peaks,
+                               const uint32_t *counts, size_t n_chunks, float *gains /* optional */);
+
 /* ---- sample_convert.h (include/sample_convert.h:19,35,50) — host buffers ------------- */
 size_t iqgpu_get_bytes_per_sample(int format);
 int    iqgpu_convert_block_to_cf32(const void *in, float *out_cf32, size_t n_frames, int format, float gain);

@@ -243,8 +243,20 @@ struct iqgpu_chain {
     size_t max_out_for(size_t n_frames) const;
     // closed-form per-chunk output frame counts from the current position (no state change)
     size_t count_outputs(const uint32_t* chunks, size_t n_chunks, uint32_t* per_chunk) const;
+    // phase: 0 = whole sub-train; 1 = front only (everything up to the per-chunk AGC peaks; the
+    // rest is left pending for run_back) — the split point of the sharded digital-AGC exchange
     int run_subtrain(const void* d_rawp, size_t n, const uint32_t* chunks, size_t n_chunks, void* d_outp,
-                     size_t* out_frames, uint32_t* per_chunk, cudaStream_t st);
+                     size_t* out_frames, uint32_t* per_chunk, cudaStream_t st, int phase = 0);
+    int run_back(void* d_outp, size_t skip_chunks, size_t* out_frames, cudaStream_t st);
+    // pending back half (between process_device_begin and process_device_finish)
+    struct Pending {
+        bool active = false;
+        const float2* src = nullptr;
+        size_t n = 0, n_chunks = 0;
+        std::vector<uint32_t> seg, counts;
+        PostParams qp{};
+        bool peaks_done = false;
+    } pend;
 };
 
 iqgpu_chain::~iqgpu_chain()
@@ -491,7 +503,7 @@ int iqgpu_chain::reset_state()
 // one sub-train on the device
 // ---------------------------------------------------------------------------------------------
 int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chunks, size_t n_chunks, void* d_outp,
-                              size_t* out_frames, uint32_t* per_chunk, cudaStream_t st)
+                              size_t* out_frames, uint32_t* per_chunk, cudaStream_t st, int phase)
 {
     const bool pre_filter = filt.impl != IQGPU_FILTER_IMPL_NONE && !filt.post_resample;
     const bool post_filter = filt.impl != IQGPU_FILTER_IMPL_NONE && filt.post_resample;
@@ -675,6 +687,46 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
     qp.nco_enable = nco_post; qp.nco_dtheta = nco_dtheta; qp.nco_sign = nco_sign; qp.nco_table = d_lut;
     qp.nco_theta0 = (uint32_t)((uint64_t)(uint32_t)n_nco_post * nco_dtheta);
     qp.agc_mode = agc_mode; qp.agc_target = agc_target; qp.agc_alpha = agc_alpha; qp.target_rate = target_rate;
+    pend.active = true;
+    pend.src = post_src; pend.n = post_n; pend.n_chunks = n_chunks;
+    pend.seg = seg; pend.counts = counts; pend.qp = qp; pend.peaks_done = false;
+    if (post_n && agc_mode == 1) {
+        // pass 1 of the digital AGC: per-chunk peaks (agc.c:117-124).  Everything after this is a
+        // function of the peaks and the carried AGC state only.
+        span_begin(IQGPU_KCLASS_POST, st);
+        if (n_chunks > max_segs) {
+            CK(cudaStreamSynchronize(st));
+            cudaFree(d_seg_start); cudaFree(d_seg_peak); cudaFree(d_seg_gain);
+            max_segs = n_chunks * 2;
+            CK(cudaMalloc(&d_seg_start, (max_segs + 1) * sizeof(uint32_t)));
+            CK(cudaMalloc(&d_seg_peak, max_segs * sizeof(float)));
+            CK(cudaMalloc(&d_seg_gain, max_segs * sizeof(float)));
+        }
+        CK(cudaMemcpyAsync(d_seg_start, seg.data(), (n_chunks + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        CK(launch_agc_peaks(post_src, post_n, qp, d_seg_start, n_chunks, d_seg_peak, st));
+        span_end(st);
+        launches += 1;
+        pend.peaks_done = true;
+    }
+    if (nco_post) n_nco_post += post_n;
+    n_in = N1;
+    n_out += post_n;
+    *out_frames = post_n;
+    if (phase == 1) return IQGPU_OK;
+    return run_back(d_outp, 0, out_frames, st);
+}
+
+// back half of a sub-train: AGC state machine over the chunk peaks, scale, output conversion.
+// skip_chunks: leading chunks that belong to a shard's halo — they get unit gain and do not
+// advance the AGC state (their output frames are dropped by the caller).
+int iqgpu_chain::run_back(void* d_outp, size_t skip_chunks, size_t* out_frames, cudaStream_t st)
+{
+    if (!pend.active) return fail(IQGPU_EINVAL, "no pending sub-train");
+    pend.active = false;
+    const float2* post_src = pend.src;
+    const size_t post_n = pend.n, n_chunks = pend.n_chunks;
+    const PostParams& qp = pend.qp;
+    if (skip_chunks > n_chunks) return fail(IQGPU_EINVAL, "skip_chunks exceeds the chunk count");
     float2* tap2 = nullptr;
     if (record_taps && post_n) {
         // reserve room in the tap buffer and let the post kernel write straight into it
@@ -684,19 +736,14 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
     if (post_n) {
         span_begin(IQGPU_KCLASS_POST, st);
         if (agc_mode == 1) {
-            if (n_chunks > max_segs) {
-                CK(cudaStreamSynchronize(st));
-                cudaFree(d_seg_start); cudaFree(d_seg_peak); cudaFree(d_seg_gain);
-                max_segs = n_chunks * 2;
-                CK(cudaMalloc(&d_seg_start, (max_segs + 1) * sizeof(uint32_t)));
-                CK(cudaMalloc(&d_seg_peak, max_segs * sizeof(float)));
-                CK(cudaMalloc(&d_seg_gain, max_segs * sizeof(float)));
+            if (skip_chunks) {
+                const std::vector<float> ones(skip_chunks, 1.0f);
+                CK(cudaMemcpyAsync(d_seg_gain, ones.data(), skip_chunks * sizeof(float), cudaMemcpyHostToDevice, st));
             }
-            CK(cudaMemcpyAsync(d_seg_start, seg.data(), (n_chunks + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-            CK(launch_agc_peaks(post_src, post_n, qp, d_seg_start, n_chunks, d_seg_peak, st));
-            CK(launch_agc_digital_scan(d_seg_start, n_chunks, d_seg_peak, qp, d_agc, d_seg_gain, st));
+            CK(launch_agc_digital_scan(d_seg_start + skip_chunks, n_chunks - skip_chunks, d_seg_peak + skip_chunks, qp, d_agc,
+                                       d_seg_gain + skip_chunks, st));
             CK(launch_post(post_src, post_n, qp, d_seg_start, n_chunks, d_seg_gain, 0, tap2, d_outp, st));
-            launches += 3;
+            launches += 2;
         } else if (agc_mode == 2) {
             if (post_n > agc_scratch_cap) {
                 CK(cudaStreamSynchronize(st));
@@ -714,10 +761,7 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
         }
         span_end(st);
     }
-    if (nco_post) n_nco_post += post_n;
-    n_in = N1;
-    n_out += post_n;
-    *out_frames = post_n;
+    if (out_frames) *out_frames = post_n;
     return IQGPU_OK;
 }
 
@@ -976,6 +1020,136 @@ int iqgpu_chain_process_device(iqgpu_chain* c, const void* dev_raw_in, size_t n_
     }
     c->launches = launches;
     *out_frames = total;
+    return IQGPU_OK;
+}
+
+// ---- sharded digital AGC: the process_device call split at its only data-dependent exchange point ----
+int iqgpu_chain_process_device_begin(iqgpu_chain* c, const void* dev_raw_in, size_t n_frames, const uint32_t* chunk_frames,
+                                     size_t n_chunks, void* cuda_stream)
+{
+    if (!c) return fail(IQGPU_EINVAL, "null argument");
+    if (c->plan_only) return fail(IQGPU_ENODEVICE, "chain was created without a device (plan only)");
+    if (n_frames == 0 || !dev_raw_in) return fail(IQGPU_EINVAL, "empty input");
+    if (c->pend.active) return fail(IQGPU_EINVAL, "a begun call is still pending (call process_device_finish)");
+    CK(cudaSetDevice(c->device));
+    int rc = c->ensure_buffers();
+    if (rc) return rc;
+    std::vector<uint32_t> chunks;
+    rc = build_chunks(c, n_frames, chunk_frames, n_chunks, chunks);
+    if (rc) return rc;
+    if (n_frames > c->subtrain_frames)
+        return fail(IQGPU_EINVAL, "a begun call must fit one sub-train (raise the subtrain_frames option)");
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+    c->last_stream = st;
+    for (auto& t : c->tap) t.len = 0;
+    size_t produced = 0;
+    rc = c->run_subtrain(dev_raw_in, n_frames, chunks.data(), chunks.size(), nullptr, &produced, nullptr, st, 1);
+    if (rc) { c->pend.active = false; return rc; }
+    return IQGPU_OK;
+}
+
+int iqgpu_chain_pending_chunk_peaks(iqgpu_chain* c, float* peaks, uint32_t* counts, size_t capacity, size_t* n_chunks)
+{
+    if (!c || !n_chunks) return fail(IQGPU_EINVAL, "null argument");
+    if (!c->pend.active) return fail(IQGPU_EINVAL, "no pending call");
+    *n_chunks = c->pend.n_chunks;
+    if (!peaks && !counts) return IQGPU_OK;
+    if (capacity < c->pend.n_chunks) return fail(IQGPU_ECAPACITY, "peak buffer too small");
+    if (counts) std::copy(c->pend.counts.begin(), c->pend.counts.end(), counts);
+    if (peaks) {
+        if (c->pend.peaks_done) {
+            CK(cudaSetDevice(c->device));
+            CK(cudaMemcpyAsync(peaks, c->d_seg_peak, c->pend.n_chunks * sizeof(float), cudaMemcpyDeviceToHost, c->last_stream));
+            CK(cudaStreamSynchronize(c->last_stream));
+        } else std::fill(peaks, peaks + c->pend.n_chunks, 0.0f);
+    }
+    return IQGPU_OK;
+}
+
+int iqgpu_chain_process_device_finish(iqgpu_chain* c, size_t skip_chunks, void* dev_out, size_t out_capacity_bytes,
+                                      size_t* out_frames, uint32_t* per_chunk_out, void* cuda_stream)
+{
+    if (!c || !out_frames) return fail(IQGPU_EINVAL, "null argument");
+    if (!c->pend.active) return fail(IQGPU_EINVAL, "no pending call");
+    if (!dev_out) return fail(IQGPU_EINVAL, "null buffer");
+    if (c->pend.n * c->out_bps > out_capacity_bytes) return fail(IQGPU_ECAPACITY, "output buffer too small");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
+    if (st != c->last_stream) CK(cudaStreamSynchronize(c->last_stream));
+    if (per_chunk_out) std::copy(c->pend.counts.begin(), c->pend.counts.end(), per_chunk_out);
+    return c->run_back(dev_out, skip_chunks, out_frames, st);
+}
+
+int iqgpu_chain_get_agc_state(iqgpu_chain* c, iqgpu_agc_state* s)
+{
+    if (!c || !s) return fail(IQGPU_EINVAL, "null argument");
+    if (c->plan_only) return fail(IQGPU_ENODEVICE, "plan-only chain");
+    CK(cudaSetDevice(c->device));
+    int rc = c->ensure_buffers();
+    if (rc) return rc;
+    if (c->last_stream) CK(cudaStreamSynchronize(c->last_stream));
+    CK(cudaStreamSynchronize(c->stream));
+    AgcState a{};
+    CK(cudaMemcpy(&a, c->d_agc, sizeof(a), cudaMemcpyDeviceToHost));
+    s->locked = (uint32_t)a.locked; s->gain = a.gain; s->peak_memory = a.peak_mem; s->samples_seen = a.seen;
+    s->last_strong_s = a.last_strong;
+    return IQGPU_OK;
+}
+
+int iqgpu_chain_set_agc_state(iqgpu_chain* c, const iqgpu_agc_state* s)
+{
+    if (!c || !s) return fail(IQGPU_EINVAL, "null argument");
+    if (c->plan_only) return fail(IQGPU_ENODEVICE, "plan-only chain");
+    CK(cudaSetDevice(c->device));
+    int rc = c->ensure_buffers();
+    if (rc) return rc;
+    cudaStream_t st = c->last_stream ? c->last_stream : c->stream;
+    AgcState a{};
+    CK(cudaMemcpyAsync(&a, c->d_agc, sizeof(a), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    a.locked = (int)s->locked; a.gain = s->gain; a.peak_mem = s->peak_memory; a.seen = s->samples_seen;
+    a.last_strong = s->last_strong_s;
+    CK(cudaMemcpyAsync(c->d_agc, &a, sizeof(a), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    return IQGPU_OK;
+}
+
+void iqgpu_agc_digital_initial_state(iqgpu_agc_state* s)
+{
+    if (!s) return;
+    s->locked = 0; s->gain = 1.0f; s->peak_memory = 0.05f; s->samples_seen = 0; s->last_strong_s = 0.0;   // agc.c:78
+}
+
+// Host restatement of the per-chunk state machine the device runs (kernels.cu AgcStep::run ==
+// reference agc.c:105-222 with the sample clock in place of the wall clock).  No device needed.
+int iqgpu_agc_digital_advance(iqgpu_agc_state* s, float target, double target_rate_hz, const float* peaks,
+                              const uint32_t* counts, size_t n_chunks, float* gains)
+{
+    if (!s || (n_chunks && (!peaks || !counts))) return fail(IQGPU_EINVAL, "null argument");
+    if (!(target_rate_hz > 0.0)) return fail(IQGPU_EINVAL, "target rate must be positive");
+    for (size_t c = 0; c < n_chunks; c++) {
+        if (counts[c] == 0) { if (gains) gains[c] = 1.0f; continue; }   // agc_apply returns on num_samples == 0
+        const float pk = peaks[c];
+        float g;
+        if (!s->locked) {
+            if (pk > s->peak_memory) s->peak_memory = pk;
+            const float safe = (s->peak_memory < 1e-4f) ? 1e-4f : s->peak_memory;
+            g = target / safe;
+            const double elapsed = (double)s->samples_seen / target_rate_hz;
+            if (elapsed > (double)2.0f) { s->locked = 1; s->gain = g; s->last_strong_s = elapsed; }
+        } else {
+            g = s->gain;
+            const float opk = pk * g;
+            const double now = (double)s->samples_seen / target_rate_hz;
+            const float thr = target * 0.75f;
+            if (opk > 1.0f) { g = 0.99f / pk; s->last_strong_s = now; }
+            else if (opk > thr) s->last_strong_s = now;
+            else if (now - s->last_strong_s > (double)4.0f) g = g * 1.0005f;
+            s->gain = g;
+        }
+        s->samples_seen += counts[c];
+        if (gains) gains[c] = g;
+    }
     return IQGPU_OK;
 }
 

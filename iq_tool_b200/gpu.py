@@ -38,6 +38,16 @@ class ChainInfoC(C.Structure):
     ]
 
 
+class AgcStateC(C.Structure):
+    """iqgpu_agc_state (include/iqgpu.h)."""
+    _fields_ = [("locked", C.c_uint32), ("gain", C.c_float), ("peak_memory", C.c_float),
+                ("samples_seen", C.c_uint64), ("last_strong_s", C.c_double)]
+
+    def as_tuple(self):
+        return (int(self.locked), float(self.gain), float(self.peak_memory), int(self.samples_seen),
+                float(self.last_strong_s))
+
+
 def _load() -> C.CDLL:
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -70,6 +80,15 @@ def _load() -> C.CDLL:
     lib.iqgpu_chain_get_arb_taps.argtypes = [vp, vp, C.c_uint32, u32p]
     lib.iqgpu_chain_seek.argtypes = [vp, C.c_uint64, C.POINTER(C.c_uint64)]
     lib.iqgpu_chain_halo_frames.argtypes = [vp, C.POINTER(sz)]
+    lib.iqgpu_chain_resampler_outputs_after.argtypes = [vp, C.c_uint64, C.POINTER(C.c_uint64)]
+    lib.iqgpu_chain_process_device_begin.argtypes = [vp, vp, sz, u32p, sz, vp]
+    lib.iqgpu_chain_pending_chunk_peaks.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
+    lib.iqgpu_chain_process_device_finish.argtypes = [vp, sz, vp, sz, C.POINTER(sz), u32p, vp]
+    lib.iqgpu_chain_get_agc_state.argtypes = [vp, C.POINTER(AgcStateC)]
+    lib.iqgpu_chain_set_agc_state.argtypes = [vp, C.POINTER(AgcStateC)]
+    lib.iqgpu_agc_digital_initial_state.argtypes = [C.POINTER(AgcStateC)]
+    lib.iqgpu_agc_digital_initial_state.restype = None
+    lib.iqgpu_agc_digital_advance.argtypes = [C.POINTER(AgcStateC), C.c_float, C.c_double, vp, vp, sz, vp]
     lib.iqgpu_get_bytes_per_sample.restype = sz
     lib.iqgpu_get_bytes_per_sample.argtypes = [C.c_int]
     lib.iqgpu_convert_block_to_cf32.argtypes = [vp, vp, sz, C.c_int, C.c_float]
@@ -80,7 +99,10 @@ def _load() -> C.CDLL:
                  "iqgpu_chain_set_iq_factors", "iqgpu_chain_process", "iqgpu_chain_process_device",
                  "iqgpu_chain_predict_output", "iqgpu_chain_read_tap", "iqgpu_chain_get_filter_taps",
                  "iqgpu_chain_get_halfband_taps", "iqgpu_chain_get_arb_taps", "iqgpu_chain_seek",
-                 "iqgpu_chain_halo_frames", "iqgpu_convert_block_to_cf32",
+                 "iqgpu_chain_halo_frames", "iqgpu_chain_resampler_outputs_after",
+                 "iqgpu_chain_process_device_begin", "iqgpu_chain_pending_chunk_peaks",
+                 "iqgpu_chain_process_device_finish", "iqgpu_chain_get_agc_state", "iqgpu_chain_set_agc_state",
+                 "iqgpu_agc_digital_advance", "iqgpu_convert_block_to_cf32",
                  "iqgpu_convert_cf32_to_block", "iqgpu_iq_optimize"):
         getattr(lib, name).restype = C.c_int
     return lib
@@ -160,6 +182,40 @@ class Chain:
         o = C.c_uint64(0)
         _check(lib.iqgpu_chain_seek(self._h, first_frame, C.byref(o)))
         return o.value
+
+    def resampler_outputs_after(self, frames_in: int) -> int:
+        """Closed form: resampler output frames after `frames_in` input frames since reset."""
+        o = C.c_uint64(0)
+        _check(lib.iqgpu_chain_resampler_outputs_after(self._h, frames_in, C.byref(o)))
+        return o.value
+
+    # ---- sharded digital AGC: process_device split at the peak exchange (include/iqgpu.h) ----
+    def process_device_begin(self, dev_in_ptr: int, n_frames: int, stream: int = 0) -> None:
+        _check(lib.iqgpu_chain_process_device_begin(self._h, dev_in_ptr, n_frames, None, 0,
+                                                    C.c_void_p(stream) if stream else None))
+
+    def pending_chunk_peaks(self):
+        """(peaks float32[n_chunks], counts uint32[n_chunks]) of the begun call."""
+        n = C.c_size_t(0)
+        _check(lib.iqgpu_chain_pending_chunk_peaks(self._h, None, None, 0, C.byref(n)))
+        peaks = np.zeros(max(1, n.value), dtype=np.float32)
+        counts = np.zeros(max(1, n.value), dtype=np.uint32)
+        _check(lib.iqgpu_chain_pending_chunk_peaks(self._h, peaks.ctypes.data, counts.ctypes.data, n.value, C.byref(n)))
+        return peaks[: n.value], counts[: n.value]
+
+    def process_device_finish(self, skip_chunks: int, dev_out_ptr: int, out_capacity_bytes: int, stream: int = 0) -> int:
+        nout = C.c_size_t(0)
+        _check(lib.iqgpu_chain_process_device_finish(self._h, skip_chunks, dev_out_ptr, out_capacity_bytes,
+                                                     C.byref(nout), None, C.c_void_p(stream) if stream else None))
+        return nout.value
+
+    def get_agc_state(self) -> AgcStateC:
+        s = AgcStateC()
+        _check(lib.iqgpu_chain_get_agc_state(self._h, C.byref(s)))
+        return s
+
+    def set_agc_state(self, s: AgcStateC) -> None:
+        _check(lib.iqgpu_chain_set_agc_state(self._h, C.byref(s)))
 
     # ---- design introspection ----
     def filter_taps(self) -> np.ndarray:
@@ -253,3 +309,22 @@ def iq_optimize(block1024: np.ndarray, directions50: np.ndarray, mag: float, pha
     m, p, a, r = C.c_float(mag), C.c_float(phase), C.c_float(0), C.c_float(0)
     _check(lib.iqgpu_iq_optimize(blk.ctypes.data, d.ctypes.data, C.byref(m), C.byref(p), C.byref(a), C.byref(r)))
     return m.value, p.value, a.value, r.value
+
+
+def agc_initial_state() -> AgcStateC:
+    s = AgcStateC()
+    lib.iqgpu_agc_digital_initial_state(C.byref(s))
+    return s
+
+
+def agc_digital_advance(state: AgcStateC, target: float, target_rate_hz: float, peaks: np.ndarray,
+                        counts: np.ndarray, want_gains: bool = False):
+    """Host-only digital-AGC state machine over per-chunk peaks (updates `state` in place)."""
+    pk = np.ascontiguousarray(peaks, dtype=np.float32)
+    ct = np.ascontiguousarray(counts, dtype=np.uint32)
+    assert pk.size == ct.size
+    g = np.zeros(max(1, pk.size), dtype=np.float32) if want_gains else None
+    _check(lib.iqgpu_agc_digital_advance(C.byref(state), target, target_rate_hz, pk.ctypes.data if pk.size else None,
+                                         ct.ctypes.data if ct.size else None, pk.size,
+                                         g.ctypes.data if want_gains else None))
+    return g[: pk.size] if want_gains else None

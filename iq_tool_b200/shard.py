@@ -1,0 +1,155 @@
+"""Time-sharding of a long capture across the GPUs of one box.
+
+A capture of `total_frames` input frames is cut into contiguous shards whose starts are
+multiples of the reference chunk (16384 frames, include/constants.h:123), so that chunk
+boundaries — and with them the per-chunk digital-AGC blocks — are those of the single stream.
+Everything that positions a shard is closed-form integer arithmetic (NCO phase, halfband
+pairing, polyphase phase, output index: `iqgpu_chain_seek`); finite-memory filter state is
+rebuilt by re-processing a halo in front of the shard and dropping its outputs.
+
+There is exactly one data-dependent exchange: the digital AGC (src/agc.c:105-222) is a scalar
+state machine over per-chunk peaks, so a shard needs the state left by all earlier chunks.
+The ranks all-gather their per-chunk peaks (4 bytes per 16384 input frames) and each replays the
+state machine on the host over the chunks that precede its shard (`exchange_agc_state`).  No
+sample data crosses GPUs.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from . import gpu
+from .configs import AGC_DIGITAL, CHUNK_SAMPLES
+
+
+@dataclass
+class Shard:
+    rank: int
+    world: int
+    start: int          # first input frame the shard owns
+    frames: int         # input frames owned
+    lead: int           # first input frame the rank reads (start - halo, chunk aligned, >= 0)
+    skip_chunks: int    # whole reference chunks in [lead, start): the halo
+    out_lead: int       # absolute output index of the first frame the chain emits from `lead`
+    out_start: int      # absolute output index of the first frame the shard owns
+    out_end: int        # one past the last output frame the shard owns
+
+    @property
+    def read_frames(self) -> int:
+        return self.start - self.lead + self.frames
+
+    @property
+    def drop(self) -> int:
+        """outputs produced from the halo, to be discarded"""
+        return self.out_start - self.out_lead
+
+    @property
+    def out_frames(self) -> int:
+        return self.out_end - self.out_start
+
+
+def plan_shards(chain: "gpu.Chain", total_frames: int, world: int, halo_frames: Optional[int] = None,
+                chunk: int = CHUNK_SAMPLES) -> List[Shard]:
+    """Cut [0, total_frames) into `world` chunk-aligned shards.  `chain` may be plan-only
+    (device=-1): only closed forms are used."""
+    if world < 1 or total_frames < 0:
+        raise ValueError("bad shard request")
+    halo = chain.halo_frames() if halo_frames is None else int(halo_frames)
+    halo += (-halo) % chunk
+    n_chunks = (total_frames + chunk - 1) // chunk
+    base, extra = divmod(n_chunks, world)
+    shards, c0 = [], 0
+    for r in range(world):
+        nc = base + (1 if r < extra else 0)
+        start = min(c0 * chunk, total_frames)
+        end = min((c0 + nc) * chunk, total_frames)
+        lead = max(0, start - halo)
+        shards.append(Shard(rank=r, world=world, start=start, frames=end - start, lead=lead,
+                            skip_chunks=(start - lead) // chunk,
+                            out_lead=chain.resampler_outputs_after(lead),
+                            out_start=chain.resampler_outputs_after(start),
+                            out_end=chain.resampler_outputs_after(end)))
+        c0 += nc
+    return shards
+
+
+def _all_gather_var(arr: np.ndarray, group, device) -> List[np.ndarray]:
+    """all_gather of per-rank 1-D arrays of different lengths (float32 / uint32 payloads)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    n = torch.tensor([arr.size], dtype=torch.int64, device=device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    m = max(max(sizes), 1)
+    buf = torch.zeros(m, dtype=torch.int32, device=device)
+    if arr.size:
+        buf[: arr.size] = torch.from_numpy(arr.view(np.int32).copy()).to(device)
+    outs = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(outs, buf, group=group)
+    return [o[:s].cpu().numpy().view(arr.dtype) for o, s in zip(outs, sizes)]
+
+
+def exchange_agc_state(peaks: np.ndarray, counts: np.ndarray, target: float, target_rate_hz: float,
+                       group=None, device="cpu") -> "gpu.AgcStateC":
+    """Digital-AGC state at the start of this rank's shard: all-gather every rank's live per-chunk
+    peaks/counts and replay the state machine over the chunks of the ranks below this one."""
+    import torch.distributed as dist
+
+    rank = dist.get_rank(group)
+    all_peaks = _all_gather_var(np.ascontiguousarray(peaks, dtype=np.float32), group, device)
+    all_counts = _all_gather_var(np.ascontiguousarray(counts, dtype=np.uint32), group, device)
+    state = gpu.agc_initial_state()
+    for r in range(rank):
+        gpu.agc_digital_advance(state, target, target_rate_hz, all_peaks[r], all_counts[r])
+    return state
+
+
+class ShardedChain:
+    """One rank's chain of a time-sharded run.  `process_device` reads the rank's frames
+    [shard.lead, shard.start + shard.frames) from device memory and writes the converted output
+    of that range; the first `shard.drop` output frames belong to the halo."""
+
+    def __init__(self, cfg, device: int, shard_frames_hint: int = 0, **options):
+        opts = dict(options)
+        self.cfg = cfg
+        self.digital_agc = bool(cfg.agc_enable and cfg.agc_profile == AGC_DIGITAL)
+        self._probe = gpu.Chain(cfg, -1)
+        halo = self._probe.halo_frames()
+        halo += (-halo) % CHUNK_SAMPLES
+        self.halo = halo
+        if self.digital_agc and shard_frames_hint:
+            # the begun call must be one sub-train: the resampled stream is kept on the device across the exchange
+            opts["subtrain_frames"] = max(int(opts.get("subtrain_frames", 0)), shard_frames_hint + halo + CHUNK_SAMPLES)
+        self.chain = gpu.Chain(cfg, device, **opts)
+        self.agc_target = cfg.agc_target_level_arg if cfg.agc_target_level_arg > 0 else 0.9   # agc.c:108-110, constants.h:184
+        self.target_rate = float(np.float32(cfg.target_rate_hz))
+
+    def plan(self, total_frames: int, world: int) -> List[Shard]:
+        return plan_shards(self._probe, total_frames, world, self.halo)
+
+    def process_device(self, shard: Shard, dev_in_ptr: int, dev_out_ptr: int, out_capacity_bytes: int,
+                       stream: int = 0, group=None, comm_device="cpu") -> Tuple[int, int]:
+        """Returns (frames written, frames to drop from the front)."""
+        ch = self.chain
+        out_lead = ch.seek(shard.lead)
+        assert out_lead == shard.out_lead
+        n = shard.read_frames
+        if n == 0:
+            if self.digital_agc and shard.world > 1:
+                exchange_agc_state(np.zeros(0, np.float32), np.zeros(0, np.uint32), self.agc_target,
+                                   self.target_rate, group, comm_device)
+            return 0, 0
+        if not (self.digital_agc and shard.world > 1):
+            return ch.process_device(dev_in_ptr, n, dev_out_ptr, out_capacity_bytes, stream), shard.drop
+        ch.process_device_begin(dev_in_ptr, n, stream)
+        peaks, counts = ch.pending_chunk_peaks()
+        state = exchange_agc_state(peaks[shard.skip_chunks:], counts[shard.skip_chunks:], self.agc_target,
+                                   self.target_rate, group, comm_device)
+        ch.set_agc_state(state)
+        produced = ch.process_device_finish(shard.skip_chunks, dev_out_ptr, out_capacity_bytes, stream)
+        return produced, shard.drop

@@ -1,0 +1,200 @@
+"""Time-sharding: host logic on CPU (plan-only chains, gloo world_size 2) and
+shard-stitch parity on the GPU (`-m gpu`): a capture processed as N shards with halo + closed-form
+seek + the digital-AGC peak exchange must equal the single-stream output byte for byte."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from iq_tool_b200.configs import AGC_DIGITAL, ChainConfig
+from oracle import loader
+from oracle.loader import CpuChain
+
+CHUNK = 16384
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _agc_amplitudes():
+    """Per-chunk constant amplitudes that walk the digital AGC through every branch at
+    rate = 65536 sps (one chunk = 0.25 s): scanning with a rising peak memory, lock after > 2.0 s,
+    ratchet down on a strong chunk, 'strong' refresh, > 4 s of weak chunks -> creep up."""
+    a = [0.10, 0.20, 0.15, 0.40, 0.30, 0.30, 0.30, 0.30, 0.30, 0.20]       # scan + lock (gain 0.9/0.4)
+    a += [0.50, 0.45]                                                          # 0.5*2.25 > 1 -> ratchet to 0.99/0.5
+    a += [0.36, 0.05] + [0.04] * 20                                            # strong refresh, then weak > 4 s -> creep
+    a += [0.30, 0.02, 0.02]
+    return np.array(a, dtype=np.float32)
+
+
+def test_agc_advance_equals_the_oracle_state_machine():
+    """iqgpu_agc_digital_advance (host, no device) against the oracle's agc_apply
+    (reference src/agc.c:105-222) driven on the sample clock."""
+    from iq_tool_b200 import gpu
+    rate = 65536.0
+    cfg = ChainConfig(input_format="cf32", output_format="cf32", input_rate_hz=rate, target_rate_hz=rate,
+                      no_resample=True, agc_enable=True, agc_profile=AGC_DIGITAL)
+    lib = loader.get_lib("oracle")[0]
+    ch = CpuChain(cfg, "oracle")
+    amps = _agc_amplitudes()
+    ref_gain = np.zeros(amps.size, dtype=np.float32)
+    try:
+        for c, a in enumerate(amps):
+            lib.iqo_set_fake_clock(1, c * CHUNK / rate)
+            x = np.full(CHUNK, a, dtype=np.complex64)
+            y = ch.process(x.view(np.float32)).view(np.complex64)
+            ref_gain[c] = np.float32(y[0].real) / a
+    finally:
+        lib.iqo_set_fake_clock(0, 0.0)
+    st = gpu.agc_initial_state()
+    gains = gpu.agc_digital_advance(st, 0.9, rate, amps, np.full(amps.size, CHUNK, np.uint32), want_gains=True)
+    assert np.allclose(gains, ref_gain, rtol=2e-7, atol=0)
+    info = ch.info()
+    assert (st.locked, st.samples_seen) == (info.agc_locked, info.agc_samples_seen)
+    assert st.gain == pytest.approx(info.agc_gain, rel=1e-7) and st.peak_memory == info.agc_peak_memory
+    assert gains[11] < gains[9] and gains[-1] > gains[14]           # ratchet happened, creep happened
+    # advancing in two pieces == advancing at once; empty chunks are ignored (agc.c:89)
+    a2 = gpu.agc_initial_state()
+    k = 13
+    cnt = np.full(amps.size, CHUNK, np.uint32)
+    gpu.agc_digital_advance(a2, 0.9, rate, amps[:k], cnt[:k])
+    gpu.agc_digital_advance(a2, 0.9, rate, np.array([9.0], np.float32), np.zeros(1, np.uint32))
+    gpu.agc_digital_advance(a2, 0.9, rate, amps[k:], cnt[k:])
+    assert a2.as_tuple() == st.as_tuple()
+
+
+@pytest.mark.parametrize("name,total", [("cfg1", 40 * CHUNK + 777), ("cfg2", 1000 * CHUNK), ("cfg5", 257 * CHUNK + 1)])
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_shard_plan_tiles_the_capture(name, total, world, workloads):
+    from iq_tool_b200 import gpu
+    from iq_tool_b200.shard import plan_shards
+    probe = gpu.Chain(workloads[name].config, -1)
+    shards = plan_shards(probe, total, world)
+    assert [s.rank for s in shards] == list(range(world))
+    assert shards[0].start == 0 and shards[0].lead == 0 and shards[0].drop == 0
+    assert sum(s.frames for s in shards) == total
+    halo = probe.halo_frames()
+    for a, b in zip(shards[:-1], shards[1:]):
+        assert a.start + a.frames == b.start and a.out_end == b.out_start
+        assert b.start % CHUNK == 0 and b.lead % CHUNK == 0
+        assert b.start - b.lead >= min(halo, b.start) and b.skip_chunks * CHUNK == b.start - b.lead
+        assert b.out_lead <= b.out_start
+    assert shards[-1].out_end == probe.predict_output(total)
+
+
+def _gloo_worker(rank, world, port, total_chunks):
+    import torch.distributed as dist
+    from iq_tool_b200 import baseline_workloads, gpu
+    from iq_tool_b200.shard import _all_gather_var, exchange_agc_state, plan_shards
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cfg = baseline_workloads()["cfg1"].config
+        probe = gpu.Chain(cfg, -1)
+        total = total_chunks * CHUNK - 1234                       # ragged last chunk
+        shard = plan_shards(probe, total, world)[rank]
+        # the whole capture's per-chunk peaks and frame counts (every rank can regenerate them)
+        rng = np.random.default_rng(7)
+        peaks_all = (0.02 + 0.5 * rng.random(total_chunks) ** 4).astype(np.float32)
+        peaks_all[total_chunks // 3] = 3.0                       # forces a ratchet once locked
+        edges = [probe.resampler_outputs_after(min(c * CHUNK, total)) for c in range(total_chunks + 1)]
+        counts_all = np.diff(np.array(edges, dtype=np.int64)).astype(np.uint32)
+        c0, c1 = shard.start // CHUNK, (shard.start + shard.frames + CHUNK - 1) // CHUNK
+        rate = float(np.float32(cfg.target_rate_hz))
+        state = exchange_agc_state(peaks_all[c0:c1], counts_all[c0:c1], 0.9, rate, None, "cpu")
+        gains = gpu.agc_digital_advance(state, 0.9, rate, peaks_all[c0:c1], counts_all[c0:c1], want_gains=True)
+        stitched = np.concatenate(_all_gather_var(gains, None, "cpu"))
+        single = gpu.agc_initial_state()
+        ref = gpu.agc_digital_advance(single, 0.9, rate, peaks_all, counts_all, want_gains=True)
+        assert stitched.size == total_chunks and np.array_equal(stitched, ref)
+        if rank == world - 1:
+            assert state.as_tuple() == single.as_tuple()
+        spans = _all_gather_var(np.array([shard.out_start, shard.out_end], dtype=np.uint32), None, "cpu")
+        assert all(int(a[1]) == int(b[0]) for a, b in zip(spans[:-1], spans[1:]))
+        assert int(spans[-1][1]) == probe.predict_output(total)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_agc_exchange_over_gloo_world2_equals_single_stream():
+    """The N>1 host path on CPU: 2 gloo ranks plan their shards, exchange per-chunk peaks and end
+    up with exactly the per-chunk gains of the single-stream state machine."""
+    import torch.multiprocessing as mp
+    mp.spawn(_gloo_worker, args=(2, _free_port(), 64 * 30), nprocs=2, join=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU: shard-stitch parity
+# ------------------------------------------------------------------------------------------------
+def _run_sharded(gpu, wl, raw, world):
+    """Process `raw` as `world` shards one after the other on cuda:0 (the data path has no
+    collective, so ranks need not run concurrently; the AGC exchange is replayed in rank order)."""
+    import torch
+    from iq_tool_b200.shard import ShardedChain
+    cfg = wl.config
+    total = raw.size // 2
+    dev = torch.device("cuda", 0)
+    raw_d = torch.from_numpy(raw).to(dev)
+    sc = ShardedChain(cfg, 0, shard_frames_hint=total)
+    shards = sc.plan(total, world)
+    parts, live_peaks, live_counts = [], [], []
+    esz = raw.dtype.itemsize * 2
+    for sh in shards:
+        ch = sc.chain
+        ch.seek(sh.lead)
+        out = torch.zeros(ch.out_capacity_frames(sh.read_frames) * cfg.out_bytes, dtype=torch.uint8, device=dev)
+        ptr = raw_d.data_ptr() + sh.lead * esz
+        if sc.digital_agc:
+            ch.process_device_begin(ptr, sh.read_frames)
+            pk, ct = ch.pending_chunk_peaks()
+            st = gpu.agc_initial_state()
+            for p_, c_ in zip(live_peaks, live_counts):
+                gpu.agc_digital_advance(st, sc.agc_target, sc.target_rate, p_, c_)
+            ch.set_agc_state(st)
+            live_peaks.append(pk[sh.skip_chunks:].copy()); live_counts.append(ct[sh.skip_chunks:].copy())
+            produced = ch.process_device_finish(sh.skip_chunks, out.data_ptr(), out.numel())
+        else:
+            produced = ch.process_device(ptr, sh.read_frames, out.data_ptr(), out.numel())
+        torch.cuda.synchronize()
+        assert produced - sh.drop == sh.out_frames
+        parts.append(out[sh.drop * cfg.out_bytes: produced * cfg.out_bytes].cpu().numpy())
+    from iq_tool_b200.configs import NUMPY_DTYPE
+    return np.concatenate(parts).view(NUMPY_DTYPE[cfg.output_format])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,chunks,world", [("cfg1", 96, 2), ("cfg1", 97, 4), ("cfg5", 256, 2), ("cfg5", 250, 8)])
+def test_sharded_output_equals_single_stream_bit_for_bit(name, chunks, world, gpu, workloads):
+    """Finite-memory chains (FIR resampler + LUT NCO + digital AGC): sharded == single, exactly."""
+    from iq_tool_b200.synth import synth_numpy
+    wl = workloads[name]
+    raw = synth_numpy(wl, chunks * CHUNK - 321)
+    # make the AGC do something: a loud burst in the second half
+    h = raw.size // 2
+    raw[h: h + 4 * CHUNK] = (raw[h: h + 4 * CHUNK].astype(np.int32) * 2).clip(-32768, 32767).astype(raw.dtype)
+    single = gpu.Chain(wl.config, 0).process(raw)
+    sharded = _run_sharded(gpu, wl, raw, world)
+    assert sharded.size == single.size
+    assert np.array_equal(sharded, single)
+
+
+@pytest.mark.gpu
+def test_sharded_cfg2_with_dc_block_halo_meets_the_bar(gpu, workloads):
+    """cfg2 has the infinite-memory DC blocker: the shard re-computes a 16-time-constant halo, so
+    the stitched output equals the single stream within +-1 LSB (cs16)."""
+    from iq_tool_b200.synth import synth_numpy
+    wl = workloads["cfg2"]
+    probe = gpu.Chain(wl.config, -1)
+    halo = probe.halo_frames()
+    total = 2 * (halo + 40 * CHUNK)
+    raw = synth_numpy(wl, total)
+    single = gpu.Chain(wl.config, 0).process(raw)
+    sharded = _run_sharded(gpu, wl, raw, 2)
+    assert sharded.size == single.size
+    d = np.abs(sharded.astype(np.int32) - single.astype(np.int32))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3
