@@ -21,10 +21,12 @@
 // pairing, the 24-bit polyphase phase and the NCO phase are closed forms of the index.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 #include "device_common.cuh"
+#include "fused_front2.cuh"
 #include "kernels.hpp"
 
 namespace iqgpu {
@@ -350,7 +352,56 @@ struct FusedFront {
     int num_sms = 148;
     int ctas_per_sm = 3;
     int format = 0;
+    // v2 (warp-streaming kernel, fused_front2.cuh): used when the cascade matches a compiled plan
+    bool v2 = false;
+    int v2_S = 0, v2_warps = 0, v2_sup = 1, v2_warm_sup = 0, v2_warp_f2 = 0;
+    size_t v2_smem = 0;
+    float v2_taps[W2_MAX_TAPS] = {0};
+    float v2_zeta = 1.f;
+    uint32_t v2_step = 0;
+    int H_tail = 0;                     // cf32 tail length of the kernel in use
 };
+
+// ---- v2 plan table ---------------------------------------------------------------------------
+template <int S> static bool v2_plan_matches(const ResamplerDesc& r)
+{
+    if ((int)r.S != S) return false;
+    for (int d = 0; d < S; d++)
+        if ((int)r.m_exec[d] != W2Plan<S>::m(d)) return false;
+    return true;
+}
+template <int S> static void v2_fill(FusedFront* f)
+{
+    f->v2_S = S;
+    f->v2_sup = W2Plan<S>::sup;
+    f->v2_warp_f2 = W2Plan<S>::warp_f2;
+    const long long warm_ticks = (W2Plan<S>::halo_frames() + W2_T0 - 1) / W2_T0;
+    f->v2_warm_sup = (int)((warm_ticks + W2Plan<S>::sup - 1) / W2Plan<S>::sup);
+    f->H_tail = (f->v2_warm_sup + 1) * W2Plan<S>::sup * W2_T0;
+}
+static bool v2_setup(FusedFront* f, const ResamplerDesc& r, bool nco)
+{
+    if (getenv("IQGPU_FUSED_V1")) return false;
+    bool ok = false;
+#define V2_TRY(SS) if (!ok && v2_plan_matches<SS>(r)) { v2_fill<SS>(f); ok = true; }
+    V2_TRY(0) V2_TRY(1) V2_TRY(2) V2_TRY(3) V2_TRY(4) V2_TRY(5) V2_TRY(6)
+#undef V2_TRY
+    if (!ok) return false;
+    const size_t fixed = (size_t)256 * W2_BANK_STRIDE * sizeof(float) + (nco ? 1024 * sizeof(float2) : 0);
+    const size_t per_warp = (size_t)f->v2_warp_f2 * sizeof(float2);
+    const size_t avail = 227 * 1024 - 1024;
+    int warps = (int)((avail - fixed) / per_warp);
+    if (warps > 16) warps = 16;
+    if (warps < 4) return false;
+    f->v2_warps = warps;
+    f->v2_smem = fixed + (size_t)warps * per_warp;
+    int k = 0;
+    for (unsigned d = 0; d < r.S; d++)
+        for (unsigned j = 0; j < 2 * r.m_exec[d]; j++) f->v2_taps[k++] = r.h1_exec[d][j];
+    f->v2_zeta = r.zeta;
+    f->v2_step = r.step;
+    return true;
+}
 
 bool fused_supported(int format, const ResamplerDesc& r)
 {
@@ -411,14 +462,16 @@ FusedFront* fused_create(int format, const ResamplerDesc& r, bool nco, const flo
     f->num_sms = num_sms;
     f->d_bank = d_bank;
     build_plan(f->plan, r, nco);
-    if (f->plan.smem_bytes > 200 * 1024) { err = "fused front: shared memory plan too large"; delete f; return nullptr; }
+    f->H_tail = f->plan.H_tail;
+    f->v2 = v2_setup(f, r, nco);
+    if (!f->v2 && f->plan.smem_bytes > 200 * 1024) { err = "fused front: shared memory plan too large"; delete f; return nullptr; }
     std::vector<float> taps;
     for (unsigned d = 0; d < r.S; d++) taps.insert(taps.end(), r.h1_exec[d], r.h1_exec[d] + 2 * r.m_exec[d]);
     if (taps.empty()) taps.push_back(0.f);
     if (cudaMalloc(&f->d_taps, taps.size() * sizeof(float)) != cudaSuccess ||
         cudaMemcpy(f->d_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMalloc(&f->d_tail[0], (size_t)f->plan.H_tail * sizeof(float2)) != cudaSuccess ||
-        cudaMalloc(&f->d_tail[1], (size_t)f->plan.H_tail * sizeof(float2)) != cudaSuccess) {
+        cudaMalloc(&f->d_tail[0], (size_t)f->H_tail * sizeof(float2)) != cudaSuccess ||
+        cudaMalloc(&f->d_tail[1], (size_t)f->H_tail * sizeof(float2)) != cudaSuccess) {
         err = "fused front: device allocation failed";
         fused_destroy(f);
         return nullptr;
@@ -438,12 +491,16 @@ void fused_destroy(FusedFront* f)
 cudaError_t fused_reset(FusedFront* f, cudaStream_t st)
 {
     f->tail_cur = 0;
-    cudaError_t e = cudaMemsetAsync(f->d_tail[0], 0, (size_t)f->plan.H_tail * sizeof(float2), st);
+    cudaError_t e = cudaMemsetAsync(f->d_tail[0], 0, (size_t)f->H_tail * sizeof(float2), st);
     if (e != cudaSuccess) return e;
-    return cudaMemsetAsync(f->d_tail[1], 0, (size_t)f->plan.H_tail * sizeof(float2), st);
+    return cudaMemsetAsync(f->d_tail[1], 0, (size_t)f->H_tail * sizeof(float2), st);
 }
 
-uint32_t fused_halo_frames(const FusedFront* f) { return (uint32_t)(f->plan.warm_blocks * f->plan.B0); }
+uint32_t fused_halo_frames(const FusedFront* f)
+{
+    return f->v2 ? (uint32_t)(f->v2_warm_sup * f->v2_sup * W2_T0) : (uint32_t)(f->plan.warm_blocks * f->plan.B0);
+}
+int fused_version(const FusedFront* f) { return f->v2 ? 2 : 1; }
 
 // DC pre-pass on the virtual range [A0, N1): frames below n0 read as zero, the carry is rewound to A0
 static cudaError_t fused_dc_prepass(FusedFront* f, const void* raw, long long n0, long long N1, const PreParams& pre,
@@ -499,10 +556,87 @@ static cudaError_t fused_dc_prepass(FusedFront* f, const void* raw, long long n0
     return launch_dc_scan(f->d_dc_sums, n_runs, 256, nv, pre.dc_c, d_carry, f->d_dc_table, f->d_dc_ws, st);
 }
 
+template <int S>
+static cudaError_t launch_v2_s(const FusedFront* f, const Fused2Args& A, int grid, bool dc, bool cs16, cudaStream_t st)
+{
+    const int threads = f->v2_warps * 32;
+    const size_t smem = f->v2_smem;
+#define V2_LAUNCH(DCF, C16)                                                                                        \
+    do {                                                                                                           \
+        cudaError_t e_ = cudaFuncSetAttribute(fused_front2_kernel<S, DCF, C16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (e_ != cudaSuccess) return e_;                                                                          \
+        fused_front2_kernel<S, DCF, C16><<<grid, threads, smem, st>>>(A, f->v2_warps);                              \
+    } while (0)
+    if (dc) { if (cs16) V2_LAUNCH(true, true); else V2_LAUNCH(true, false); }
+    else    { if (cs16) V2_LAUNCH(false, true); else V2_LAUNCH(false, false); }
+#undef V2_LAUNCH
+    return cudaGetLastError();
+}
+
+static cudaError_t fused_launch_v2(FusedFront* f, const void* raw, int64_t n0, size_t n, const PreParams& pre,
+                                   double2* d_dc_carry, int64_t O0, size_t n_out, float2* y, uint32_t* launches, cudaStream_t st)
+{
+    Fused2Args A{};
+    A.raw = raw; A.n0 = n0; A.N1 = n0 + (long long)n;
+    A.tail_in = f->d_tail[f->tail_cur];
+    A.tail_out = f->d_tail[f->tail_cur ^ 1];
+    A.H_tail = f->H_tail;
+    A.pre = pre;
+    A.dc = make_dc_dev16(pre.dc_enable ? pre.dc_c : 0.f, pre.dc_a);
+    A.A0 = (n0 / W2_T0) * W2_T0;                 // the tick that contains n0 starts the DC table
+    A.bank = f->d_bank;
+    A.O0 = O0; A.O1 = O0 + (long long)n_out; A.y = y;
+    A.step = f->v2_step; A.zeta = f->v2_zeta;
+    memcpy(A.taps, f->v2_taps, sizeof(A.taps));
+    const long long sup_frames = (long long)f->v2_sup * W2_T0;
+    A.sup_first = n0 / sup_frames;
+    A.sup_last = (A.N1 - 1) / sup_frames;
+    A.warm_sup = f->v2_warm_sup;
+    const long long nsup = A.sup_last - A.sup_first + 1;
+    const long long total_warps = (long long)f->num_sms * f->v2_warps;
+    long long per = (nsup + total_warps - 1) / total_warps;
+    // do not let the warm-up dominate: at least 6 warm-up lengths of own work per warp
+    const long long min_per = std::max<long long>(1, 6LL * f->v2_warm_sup);
+    if (per < min_per) per = min_per;
+    A.sup_per_warp = (int)per;
+    const long long warps_needed = (nsup + per - 1) / per;
+    const int grid = (int)((warps_needed + f->v2_warps - 1) / f->v2_warps);
+    A.raw_aligned = ((reinterpret_cast<size_t>(raw) & 15) == 0) && (n0 % 4 == 0);
+    cudaError_t e;
+    if ((long long)n < f->H_tail) {
+        const size_t keep = (size_t)f->H_tail - n;
+        e = cudaMemcpyAsync(f->d_tail[f->tail_cur ^ 1], f->d_tail[f->tail_cur] + n, keep * sizeof(float2),
+                            cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return e;
+    }
+    if (pre.dc_enable) {
+        e = fused_dc_prepass(f, raw, n0, A.N1, pre, d_dc_carry, A.A0, st);
+        if (e != cudaSuccess) return e;
+        A.dc_table = f->d_dc_table;
+        if (launches) *launches += 2;
+    }
+    const bool dc = pre.dc_enable != 0;
+    const bool cs16 = pre.format == IQGPU_FMT_CS16 || pre.format == IQGPU_FMT_SC16Q11;
+    switch (f->v2_S) {
+        case 0: e = launch_v2_s<0>(f, A, grid, dc, cs16, st); break;
+        case 1: e = launch_v2_s<1>(f, A, grid, dc, cs16, st); break;
+        case 2: e = launch_v2_s<2>(f, A, grid, dc, cs16, st); break;
+        case 3: e = launch_v2_s<3>(f, A, grid, dc, cs16, st); break;
+        case 4: e = launch_v2_s<4>(f, A, grid, dc, cs16, st); break;
+        case 5: e = launch_v2_s<5>(f, A, grid, dc, cs16, st); break;
+        case 6: e = launch_v2_s<6>(f, A, grid, dc, cs16, st); break;
+        default: return cudaErrorInvalidValue;
+    }
+    if (launches) *launches += 1;
+    f->tail_cur ^= 1;
+    return e;
+}
+
 cudaError_t fused_launch(FusedFront* f, const void* raw, int64_t n0, size_t n, const PreParams& pre, double2* d_dc_carry,
                          int64_t O0, size_t n_out, float2* y, uint32_t* launches, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
+    if (f->v2) return fused_launch_v2(f, raw, n0, n, pre, d_dc_carry, O0, n_out, y, launches, st);
     const FusedPlan& P = f->plan;
     FusedArgs A{};
     A.plan = P;

@@ -1,0 +1,484 @@
+// fused_front2.cuh — "warp-streaming" fused front (v2): the same computation as fused_front.cu's
+// block-synchronous kernel (convert -> [DC] -> [I/Q] -> [NCO] -> S halfband decimators -> 256-arm
+// polyphase stage, reference src/pre_processor.c:10-55 + src/resampler.c:49), restructured around
+// what ncu showed about v1 (profiles/r01a_fused_front_full_cfg2.md): the kernel is instruction-issue
+// bound (54 % issue active, 15 % FMA pipe, 7 % DRAM) with most issue slots going to address
+// arithmetic, run-time plan lookups and block barriers.
+//
+//   * Every WARP owns a contiguous run of the stream and a private set of level FIFOs in shared
+//     memory; nothing is shared between warps except read-only tables, so the kernel has no
+//     __syncthreads in its steady state (only __syncwarp between producer and consumer phases).
+//   * The plan (stage count S, semi-lengths m, tile sizes, padded layouts) is a template
+//     parameter: every shared-memory offset is an immediate, halfband taps are read straight from
+//     the kernel-parameter constant bank as FFMA operands.
+//   * A tick is 512 raw frames per warp; a lane owns 16 consecutive frames (4 x LDG.128 for
+//     cs16), so the DC blocker's weighted prefix needs one warp scan per 512 frames instead of
+//     four, and stage d gives every lane R = 8, 4, 2, 1 consecutive outputs (register tiles fed
+//     by LDS.128 from group-padded planes, bank-conflict free).  Stages deeper than 3 run every
+//     2^(d-3) ticks on 32 outputs.
+//   * Accumulation order is the reference's (oldest tap first), so results are bit-identical to
+//     the stage-by-stage kernels; all indices are absolute, so results do not depend on how the
+//     host cuts the stream into calls.
+#pragma once
+#include "device_common.cuh"
+#include "kernels.hpp"
+
+namespace iqgpu {
+
+constexpr int W2_T0 = 512;          // raw frames per warp tick
+constexpr int W2_MAXS = 6;          // deepest cascade with a compiled plan
+constexpr int W2_ARB_HIST = 16;     // >= 13 decimated samples of look-back
+constexpr int W2_BANK_STRIDE = 18;  // floats per polyphase row: 8-byte aligned rows, LDS.64 pairs
+constexpr int W2_MAX_TAPS = 72;     // sum of 2m over the cascade (6*4 + 10 + 20 = 54 for S = 6)
+
+// compile-time plan of a cascade of S halfband stages; semi-lengths by execution depth are
+// 3,...,3,5,10 (liquid msresamp2 at As = 60 dB) — checked against the run-time
+// design in fused2_supported().
+template <int S>
+struct W2Plan {
+    __host__ __device__ static constexpr int m(int d) { return (d == S - 1) ? 10 : ((d == S - 2) ? 5 : 3); }
+    __host__ __device__ static constexpr int out(int d) { return d < 3 ? (256 >> d) : 32; }   // outputs of stage d per run
+    __host__ __device__ static constexpr int R(int d) { return out(d) / 32; }                 // consecutive outputs per lane
+    __host__ __device__ static constexpr int PAD(int d) { return R(d) >= 4 ? 2 : (R(d) == 2 ? 1 : 0); }
+    __host__ __device__ static constexpr int Hh(int d) { return ((2 * m(d) - 1 + R(d) - 1) / R(d)) * R(d); }   // history entries per plane
+    __host__ __device__ static constexpr int entries(int d) { return Hh(d) + out(d); }
+    __host__ __device__ static constexpr int phys(int d, int p) { return p + PAD(d) * (p / R(d)); }
+    __host__ __device__ static constexpr int plane_size(int d) { return (phys(d, entries(d)) + 3) & ~1; }
+    __host__ __device__ static constexpr int e_off(int d)
+    {
+        int o = 0;
+        for (int i = 0; i < d; i++) o += 2 * plane_size(i);
+        return o;
+    }
+    __host__ __device__ static constexpr int o_off(int d) { return e_off(d) + plane_size(d); }
+    __host__ __device__ static constexpr int taps_off(int d)
+    {
+        int o = 0;
+        for (int i = 0; i < d; i++) o += 2 * m(i);
+        return o;
+    }
+    static constexpr int flat_new = (S == 0) ? W2_T0 : out(S - 1);        // new polyphase inputs per arb run
+    static constexpr int flat_off = e_off(S);
+    static constexpr int flat_size = (W2_ARB_HIST + flat_new + 3) & ~1;
+    static constexpr int warp_f2 = flat_off + flat_size;                 // float2 per warp
+    __host__ __device__ static constexpr int period(int d) { return d <= 3 ? 1 : (1 << (d - 3)); }   // stage d runs every `period` ticks
+    static constexpr int sup = (S > 4) ? (1 << (S - 4)) : 1;             // ticks per super-tick (period of the last stage)
+    __host__ __device__ static constexpr long long halo_frames()
+    {
+        long long h = 0;
+        for (int d = 0; d < S; d++) h += (long long)(4 * m(d)) << d;
+        return h + ((long long)W2_ARB_HIST << S);
+    }
+};
+
+struct DcDev16 {
+    float c, a;          // pole, 1-pole
+    float w[5];          // c^(16*2^s)
+    float lanepow[32];   // c^(16*lane)
+};
+__host__ static inline DcDev16 make_dc_dev16(float c, float a)
+{
+    DcDev16 d;
+    d.c = c; d.a = a;
+    for (int k = 0; k < 5; k++) d.w[k] = (float)pow((double)c, 16.0 * (double)(1 << k));
+    for (int l = 0; l < 32; l++) d.lanepow[l] = (float)pow((double)c, 16.0 * l);
+    return d;
+}
+
+struct Fused2Args {
+    const void* raw;
+    long long n0, N1;                   // absolute index range of raw
+    const float2* tail_in;
+    float2* tail_out;
+    int H_tail;
+    PreParams pre;
+    DcDev16 dc;
+    const double2* dc_table;            // v at absolute multiples of 256, starting at A0
+    long long A0;
+    const float* bank;                  // device, [256][14]
+    long long O0, O1;
+    float2* y;
+    long long sup_first, sup_last;      // absolute super-tick range of the call
+    int sup_per_warp, warm_sup;
+    int raw_aligned;
+    uint32_t step;
+    float zeta;
+    float taps[W2_MAX_TAPS];            // h1 by execution depth, concatenated (constant-bank FFMA operands)
+};
+
+// ------------------------------------------------------------------------------------------------
+// raw loaders (16 consecutive frames of one lane)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float w2_scale(int fmt, float gain)
+{
+    switch (fmt) {
+        case IQGPU_FMT_CS16: case IQGPU_FMT_CU16: return gain * (1.0f / 32768.0f);
+        case IQGPU_FMT_SC16Q11: return gain * (1.0f / 2048.0f);
+        case IQGPU_FMT_CS8: case IQGPU_FMT_CU8: return gain * (1.0f / 128.0f);
+        default: return gain;
+    }
+}
+__device__ __forceinline__ float2 w2_load_frame(int fmt, const void* __restrict__ raw, size_t i, float sc, float gain)
+{
+    switch (fmt) {
+        case IQGPU_FMT_CS16: case IQGPU_FMT_SC16Q11: return load_frame<IQGPU_FMT_CS16>(raw, i, sc, gain);
+        case IQGPU_FMT_CU16: return load_frame<IQGPU_FMT_CU16>(raw, i, sc, gain);
+        case IQGPU_FMT_CS8: return load_frame<IQGPU_FMT_CS8>(raw, i, sc, gain);
+        case IQGPU_FMT_CU8: return load_frame<IQGPU_FMT_CU8>(raw, i, sc, gain);
+        default: return load_frame<IQGPU_FMT_CF32>(raw, i, sc, gain);
+    }
+}
+__device__ __forceinline__ void w2_load_quad(int fmt, const void* __restrict__ raw, size_t i, float sc, float gain, float2 (&x)[4])
+{
+    const size_t big = ~(size_t)0 >> 1;
+    switch (fmt) {
+        case IQGPU_FMT_CS16: case IQGPU_FMT_SC16Q11: load_quad<IQGPU_FMT_CS16>(raw, i, big, sc, gain, true, x); break;
+        case IQGPU_FMT_CS8: load_quad<IQGPU_FMT_CS8>(raw, i, big, sc, gain, true, x); break;
+        case IQGPU_FMT_CU8: load_quad<IQGPU_FMT_CU8>(raw, i, big, sc, gain, true, x); break;
+        case IQGPU_FMT_CF32: load_quad<IQGPU_FMT_CF32>(raw, i, big, sc, gain, true, x); break;
+        default:
+#pragma unroll
+            for (int k = 0; k < 4; k++) x[k] = w2_load_frame(fmt, raw, i + k, sc, gain);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// P0: one tick (512 frames) of the pre-processor chain into level 0 (or the flat level when S == 0)
+// ------------------------------------------------------------------------------------------------
+template <int S, bool DC, bool CS16>
+__device__ __forceinline__ void w2_p0(const Fused2Args& A, float2* __restrict__ wsm, const float2* __restrict__ lut2,
+                                      long long tick_start, int lane)
+{
+    using P = W2Plan<S>;
+    const PreParams& p = A.pre;
+    const int fmt = CS16 ? IQGPU_FMT_CS16 : p.format;
+    const float sc = CS16 ? p.gain * ((p.format == IQGPU_FMT_SC16Q11) ? (1.0f / 2048.0f) : (1.0f / 32768.0f)) : w2_scale(fmt, p.gain);
+    const long long a0 = tick_start + lane * 16;               // first frame of this lane
+    const bool active = (tick_start + W2_T0 > A.n0) && (tick_start < A.N1);
+    const bool fast = A.raw_aligned && (tick_start >= A.n0) && (tick_start + W2_T0 <= A.N1 - A.H_tail);
+    float2 x[16];
+    if (fast) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float2 q[4];
+            w2_load_quad(fmt, A.raw, (size_t)(a0 - A.n0) + 4 * j, sc, p.gain, q);
+#pragma unroll
+            for (int k = 0; k < 4; k++) x[4 * j + k] = q[k];
+        }
+    } else if (active) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const long long i = a0 + k;
+            x[k] = (i >= A.n0 && i < A.N1) ? w2_load_frame(fmt, A.raw, (size_t)(i - A.n0), sc, p.gain) : make_float2(0.f, 0.f);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 16; k++) x[k] = make_float2(0.f, 0.f);
+    }
+    if (active) {
+        if (DC) {
+            // DC blocker (dc_block.c:76 -> liquid iirfilt): v[n] = x[n] + c v[n-1], y[n] = x[n] - (1-c) v[n-1].
+            // lane-local weighted sum, one warp scan per tick, state at the tick start from the table
+            const double2 vt = A.dc_table[(tick_start - A.A0) >> 8];
+            float pr = x[0].x, pi = x[0].y;
+#pragma unroll
+            for (int k = 1; k < 16; k++) { pr = fmaf(pr, A.dc.c, x[k].x); pi = fmaf(pi, A.dc.c, x[k].y); }
+#pragma unroll
+            for (int s = 0; s < 5; s++) {
+                const int dist = 1 << s;
+                const float qr = __shfl_up_sync(0xffffffffu, pr, dist);
+                const float qi = __shfl_up_sync(0xffffffffu, pi, dist);
+                if (lane >= dist) { pr = fmaf(A.dc.w[s], qr, pr); pi = fmaf(A.dc.w[s], qi, pi); }
+            }
+            float er = __shfl_up_sync(0xffffffffu, pr, 1), ei = __shfl_up_sync(0xffffffffu, pi, 1);
+            if (lane == 0) { er = 0.f; ei = 0.f; }
+            const float lp = A.dc.lanepow[lane];
+            float wr = fmaf(lp, (float)vt.x, er), wi = fmaf(lp, (float)vt.y, ei);   // v just before the lane's first frame
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const float xr = x[k].x, xi = x[k].y;
+                x[k].x = fmaf(-A.dc.a, wr, xr);
+                x[k].y = fmaf(-A.dc.a, wi, xi);
+                wr = fmaf(A.dc.c, wr, xr);
+                wi = fmaf(A.dc.c, wi, xi);
+            }
+        }
+        if (p.iq_enable) {   // iq_correct.c:307-313
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const float re = x[k].x;
+                x[k].x = __fmul_rn(re, p.iq_magp1);
+                x[k].y = __fadd_rn(x[k].y, __fmul_rn(p.iq_phase, re));
+            }
+        }
+        if (p.nco_enable) {  // liquid LIQUID_NCO: 32-bit phase, 1024-entry table, nearest entry
+            uint32_t th = p.nco_theta0 + (uint32_t)(a0 - A.n0) * p.nco_dtheta;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const float2 sc2 = lut2[((th + (1u << 21)) >> 22) & 0x3ffu];   // {sign*sin, cos}
+                const float xr = x[k].x, xi = x[k].y;
+                x[k].x = __fsub_rn(__fmul_rn(xr, sc2.y), __fmul_rn(xi, sc2.x));
+                x[k].y = __fadd_rn(__fmul_rn(xr, sc2.x), __fmul_rn(xi, sc2.y));
+                th += p.nco_dtheta;
+            }
+        }
+    }
+    if (!fast) {
+        if (a0 < A.n0) {      // frames of an earlier call: already pre-processed, kept in the tail
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                if (a0 + k < A.n0) {
+                    const long long j = a0 + k - (A.n0 - A.H_tail);
+                    x[k] = (j >= 0) ? A.tail_in[j] : make_float2(0.f, 0.f);
+                }
+            }
+        }
+        if (a0 + 16 > A.N1 - A.H_tail && a0 < A.N1) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const long long j = a0 + k - (A.N1 - A.H_tail);
+                if (j >= 0 && a0 + k < A.N1) A.tail_out[j] = x[k];
+            }
+        }
+    }
+    if (S == 0) {
+        float4* f = reinterpret_cast<float4*>(wsm + P::flat_off + W2_ARB_HIST + 16 * lane);
+#pragma unroll
+        for (int j = 0; j < 8; j++) f[j] = make_float4(x[2 * j].x, x[2 * j].y, x[2 * j + 1].x, x[2 * j + 1].y);
+    } else {
+        // level 0 planes: lane owns plane entries Hh + 8*lane .. +7 = one padded group of 8
+        constexpr int c0 = P::Hh(0);
+        float2* E = wsm + P::e_off(0) + (8 + P::PAD(0)) * lane;
+        float2* O = wsm + P::o_off(0) + (8 + P::PAD(0)) * lane;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int ph = P::phys(0, c0 + 2 * j);
+            *reinterpret_cast<float4*>(E + ph) = make_float4(x[4 * j].x, x[4 * j].y, x[4 * j + 2].x, x[4 * j + 2].y);
+            *reinterpret_cast<float4*>(O + ph) = make_float4(x[4 * j + 1].x, x[4 * j + 1].y, x[4 * j + 3].x, x[4 * j + 3].y);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// one halfband decimator run (liquid resamp2_crcf_decim_execute):
+//   y[q] = ( O[q-m] + sum_{j<2m} h1[j] E[q-2m+1+j] ) * scale       (plane-local indices)
+// lane owns outputs q0 = R*lane .. q0+R-1.
+// ------------------------------------------------------------------------------------------------
+template <int S, int D>
+__device__ __forceinline__ void w2_stage(const Fused2Args& A, float2* __restrict__ wsm, int lane, int half)
+{
+    using P = W2Plan<S>;
+    constexpr int M = P::m(D), R = P::R(D), HH = P::Hh(D), PADD = P::PAD(D);
+    constexpr int NE = 2 * M + R - 1;                 // E entries a lane reads
+    constexpr int CE = HH - (2 * M - 1);              // plane index (before + R*lane) of the first one
+    constexpr int CO = HH - M;                        // plane index of O[q0 - m]
+    constexpr bool VEC = (R >= 4);                    // padded layouts keep even-aligned pairs 16-byte aligned
+    const float2* __restrict__ E = wsm + P::e_off(D) + (R + PADD) * lane;
+    const float2* __restrict__ O = wsm + P::o_off(D) + (R + PADD) * lane;
+    float2 ent[NE], oc[R];
+    // even-aligned pairs of a padded plane are 16-byte aligned: one LDS.128 per pair
+#pragma unroll
+    for (int e = 0; e < NE; e++) {
+        const int c = CE + e;
+        const bool first = VEC && (c % 2 == 0) && (e + 1 < NE);
+        const bool second = VEC && (c % 2 != 0) && (e >= 1);
+        if (first) {
+            const float4 v = *reinterpret_cast<const float4*>(E + P::phys(D, c));
+            ent[e] = make_float2(v.x, v.y);
+            ent[e + 1] = make_float2(v.z, v.w);
+        } else if (!second) ent[e] = E[P::phys(D, c)];
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int c = CO + r;
+        const bool first = VEC && (c % 2 == 0) && (r + 1 < R);
+        const bool second = VEC && (c % 2 != 0) && (r >= 1);
+        if (first) {
+            const float4 v = *reinterpret_cast<const float4*>(O + P::phys(D, c));
+            oc[r] = make_float2(v.x, v.y);
+            oc[r + 1] = make_float2(v.z, v.w);
+        } else if (!second) oc[r] = O[P::phys(D, c)];
+    }
+    float2 acc[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) acc[r] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 2 * M; j++) {
+        const float h = A.taps[P::taps_off(D) + j];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            acc[r].x = fmaf(h, ent[r + j].x, acc[r].x);
+            acc[r].y = fmaf(h, ent[r + j].y, acc[r].y);
+        }
+    }
+    float2 v[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        if (D + 1 == S) v[r] = make_float2((oc[r].x + acc[r].x) * A.zeta, (oc[r].y + acc[r].y) * A.zeta);
+        else v[r] = make_float2(oc[r].x + acc[r].x, oc[r].y + acc[r].y);
+    }
+    if (D + 1 == S) {
+        float2* f = wsm + P::flat_off + W2_ARB_HIST + R * lane;
+        if (R >= 2) {
+#pragma unroll
+            for (int r = 0; r < R; r += 2) *reinterpret_cast<float4*>(f + r) = make_float4(v[r].x, v[r].y, v[r + 1].x, v[r + 1].y);
+        } else f[0] = v[0];
+    } else if (R >= 2) {
+        constexpr int R2 = R / 2, HN = P::Hh(D + 1), PN = P::PAD(D + 1);
+        float2* nE = wsm + P::e_off(D + 1) + (R2 + PN) * lane;
+        float2* nO = wsm + P::o_off(D + 1) + (R2 + PN) * lane;
+        if (R2 >= 4 || (R2 == 2 && PN == 2)) {
+#pragma unroll
+            for (int i = 0; i < R2; i += 2) {
+                const int ph = P::phys(D + 1, HN + i);
+                *reinterpret_cast<float4*>(nE + ph) = make_float4(v[2 * i].x, v[2 * i].y, v[2 * i + 2].x, v[2 * i + 2].y);
+                *reinterpret_cast<float4*>(nO + ph) = make_float4(v[2 * i + 1].x, v[2 * i + 1].y, v[2 * i + 3].x, v[2 * i + 3].y);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < R2; i++) {
+                const int ph = P::phys(D + 1, HN + i);
+                nE[ph] = v[2 * i];
+                nO[ph] = v[2 * i + 1];
+            }
+        }
+    } else {
+        // R == 1: lane's single output q = lane (+32*half in the consumer's run) -> E'/O' entry q/2
+        constexpr int HN = P::Hh(D + 1);
+        float2* pl = wsm + ((lane & 1) ? P::o_off(D + 1) : P::e_off(D + 1));
+        pl[HN + 16 * half + (lane >> 1)] = v[0];
+    }
+}
+
+// move the last Hh entries of both planes of level D to the history slots (all lanes call)
+template <int S, int D>
+__device__ __forceinline__ void w2_slide(float2* __restrict__ wsm, int lane)
+{
+    using P = W2Plan<S>;
+    constexpr int HH = P::Hh(D), N = P::out(D);
+    float2 t = make_float2(0.f, 0.f);
+    float2* pl = wsm + ((lane < HH) ? P::e_off(D) : P::o_off(D));
+    const int i = (lane < HH) ? lane : lane - HH;
+    const bool act = lane < 2 * HH;
+    static_assert(2 * HH <= 64, "history too long for the two-round slide");
+    float2 t2 = make_float2(0.f, 0.f);
+    float2* pl2 = wsm + ((lane + 32 < HH) ? P::e_off(D) : P::o_off(D));
+    const int i2 = (lane + 32 < HH) ? lane + 32 : lane + 32 - HH;
+    const bool act2 = (2 * HH > 32) && (lane + 32 < 2 * HH);
+    if (act) t = pl[P::phys(D, i + N)];
+    if (act2) t2 = pl2[P::phys(D, i2 + N)];
+    __syncwarp();
+    if (act) pl[P::phys(D, i)] = t;
+    if (act2) pl2[P::phys(D, i2)] = t2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// polyphase arbitrary-rate stage (liquid resamp_crcf, fixed-point phase) on the new flat entries
+//   output o: P = o*step, k = P >> 24, bank row = (P >> 16) & 255, y = sum_{i<14} row[i] * x[k-13+i]
+// ------------------------------------------------------------------------------------------------
+// o_cur = first output whose push index is >= kA (carried from run to run: one exact 64-bit
+// division per warp at start, then a float estimate + integer fix-up per run).
+template <int S>
+__device__ __forceinline__ void w2_arb(const Fused2Args& A, const float2* __restrict__ flat, const float* __restrict__ sbank,
+                                       long long kA, long long& o_cur, int lane)
+{
+    using P = W2Plan<S>;
+    const unsigned long long step = A.step;
+    const unsigned long long kb = (unsigned long long)kA + P::flat_new;
+    // outputs of this run: o >= o_cur with o*step < kb << 24
+    const unsigned long long Dn = (kb << 24) - (unsigned long long)o_cur * step;      // in (0, (flat_new+2) << 24]
+    unsigned cnt = (unsigned)__fdividef((float)Dn, (float)step);
+    while ((unsigned long long)cnt * step < Dn) cnt++;
+    while (cnt > 0 && (unsigned long long)(cnt - 1) * step >= Dn) cnt--;
+    long long oa = o_cur, ob = o_cur + cnt;
+    o_cur = ob;
+    if (oa < A.O0) oa = A.O0;
+    if (ob > A.O1) ob = A.O1;
+    for (long long o = oa + lane; o < ob; o += 32) {
+        const unsigned long long Pp = (unsigned long long)o * step;
+        const int rel = (int)((long long)(Pp >> 24) - kA);
+        const unsigned idx = (unsigned)(Pp >> 16) & 0xffu;
+        const float2* __restrict__ w = flat + rel + (W2_ARB_HIST - 13);
+        const float2* __restrict__ b = reinterpret_cast<const float2*>(sbank + idx * W2_BANK_STRIDE);
+        float sr = 0.f, si = 0.f;
+#pragma unroll
+        for (int i = 0; i < 7; i++) {
+            const float2 h = b[i];
+            const float2 v0 = w[2 * i], v1 = w[2 * i + 1];
+            sr = fmaf(h.x, v0.x, sr); si = fmaf(h.x, v0.y, si);
+            sr = fmaf(h.y, v1.x, sr); si = fmaf(h.y, v1.y, si);
+        }
+        A.y[o - A.O0] = make_float2(sr, si);
+    }
+}
+
+template <int S, int D>
+struct W2Cascade {
+    // run stage D (and everything below it) for tick `t` (absolute tick index)
+    static __device__ __forceinline__ void run(const Fused2Args& A, float2* __restrict__ wsm, long long t, int lane, bool& arb_due)
+    {
+        using P = W2Plan<S>;
+        constexpr int PER = P::period(D);
+        if (PER > 1 && ((t & (PER - 1)) != (PER - 1))) { arb_due = false; return; }
+        // producer-run parity of this stage inside its consumer's run (levels deeper than 3 take two runs)
+        const int half = (D >= 3) ? (int)((t >> (D - 3)) & 1) : 0;
+        w2_stage<S, D>(A, wsm, lane, (D + 1 < S && D + 1 >= 4) ? half : 0);
+        __syncwarp();
+        w2_slide<S, D>(wsm, lane);
+        __syncwarp();
+        if constexpr (D + 1 < S) W2Cascade<S, D + 1>::run(A, wsm, t, lane, arb_due);
+    }
+};
+
+template <int S, bool DC, bool CS16>
+__global__ void __launch_bounds__(512, 1) fused_front2_kernel(const __grid_constant__ Fused2Args A, int warps_per_cta)
+{
+    using P = W2Plan<S>;
+    extern __shared__ __align__(16) float2 sm2[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // shared tables: polyphase bank [256][18 floats], NCO table {sign*sin, cos}[1024]
+    float* sbank = reinterpret_cast<float*>(sm2);
+    float2* lut2 = sm2 + (256 * W2_BANK_STRIDE) / 2;
+    float2* wsm = lut2 + (A.pre.nco_enable ? 1024 : 0) + warp * P::warp_f2;
+    for (int i = tid; i < 256 * 14; i += blockDim.x) sbank[(i / 14) * W2_BANK_STRIDE + (i % 14)] = A.bank[i];
+    if (A.pre.nco_enable)
+        for (int i = tid; i < 1024; i += blockDim.x)
+            lut2[i] = make_float2(A.pre.nco_table[i] * A.pre.nco_sign, A.pre.nco_table[(i + 256) & 1023]);
+    for (int i = lane; i < P::warp_f2; i += 32) wsm[i] = make_float2(0.f, 0.f);
+    __syncthreads();
+
+    const long long gw = (long long)blockIdx.x * warps_per_cta + warp;
+    const long long seg_first = A.sup_first + gw * A.sup_per_warp;       // in super-ticks
+    if (seg_first > A.sup_last) return;
+    long long seg_last = seg_first + A.sup_per_warp - 1;
+    if (seg_last > A.sup_last) seg_last = A.sup_last;
+    float2* flat = wsm + P::flat_off;
+
+    const long long t_begin = (seg_first - A.warm_sup) * P::sup, t_emit = seg_first * P::sup, t_end = (seg_last + 1) * P::sup;
+    // first output of the first emitting run (exact), carried from run to run afterwards
+    long long o_cur;
+    {
+        const unsigned long long k_emit = (unsigned long long)((t_emit * W2_T0) >> S);
+        o_cur = (long long)(((k_emit << 24) + A.step - 1) / A.step);
+    }
+    for (long long t = t_begin; t < t_end; t++) {
+        const long long tick_start = t * W2_T0;
+        w2_p0<S, DC, CS16>(A, wsm, lut2, tick_start, lane);
+        __syncwarp();
+        bool arb_due = true;
+        if constexpr (S > 0) W2Cascade<S, 0>::run(A, wsm, t, lane, arb_due);
+        if (arb_due) {
+            // the new flat entries are the last stage's outputs of this run: absolute decimated index
+            const long long kA = ((tick_start + W2_T0) >> S) - P::flat_new;
+            if (t >= t_emit) w2_arb<S>(A, flat, sbank, kA, o_cur, lane);
+            __syncwarp();
+            float2 h = make_float2(0.f, 0.f);
+            if (lane < W2_ARB_HIST) h = flat[lane + P::flat_new];
+            __syncwarp();
+            if (lane < W2_ARB_HIST) flat[lane] = h;
+            __syncwarp();
+        }
+    }
+}
+
+}  // namespace iqgpu

@@ -633,68 +633,91 @@ struct AgcStep {   // sequential reference step, shared by both paths
         return g;
     }
 };
-__global__ void __launch_bounds__(32) agc_digital_scan_kernel(const uint32_t* __restrict__ seg_start, unsigned nseg,
-                                                              const float* __restrict__ seg_peak, PostParams p,
-                                                              AgcState* __restrict__ st, float* __restrict__ seg_gain)
+// The chunk table (frame counts + peaks) is staged through shared memory in tiles by the whole
+// CTA (coalesced), so the serial warp never waits on a dependent global load.
+constexpr int AGC_SCAN_TILE = 3072;
+constexpr int AGC_SCAN_THREADS = 512;
+__global__ void __launch_bounds__(AGC_SCAN_THREADS) agc_digital_scan_kernel(const uint32_t* __restrict__ seg_start, unsigned nseg,
+                                                                            const float* __restrict__ seg_peak, PostParams p,
+                                                                            AgcState* __restrict__ st, float* __restrict__ seg_gain)
 {
-    const unsigned lane = threadIdx.x;
-    AgcState s = *st;
+    __shared__ unsigned s_cnt[AGC_SCAN_TILE];
+    __shared__ float s_pk[AGC_SCAN_TILE];
+    __shared__ float s_gain[AGC_SCAN_TILE];
+    __shared__ AgcState s_state;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_state = *st;
     const float target = p.agc_target;
     const float strong_thr = __fmul_rn(target, 0.75f);
-    for (unsigned base = 0; base < nseg; base += 32) {
-        const unsigned c = base + lane;
-        const bool valid = c < nseg;
-        const unsigned cnt = valid ? (__ldg(seg_start + c + 1) - __ldg(seg_start + c)) : 0u;
-        const float pk = valid ? __ldg(seg_peak + c) : 0.f;
-        const bool act = cnt != 0;                               // agc_apply returns on num_samples == 0
-        // exclusive prefix of the sample counter
-        unsigned long long pre = cnt;
+    for (unsigned tile0 = 0; tile0 < nseg; tile0 += AGC_SCAN_TILE) {
+        const unsigned tn = min((unsigned)AGC_SCAN_TILE, nseg - tile0);
+        for (unsigned i = threadIdx.x; i < tn; i += AGC_SCAN_THREADS) {
+            s_cnt[i] = __ldg(seg_start + tile0 + i + 1) - __ldg(seg_start + tile0 + i);
+            s_pk[i] = __ldg(seg_peak + tile0 + i);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            AgcState s = s_state;
+            for (unsigned base = 0; base < tn; base += 32) {
+                const unsigned c = base + lane;
+                const bool valid = c < tn;
+                const unsigned cnt = valid ? s_cnt[c] : 0u;
+                const float pk = valid ? s_pk[c] : 0.f;
+                const bool act = cnt != 0;                               // agc_apply returns on num_samples == 0
+                // exclusive prefix of the sample counter
+                unsigned long long pre = cnt;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned long long q = __shfl_up_sync(0xffffffffu, pre, d);
-            if (lane >= (unsigned)d) pre += q;
-        }
-        const unsigned long long total = __shfl_sync(0xffffffffu, pre, 31);
-        const unsigned long long seen_before = s.seen + pre - cnt;
-        bool fast = false;
-        float g = 1.0f;
-        if (s.locked) {
-            const float opk = __fmul_rn(pk, s.gain);
-            const double now = (double)seen_before / p.target_rate;
-            const bool ratchet = act && opk > 1.0f;
-            const bool strong = act && opk > strong_thr;
-            // time of the latest strong chunk strictly before this lane (now is non-decreasing)
-            double ls = strong ? now : -1.0;
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned long long q = __shfl_up_sync(0xffffffffu, pre, d);
+                    if (lane >= (unsigned)d) pre += q;
+                }
+                const unsigned long long total = __shfl_sync(0xffffffffu, pre, 31);
+                const unsigned long long seen_before = s.seen + pre - cnt;
+                bool fast = false;
+                float g = 1.0f;
+                if (s.locked) {
+                    const float opk = __fmul_rn(pk, s.gain);
+                    const double now = (double)seen_before / p.target_rate;
+                    const bool ratchet = act && opk > 1.0f;
+                    const bool strong = act && opk > strong_thr;
+                    // time of the latest strong chunk strictly before this lane (now is non-decreasing)
+                    double ls = strong ? now : -1.0;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const double q = __shfl_up_sync(0xffffffffu, ls, d);
-                if (lane >= (unsigned)d) ls = fmax(ls, q);
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const double q = __shfl_up_sync(0xffffffffu, ls, d);
+                        if (lane >= (unsigned)d) ls = fmax(ls, q);
+                    }
+                    const double ls_incl = ls;
+                    double ls_excl = __shfl_up_sync(0xffffffffu, ls, 1);
+                    if (lane == 0) ls_excl = -1.0;
+                    ls_excl = fmax(ls_excl, s.last_strong);
+                    const bool creep = act && !strong && (now - ls_excl > (double)4.0f);
+                    if (!__any_sync(0xffffffffu, ratchet || creep)) {
+                        fast = true;
+                        g = s.gain;
+                        s.last_strong = fmax(s.last_strong, __shfl_sync(0xffffffffu, ls_incl, 31));
+                        s.seen += total;
+                    }
+                }
+                if (!fast) {
+                    // replay: warp-uniform sequential walk over the group's chunks
+                    for (unsigned k = 0; k < 32 && base + k < tn; k++) {
+                        const unsigned ck = __shfl_sync(0xffffffffu, cnt, k);
+                        const float pkk = __shfl_sync(0xffffffffu, pk, k);
+                        if (ck == 0) continue;
+                        const float gk = AgcStep::run(s, pkk, ck, target, p.target_rate);
+                        if (lane == k) g = gk;
+                    }
+                }
+                if (valid) s_gain[c] = act ? g : 1.0f;
             }
-            const double ls_incl = ls;
-            double ls_excl = __shfl_up_sync(0xffffffffu, ls, 1);
-            if (lane == 0) ls_excl = -1.0;
-            ls_excl = fmax(ls_excl, s.last_strong);
-            const bool creep = act && !strong && (now - ls_excl > (double)4.0f);
-            if (!__any_sync(0xffffffffu, ratchet || creep)) {
-                fast = true;
-                g = s.gain;
-                s.last_strong = fmax(s.last_strong, __shfl_sync(0xffffffffu, ls_incl, 31));
-                s.seen += total;
-            }
+            if (lane == 0) s_state = s;
         }
-        if (!fast) {
-            // replay: warp-uniform sequential walk over the group's chunks
-            for (unsigned k = 0; k < 32 && base + k < nseg; k++) {
-                const unsigned ck = __shfl_sync(0xffffffffu, cnt, k);
-                const float pkk = __shfl_sync(0xffffffffu, pk, k);
-                if (ck == 0) continue;
-                const float gk = AgcStep::run(s, pkk, ck, target, p.target_rate);
-                if (lane == k) g = gk;
-            }
-        }
-        if (valid) seg_gain[c] = act ? g : 1.0f;
+        __syncthreads();
+        for (unsigned i = threadIdx.x; i < tn; i += AGC_SCAN_THREADS) seg_gain[tile0 + i] = s_gain[i];
+        __syncthreads();
     }
-    if (lane == 0) *st = s;
+    if (threadIdx.x == 0) *st = s_state;
 }
 
 // liquid agc_crcf_execute_block (agc.c:92-100): nonlinear per-sample recurrence; serial.
@@ -879,7 +902,7 @@ cudaError_t launch_agc_digital_scan(const uint32_t* seg_start, size_t nseg, cons
                                     const PostParams& p, AgcState* state, float* seg_gain, cudaStream_t st)
 {
     if (nseg == 0) return cudaSuccess;
-    agc_digital_scan_kernel<<<1, 32, 0, st>>>(seg_start, (unsigned)nseg, seg_peak, p, state, seg_gain);
+    agc_digital_scan_kernel<<<1, AGC_SCAN_THREADS, 0, st>>>(seg_start, (unsigned)nseg, seg_peak, p, state, seg_gain);
     return cudaGetLastError();
 }
 cudaError_t launch_agc_rms(const float2* x, size_t n, const PostParams& p, AgcState* state, float2* y,

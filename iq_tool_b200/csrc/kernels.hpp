@@ -128,6 +128,7 @@ FusedFront* fused_create(int format, const ResamplerDesc& r, bool nco, const flo
 void fused_destroy(FusedFront* f);
 cudaError_t fused_reset(FusedFront* f, cudaStream_t st);
 uint32_t fused_halo_frames(const FusedFront* f);
+int fused_version(const FusedFront* f);   // 1 = block-synchronous kernel, 2 = warp-streaming kernel
 // raw[0] has absolute index n0; produces outputs [O0, O0+n_out) into y; d_dc_carry is the DC state at n0
 // (updated to the state at n0+n).  *launches is incremented by the kernels launched.
 cudaError_t fused_launch(FusedFront* f, const void* raw, int64_t n0, size_t n, const PreParams& pre, double2* d_dc_carry,
