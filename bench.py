@@ -211,7 +211,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    wl = baseline_workloads()[args.workload]
+    from iq_tool_b200.configs import stage_workloads
+    wl = {**baseline_workloads(), **stage_workloads()}[args.workload]
     cfg = wl.config
     n = args.samples or wl.throughput_samples
     n -= n % 16384

@@ -222,3 +222,17 @@ def baseline_workloads() -> dict:
         parity_samples=1 << 24, throughput_samples=1 << 30,
         description="cs16 @ 61.44 Msps -> 744187.5 sps, pre shift, digital AGC; time-sharded")
     return w
+
+
+def stage_workloads() -> dict:
+    """Single-stage workloads for the per-kernel roofline rows of SURVEY.md 8(d) (not BASELINE configs)."""
+    w = {}
+    # K1 alone: convert + pre-resample LUT-NCO shift, cs16 -> cf32 at the native rate (4 + 8 B per frame, HBM bound)
+    w["k1"] = Workload(
+        "k1",
+        ChainConfig(input_format="cs16", output_format="cf32", input_rate_hz=20.0e6, target_rate_hz=20.0e6,
+                    no_resample=True, freq_shift_hz=-100e3),
+        tones=[(0.30, 100e3), (0.10, -150e3)], dc=0.0, sigma=0.01,
+        parity_samples=1 << 22, throughput_samples=1 << 28,
+        description="stage K1 alone: cs16 -> convert + LUT-NCO shift -> cf32 (no resampling)")
+    return w

@@ -184,6 +184,8 @@ struct iqgpu_chain {
     size_t max_segs = 0;
     float2* d_agc_scratch = nullptr;
     size_t agc_scratch_cap = 0;
+    void* d_agc_ws = nullptr;           // RMS-AGC time-parallel workspace (block end states + sweep flags)
+    size_t agc_ws_bytes = 0;
     // streams: s_in = pre output; s_stage[d] = output of executed halfband stage d; s_rs = resampler
     // output; s_f = post-filter output (or pre-filter output when the filter is pre-resample)
     DevStream s_in, s_pref, s_arb_in, s_rs, s_f;
@@ -270,7 +272,7 @@ iqgpu_chain::~iqgpu_chain()
     for (auto* t : d_hb_taps) cudaFree(t);
     cudaFree(d_lut); cudaFree(d_dc_carry); cudaFree(d_run_sums); cudaFree(d_run_start); cudaFree(d_scan_ws); cudaFree(d_bank);
     cudaFree(d_fir_taps); cudaFree(d_fft_H); cudaFree(d_fft_tw); cudaFree(d_fft_scratch); cudaFree(d_agc); cudaFree(d_seg_start);
-    cudaFree(d_seg_peak); cudaFree(d_seg_gain); cudaFree(d_agc_scratch);
+    cudaFree(d_seg_peak); cudaFree(d_seg_gain); cudaFree(d_agc_scratch); cudaFree(d_agc_ws);
     s_in.release(); s_pref.release(); s_arb_in.release(); s_rs.release(); s_f.release();
     for (auto& s : s_stage) s.release();
     for (auto& t : tap) t.release();
@@ -752,7 +754,15 @@ int iqgpu_chain::run_back(void* d_outp, size_t skip_chunks, size_t* out_frames, 
                 CK(cudaMalloc(&d_agc_scratch, agc_scratch_cap * sizeof(float2)));
             }
             float2* y = d_agc_scratch;
-            CK(launch_agc_rms(post_src, post_n, qp, d_agc, y, st));
+            const size_t ws_need = agc_rms_workspace_bytes(post_n, qp.agc_alpha);
+            if (ws_need > agc_ws_bytes) {
+                CK(cudaStreamSynchronize(st));
+                cudaFree(d_agc_ws);
+                d_agc_ws = nullptr; agc_ws_bytes = 0;
+                CK(cudaMalloc(&d_agc_ws, ws_need * 2));
+                agc_ws_bytes = ws_need * 2;
+            }
+            CK(launch_agc_rms(post_src, post_n, qp, d_agc, y, d_agc_ws, st));
             CK(launch_post(y, post_n, qp, nullptr, 0, nullptr, 1, tap2, d_outp, st));
             launches += 2;
         } else {

@@ -360,6 +360,7 @@ struct FusedFront {
     float v2_zeta = 1.f;
     uint32_t v2_step = 0;
     int H_tail = 0;                     // cf32 tail length of the kernel in use
+    float2* d_bank_image = nullptr;     // polyphase bank in the v2 shared-memory layout (w2_bank_row)
 };
 
 // ---- v2 plan table ---------------------------------------------------------------------------
@@ -387,7 +388,7 @@ static bool v2_setup(FusedFront* f, const ResamplerDesc& r, bool nco)
     V2_TRY(0) V2_TRY(1) V2_TRY(2) V2_TRY(3) V2_TRY(4) V2_TRY(5) V2_TRY(6)
 #undef V2_TRY
     if (!ok) return false;
-    const size_t fixed = (size_t)256 * W2_BANK_STRIDE * sizeof(float) + (nco ? 1024 * sizeof(float2) : 0);
+    const size_t fixed = (size_t)W2_BANK_F2 * sizeof(float2) + (nco ? 1024 * sizeof(float2) : 0);
     const size_t per_warp = (size_t)f->v2_warp_f2 * sizeof(float2);
     const size_t avail = 227 * 1024 - 1024;
     int warps = (int)((avail - fixed) / per_warp);
@@ -477,6 +478,24 @@ FusedFront* fused_create(int format, const ResamplerDesc& r, bool nco, const flo
         return nullptr;
     }
     f->ctas_per_sm = std::max(1, std::min(4, (int)((220 * 1024) / f->plan.smem_bytes)));
+    if (f->v2) {
+        // lay the bank out the way the kernel reads it, so one TMA bulk copy stages it per CTA
+        std::vector<float> hb(256 * 14);
+        std::vector<float2> img(W2_BANK_F2, make_float2(0.f, 0.f));
+        if (cudaMemcpy(hb.data(), d_bank, hb.size() * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMalloc(&f->d_bank_image, img.size() * sizeof(float2)) != cudaSuccess) {
+            err = "fused front: bank image allocation failed";
+            fused_destroy(f);
+            return nullptr;
+        }
+        for (int idx = 0; idx < 256; idx++)
+            for (int i = 0; i < 7; i++) img[w2_bank_row(idx) + i] = make_float2(hb[idx * 14 + 2 * i], hb[idx * 14 + 2 * i + 1]);
+        if (cudaMemcpy(f->d_bank_image, img.data(), img.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) {
+            err = "fused front: bank image upload failed";
+            fused_destroy(f);
+            return nullptr;
+        }
+    }
     return f;
 }
 
@@ -484,7 +503,7 @@ void fused_destroy(FusedFront* f)
 {
     if (!f) return;
     cudaFree(f->d_taps); cudaFree(f->d_tail[0]); cudaFree(f->d_tail[1]);
-    cudaFree(f->d_dc_table); cudaFree(f->d_dc_sums); cudaFree(f->d_dc_ws);
+    cudaFree(f->d_dc_table); cudaFree(f->d_dc_sums); cudaFree(f->d_dc_ws); cudaFree(f->d_bank_image);
     delete f;
 }
 
@@ -584,7 +603,7 @@ static cudaError_t fused_launch_v2(FusedFront* f, const void* raw, int64_t n0, s
     A.pre = pre;
     A.dc = make_dc_dev16(pre.dc_enable ? pre.dc_c : 0.f, pre.dc_a);
     A.A0 = (n0 / W2_T0) * W2_T0;                 // the tick that contains n0 starts the DC table
-    A.bank = f->d_bank;
+    A.bank_image = f->d_bank_image;
     A.O0 = O0; A.O1 = O0 + (long long)n_out; A.y = y;
     A.step = f->v2_step; A.zeta = f->v2_zeta;
     memcpy(A.taps, f->v2_taps, sizeof(A.taps));

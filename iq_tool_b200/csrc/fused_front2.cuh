@@ -28,7 +28,14 @@ namespace iqgpu {
 constexpr int W2_T0 = 512;          // raw frames per warp tick
 constexpr int W2_MAXS = 6;          // deepest cascade with a compiled plan
 constexpr int W2_ARB_HIST = 16;     // >= 13 decimated samples of look-back
-constexpr int W2_BANK_STRIDE = 18;  // floats per polyphase row: 8-byte aligned rows, LDS.64 pairs
+// polyphase bank image in shared memory: row `idx` (14 taps = 7 float2) starts at float2 offset
+// 9*idx + (idx >> 2).  The odd stride plus the slow skew keeps the 16 lanes of a half-warp, whose
+// rows advance by a configuration-dependent step, spread over the 16 LDS.64 bank pairs (a plain
+// stride degenerates to 16-way conflicts when the step has a factor of 8; measured on cfg1:
+// profiles/r01c_fused_front2_full_cfg1.md).  The image is laid out by the host and pulled in with
+// one TMA bulk copy (cp.async.bulk) per CTA.
+constexpr int W2_BANK_F2 = 2368;    // float2 entries of the image (9*255 + 63 + 7 = 2365, padded to 16 B)
+__host__ __device__ constexpr int w2_bank_row(int idx) { return 9 * idx + (idx >> 2); }
 constexpr int W2_MAX_TAPS = 72;     // sum of 2m over the cascade (6*4 + 10 + 20 = 54 for S = 6)
 
 // compile-time plan of a cascade of S halfband stages; semi-lengths by execution depth are
@@ -95,7 +102,7 @@ struct Fused2Args {
     DcDev16 dc;
     const double2* dc_table;            // v at absolute multiples of 256, starting at A0
     long long A0;
-    const float* bank;                  // device, [256][14]
+    const float2* bank_image;           // device, W2_BANK_F2 float2 in the w2_bank_row layout
     long long O0, O1;
     float2* y;
     long long sup_first, sup_last;      // absolute super-tick range of the call
@@ -105,6 +112,30 @@ struct Fused2Args {
     float zeta;
     float taps[W2_MAX_TAPS];            // h1 by execution depth, concatenated (constant-bank FFMA operands)
 };
+
+// ------------------------------------------------------------------------------------------------
+// TMA bulk copy global -> shared with mbarrier completion (cp.async.bulk, sm_90+/sm_100a)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t w2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void w2_mbar_init(uint64_t* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(w2_smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void w2_tma_load(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(w2_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(w2_smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(w2_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void w2_mbar_wait(uint64_t* bar, unsigned parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(w2_smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
 
 // ------------------------------------------------------------------------------------------------
 // raw loaders (16 consecutive frames of one lane)
@@ -142,12 +173,30 @@ __device__ __forceinline__ void w2_load_quad(int fmt, const void* __restrict__ r
     }
 }
 
+// a tick is "fast" when all of its 512 frames come straight from this call's raw buffer with aligned
+// vector loads and none of them belongs to the cf32 tail kept for the next call
+__device__ __forceinline__ bool w2_tick_fast(const Fused2Args& A, long long tick_start)
+{
+    return A.raw_aligned && (tick_start >= A.n0) && (tick_start + W2_T0 <= A.N1 - A.H_tail);
+}
+// software prefetch (cs16 fast path): the lane's 64 raw bytes of the NEXT tick are requested one
+// whole tick ahead and sit in 16 registers while the cascade of the current tick runs
+struct W2Raw { uint4 q[4]; };
+__device__ __forceinline__ void w2_prefetch(const Fused2Args& A, long long tick_start, int lane, W2Raw& r)
+{
+    if (w2_tick_fast(A, tick_start)) {
+        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(A.raw) + (tick_start - A.n0 + lane * 16) * 4);
+#pragma unroll
+        for (int j = 0; j < 4; j++) r.q[j] = __ldg(src + j);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // P0: one tick (512 frames) of the pre-processor chain into level 0 (or the flat level when S == 0)
 // ------------------------------------------------------------------------------------------------
 template <int S, bool DC, bool CS16>
 __device__ __forceinline__ void w2_p0(const Fused2Args& A, float2* __restrict__ wsm, const float2* __restrict__ lut2,
-                                      long long tick_start, int lane)
+                                      long long tick_start, int lane, const W2Raw& pre)
 {
     using P = W2Plan<S>;
     const PreParams& p = A.pre;
@@ -155,9 +204,20 @@ __device__ __forceinline__ void w2_p0(const Fused2Args& A, float2* __restrict__ 
     const float sc = CS16 ? p.gain * ((p.format == IQGPU_FMT_SC16Q11) ? (1.0f / 2048.0f) : (1.0f / 32768.0f)) : w2_scale(fmt, p.gain);
     const long long a0 = tick_start + lane * 16;               // first frame of this lane
     const bool active = (tick_start + W2_T0 > A.n0) && (tick_start < A.N1);
-    const bool fast = A.raw_aligned && (tick_start >= A.n0) && (tick_start + W2_T0 <= A.N1 - A.H_tail);
+    const bool fast = w2_tick_fast(A, tick_start);
     float2 x[16];
-    if (fast) {
+    if (fast && CS16) {
+        // sample_convert.c:136-141: x / 32768 * gain (exact power-of-two scale folded into sc)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const unsigned w[4] = {pre.q[j].x, pre.q[j].y, pre.q[j].z, pre.q[j].w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                x[4 * j + k].x = __fmul_rn((float)(short)(w[k] & 0xffffu), sc);
+                x[4 * j + k].y = __fmul_rn((float)(short)(w[k] >> 16), sc);
+            }
+        }
+    } else if (fast) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             float2 q[4];
@@ -379,7 +439,7 @@ __device__ __forceinline__ void w2_slide(float2* __restrict__ wsm, int lane)
 // o_cur = first output whose push index is >= kA (carried from run to run: one exact 64-bit
 // division per warp at start, then a float estimate + integer fix-up per run).
 template <int S>
-__device__ __forceinline__ void w2_arb(const Fused2Args& A, const float2* __restrict__ flat, const float* __restrict__ sbank,
+__device__ __forceinline__ void w2_arb(const Fused2Args& A, const float2* __restrict__ flat, const float2* __restrict__ sbank,
                                        long long kA, long long& o_cur, int lane)
 {
     using P = W2Plan<S>;
@@ -399,7 +459,7 @@ __device__ __forceinline__ void w2_arb(const Fused2Args& A, const float2* __rest
         const int rel = (int)((long long)(Pp >> 24) - kA);
         const unsigned idx = (unsigned)(Pp >> 16) & 0xffu;
         const float2* __restrict__ w = flat + rel + (W2_ARB_HIST - 13);
-        const float2* __restrict__ b = reinterpret_cast<const float2*>(sbank + idx * W2_BANK_STRIDE);
+        const float2* __restrict__ b = sbank + w2_bank_row((int)idx);
         float sr = 0.f, si = 0.f;
 #pragma unroll
         for (int i = 0; i < 7; i++) {
@@ -436,15 +496,19 @@ __global__ void __launch_bounds__(512, 1) fused_front2_kernel(const __grid_const
     using P = W2Plan<S>;
     extern __shared__ __align__(16) float2 sm2[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // shared tables: polyphase bank [256][18 floats], NCO table {sign*sin, cos}[1024]
-    float* sbank = reinterpret_cast<float*>(sm2);
-    float2* lut2 = sm2 + (256 * W2_BANK_STRIDE) / 2;
+    // shared tables: polyphase bank image (TMA bulk copy), NCO table {sign*sin, cos}[1024]
+    __shared__ __align__(8) uint64_t tma_bar;
+    float2* sbank = sm2;
+    float2* lut2 = sm2 + W2_BANK_F2;
     float2* wsm = lut2 + (A.pre.nco_enable ? 1024 : 0) + warp * P::warp_f2;
-    for (int i = tid; i < 256 * 14; i += blockDim.x) sbank[(i / 14) * W2_BANK_STRIDE + (i % 14)] = A.bank[i];
+    if (tid == 0) w2_mbar_init(&tma_bar, 1);
+    __syncthreads();
+    if (tid == 0) w2_tma_load(sbank, A.bank_image, W2_BANK_F2 * sizeof(float2), &tma_bar);
     if (A.pre.nco_enable)
         for (int i = tid; i < 1024; i += blockDim.x)
             lut2[i] = make_float2(A.pre.nco_table[i] * A.pre.nco_sign, A.pre.nco_table[(i + 256) & 1023]);
     for (int i = lane; i < P::warp_f2; i += 32) wsm[i] = make_float2(0.f, 0.f);
+    w2_mbar_wait(&tma_bar, 0);
     __syncthreads();
 
     const long long gw = (long long)blockIdx.x * warps_per_cta + warp;
@@ -461,9 +525,15 @@ __global__ void __launch_bounds__(512, 1) fused_front2_kernel(const __grid_const
         const unsigned long long k_emit = (unsigned long long)((t_emit * W2_T0) >> S);
         o_cur = (long long)(((k_emit << 24) + A.step - 1) / A.step);
     }
+    W2Raw nxt;
+#pragma unroll
+    for (int j = 0; j < 4; j++) nxt.q[j] = make_uint4(0u, 0u, 0u, 0u);
+    if (CS16) w2_prefetch(A, t_begin * W2_T0, lane, nxt);
     for (long long t = t_begin; t < t_end; t++) {
         const long long tick_start = t * W2_T0;
-        w2_p0<S, DC, CS16>(A, wsm, lut2, tick_start, lane);
+        const W2Raw cur = nxt;
+        if (CS16 && t + 1 < t_end) w2_prefetch(A, tick_start + W2_T0, lane, nxt);
+        w2_p0<S, DC, CS16>(A, wsm, lut2, tick_start, lane, cur);
         __syncwarp();
         bool arb_due = true;
         if constexpr (S > 0) W2Cascade<S, 0>::run(A, wsm, t, lane, arb_due);

@@ -6,10 +6,15 @@
 // (filter history) live at negative offsets in the same allocation (see chain.cu DevStream).
 #include "kernels.hpp"
 
+#include <cooperative_groups.h>
+
+#include <algorithm>
 #include <cstdio>
 
 #include "../../include/iqgpu.h"
 #include "device_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace iqgpu {
 
@@ -720,20 +725,24 @@ __global__ void __launch_bounds__(AGC_SCAN_THREADS) agc_digital_scan_kernel(cons
     if (threadIdx.x == 0) *st = s_state;
 }
 
-// liquid agc_crcf_execute_block (agc.c:92-100): nonlinear per-sample recurrence; serial.
-__global__ void agc_rms_kernel(const float2* __restrict__ x, size_t n, PostParams p, AgcState* __restrict__ st,
-                               float2* __restrict__ y)
+// liquid agc_crcf_execute_block (agc.c:92-100): a nonlinear per-sample recurrence in (g, y2').
+//
+// Time-parallel evaluation that is bit-identical to the serial loop.  The stream is cut into
+// blocks of B samples, one thread per block.  Every thread runs the serial recurrence over its
+// block from a guessed start state and publishes its end state; then every block takes its
+// predecessor's end state as its new start state, and only blocks whose start state changed run
+// again.  Block 0 always starts from the carried (exact) state, so a sweep in which NO start
+// state changes is a fixed point in which, by induction over the blocks, every block ran from
+// the exact state: the outputs equal those of the sequential loop bit for bit.  Because the AGC
+// loop forgets its state with time constant 1/alpha samples, the fixed point is reached after
+// about 1 + 17/(alpha B) sweeps instead of one sweep per block.
+__device__ __forceinline__ void agc_rms_block(const float2* __restrict__ x, size_t i0, size_t i1, const PostParams& p,
+                                              const float* __restrict__ lut, float& g, float& y2p, float2* __restrict__ y)
 {
-    __shared__ float lut[1024];
-    if (p.nco_enable) {
-        for (int i = threadIdx.x; i < 1024; i += blockDim.x) lut[i] = p.nco_table[i];
-    }
-    __syncthreads();
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    float g = st->rms_g, y2p = st->rms_y2;
     const float alpha = p.agc_alpha;
     const double oma = 1.0 - (double)alpha;
-    for (size_t i = 0; i < n; i++) {
+    const float mha = __fmul_rn(-0.5f, alpha);
+    for (size_t i = i0; i < i1; i++) {
         float2 v = x[i];
         if (p.nco_enable) v = nco_mix(v, p.nco_theta0 + (uint32_t)i * p.nco_dtheta, p.nco_sign, lut);
         const float yr = __fmul_rn(v.x, g), yi = __fmul_rn(v.y, g);
@@ -742,13 +751,49 @@ __global__ void agc_rms_kernel(const float2* __restrict__ x, size_t n, PostParam
         if (y2p > 1e-6f) {
             // logf/expf evaluated in double and rounded once: matches a correctly rounded libm
             const float lf = (float)log((double)y2p);
-            const float ex = (float)exp((double)__fmul_rn(__fmul_rn(-0.5f, alpha), lf));
+            const float ex = (float)exp((double)__fmul_rn(mha, lf));
             g = __fmul_rn(g, ex);
         }
         if (g > 1e6f) g = 1e6f;
         y[i] = make_float2(yr, yi);
     }
-    st->rms_g = g; st->rms_y2 = y2p;
+}
+
+constexpr int AGC_RMS_THREADS = 128;
+__global__ void __launch_bounds__(AGC_RMS_THREADS) agc_rms_parallel_kernel(const float2* __restrict__ x, size_t n, PostParams p,
+                                                                            AgcState* __restrict__ st, float2* __restrict__ y,
+                                                                            size_t B, unsigned nblocks, float2* __restrict__ fin,
+                                                                            unsigned* __restrict__ flags)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ float lut[1024];
+    if (p.nco_enable)
+        for (int i = threadIdx.x; i < 1024; i += blockDim.x) lut[i] = p.nco_table[i];
+    __syncthreads();
+    const unsigned b = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = b < nblocks;
+    const size_t i0 = (size_t)b * B, i1 = (i0 + B < n) ? i0 + B : n;
+    const float2 carried = make_float2(st->rms_g, st->rms_y2);
+    float2 start = carried;            // block 0: exact; others: first guess
+    bool run = true;
+    for (unsigned it = 0; it <= nblocks; it++) {
+        if (active && run) {
+            float g = start.x, y2p = start.y;
+            agc_rms_block(x, i0, i1, p, lut, g, y2p, y);
+            fin[b] = make_float2(g, y2p);
+        }
+        grid.sync();
+        run = false;
+        if (active && b > 0) {
+            const float2 ns = fin[b - 1];
+            run = (__float_as_uint(ns.x) != __float_as_uint(start.x)) || (__float_as_uint(ns.y) != __float_as_uint(start.y));
+            start = ns;
+        }
+        if (run) flags[it] = 1u;
+        grid.sync();
+        if (flags[it] == 0u) break;    // no start state changed anywhere: fixed point
+    }
+    if (b == nblocks - 1) { const float2 f = fin[b]; st->rms_g = f.x; st->rms_y2 = f.y; }
 }
 
 // cf32 -> output sample formats, reference sample_convert.c:40-73, 213-306
@@ -905,12 +950,49 @@ cudaError_t launch_agc_digital_scan(const uint32_t* seg_start, size_t nseg, cons
     agc_digital_scan_kernel<<<1, AGC_SCAN_THREADS, 0, st>>>(seg_start, (unsigned)nseg, seg_peak, p, state, seg_gain);
     return cudaGetLastError();
 }
-cudaError_t launch_agc_rms(const float2* x, size_t n, const PostParams& p, AgcState* state, float2* y,
+// co-resident thread budget of the cooperative RMS-AGC kernel on the current device
+static unsigned agc_rms_max_threads()
+{
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && cached[dev]) return (unsigned)cached[dev];
+    int per_sm = 0, sms = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, agc_rms_parallel_kernel, AGC_RMS_THREADS, 0);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int t = std::max(1, per_sm) * std::max(1, sms) * AGC_RMS_THREADS;
+    if (dev >= 0 && dev < 64) cached[dev] = t;
+    return (unsigned)t;
+}
+static void agc_rms_plan(size_t n, float alpha, size_t& B, unsigned& nblocks)
+{
+    const unsigned tmax = agc_rms_max_threads();
+    B = (n + tmax - 1) / tmax;
+    // blocks shorter than ~2 time constants only add sweeps
+    const size_t floorB = (size_t)std::min(65536.0, std::max(256.0, 2.0 / std::max((double)alpha, 1e-6)));
+    if (B < floorB) B = floorB;
+    nblocks = (unsigned)((n + B - 1) / B);
+}
+size_t agc_rms_workspace_bytes(size_t n, float alpha)
+{
+    size_t B; unsigned nb;
+    agc_rms_plan(n, alpha, B, nb);
+    return (size_t)nb * sizeof(float2) + ((size_t)nb + 2) * sizeof(unsigned);
+}
+cudaError_t launch_agc_rms(const float2* x, size_t n, const PostParams& p, AgcState* state, float2* y, void* ws,
                            cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
-    agc_rms_kernel<<<1, 256, 0, st>>>(x, n, p, state, y);
-    return cudaGetLastError();
+    size_t B; unsigned nb;
+    agc_rms_plan(n, p.agc_alpha, B, nb);
+    float2* fin = reinterpret_cast<float2*>(ws);
+    unsigned* flags = reinterpret_cast<unsigned*>(fin + nb);
+    cudaError_t e = cudaMemsetAsync(flags, 0, ((size_t)nb + 2) * sizeof(unsigned), st);
+    if (e != cudaSuccess) return e;
+    PostParams pp = p;
+    void* args[] = {(void*)&x, (void*)&n, (void*)&pp, (void*)&state, (void*)&y, (void*)&B, (void*)&nb, (void*)&fin, (void*)&flags};
+    const unsigned grid = (nb + AGC_RMS_THREADS - 1) / AGC_RMS_THREADS;
+    return cudaLaunchCooperativeKernel((void*)agc_rms_parallel_kernel, dim3(grid), dim3(AGC_RMS_THREADS), args, 0, st);
 }
 cudaError_t launch_post(const float2* x, size_t n, const PostParams& p, const uint32_t* seg_start, size_t nseg,
                         const float* seg_gain, int nco_done, float2* tap, void* out, cudaStream_t st)

@@ -98,8 +98,10 @@ cudaError_t launch_agc_peaks(const float2* x, size_t n, const PostParams& p, con
                              size_t nseg, float* seg_peak, cudaStream_t st);
 cudaError_t launch_agc_digital_scan(const uint32_t* seg_start, size_t nseg, const float* seg_peak,
                                     const PostParams& p, AgcState* state, float* seg_gain, cudaStream_t st);
-// rms AGC: sequential recurrence, in place on x (after NCO if enabled -> writes mixed+scaled cf32 to y)
-cudaError_t launch_agc_rms(const float2* x, size_t n, const PostParams& p, AgcState* state, float2* y,
+// rms AGC (liquid agc_crcf): the sequential recurrence evaluated time-parallel to its exact fixed point
+// (after NCO if enabled -> writes mixed+scaled cf32 to y); ws: agc_rms_workspace_bytes(n, alpha) device bytes
+size_t agc_rms_workspace_bytes(size_t n, float alpha);
+cudaError_t launch_agc_rms(const float2* x, size_t n, const PostParams& p, AgcState* state, float2* y, void* ws,
                            cudaStream_t st);
 // y_cf32 (optional tap) and converted out
 cudaError_t launch_post(const float2* x, size_t n, const PostParams& p, const uint32_t* seg_start,
