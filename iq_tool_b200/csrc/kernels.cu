@@ -638,9 +638,15 @@ struct AgcStep {   // sequential reference step, shared by both paths
         return g;
     }
 };
-// The chunk table (frame counts + peaks) is staged through shared memory in tiles by the whole
-// CTA (coalesced), so the serial warp never waits on a dependent global load.
-constexpr int AGC_SCAN_TILE = 3072;
+// Per tile of AGC_SCAN_TILE chunks: (1) the whole CTA stages the chunk table in shared memory and
+// evaluates everything that is not state dependent in parallel — the running sample counter (block
+// prefix sum) and each chunk's sample-clock time seen/rate (one double division per chunk, off the
+// serial path); (2) one warp walks the tile 32 chunks at a time.  While nothing data dependent
+// happens inside a group all 32 gains come out in one step: scanning (unlocked) groups are a
+// prefix maximum of the peaks, locked groups without a ratchet or creep keep their gain.  A group
+// that contains a lock transition, a ratchet or a creep is replayed chunk by chunk with the
+// reference's sequential step (AgcStep::run), so the results are those of the sequential loop.
+constexpr int AGC_SCAN_TILE = 2048;
 constexpr int AGC_SCAN_THREADS = 512;
 __global__ void __launch_bounds__(AGC_SCAN_THREADS) agc_digital_scan_kernel(const uint32_t* __restrict__ seg_start, unsigned nseg,
                                                                             const float* __restrict__ seg_peak, PostParams p,
@@ -649,65 +655,103 @@ __global__ void __launch_bounds__(AGC_SCAN_THREADS) agc_digital_scan_kernel(cons
     __shared__ unsigned s_cnt[AGC_SCAN_TILE];
     __shared__ float s_pk[AGC_SCAN_TILE];
     __shared__ float s_gain[AGC_SCAN_TILE];
+    __shared__ double s_now[AGC_SCAN_TILE];         // seen_before / rate of every chunk
+    __shared__ unsigned long long s_warp_tot[AGC_SCAN_THREADS / 32];
     __shared__ AgcState s_state;
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_state = *st;
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_state = *st;
+    __syncthreads();
     const float target = p.agc_target;
     const float strong_thr = __fmul_rn(target, 0.75f);
+    constexpr int PER_THREAD = AGC_SCAN_TILE / AGC_SCAN_THREADS;
     for (unsigned tile0 = 0; tile0 < nseg; tile0 += AGC_SCAN_TILE) {
         const unsigned tn = min((unsigned)AGC_SCAN_TILE, nseg - tile0);
-        for (unsigned i = threadIdx.x; i < tn; i += AGC_SCAN_THREADS) {
-            s_cnt[i] = __ldg(seg_start + tile0 + i + 1) - __ldg(seg_start + tile0 + i);
-            s_pk[i] = __ldg(seg_peak + tile0 + i);
+        // ---- (1) parallel part: table, exclusive prefix of the sample counter, chunk times ----
+        unsigned cnt[PER_THREAD];
+        unsigned long long run = 0;
+#pragma unroll
+        for (int k = 0; k < PER_THREAD; k++) {
+            const unsigned i = tid * PER_THREAD + k;
+            cnt[k] = (i < tn) ? (__ldg(seg_start + tile0 + i + 1) - __ldg(seg_start + tile0 + i)) : 0u;
+            if (i < tn) { s_cnt[i] = cnt[k]; s_pk[i] = __ldg(seg_peak + tile0 + i); }
+            run += cnt[k];
+        }
+        unsigned long long inc = run;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long q = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= (unsigned)d) inc += q;
+        }
+        if (lane == 31) s_warp_tot[warp] = inc;
+        __syncthreads();
+        unsigned long long base = s_state.seen;
+        for (unsigned w = 0; w < warp; w++) base += s_warp_tot[w];
+        unsigned long long seen_before = base + inc - run;
+#pragma unroll
+        for (int k = 0; k < PER_THREAD; k++) {
+            const unsigned i = tid * PER_THREAD + k;
+            if (i < tn) s_now[i] = (double)seen_before / p.target_rate;
+            seen_before += cnt[k];
         }
         __syncthreads();
+        // ---- (2) serial part: one warp, 32 chunks per step ----
         if (warp == 0) {
             AgcState s = s_state;
-            for (unsigned base = 0; base < tn; base += 32) {
-                const unsigned c = base + lane;
+            for (unsigned gbase = 0; gbase < tn; gbase += 32) {
+                const unsigned c = gbase + lane;
                 const bool valid = c < tn;
-                const unsigned cnt = valid ? s_cnt[c] : 0u;
+                const unsigned cn = valid ? s_cnt[c] : 0u;
                 const float pk = valid ? s_pk[c] : 0.f;
-                const bool act = cnt != 0;                               // agc_apply returns on num_samples == 0
-                // exclusive prefix of the sample counter
-                unsigned long long pre = cnt;
+                const double now = valid ? s_now[c] : 0.0;
+                const bool act = cn != 0;                                // agc_apply returns on num_samples == 0
+                unsigned gsum = cn;
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const unsigned long long q = __shfl_up_sync(0xffffffffu, pre, d);
-                    if (lane >= (unsigned)d) pre += q;
-                }
-                const unsigned long long total = __shfl_sync(0xffffffffu, pre, 31);
-                const unsigned long long seen_before = s.seen + pre - cnt;
+                for (int d = 16; d > 0; d >>= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, d);
                 bool fast = false;
                 float g = 1.0f;
-                if (s.locked) {
+                if (!s.locked) {
+                    // scanning mode (agc.c:117-160): gain from the running peak maximum; the lock test uses the
+                    // sample count BEFORE the chunk.  Fast when no chunk of the group reaches the lock time.
+                    const bool locks = act && (now > (double)2.0f);
+                    if (!__any_sync(0xffffffffu, locks)) {
+                        float mx = act ? pk : 0.f;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const float q = __shfl_up_sync(0xffffffffu, mx, d);
+                            if (lane >= (unsigned)d) mx = fmaxf(mx, q);
+                        }
+                        const float mem = fmaxf(s.peak_mem, mx);
+                        const float safe = (mem < 1e-4f) ? 1e-4f : mem;
+                        g = __fdiv_rn(target, safe);
+                        s.peak_mem = __shfl_sync(0xffffffffu, mem, 31);
+                        s.seen += gsum;
+                        fast = true;
+                    }
+                } else {
                     const float opk = __fmul_rn(pk, s.gain);
-                    const double now = (double)seen_before / p.target_rate;
                     const bool ratchet = act && opk > 1.0f;
                     const bool strong = act && opk > strong_thr;
-                    // time of the latest strong chunk strictly before this lane (now is non-decreasing)
-                    double ls = strong ? now : -1.0;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const double q = __shfl_up_sync(0xffffffffu, ls, d);
-                        if (lane >= (unsigned)d) ls = fmax(ls, q);
-                    }
-                    const double ls_incl = ls;
-                    double ls_excl = __shfl_up_sync(0xffffffffu, ls, 1);
-                    if (lane == 0) ls_excl = -1.0;
-                    ls_excl = fmax(ls_excl, s.last_strong);
+                    // time of the latest strong chunk strictly before this lane (chunk times are non-decreasing)
+                    const unsigned smask = __ballot_sync(0xffffffffu, strong);
+                    const unsigned below = smask & ((1u << lane) - 1u);
+                    const int prev = below ? (31 - __clz(below)) : 0;
+                    const double prev_now = __shfl_sync(0xffffffffu, now, prev);
+                    const double ls_excl = below ? fmax(prev_now, s.last_strong) : s.last_strong;
                     const bool creep = act && !strong && (now - ls_excl > (double)4.0f);
                     if (!__any_sync(0xffffffffu, ratchet || creep)) {
                         fast = true;
                         g = s.gain;
-                        s.last_strong = fmax(s.last_strong, __shfl_sync(0xffffffffu, ls_incl, 31));
-                        s.seen += total;
+                        if (smask) {
+                            const double top = __shfl_sync(0xffffffffu, now, 31 - __clz(smask));
+                            s.last_strong = fmax(s.last_strong, top);
+                        }
+                        s.seen += gsum;
                     }
                 }
                 if (!fast) {
                     // replay: warp-uniform sequential walk over the group's chunks
-                    for (unsigned k = 0; k < 32 && base + k < tn; k++) {
-                        const unsigned ck = __shfl_sync(0xffffffffu, cnt, k);
+                    for (unsigned k = 0; k < 32 && gbase + k < tn; k++) {
+                        const unsigned ck = __shfl_sync(0xffffffffu, cn, k);
                         const float pkk = __shfl_sync(0xffffffffu, pk, k);
                         if (ck == 0) continue;
                         const float gk = AgcStep::run(s, pkk, ck, target, p.target_rate);
@@ -719,10 +763,10 @@ __global__ void __launch_bounds__(AGC_SCAN_THREADS) agc_digital_scan_kernel(cons
             if (lane == 0) s_state = s;
         }
         __syncthreads();
-        for (unsigned i = threadIdx.x; i < tn; i += AGC_SCAN_THREADS) seg_gain[tile0 + i] = s_gain[i];
+        for (unsigned i = tid; i < tn; i += AGC_SCAN_THREADS) seg_gain[tile0 + i] = s_gain[i];
         __syncthreads();
     }
-    if (threadIdx.x == 0) *st = s_state;
+    if (tid == 0) *st = s_state;
 }
 
 // liquid agc_crcf_execute_block (agc.c:92-100): a nonlinear per-sample recurrence in (g, y2').

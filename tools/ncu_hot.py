@@ -50,3 +50,36 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def by_source_line(rep, top=40):
+    """Instruction / stall-sample share per CUDA source line (needs -lineinfo + --import-source on)."""
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"],
+                         capture_output=True, text=True).stdout
+    cur_file, hdr, rows = None, None, []
+    for l in out.splitlines():
+        if l.startswith('"File Path"'):
+            cur_file = next(csv.reader([l]))[1]
+            hdr = None
+            continue
+        if l.startswith('"Line No"'):
+            hdr = next(csv.reader([l]))
+            continue
+        if hdr and l.startswith('"') and not l.startswith('"Function Name"'):
+            r = next(csv.reader([l]))
+            if len(r) == len(hdr) and r[0]:          # source-line rows carry the line number; SASS rows have it empty
+                d = {"file": cur_file, "line": r[0], "src": r[1]}
+                for k, v in zip(hdr[2:], r[2:]):
+                    d[k] = v
+                rows.append(d)
+    f = lambda d, k: float((d.get(k) or "0").replace(",", "") or 0)
+    tot = sum(f(d, "Instructions Executed") for d in rows) or 1
+    ts = sum(f(d, "# Samples") for d in rows) or 1
+    print(f"\nper source line (total warp instructions {tot:.0f}, samples {ts:.0f})")
+    for d in sorted(rows, key=lambda d: -f(d, "Instructions Executed"))[:top]:
+        print(f'{d["file"].split("/")[-1][:20]:20s} L{d["line"]:>4} inst {100 * f(d, "Instructions Executed") / tot:5.2f}% '
+              f'samp {100 * f(d, "# Samples") / ts:5.2f}%  {d["src"].strip()[:88]}')
+
+
+if __name__ == "__main__" and len(sys.argv) > 3 and sys.argv[3] == "lines":
+    by_source_line(sys.argv[1], int(sys.argv[2]))
