@@ -155,6 +155,13 @@ struct iqgpu_chain {
 
     // ---- device state ----
     cudaStream_t stream = nullptr, h2d = nullptr, d2h = nullptr;
+    // second compute stream: the DC pre-pass of sub-train k+1 (HBM bound) runs underneath the fused front
+    // kernel of sub-train k (issue bound); ordered with events
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_pre[2] = {nullptr, nullptr}, ev_front[2] = {nullptr, nullptr}, ev_call = nullptr;
+    bool front_recorded[2] = {false, false};
+    int dc_slot = 0;                    // table slot of the sub-train run_subtrain is about to launch
+    bool dc_prepared = false;           // ... and whether its pre-pass was issued on `aux`
     cudaStream_t last_stream = nullptr;   // stream of the most recent process call
     float* d_lut = nullptr;
     double2* d_dc_carry = nullptr;
@@ -250,6 +257,8 @@ struct iqgpu_chain {
     int run_subtrain(const void* d_rawp, size_t n, const uint32_t* chunks, size_t n_chunks, void* d_outp,
                      size_t* out_frames, uint32_t* per_chunk, cudaStream_t st, int phase = 0);
     int run_back(void* d_outp, size_t skip_chunks, size_t* out_frames, cudaStream_t st);
+    PreParams pre_params(uint64_t N0) const;
+    int prepare_dc(int slot, const void* d_rawp, uint64_t N0, size_t n, cudaStream_t st);
     // pending back half (between process_device_begin and process_device_finish)
     struct Pending {
         bool active = false;
@@ -282,6 +291,12 @@ iqgpu_chain::~iqgpu_chain()
         if (ev_done[i]) cudaEventDestroy(ev_done[i]);
         if (ev_d2h[i]) cudaEventDestroy(ev_d2h[i]);
     }
+    for (int i = 0; i < 2; i++) {
+        if (ev_pre[i]) cudaEventDestroy(ev_pre[i]);
+        if (ev_front[i]) cudaEventDestroy(ev_front[i]);
+    }
+    if (ev_call) cudaEventDestroy(ev_call);
+    if (aux) { cudaStreamSynchronize(aux); cudaStreamDestroy(aux); }
     if (stream) cudaStreamDestroy(stream);
     if (h2d) cudaStreamDestroy(h2d);
     if (d2h) cudaStreamDestroy(d2h);
@@ -337,6 +352,12 @@ int iqgpu_chain::init_device()
     CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h2d, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ev_call, cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) {
+        CK(cudaEventCreateWithFlags(&ev_pre[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_front[i], cudaEventDisableTiming));
+    }
     for (int i = 0; i < 2; i++) {
         CK(cudaEventCreateWithFlags(&ev_h2d[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
@@ -484,6 +505,8 @@ int iqgpu_chain::reset_state()
     if (plan_only || !buffers_ready) return IQGPU_OK;
     CK(cudaSetDevice(device));
     if (last_stream && last_stream != stream) CK(cudaStreamSynchronize(last_stream));   // queued work still reads the state
+    if (aux) CK(cudaStreamSynchronize(aux));
+    dc_prepared = false;
     CK(cudaMemsetAsync(d_dc_carry, 0, sizeof(double2), stream));
     AgcState a{};
     a.locked = 0; a.gain = 1.0f; a.seen = 0; a.last_strong = 0.0;
@@ -498,6 +521,30 @@ int iqgpu_chain::reset_state()
     CK(s_rs.reset(stream));
     if (s_f.base) CK(s_f.reset(stream));
     CK(cudaStreamSynchronize(stream));
+    return IQGPU_OK;
+}
+
+PreParams iqgpu_chain::pre_params(uint64_t N0) const
+{
+    PreParams pp{};
+    pp.format = cfg.input_format; pp.gain = cfg.gain;
+    pp.dc_enable = dc.enable; pp.dc_c = dc.c; pp.dc_a = dc.one_minus_c;
+    pp.iq_enable = cfg.iq_correction_enable; pp.iq_magp1 = 1.0f + iq_mag; pp.iq_phase = iq_phase;
+    pp.nco_enable = nco_pre; pp.nco_dtheta = nco_dtheta; pp.nco_sign = nco_sign; pp.nco_table = d_lut;
+    pp.nco_theta0 = (uint32_t)((uint64_t)(uint32_t)N0 * nco_dtheta);
+    return pp;
+}
+
+// DC pre-pass of the sub-train that starts at absolute frame N0, on the second stream, into table `slot`.
+// `st` is the stream the front kernels run on: the slot's previous reader must have finished first.
+int iqgpu_chain::prepare_dc(int slot, const void* d_rawp, uint64_t N0, size_t n, cudaStream_t st)
+{
+    (void)st;
+    if (front_recorded[slot]) CK(cudaStreamWaitEvent(aux, ev_front[slot], 0));
+    const PreParams pp = pre_params(N0);
+    uint32_t l = 0;
+    CK(fused_prepare_dc(fused, slot, d_rawp, (int64_t)N0, n, pp, d_dc_carry, &l, aux));
+    CK(cudaEventRecord(ev_pre[slot], aux));
     return IQGPU_OK;
 }
 
@@ -522,12 +569,7 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
     launches = 0;
 
     // ---------------- K1: pre-processor ----------------
-    PreParams pp{};
-    pp.format = cfg.input_format; pp.gain = cfg.gain;
-    pp.dc_enable = dc.enable; pp.dc_c = dc.c; pp.dc_a = dc.one_minus_c;
-    pp.iq_enable = cfg.iq_correction_enable; pp.iq_magp1 = 1.0f + iq_mag; pp.iq_phase = iq_phase;
-    pp.nco_enable = nco_pre; pp.nco_dtheta = nco_dtheta; pp.nco_sign = nco_sign; pp.nco_table = d_lut;
-    pp.nco_theta0 = (uint32_t)((uint64_t)(uint32_t)N0 * nco_dtheta);
+    const PreParams pp = pre_params(N0);
     const bool use_fused = fused_active;
     const float2* post_src = nullptr;
     size_t post_n = 0;
@@ -536,9 +578,12 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
         const uint64_t O0 = resampler_outputs_after(rs, N0), O1 = resampler_outputs_after(rs, N1);
         float2* y_rs = nullptr;
         CK(s_rs.begin((size_t)(O1 - O0), st, &y_rs));
+        if (dc_prepared) CK(cudaStreamWaitEvent(st, ev_pre[dc_slot], 0));   // the slot's table was built on `aux`
         span_begin(IQGPU_KCLASS_FUSED_FRONT, st);
-        CK(fused_launch(fused, d_rawp, (int64_t)N0, n, pp, d_dc_carry, (int64_t)O0, (size_t)(O1 - O0), y_rs, &launches, st));
+        CK(fused_launch(fused, d_rawp, (int64_t)N0, n, pp, d_dc_carry, (int64_t)O0, (size_t)(O1 - O0), y_rs, &launches, dc_slot, st));
         span_end(st);
+        if (dc.enable) { CK(cudaEventRecord(ev_front[dc_slot], st)); front_recorded[dc_slot] = true; }
+        dc_prepared = false;
         s_rs.commit((size_t)(O1 - O0));
         post_src = y_rs; post_n = (size_t)(O1 - O0);
         fused_used = true;
@@ -1015,19 +1060,51 @@ int iqgpu_chain_process_device(iqgpu_chain* c, const void* dev_raw_in, size_t n_
     if (c->count_outputs(chunks.data(), chunks.size(), nullptr) * c->out_bps > out_capacity_bytes)
         return fail(IQGPU_ECAPACITY, "output buffer too small");
     for (auto& t : c->tap) t.len = 0;
-    size_t ci = 0, in_off = 0, out_off = 0, total = 0;
+    // cut the train into sub-trains up front so that the DC pre-pass can run one sub-train ahead
+    struct Sub { size_t c0, c1, in_off, n; };
+    std::vector<Sub> subs;
+    {
+        size_t ci = 0, in_off = 0;
+        while (ci < chunks.size()) {
+            size_t cj = ci, n = 0;
+            while (cj < chunks.size() && n + chunks[cj] <= c->subtrain_frames) { n += chunks[cj]; cj++; }
+            subs.push_back({ci, cj, in_off, n});
+            in_off += n;
+            ci = cj;
+        }
+    }
+    const bool overlap_dc = c->fused_active && c->dc.enable;
+    const uint64_t base_in = c->n_in;
+    auto raw_at = [&](const Sub& sb) { return (const void*)((const char*)dev_raw_in + sb.in_off * c->in_bps); };
+    int slot = 0;
+    if (overlap_dc) {
+        // the second stream starts after everything already queued on the caller's stream
+        CK(cudaEventRecord(c->ev_call, st));
+        CK(cudaStreamWaitEvent(c->aux, c->ev_call, 0));
+        rc = c->prepare_dc(slot, raw_at(subs[0]), base_in + subs[0].in_off, subs[0].n, st);
+        if (rc) return rc;
+    }
+    size_t out_off = 0, total = 0;
     uint32_t launches = 0;
-    while (ci < chunks.size()) {
-        size_t cj = ci, n = 0;
-        while (cj < chunks.size() && n + chunks[cj] <= c->subtrain_frames) { n += chunks[cj]; cj++; }
+    for (size_t k = 0; k < subs.size(); k++) {
+        const Sub& sb = subs[k];
+        if (overlap_dc) {
+            if (k + 1 < subs.size()) {
+                rc = c->prepare_dc(slot ^ 1, raw_at(subs[k + 1]), base_in + subs[k + 1].in_off, subs[k + 1].n, st);
+                if (rc) return rc;
+                launches += 2;
+            }
+            c->dc_slot = slot; c->dc_prepared = true;
+        } else { c->dc_slot = 0; c->dc_prepared = false; }
         size_t produced = 0;
-        rc = c->run_subtrain((const char*)dev_raw_in + in_off * c->in_bps, n, chunks.data() + ci, cj - ci,
-                             (char*)dev_out + out_off, &produced, per_chunk_out ? per_chunk_out + ci : nullptr, st);
+        rc = c->run_subtrain(raw_at(sb), sb.n, chunks.data() + sb.c0, sb.c1 - sb.c0,
+                             (char*)dev_out + out_off, &produced, per_chunk_out ? per_chunk_out + sb.c0 : nullptr, st);
         if (rc) return rc;
         launches += c->launches;
-        in_off += n; out_off += produced * c->out_bps; total += produced;
-        ci = cj;
+        out_off += produced * c->out_bps; total += produced;
+        slot ^= 1;
     }
+    if (overlap_dc) launches += 2;   // the first sub-train's pre-pass
     c->launches = launches;
     *out_frames = total;
     return IQGPU_OK;
@@ -1053,6 +1130,7 @@ int iqgpu_chain_process_device_begin(iqgpu_chain* c, const void* dev_raw_in, siz
     c->last_stream = st;
     for (auto& t : c->tap) t.len = 0;
     size_t produced = 0;
+    c->dc_slot = 0; c->dc_prepared = false;
     rc = c->run_subtrain(dev_raw_in, n_frames, chunks.data(), chunks.size(), nullptr, &produced, nullptr, st, 1);
     if (rc) { c->pend.active = false; return rc; }
     return IQGPU_OK;
@@ -1205,6 +1283,7 @@ int iqgpu_chain_process(iqgpu_chain* c, const void* raw_in, size_t n_frames, con
         CK(cudaEventRecord(c->ev_h2d[slot], c->h2d));
         CK(cudaStreamWaitEvent(c->stream, c->ev_h2d[slot], 0));
         size_t produced = 0;
+        c->dc_slot = 0; c->dc_prepared = false;      // host path is PCIe bound: DC pre-pass inline on the compute stream
         rc = c->run_subtrain(c->d_raw[slot], n, chunks.data() + ci, cj - ci, c->d_out[slot], &produced,
                              per_chunk_out ? per_chunk_out + ci : nullptr, c->stream);
         if (rc) return rc;

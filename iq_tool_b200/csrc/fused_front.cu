@@ -345,10 +345,13 @@ struct FusedFront {
     const float* d_bank = nullptr;
     float2* d_tail[2] = {nullptr, nullptr};
     int tail_cur = 0;
-    double2* d_dc_table = nullptr;
-    double2* d_dc_sums = nullptr;
-    double* d_dc_ws = nullptr;
-    size_t dc_cap = 0;
+    // DC pre-pass products, double buffered so that the (HBM-bound) pre-pass of the next sub-train can
+    // run on a second stream underneath the (issue-bound) front kernel of the current one
+    double2* d_dc_table[2] = {nullptr, nullptr};
+    double2* d_dc_sums[2] = {nullptr, nullptr};
+    double* d_dc_ws[2] = {nullptr, nullptr};
+    size_t dc_cap[2] = {0, 0};
+    bool dc_ready[2] = {false, false};  // slot holds the table of the sub-train about to be launched
     int num_sms = 148;
     int ctas_per_sm = 3;
     int format = 0;
@@ -503,13 +506,15 @@ void fused_destroy(FusedFront* f)
 {
     if (!f) return;
     cudaFree(f->d_taps); cudaFree(f->d_tail[0]); cudaFree(f->d_tail[1]);
-    cudaFree(f->d_dc_table); cudaFree(f->d_dc_sums); cudaFree(f->d_dc_ws); cudaFree(f->d_bank_image);
+    for (int i = 0; i < 2; i++) { cudaFree(f->d_dc_table[i]); cudaFree(f->d_dc_sums[i]); cudaFree(f->d_dc_ws[i]); }
+    cudaFree(f->d_bank_image);
     delete f;
 }
 
 cudaError_t fused_reset(FusedFront* f, cudaStream_t st)
 {
     f->tail_cur = 0;
+    f->dc_ready[0] = f->dc_ready[1] = false;
     cudaError_t e = cudaMemsetAsync(f->d_tail[0], 0, (size_t)f->H_tail * sizeof(float2), st);
     if (e != cudaSuccess) return e;
     return cudaMemsetAsync(f->d_tail[1], 0, (size_t)f->H_tail * sizeof(float2), st);
@@ -522,7 +527,7 @@ uint32_t fused_halo_frames(const FusedFront* f)
 int fused_version(const FusedFront* f) { return f->v2 ? 2 : 1; }
 
 // DC pre-pass on the virtual range [A0, N1): frames below n0 read as zero, the carry is rewound to A0
-static cudaError_t fused_dc_prepass(FusedFront* f, const void* raw, long long n0, long long N1, const PreParams& pre,
+static cudaError_t fused_dc_prepass(FusedFront* f, int slot, const void* raw, long long n0, long long N1, const PreParams& pre,
                                     double2* d_carry, long long A0, cudaStream_t st);
 
 template <int FMT>
@@ -549,30 +554,45 @@ __global__ void dc_rewind_kernel(double2* carry, double c, long long k)
     *carry = make_double2(carry->x * f, carry->y * f);
 }
 
-static cudaError_t fused_dc_prepass(FusedFront* f, const void* raw, long long n0, long long N1, const PreParams& pre,
+static cudaError_t fused_dc_prepass(FusedFront* f, int slot, const void* raw, long long n0, long long N1, const PreParams& pre,
                                     double2* d_carry, long long A0, cudaStream_t st)
 {
     const size_t nv = (size_t)(N1 - A0);
     const size_t n_runs = (nv + 255) / 256;
-    if (n_runs + 2 > f->dc_cap) {
-        cudaStreamSynchronize(st);
-        cudaFree(f->d_dc_table); cudaFree(f->d_dc_sums); cudaFree(f->d_dc_ws);
-        f->d_dc_table = nullptr; f->d_dc_sums = nullptr; f->d_dc_ws = nullptr;
-        f->dc_cap = n_runs * 2 + 16;
-        cudaError_t e = cudaMalloc(&f->d_dc_table, f->dc_cap * sizeof(double2));
+    if (n_runs + 2 > f->dc_cap[slot]) {
+        cudaDeviceSynchronize();        // rare (first use / larger sub-train): nothing may still read the old buffers
+        cudaFree(f->d_dc_table[slot]); cudaFree(f->d_dc_sums[slot]); cudaFree(f->d_dc_ws[slot]);
+        f->d_dc_table[slot] = nullptr; f->d_dc_sums[slot] = nullptr; f->d_dc_ws[slot] = nullptr;
+        f->dc_cap[slot] = n_runs * 2 + 16;
+        cudaError_t e = cudaMalloc(&f->d_dc_table[slot], f->dc_cap[slot] * sizeof(double2));
         if (e != cudaSuccess) return e;
-        e = cudaMalloc(&f->d_dc_sums, f->dc_cap * sizeof(double2));
+        e = cudaMalloc(&f->d_dc_sums[slot], f->dc_cap[slot] * sizeof(double2));
         if (e != cudaSuccess) return e;
-        e = cudaMalloc(&f->d_dc_ws, dc_scan_workspace_doubles(f->dc_cap) * sizeof(double));
+        e = cudaMalloc(&f->d_dc_ws[slot], dc_scan_workspace_doubles(f->dc_cap[slot]) * sizeof(double));
         if (e != cudaSuccess) return e;
     }
     const size_t bps = (pre.format == IQGPU_FMT_CS8 || pre.format == IQGPU_FMT_CU8) ? 2 : (pre.format == IQGPU_FMT_CF32 ? 8 : 4);
     const long long back = n0 - A0;
     const char* vraw = reinterpret_cast<const char*>(raw) - back * (long long)bps;
     if (back) dc_rewind_kernel<<<1, 1, 0, st>>>(d_carry, (double)pre.dc_c, back);
-    cudaError_t e = launch_dc_run_sums_masked(vraw, nv, (size_t)back, pre, 256, f->d_dc_sums, st);
+    cudaError_t e = launch_dc_run_sums_masked(vraw, nv, (size_t)back, pre, 256, f->d_dc_sums[slot], st);
     if (e != cudaSuccess) return e;
-    return launch_dc_scan(f->d_dc_sums, n_runs, 256, nv, pre.dc_c, d_carry, f->d_dc_table, f->d_dc_ws, st);
+    return launch_dc_scan(f->d_dc_sums[slot], n_runs, 256, nv, pre.dc_c, d_carry, f->d_dc_table[slot], f->d_dc_ws[slot], st);
+}
+
+// DC pre-pass of the sub-train [n0, n0+n) into table slot `slot`, on stream `st` (which may differ from the
+// stream of the front kernel: the caller orders them with events).  fused_launch() then skips its own pre-pass.
+cudaError_t fused_prepare_dc(FusedFront* f, int slot, const void* raw, int64_t n0, size_t n, const PreParams& pre,
+                             double2* d_dc_carry, uint32_t* launches, cudaStream_t st)
+{
+    if (n == 0 || !pre.dc_enable) return cudaSuccess;
+    const long long align = f->v2 ? W2_T0 : 256;
+    const long long A0 = (n0 / align) * align;
+    cudaError_t e = fused_dc_prepass(f, slot, raw, n0, n0 + (long long)n, pre, d_dc_carry, A0, st);
+    if (e != cudaSuccess) return e;
+    f->dc_ready[slot] = true;
+    if (launches) *launches += 2;
+    return cudaSuccess;
 }
 
 template <int S>
@@ -593,7 +613,8 @@ static cudaError_t launch_v2_s(const FusedFront* f, const Fused2Args& A, int gri
 }
 
 static cudaError_t fused_launch_v2(FusedFront* f, const void* raw, int64_t n0, size_t n, const PreParams& pre,
-                                   double2* d_dc_carry, int64_t O0, size_t n_out, float2* y, uint32_t* launches, cudaStream_t st)
+                                   double2* d_dc_carry, int64_t O0, size_t n_out, float2* y, uint32_t* launches, int dc_slot,
+                                   cudaStream_t st)
 {
     Fused2Args A{};
     A.raw = raw; A.n0 = n0; A.N1 = n0 + (long long)n;
@@ -629,10 +650,13 @@ static cudaError_t fused_launch_v2(FusedFront* f, const void* raw, int64_t n0, s
         if (e != cudaSuccess) return e;
     }
     if (pre.dc_enable) {
-        e = fused_dc_prepass(f, raw, n0, A.N1, pre, d_dc_carry, A.A0, st);
-        if (e != cudaSuccess) return e;
-        A.dc_table = f->d_dc_table;
-        if (launches) *launches += 2;
+        if (!f->dc_ready[dc_slot]) {
+            e = fused_dc_prepass(f, dc_slot, raw, n0, A.N1, pre, d_dc_carry, A.A0, st);
+            if (e != cudaSuccess) return e;
+            if (launches) *launches += 2;
+        }
+        f->dc_ready[dc_slot] = false;
+        A.dc_table = f->d_dc_table[dc_slot];
     }
     const bool dc = pre.dc_enable != 0;
     const bool cs16 = pre.format == IQGPU_FMT_CS16 || pre.format == IQGPU_FMT_SC16Q11;
@@ -652,10 +676,11 @@ static cudaError_t fused_launch_v2(FusedFront* f, const void* raw, int64_t n0, s
 }
 
 cudaError_t fused_launch(FusedFront* f, const void* raw, int64_t n0, size_t n, const PreParams& pre, double2* d_dc_carry,
-                         int64_t O0, size_t n_out, float2* y, uint32_t* launches, cudaStream_t st)
+                         int64_t O0, size_t n_out, float2* y, uint32_t* launches, int dc_slot, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
-    if (f->v2) return fused_launch_v2(f, raw, n0, n, pre, d_dc_carry, O0, n_out, y, launches, st);
+    if (dc_slot < 0 || dc_slot > 1) dc_slot = 0;
+    if (f->v2) return fused_launch_v2(f, raw, n0, n, pre, d_dc_carry, O0, n_out, y, launches, dc_slot, st);
     const FusedPlan& P = f->plan;
     FusedArgs A{};
     A.plan = P;
@@ -689,10 +714,13 @@ cudaError_t fused_launch(FusedFront* f, const void* raw, int64_t n0, size_t n, c
         if (e != cudaSuccess) return e;
     }
     if (pre.dc_enable) {
-        e = fused_dc_prepass(f, raw, n0, A.N1, pre, d_dc_carry, A.A0, st);
-        if (e != cudaSuccess) return e;
-        A.dc_table = f->d_dc_table;
-        if (launches) *launches += 2;
+        if (!f->dc_ready[dc_slot]) {
+            e = fused_dc_prepass(f, dc_slot, raw, n0, A.N1, pre, d_dc_carry, A.A0, st);
+            if (e != cudaSuccess) return e;
+            if (launches) *launches += 2;
+        }
+        f->dc_ready[dc_slot] = false;
+        A.dc_table = f->d_dc_table[dc_slot];
     }
     const bool dc = pre.dc_enable != 0;
     switch (pre.format) {

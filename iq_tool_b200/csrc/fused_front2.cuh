@@ -34,6 +34,10 @@ constexpr int W2_ARB_HIST = 16;     // >= 13 decimated samples of look-back
 // stride degenerates to 16-way conflicts when the step has a factor of 8; measured on cfg1:
 // profiles/r01c_fused_front2_full_cfg1.md).  The image is laid out by the host and pulled in with
 // one TMA bulk copy (cp.async.bulk) per CTA.
+// NCO table {sign*sin, cos}[1024] in shared memory, XOR-swizzled: lanes look up phases that advance by a
+// configuration-dependent stride (16 frames apart), which on a plain table piles a half-warp onto a few
+// bank pairs (6-way on cfg5); folding index bits 4..7 into the bank bits spreads any stride.
+__host__ __device__ constexpr unsigned w2_lut_slot(unsigned idx) { return idx ^ ((idx >> 4) & 15u); }
 constexpr int W2_BANK_F2 = 2368;    // float2 entries of the image (9*255 + 63 + 7 = 2365, padded to 16 B)
 __host__ __device__ constexpr int w2_bank_row(int idx) { return 9 * idx + (idx >> 2); }
 constexpr int W2_MAX_TAPS = 72;     // sum of 2m over the cascade (6*4 + 10 + 20 = 54 for S = 6)
@@ -275,7 +279,7 @@ __device__ __forceinline__ void w2_p0(const Fused2Args& A, float2* __restrict__ 
             uint32_t th = p.nco_theta0 + (uint32_t)(a0 - A.n0) * p.nco_dtheta;
 #pragma unroll
             for (int k = 0; k < 16; k++) {
-                const float2 sc2 = lut2[((th + (1u << 21)) >> 22) & 0x3ffu];   // {sign*sin, cos}
+                const float2 sc2 = lut2[w2_lut_slot(((th + (1u << 21)) >> 22) & 0x3ffu)];   // {sign*sin, cos}
                 const float xr = x[k].x, xi = x[k].y;
                 x[k].x = __fsub_rn(__fmul_rn(xr, sc2.y), __fmul_rn(xi, sc2.x));
                 x[k].y = __fadd_rn(__fmul_rn(xr, sc2.x), __fmul_rn(xi, sc2.y));
@@ -506,7 +510,7 @@ __global__ void __launch_bounds__(512, 1) fused_front2_kernel(const __grid_const
     if (tid == 0) w2_tma_load(sbank, A.bank_image, W2_BANK_F2 * sizeof(float2), &tma_bar);
     if (A.pre.nco_enable)
         for (int i = tid; i < 1024; i += blockDim.x)
-            lut2[i] = make_float2(A.pre.nco_table[i] * A.pre.nco_sign, A.pre.nco_table[(i + 256) & 1023]);
+            lut2[w2_lut_slot((unsigned)i)] = make_float2(A.pre.nco_table[i] * A.pre.nco_sign, A.pre.nco_table[(i + 256) & 1023]);
     for (int i = lane; i < P::warp_f2; i += 32) wsm[i] = make_float2(0.f, 0.f);
     w2_mbar_wait(&tma_bar, 0);
     __syncthreads();

@@ -133,7 +133,11 @@ uint32_t fused_halo_frames(const FusedFront* f);
 int fused_version(const FusedFront* f);   // 1 = block-synchronous kernel, 2 = warp-streaming kernel
 // raw[0] has absolute index n0; produces outputs [O0, O0+n_out) into y; d_dc_carry is the DC state at n0
 // (updated to the state at n0+n).  *launches is incremented by the kernels launched.
+// dc_slot (0/1): DC table slot; if fused_prepare_dc() filled it (possibly on another stream, ordered by
+// the caller) the launch uses it, otherwise the pre-pass runs inline on `st`.
 cudaError_t fused_launch(FusedFront* f, const void* raw, int64_t n0, size_t n, const PreParams& pre, double2* d_dc_carry,
-                         int64_t O0, size_t n_out, float2* y, uint32_t* launches, cudaStream_t st);
+                         int64_t O0, size_t n_out, float2* y, uint32_t* launches, int dc_slot, cudaStream_t st);
+cudaError_t fused_prepare_dc(FusedFront* f, int slot, const void* raw, int64_t n0, size_t n, const PreParams& pre,
+                             double2* d_dc_carry, uint32_t* launches, cudaStream_t st);
 
 }  // namespace iqgpu
