@@ -15,8 +15,10 @@
 // split: radix-2 DIF stages over a global scratch down to 16384-point sub-blocks, the shared
 // memory kernel on each sub-block, radix-2 DIT stages back up.
 #include <cstdio>
+#include <cstdlib>
 
 #include "fft_core.cuh"
+#include "fft_filter2.cuh"
 #include "kernels.hpp"
 
 namespace iqgpu {
@@ -148,9 +150,20 @@ static cudaError_t launch_smem(const float2* src, float2* dst, unsigned M, unsig
     return cudaGetLastError();
 }
 
+// v2 (radix-16 register butterflies, fft_filter2.cuh) serves every transform that fits one CTA
+static bool use_v2(unsigned nfft) { return nfft >= 64 && nfft <= fft2::MAX_POINTS && !getenv("IQGPU_FFT_V1"); }
+static size_t v2_smem_bytes(unsigned nfft) { return (size_t)(fft2::pad(nfft) + 8) * sizeof(float2); }
+
 cudaError_t launch_fft_forward(const float2* in, unsigned nfft, const float2* twiddle, float2* out, cudaStream_t st)
 {
     if (!is_pow2(nfft) || nfft < 2 || nfft > FFT_MAX_POINTS) return cudaErrorInvalidValue;
+    if (use_v2(nfft)) {
+        cudaError_t ea = cudaFuncSetAttribute(fft2::fft2_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)(fft2::SMEM_F2 * sizeof(float2)));
+        if (ea != cudaSuccess) return ea;
+        fft2::fft2_forward_kernel<<<1, fft2::THREADS, v2_smem_bytes(nfft), st>>>(in, out, nfft, twiddle);
+        return cudaGetLastError();
+    }
     if (nfft <= FFT_SMEM_MAX) return launch_smem(in, out, nfft, nfft, 0, 1, twiddle, nullptr, FFT_FWD, 1.f, st);
     cudaError_t e = cudaMemcpyAsync(out, in, nfft * sizeof(float2), cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return e;
@@ -168,6 +181,14 @@ cudaError_t launch_fftfilt(const float2* x, size_t nblocks, unsigned B, const fl
     if (!fftfilt_supported(B)) return cudaErrorInvalidValue;
     const unsigned N = 2 * B;
     const float scale = 1.0f / (float)N;
+    if (use_v2(N)) {
+        cudaError_t ea = cudaFuncSetAttribute(fft2::fftfilt2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)(fft2::SMEM_F2 * sizeof(float2)));
+        if (ea != cudaSuccess) return ea;
+        if (launches) *launches += 1;
+        fft2::fftfilt2_kernel<<<(unsigned)nblocks, fft2::THREADS, v2_smem_bytes(N), st>>>(x, y, N, twiddle, H, scale);
+        return cudaGetLastError();
+    }
     if (N <= FFT_SMEM_MAX) {
         if (launches) *launches += 1;
         return launch_smem(x, y, N, N, B, nblocks, twiddle, H, FFT_WINDOW | FFT_FWD | FFT_MULH | FFT_INV, scale, st);

@@ -364,6 +364,9 @@ struct FusedFront {
     uint32_t v2_step = 0;
     int H_tail = 0;                     // cf32 tail length of the kernel in use
     float2* d_bank_image = nullptr;     // polyphase bank in the v2 shared-memory layout (w2_bank_row)
+    uint32_t lut_dtheta = 0;            // NCO table swizzle chosen for this phase increment
+    unsigned lut_sh = 4, lut_mask = 0;
+    bool lut_picked = false;
 };
 
 // ---- v2 plan table ---------------------------------------------------------------------------
@@ -627,6 +630,14 @@ static cudaError_t fused_launch_v2(FusedFront* f, const void* raw, int64_t n0, s
     A.bank_image = f->d_bank_image;
     A.O0 = O0; A.O1 = O0 + (long long)n_out; A.y = y;
     A.step = f->v2_step; A.zeta = f->v2_zeta;
+    A.lut_sh = 4; A.lut_mask = 0;
+    if (pre.nco_enable) {
+        if (f->lut_dtheta != pre.nco_dtheta || !f->lut_picked) {
+            w2_pick_lut_swizzle(pre.nco_dtheta, f->lut_sh, f->lut_mask);
+            f->lut_dtheta = pre.nco_dtheta; f->lut_picked = true;
+        }
+        A.lut_sh = f->lut_sh; A.lut_mask = f->lut_mask;
+    }
     memcpy(A.taps, f->v2_taps, sizeof(A.taps));
     const long long sup_frames = (long long)f->v2_sup * W2_T0;
     A.sup_first = n0 / sup_frames;

@@ -37,7 +37,38 @@ constexpr int W2_ARB_HIST = 16;     // >= 13 decimated samples of look-back
 // NCO table {sign*sin, cos}[1024] in shared memory, XOR-swizzled: lanes look up phases that advance by a
 // configuration-dependent stride (16 frames apart), which on a plain table piles a half-warp onto a few
 // bank pairs (6-way on cfg5); folding index bits 4..7 into the bank bits spreads any stride.
-__host__ __device__ constexpr unsigned w2_lut_slot(unsigned idx) { return idx ^ ((idx >> 4) & 15u); }
+// Which fold (none, or index bits sh..sh+3 with sh = 4, 5, 6) is best depends on the phase increment, so the
+// host simulates the half-warp access pattern for the actual increment and picks one (w2_pick_lut_swizzle).
+__host__ __device__ constexpr unsigned w2_lut_slot(unsigned idx, unsigned sh, unsigned mask) { return idx ^ ((idx >> sh) & mask); }
+__host__ static inline void w2_pick_lut_swizzle(uint32_t dtheta, unsigned& sh, unsigned& mask)
+{
+    const unsigned cand_sh[4] = {4, 4, 5, 6}, cand_mask[4] = {0, 15, 15, 15};
+    double best = 1e30;
+    sh = 4; mask = 0;
+    for (int c = 0; c < 4; c++) {
+        double cost = 0;
+        for (uint32_t trial = 0; trial < 64; trial++) {
+            const uint32_t th0 = trial * 0x9e3779b9u;          // arbitrary start phases
+            for (int half = 0; half < 2; half++) {
+                int hits[16] = {0};
+                unsigned seen_idx[16];
+                int deg = 0;
+                for (int l = 0; l < 16; l++) {
+                    const uint32_t th = th0 + (uint32_t)((half * 16 + l) * 16) * dtheta;
+                    const unsigned idx = ((th + (1u << 21)) >> 22) & 0x3ffu;
+                    seen_idx[l] = idx;
+                    bool dup = false;                          // identical addresses broadcast
+                    for (int m = 0; m < l; m++) dup |= (seen_idx[m] == idx);
+                    if (dup) continue;
+                    const unsigned b = w2_lut_slot(idx, cand_sh[c], cand_mask[c]) & 15u;
+                    if (++hits[b] > deg) deg = hits[b];
+                }
+                cost += deg;
+            }
+        }
+        if (cost < best - 1e-9) { best = cost; sh = cand_sh[c]; mask = cand_mask[c]; }
+    }
+}
 constexpr int W2_BANK_F2 = 2368;    // float2 entries of the image (9*255 + 63 + 7 = 2365, padded to 16 B)
 __host__ __device__ constexpr int w2_bank_row(int idx) { return 9 * idx + (idx >> 2); }
 constexpr int W2_MAX_TAPS = 72;     // sum of 2m over the cascade (6*4 + 10 + 20 = 54 for S = 6)
@@ -114,6 +145,7 @@ struct Fused2Args {
     int raw_aligned;
     uint32_t step;
     float zeta;
+    unsigned lut_sh, lut_mask;          // NCO table swizzle (w2_lut_slot)
     float taps[W2_MAX_TAPS];            // h1 by execution depth, concatenated (constant-bank FFMA operands)
 };
 
@@ -279,7 +311,7 @@ __device__ __forceinline__ void w2_p0(const Fused2Args& A, float2* __restrict__ 
             uint32_t th = p.nco_theta0 + (uint32_t)(a0 - A.n0) * p.nco_dtheta;
 #pragma unroll
             for (int k = 0; k < 16; k++) {
-                const float2 sc2 = lut2[w2_lut_slot(((th + (1u << 21)) >> 22) & 0x3ffu)];   // {sign*sin, cos}
+                const float2 sc2 = lut2[w2_lut_slot(((th + (1u << 21)) >> 22) & 0x3ffu, A.lut_sh, A.lut_mask)];   // {sign*sin, cos}
                 const float xr = x[k].x, xi = x[k].y;
                 x[k].x = __fsub_rn(__fmul_rn(xr, sc2.y), __fmul_rn(xi, sc2.x));
                 x[k].y = __fadd_rn(__fmul_rn(xr, sc2.x), __fmul_rn(xi, sc2.y));
@@ -510,7 +542,7 @@ __global__ void __launch_bounds__(512, 1) fused_front2_kernel(const __grid_const
     if (tid == 0) w2_tma_load(sbank, A.bank_image, W2_BANK_F2 * sizeof(float2), &tma_bar);
     if (A.pre.nco_enable)
         for (int i = tid; i < 1024; i += blockDim.x)
-            lut2[w2_lut_slot((unsigned)i)] = make_float2(A.pre.nco_table[i] * A.pre.nco_sign, A.pre.nco_table[(i + 256) & 1023]);
+            lut2[w2_lut_slot((unsigned)i, A.lut_sh, A.lut_mask)] = make_float2(A.pre.nco_table[i] * A.pre.nco_sign, A.pre.nco_table[(i + 256) & 1023]);
     for (int i = lane; i < P::warp_f2; i += 32) wsm[i] = make_float2(0.f, 0.f);
     w2_mbar_wait(&tma_bar, 0);
     __syncthreads();
