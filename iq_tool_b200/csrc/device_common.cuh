@@ -140,6 +140,21 @@ __host__ static inline DcDev make_dc_dev(float c, float a)
     return d;
 }
 
+// the same for a lane that owns 16 consecutive frames of a 512-frame tick (fused front v2, tick pre-pass)
+struct DcDev16 {
+    float c, a;          // pole, 1-pole
+    float w[5];          // c^(16*2^s)
+    float lanepow[32];   // c^(16*lane)
+};
+__host__ static inline DcDev16 make_dc_dev16(float c, float a)
+{
+    DcDev16 d;
+    d.c = c; d.a = a;
+    for (int k = 0; k < 5; k++) d.w[k] = (float)pow((double)c, 16.0 * (double)(1 << k));
+    for (int l = 0; l < 32; l++) d.lanepow[l] = (float)pow((double)c, 16.0 * l);
+    return d;
+}
+
 // returns the row's inclusive weighted total in lane 31 (all lanes get it via shfl) and, per lane,
 // E = v contribution of the lanes below (relative to a zero state at the row start)
 __device__ __forceinline__ void dc_row_scan(const float2 (&x)[4], const DcDev& d, int lane, float2& E, float2& T)

@@ -561,7 +561,8 @@ static cudaError_t fused_dc_prepass(FusedFront* f, int slot, const void* raw, lo
                                     double2* d_carry, long long A0, cudaStream_t st)
 {
     const size_t nv = (size_t)(N1 - A0);
-    const size_t n_runs = (nv + 255) / 256;
+    const bool ticks = f->v2;                       // v2 keeps one table entry per 512-frame tick
+    const size_t n_runs = ticks ? (nv + 511) / 512 : (nv + 255) / 256;
     if (n_runs + 2 > f->dc_cap[slot]) {
         cudaDeviceSynchronize();        // rare (first use / larger sub-train): nothing may still read the old buffers
         cudaFree(f->d_dc_table[slot]); cudaFree(f->d_dc_sums[slot]); cudaFree(f->d_dc_ws[slot]);
@@ -578,6 +579,11 @@ static cudaError_t fused_dc_prepass(FusedFront* f, int slot, const void* raw, lo
     const long long back = n0 - A0;
     const char* vraw = reinterpret_cast<const char*>(raw) - back * (long long)bps;
     if (back) dc_rewind_kernel<<<1, 1, 0, st>>>(d_carry, (double)pre.dc_c, back);
+    if (ticks) {
+        cudaError_t e = launch_dc_tick_sums(vraw, nv, (size_t)back, pre, f->d_dc_sums[slot], st);
+        if (e != cudaSuccess) return e;
+        return launch_dc_scan(f->d_dc_sums[slot], n_runs, 512, nv, pre.dc_c, d_carry, f->d_dc_table[slot], f->d_dc_ws[slot], st, 512);
+    }
     cudaError_t e = launch_dc_run_sums_masked(vraw, nv, (size_t)back, pre, 256, f->d_dc_sums[slot], st);
     if (e != cudaSuccess) return e;
     return launch_dc_scan(f->d_dc_sums[slot], n_runs, 256, nv, pre.dc_c, d_carry, f->d_dc_table[slot], f->d_dc_ws[slot], st);
@@ -668,6 +674,7 @@ static cudaError_t fused_launch_v2(FusedFront* f, const void* raw, int64_t n0, s
         }
         f->dc_ready[dc_slot] = false;
         A.dc_table = f->d_dc_table[dc_slot];
+        A.dc_table_shift = 9;
     }
     const bool dc = pre.dc_enable != 0;
     const bool cs16 = pre.format == IQGPU_FMT_CS16 || pre.format == IQGPU_FMT_SC16Q11;

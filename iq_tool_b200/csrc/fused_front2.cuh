@@ -113,20 +113,6 @@ struct W2Plan {
     }
 };
 
-struct DcDev16 {
-    float c, a;          // pole, 1-pole
-    float w[5];          // c^(16*2^s)
-    float lanepow[32];   // c^(16*lane)
-};
-__host__ static inline DcDev16 make_dc_dev16(float c, float a)
-{
-    DcDev16 d;
-    d.c = c; d.a = a;
-    for (int k = 0; k < 5; k++) d.w[k] = (float)pow((double)c, 16.0 * (double)(1 << k));
-    for (int l = 0; l < 32; l++) d.lanepow[l] = (float)pow((double)c, 16.0 * l);
-    return d;
-}
-
 struct Fused2Args {
     const void* raw;
     long long n0, N1;                   // absolute index range of raw
@@ -135,7 +121,8 @@ struct Fused2Args {
     int H_tail;
     PreParams pre;
     DcDev16 dc;
-    const double2* dc_table;            // v at absolute multiples of 256, starting at A0
+    const double2* dc_table;            // v at absolute multiples of 2^dc_table_shift frames, starting at A0
+    int dc_table_shift;                 // 9: per-tick table (dc_tick_sums pre-pass)
     long long A0;
     const float2* bank_image;           // device, W2_BANK_F2 float2 in the w2_bank_row layout
     long long O0, O1;
@@ -275,7 +262,7 @@ __device__ __forceinline__ void w2_p0(const Fused2Args& A, float2* __restrict__ 
         if (DC) {
             // DC blocker (dc_block.c:76 -> liquid iirfilt): v[n] = x[n] + c v[n-1], y[n] = x[n] - (1-c) v[n-1].
             // lane-local weighted sum, one warp scan per tick, state at the tick start from the table
-            const double2 vt = A.dc_table[(tick_start - A.A0) >> 8];
+            const double2 vt = A.dc_table[(tick_start - A.A0) >> A.dc_table_shift];
             float pr = x[0].x, pi = x[0].y;
 #pragma unroll
             for (int k = 1; k < 16; k++) { pr = fmaf(pr, A.dc.c, x[k].x); pi = fmaf(pi, A.dc.c, x[k].y); }

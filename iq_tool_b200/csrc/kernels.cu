@@ -48,6 +48,75 @@ __global__ void __launch_bounds__(256) dc_run_sums_kernel(const void* __restrict
     }
 }
 
+// DC pre-pass for the fused front v2: one weighted sum per 512-frame tick, S_t = sum_k c^(511-k) x[k].
+// A lane owns 16 consecutive frames (4 x LDG.128 issued back to back for cs16), folds them serially and
+// the warp combines the 32 partial sums with a weighted shuffle tree; frames below `lo` and at or beyond
+// `n` read as zero.
+__global__ void __launch_bounds__(256) dc_tick_sums_kernel(const void* __restrict__ raw, size_t n, size_t lo, int fmt, float gain,
+                                                           DcDev16 d, size_t n_ticks, bool aligned, double2* __restrict__ sums)
+{
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const bool cs16 = (fmt == IQGPU_FMT_CS16 || fmt == IQGPU_FMT_SC16Q11);
+    float sc;
+    switch (fmt) {
+        case IQGPU_FMT_CS16: case IQGPU_FMT_CU16: sc = gain * (1.0f / 32768.0f); break;
+        case IQGPU_FMT_SC16Q11: sc = gain * (1.0f / 2048.0f); break;
+        case IQGPU_FMT_CS8: case IQGPU_FMT_CU8: sc = gain * (1.0f / 128.0f); break;
+        default: sc = gain;
+    }
+    for (size_t tick = warp; tick < n_ticks; tick += nwarps) {
+        const size_t t0 = tick * 512, a0 = t0 + (size_t)lane * 16;
+        float2 x[16];
+        if (cs16 && aligned && t0 >= lo && t0 + 512 <= n) {
+            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(raw) + a0 * 4);
+            uint4 q[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) q[j] = __ldg(src + j);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const unsigned w[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
+#pragma unroll
+                for (int kk = 0; kk < 4; kk++) {
+                    x[4 * j + kk].x = __fmul_rn((float)(short)(w[kk] & 0xffffu), sc);
+                    x[4 * j + kk].y = __fmul_rn((float)(short)(w[kk] >> 16), sc);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int kk = 0; kk < 16; kk++) {
+                const size_t i = a0 + kk;
+                float2 v = make_float2(0.f, 0.f);
+                if (i >= lo && i < n) {
+                    switch (fmt) {
+                        case IQGPU_FMT_CS16: case IQGPU_FMT_SC16Q11: v = load_frame<IQGPU_FMT_CS16>(raw, i, sc, gain); break;
+                        case IQGPU_FMT_CU16: v = load_frame<IQGPU_FMT_CU16>(raw, i, sc, gain); break;
+                        case IQGPU_FMT_CS8: v = load_frame<IQGPU_FMT_CS8>(raw, i, sc, gain); break;
+                        case IQGPU_FMT_CU8: v = load_frame<IQGPU_FMT_CU8>(raw, i, sc, gain); break;
+                        default: v = load_frame<IQGPU_FMT_CF32>(raw, i, sc, gain);
+                    }
+                }
+                x[kk] = v;
+            }
+        }
+        float pr = x[0].x, pi = x[0].y;
+#pragma unroll
+        for (int kk = 1; kk < 16; kk++) { pr = fmaf(pr, d.c, x[kk].x); pi = fmaf(pi, d.c, x[kk].y); }
+        // weighted tree: after the step with distance dist, lanes that are multiples of 2*dist hold
+        // c^(16*dist) * (own 16*dist frames) + (the next 16*dist frames)
+#pragma unroll
+        for (int s = 0; s < 5; s++) {
+            const int dist = 1 << s;
+            const float qr = __shfl_down_sync(0xffffffffu, pr, dist);
+            const float qi = __shfl_down_sync(0xffffffffu, pi, dist);
+            pr = fmaf(pr, d.w[s], qr);
+            pi = fmaf(pi, d.w[s], qi);
+        }
+        if (lane == 0) sums[tick] = make_double2((double)pr, (double)pi);
+    }
+}
+
 // ---- DC carry scan over the runs: v_start[r+1] = A_r v_start[r] + S_r -------------------------------
 // Two small kernels.  (1) one warp per group of DC_GROUP runs folds the group into one affine map;
 // (2) every CTA folds the groups in front of it (a few thousand at most), then one warp per group
@@ -291,8 +360,20 @@ cudaError_t launch_dc_run_sums_masked(const void* raw, size_t n, size_t lo, cons
     return cudaGetLastError();
 }
 
+cudaError_t launch_dc_tick_sums(const void* raw, size_t n, size_t lo, const PreParams& p, double2* sums, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    const size_t n_ticks = (n + 511) / 512;
+    const DcDev16 d = make_dc_dev16(p.dc_c, p.dc_a);
+    const bool aligned = (reinterpret_cast<size_t>(raw) & 15) == 0;
+    const int grid = grid_for_warps(n_ticks, 256);
+    dc_tick_sums_kernel<<<grid, 256, 0, st>>>(raw, n, lo, p.format, p.gain, d, n_ticks, aligned, sums);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_dc_scan(const double2* run_sums, size_t n_runs, uint32_t run_len, size_t n,
-                           float dc_c, double2* carry_inout, double2* run_start, double* scan_ws, cudaStream_t st)
+                           float dc_c, double2* carry_inout, double2* run_start, double* scan_ws, cudaStream_t st,
+                           uint32_t row_len)
 {
     if (n_runs == 0) return cudaSuccess;
     DcScanParams p{};
@@ -301,7 +382,7 @@ cudaError_t launch_dc_scan(const double2* run_sums, size_t n_runs, uint32_t run_
     const double c = (double)dc_c;
     // rows are processed whole (128 frames); the zero padding of the last run only decays the state
     const size_t last_len = n - (n_runs - 1) * (size_t)run_len;
-    const size_t last_pad = ((last_len + 127) / 128) * 128;
+    const size_t last_pad = ((last_len + row_len - 1) / row_len) * row_len;
     p.A = pow(c, (double)run_len);
     p.A_last = pow(c, (double)last_pad);
     p.undo = pow(c, -(double)(last_pad - last_len));

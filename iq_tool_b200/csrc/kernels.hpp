@@ -32,8 +32,12 @@ cudaError_t launch_dc_run_sums_masked(const void* raw, size_t n, size_t lo, cons
                                       double2* run_sums, cudaStream_t st);
 // DC pass 2: v at the start of every run from the carried state; updates the carry in place
 // scan_ws: device workspace of dc_scan_workspace_doubles(n_runs) doubles
+// row_len: granularity the sums were zero-padded to (128 for launch_dc_run_sums rows, 512 for tick sums)
 cudaError_t launch_dc_scan(const double2* run_sums, size_t n_runs, uint32_t run_len, size_t n,
-                           float dc_c, double2* carry_inout, double2* run_start, double* scan_ws, cudaStream_t st);
+                           float dc_c, double2* carry_inout, double2* run_start, double* scan_ws, cudaStream_t st,
+                           uint32_t row_len = 128);
+// DC pre-pass of the fused front v2: one weighted sum per 512-frame tick (frames below lo / beyond n read as zero)
+cudaError_t launch_dc_tick_sums(const void* raw, size_t n, size_t lo, const PreParams& p, double2* sums, cudaStream_t st);
 size_t dc_scan_workspace_doubles(size_t n_runs);
 // convert + (DC apply) + I/Q + NCO -> cf32
 cudaError_t launch_pre(const void* raw, size_t n, const PreParams& p, uint32_t run_len,
