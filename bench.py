@@ -185,7 +185,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--samples", type=int, default=0, help="input frames per GPU per step (default: workload's)")
-    ap.add_argument("--cpu-samples", type=int, default=1 << 26)
+    ap.add_argument("--cpu-samples", type=int, default=1 << 26,
+                    help="input frames of the CPU sample: per step for --impl reference, x8 (about 10 s) for the cpu_baseline leg")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fused", type=int, default=1)
@@ -347,7 +348,7 @@ def main():
         if os.path.exists(tp):
             with open(tp) as f:
                 tj = json.load(f)
-            if tj.get(dom, {}).get("bytes_per_input_frame"):
+            if tj.get(dom, {}).get("bytes_per_input_frame") and tj[dom].get("workload", wl.name) == wl.name:
                 traffic = tj[dom]["bytes_per_input_frame"] * frames_per_launch
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                     "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
@@ -365,7 +366,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         from oracle.loader import CpuChain, have_ref
         kind = "ref_fast" if have_ref(fast=True) else "oracle"
-        m = min(n, args.cpu_samples)
+        m = min(n, 8 * args.cpu_samples)          # about 10 s of CPU work at ~50 Msamples/s
         sample = raw[: 2 * m].cpu().numpy()
         ch = CpuChain(cfg, kind)
         ch.process(sample[: 2 * (1 << 20)], threaded=(kind != "oracle"))

