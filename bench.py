@@ -190,6 +190,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fused", type=int, default=1)
+    ap.add_argument("--subtrain", type=int, default=1 << 28, help="frames per sub-train (kernel launch group) of the HBM-resident leg")
+    ap.add_argument("--e2e-subtrain", type=int, default=1 << 25, help="frames per sub-train of the host-buffer leg (H2D/compute/D2H pipeline depth)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -223,7 +225,7 @@ def main():
     # every step (the only collective; no sample data crosses GPUs)
     from iq_tool_b200.shard import ShardedChain
     sc = ShardedChain(cfg, local_rank, shard_frames_hint=n if world > 1 else 0, time_kernels=1, fused=args.fused,
-                      subtrain_frames=1 << 26)
+                      subtrain_frames=args.subtrain)
     chain = sc.chain
     info = chain.info()
     replicas = False
@@ -297,6 +299,8 @@ def main():
             host_in = torch.frombuffer((C.c_uint8 * nbytes).from_address(hin), dtype=torch.uint8)
             host_in.copy_(raw.view(torch.uint8))
             nout = C.c_size_t(0)
+            # the host-buffer leg pipelines H2D / compute / D2H over sub-trains: its own chain with shorter sub-trains
+            e2e_chain = chain if exchange else gpu.Chain(cfg, local_rank, fused=args.fused, subtrain_frames=args.e2e_subtrain)
             host_out = torch.frombuffer((C.c_uint8 * out.numel()).from_address(hout), dtype=torch.uint8)
             def e2e_step():
                 if exchange:
@@ -307,8 +311,11 @@ def main():
                     torch.cuda.synchronize()
                     nout.value = k
                     return
-                rewind()
-                gpu._check(gpu.lib.iqgpu_chain_process(chain._h, hin, n + halo, None, 0, hout, out.numel(),
+                if world == 1 or replicas:
+                    e2e_chain.reset()
+                else:
+                    e2e_chain.seek(shard.lead)
+                gpu._check(gpu.lib.iqgpu_chain_process(e2e_chain._h, hin, n + halo, None, 0, hout, out.numel(),
                                                        C.byref(nout), None))
             e2e_step()
             if world > 1:

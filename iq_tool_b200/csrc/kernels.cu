@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/iqgpu.h"
 #include "device_common.cuh"
@@ -949,7 +950,10 @@ __global__ void __launch_bounds__(AGC_RMS_THREADS) agc_rms_parallel_kernel(const
         }
         if (run) flags[it] = 1u;
         grid.sync();
-        if (flags[it] == 0u) break;    // no start state changed anywhere: fixed point
+        if (flags[it] == 0u) {         // no start state changed anywhere: fixed point
+            if (b == 0) flags[nblocks + 1] = it + 1;   // sweeps used (diagnostics)
+            break;
+        }
     }
     if (b == nblocks - 1) { const float2 f = fin[b]; st->rms_g = f.x; st->rms_y2 = f.y; }
 }
@@ -1150,7 +1154,14 @@ cudaError_t launch_agc_rms(const float2* x, size_t n, const PostParams& p, AgcSt
     PostParams pp = p;
     void* args[] = {(void*)&x, (void*)&n, (void*)&pp, (void*)&state, (void*)&y, (void*)&B, (void*)&nb, (void*)&fin, (void*)&flags};
     const unsigned grid = (nb + AGC_RMS_THREADS - 1) / AGC_RMS_THREADS;
-    return cudaLaunchCooperativeKernel((void*)agc_rms_parallel_kernel, dim3(grid), dim3(AGC_RMS_THREADS), args, 0, st);
+    e = cudaLaunchCooperativeKernel((void*)agc_rms_parallel_kernel, dim3(grid), dim3(AGC_RMS_THREADS), args, 0, st);
+    if (e == cudaSuccess && getenv("IQGPU_DEBUG_AGC")) {
+        unsigned sweeps = 0;
+        cudaStreamSynchronize(st);
+        cudaMemcpy(&sweeps, flags + nb + 1, sizeof(unsigned), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[iqgpu] rms agc: n=%zu alpha=%g block=%zu blocks=%u sweeps=%u\n", n, (double)p.agc_alpha, B, nb, sweeps);
+    }
+    return e;
 }
 cudaError_t launch_post(const float2* x, size_t n, const PostParams& p, const uint32_t* seg_start, size_t nseg,
                         const float* seg_gain, int nco_done, float2* tap, void* out, cudaStream_t st)
