@@ -171,6 +171,7 @@ struct iqgpu_chain {
     std::vector<float*> d_hb_taps;  // per design index
     float* d_bank = nullptr;
     float* d_fir_taps = nullptr;
+    std::vector<float> h_fir_taps;      // host copy (kernel-parameter taps)
     unsigned fir_taps_padded = 0;
     float2 *d_fft_H = nullptr, *d_fft_tw = nullptr, *d_fft_scratch = nullptr;
     size_t fft_scratch_bytes = 0;
@@ -412,6 +413,7 @@ int iqgpu_chain::init_device()
         }
         CK(cudaMalloc(&d_fir_taps, h.size() * sizeof(float)));
         CK(cudaMemcpy(d_fir_taps, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+        h_fir_taps = h;
     }
     if (filter_is_fft(filt)) {
         if (!fftfilt_supported(filt.block)) return fail(IQGPU_EINVAL, "FFT filter block size not supported by the GPU FFT kernel");
@@ -617,7 +619,7 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
             if (filter_is_fir(filt)) {
                 float2* y = nullptr;
                 CK(s_pref.begin(n, st, &y));
-                CK(launch_fir(x_in, n, d_fir_taps, fir_taps_padded, filt.impl == IQGPU_FILTER_IMPL_FIR_ASYM, y, st));
+                CK(launch_fir(x_in, n, d_fir_taps, fir_taps_padded, filt.impl == IQGPU_FILTER_IMPL_FIR_ASYM, y, st, h_fir_taps.data()));
                 launches++;
                 s_pref.commit(n);
                 rs_src = y;
@@ -708,7 +710,7 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
         if (filter_is_fir(filt)) {
             float2* y = nullptr;
             CK(s_f.begin(post_n, st, &y));
-            CK(launch_fir(post_src, post_n, d_fir_taps, fir_taps_padded, filt.impl == IQGPU_FILTER_IMPL_FIR_ASYM, y, st));
+            CK(launch_fir(post_src, post_n, d_fir_taps, fir_taps_padded, filt.impl == IQGPU_FILTER_IMPL_FIR_ASYM, y, st, h_fir_taps.data()));
             launches++;
             s_f.commit(post_n);
             post_src = y;

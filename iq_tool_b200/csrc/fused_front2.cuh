@@ -470,9 +470,13 @@ __device__ __forceinline__ void w2_arb(const Fused2Args& A, const float2* __rest
     const unsigned long long kb = (unsigned long long)kA + P::flat_new;
     // outputs of this run: o >= o_cur with o*step < kb << 24
     const unsigned long long Dn = (kb << 24) - (unsigned long long)o_cur * step;      // in (0, (flat_new+2) << 24]
+    // cnt = ceil(Dn / step): float estimate of the quotient (Dn < 2^34, step in [2^24, 2^25]: off by at most one),
+    // then an exact remainder fix-up without loops
     unsigned cnt = (unsigned)__fdividef((float)Dn, (float)step);
-    while ((unsigned long long)cnt * step < Dn) cnt++;
-    while (cnt > 0 && (unsigned long long)(cnt - 1) * step >= Dn) cnt--;
+    long long rem = (long long)Dn - (long long)((unsigned long long)cnt * step);
+    if (rem < 0) { cnt--; rem += (long long)step; }
+    if (rem >= (long long)step) { cnt++; rem -= (long long)step; }
+    cnt += (rem > 0) ? 1u : 0u;
     long long oa = o_cur, ob = o_cur + cnt;
     o_cur = ob;
     if (oa < A.O0) oa = A.O0;

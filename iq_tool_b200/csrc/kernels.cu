@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "../../include/iqgpu.h"
 #include "device_common.cuh"
@@ -593,11 +594,79 @@ __global__ void __launch_bounds__(FIR_THREADS) fir_kernel(const float2* __restri
     }
 }
 
+// Same tiling with the taps held in the kernel-parameter constant bank: every FFMA then reads its tap
+// as a uniform/constant operand (two register reads instead of three).  On this part the three-register
+// FFMA issues every other cycle per scheduler; the smem-tap kernel above sits exactly at that limit
+// (cfg2: 22.3 M outputs x 255 taps in 0.62 ms = 0.5 FFMA/clk/SMSP).
+constexpr unsigned FIR_PARAM_TAPS = 4096;           // floats (real taps) or 2048 complex taps: 16 KB of parameters
+struct FirTaps { float h[FIR_PARAM_TAPS]; };
+
+template <bool CPLX>
+__global__ void __launch_bounds__(FIR_THREADS) fir_param_kernel(const float2* __restrict__ x, size_t n, unsigned ntaps,
+                                                                float2* __restrict__ y, const __grid_constant__ FirTaps T)
+{
+    constexpr int WIN = FIR_TILE + FIR_TC;
+    __shared__ float2 sx[WIN + WIN / 8 + 8];
+    const int t = threadIdx.x;
+    const long long tile0 = (long long)blockIdx.x * FIR_TILE;
+    float2 acc[FIR_R];
+#pragma unroll
+    for (int r = 0; r < FIR_R; r++) acc[r] = make_float2(0.f, 0.f);
+    for (unsigned c0 = 0; c0 < ntaps; c0 += FIR_TC) {
+        const int tc = (ntaps - c0 < (unsigned)FIR_TC) ? (int)(ntaps - c0) : FIR_TC;
+        const long long wbase = tile0 - (long long)(ntaps - 1) + c0;
+        __syncthreads();
+        for (int j = t; j < FIR_TILE + tc - 1; j += FIR_THREADS) {
+            const long long g = wbase + j;
+            sx[fir_pad(j)] = (g < (long long)n) ? x[g] : make_float2(0.f, 0.f);
+        }
+        __syncthreads();
+        float2 win[FIR_R];
+        const int o0 = t * FIR_R;
+#pragma unroll
+        for (int r = 0; r < FIR_R; r++) win[r] = sx[fir_pad(o0 + r)];
+        for (int i0 = 0; i0 < tc; i0 += FIR_R) {
+#pragma unroll
+            for (int u = 0; u < FIR_R; u++) {
+                const float hx = CPLX ? T.h[2 * (c0 + i0 + u)] : T.h[c0 + i0 + u];
+                const float hy = CPLX ? T.h[2 * (c0 + i0 + u) + 1] : 0.f;
+#pragma unroll
+                for (int r = 0; r < FIR_R; r++) {
+                    const float2 v = win[(r + u) % FIR_R];
+                    if (CPLX) {
+                        acc[r].x = fmaf(hx, v.x, acc[r].x);
+                        acc[r].x = fmaf(-hy, v.y, acc[r].x);
+                        acc[r].y = fmaf(hx, v.y, acc[r].y);
+                        acc[r].y = fmaf(hy, v.x, acc[r].y);
+                    } else {
+                        acc[r].x = fmaf(hx, v.x, acc[r].x);
+                        acc[r].y = fmaf(hx, v.y, acc[r].y);
+                    }
+                }
+                win[u % FIR_R] = sx[fir_pad(o0 + i0 + u + FIR_R)];
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < FIR_R; r++) {
+        const long long o = tile0 + t * FIR_R + r;
+        if (o < (long long)n) y[o] = acc[r];
+    }
+}
+
 cudaError_t launch_fir(const float2* x, size_t n, const float* hrev, unsigned ntaps_padded, int complex_taps,
-                       float2* y, cudaStream_t st)
+                       float2* y, cudaStream_t st, const float* hrev_host)
 {
     if (n == 0) return cudaSuccess;
     const int grid = (int)((n + FIR_TILE - 1) / FIR_TILE);
+    const unsigned nfloats = ntaps_padded * (complex_taps ? 2u : 1u);
+    if (hrev_host && nfloats <= FIR_PARAM_TAPS && !getenv("IQGPU_FIR_SMEM_TAPS")) {
+        static thread_local FirTaps T;      // 16 KB: copied into the launch's parameter buffer
+        memcpy(T.h, hrev_host, nfloats * sizeof(float));
+        if (complex_taps) fir_param_kernel<true><<<grid, FIR_THREADS, 0, st>>>(x, n, ntaps_padded, y, T);
+        else fir_param_kernel<false><<<grid, FIR_THREADS, 0, st>>>(x, n, ntaps_padded, y, T);
+        return cudaGetLastError();
+    }
     if (complex_taps) fir_kernel<true><<<grid, FIR_THREADS, 0, st>>>(x, n, hrev, ntaps_padded, y);
     else fir_kernel<false><<<grid, FIR_THREADS, 0, st>>>(x, n, hrev, ntaps_padded, y);
     return cudaGetLastError();
@@ -1130,8 +1199,11 @@ static void agc_rms_plan(size_t n, float alpha, size_t& B, unsigned& nblocks)
 {
     const unsigned tmax = agc_rms_max_threads();
     B = (n + tmax - 1) / tmax;
-    // blocks shorter than ~2 time constants only add sweeps
-    const size_t floorB = (size_t)std::min(65536.0, std::max(256.0, 2.0 / std::max((double)alpha, 1e-6)));
+    // The loop forgets a wrong start state with time constant 2/alpha samples (|eigenvalue| = 1 - alpha/2).  With
+    // blocks of ~20 time constants the second sweep already starts every block within ~e^-20 of the truth, so two
+    // or three full sweeps plus a short tail of partial ones reach the fixed point; shorter blocks need one full
+    // sweep per block length of convergence (measured: 25 sweeps at 493 samples, alpha = 1e-2).
+    const size_t floorB = (size_t)std::min(65536.0, std::max(256.0, 40.0 / std::max((double)alpha, 1e-6)));
     if (B < floorB) B = floorB;
     nblocks = (unsigned)((n + B - 1) / B);
 }

@@ -59,8 +59,10 @@ cudaError_t launch_arb(const float2* x, int64_t a0, const float* bank, uint32_t 
 // ---- K3: time-domain FIR ---------------------------------------------------------------------
 // y[n] = sum_{i<ntaps} hrev[i] * x[n - (ntaps-1) + i]; x points at the first NEW sample.
 // hrev: ntaps_padded complex or real taps, oldest first, zero-padded at the FRONT to a multiple of 8.
+// hrev_host (optional): the same taps in host memory; when they fit the parameter bank (4096 floats) they
+// travel as kernel parameters and are read as constant-bank FFMA operands.
 cudaError_t launch_fir(const float2* x, size_t n, const float* hrev, unsigned ntaps_padded,
-                       int complex_taps, float2* y, cudaStream_t st);
+                       int complex_taps, float2* y, cudaStream_t st, const float* hrev_host = nullptr);
 
 // ---- K4: FFT block filter (overlap-save form of liquid's fftfilt) --------------------------
 // For each block b in [0,nblocks): window = x[(b-1)*B .. (b+1)*B), y[b*B .. (b+1)*B) =
