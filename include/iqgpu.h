@@ -234,6 +234,23 @@ void iqgpu_agc_digital_initial_state(iqgpu_agc_state *s);
 int  iqgpu_agc_digital_advance(iqgpu_agc_state *s, float target, double target_rate_hz, const float *peaks,
                                const uint32_t *counts, size_t n_chunks, float *gains /* optional */);
 
+/* ---- raw-file streaming (the callers either side of the path): replaces the Reader and
+ *      Writer threads of a raw-file run (src/input_rawfile.c:188-249: sf_read_raw per 16384-frame chunk;
+ *      src/output_raw_file.c:146-184: 1 MB fwrites from a ring buffer) with large reads of whole chunk
+ *      trains into pinned memory, the chain, and one write per train, overlapped on three threads.  The
+ *      file is cut into reference chunks exactly as the reference does (short last chunk, trailing partial
+ *      frame dropped, nothing flushed at end of stream). ------------------------------------------------- */
+typedef struct {
+    uint64_t frames_in;       /* input frames read and processed */
+    uint64_t frames_out;      /* output frames written */
+    uint64_t bytes_written;
+    uint64_t trains;          /* chain calls made */
+} iqgpu_rawfile_stats;
+int         iqgpu_rawfile_run(const iqgpu_chain_config *cfg, int device, const char *in_path, const char *out_path,
+                              size_t train_chunks /* reference chunks per chain call, 0 = 256 */,
+                              iqgpu_rawfile_stats *stats /* optional */);
+const char *iqgpu_rawfile_last_error(void);
+
 /* ---- sample_convert.h (include/sample_convert.h:19,35,50) — host buffers ------------- */
 size_t iqgpu_get_bytes_per_sample(int format);
 int    iqgpu_convert_block_to_cf32(const void *in, float *out_cf32, size_t n_frames, int format, float gain);

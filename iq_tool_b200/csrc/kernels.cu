@@ -963,28 +963,43 @@ __device__ __forceinline__ double agc_exp_small(double t)   // |t| <= 0.5 (t = -
     return fma(p, t, 1.0);
 }
 
+__device__ __forceinline__ float2 agc_rms_step(float2 v, size_t i, const PostParams& p, const float* __restrict__ lut,
+                                               float alpha, double oma, float mha, float& g, float& y2p)
+{
+    if (p.nco_enable) v = nco_mix(v, p.nco_theta0 + (uint32_t)i * p.nco_dtheta, p.nco_sign, lut);
+    const float yr = __fmul_rn(v.x, g), yi = __fmul_rn(v.y, g);
+    const float y2 = __fadd_rn(__fmul_rn(yr, yr), __fmul_rn(yi, yi));
+    y2p = (float)(oma * (double)y2p + (double)__fmul_rn(alpha, y2));
+    if (y2p > 1e-6f) {
+        // logf/expf evaluated in double and rounded once: matches a correctly rounded libm
+        const float lf = (float)agc_log_pos(y2p);
+        const float tt = __fmul_rn(mha, lf);
+        const float ex = (fabsf(tt) <= 0.5f) ? (float)agc_exp_small((double)tt) : (float)exp((double)tt);
+        g = __fmul_rn(g, ex);
+    }
+    if (g > 1e6f) g = 1e6f;
+    return make_float2(yr, yi);
+}
+
+// one block of the recurrence; samples are fetched eight at a time ahead of the serial chain so that memory
+// latency stays off the critical path (a thread's samples are contiguous, lanes are a whole block apart)
 __device__ __forceinline__ void agc_rms_block(const float2* __restrict__ x, size_t i0, size_t i1, const PostParams& p,
                                               const float* __restrict__ lut, float& g, float& y2p, float2* __restrict__ y)
 {
     const float alpha = p.agc_alpha;
     const double oma = 1.0 - (double)alpha;
     const float mha = __fmul_rn(-0.5f, alpha);
-    for (size_t i = i0; i < i1; i++) {
-        float2 v = x[i];
-        if (p.nco_enable) v = nco_mix(v, p.nco_theta0 + (uint32_t)i * p.nco_dtheta, p.nco_sign, lut);
-        const float yr = __fmul_rn(v.x, g), yi = __fmul_rn(v.y, g);
-        const float y2 = __fadd_rn(__fmul_rn(yr, yr), __fmul_rn(yi, yi));
-        y2p = (float)(oma * (double)y2p + (double)__fmul_rn(alpha, y2));
-        if (y2p > 1e-6f) {
-            // logf/expf evaluated in double and rounded once: matches a correctly rounded libm
-            const float lf = (float)agc_log_pos(y2p);
-            const float tt = __fmul_rn(mha, lf);
-            const float ex = (fabsf(tt) <= 0.5f) ? (float)agc_exp_small((double)tt) : (float)exp((double)tt);
-            g = __fmul_rn(g, ex);
-        }
-        if (g > 1e6f) g = 1e6f;
-        y[i] = make_float2(yr, yi);
+    size_t i = i0;
+    for (; i + 8 <= i1; i += 8) {
+        float2 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = x[i + k];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = agc_rms_step(v[k], i + k, p, lut, alpha, oma, mha, g, y2p);
+#pragma unroll
+        for (int k = 0; k < 8; k++) y[i + k] = v[k];
     }
+    for (; i < i1; i++) y[i] = agc_rms_step(x[i], i, p, lut, alpha, oma, mha, g, y2p);
 }
 
 constexpr int AGC_RMS_THREADS = 128;

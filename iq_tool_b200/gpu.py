@@ -48,6 +48,12 @@ class AgcStateC(C.Structure):
                 float(self.last_strong_s))
 
 
+class RawfileStatsC(C.Structure):
+    """iqgpu_rawfile_stats (include/iqgpu.h)."""
+    _fields_ = [("frames_in", C.c_uint64), ("frames_out", C.c_uint64), ("bytes_written", C.c_uint64),
+                ("trains", C.c_uint64)]
+
+
 def _load() -> C.CDLL:
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -89,6 +95,9 @@ def _load() -> C.CDLL:
     lib.iqgpu_agc_digital_initial_state.argtypes = [C.POINTER(AgcStateC)]
     lib.iqgpu_agc_digital_initial_state.restype = None
     lib.iqgpu_agc_digital_advance.argtypes = [C.POINTER(AgcStateC), C.c_float, C.c_double, vp, vp, sz, vp]
+    lib.iqgpu_rawfile_run.restype = C.c_int
+    lib.iqgpu_rawfile_run.argtypes = [C.POINTER(ChainConfigC), C.c_int, C.c_char_p, C.c_char_p, sz, C.POINTER(RawfileStatsC)]
+    lib.iqgpu_rawfile_last_error.restype = C.c_char_p
     lib.iqgpu_get_bytes_per_sample.restype = sz
     lib.iqgpu_get_bytes_per_sample.argtypes = [C.c_int]
     lib.iqgpu_convert_block_to_cf32.argtypes = [vp, vp, sz, C.c_int, C.c_float]
@@ -328,3 +337,13 @@ def agc_digital_advance(state: AgcStateC, target: float, target_rate_hz: float, 
                                          ct.ctypes.data if ct.size else None, pk.size,
                                          g.ctypes.data if want_gains else None))
     return g[: pk.size] if want_gains else None
+
+
+def rawfile_run(cfg: ChainConfig, in_path: str, out_path: str, device: int = 0, train_chunks: int = 0) -> RawfileStatsC:
+    """Stream a raw I/Q file through the chain into a raw output file (reader / chain / writer overlapped)."""
+    st = RawfileStatsC()
+    c = cfg.to_c()
+    rc = lib.iqgpu_rawfile_run(C.byref(c), device, os.fsencode(in_path), os.fsencode(out_path), train_chunks, C.byref(st))
+    if rc != 0:
+        raise IqGpuError(rc, lib.iqgpu_rawfile_last_error().decode("utf-8", "replace"))
+    return st
