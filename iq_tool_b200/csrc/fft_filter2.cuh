@@ -111,18 +111,29 @@ __device__ __forceinline__ void dft_r(float2 (&u)[R])
     else { const float2 a = u[0], b = u[1]; u[0] = cadd(a, b); u[1] = csub(a, b); }
 }
 
+// Padded address of element base + q*s of a butterfly (base = blk*L + j, j < s, L = R*s): when s >= 64 the pad
+// term is linear in q, and when the whole butterfly lies inside one 64-point group (L <= 64) it is constant, so
+// the R addresses are p0 + q*stride with one pad() per butterfly; otherwise (s < 64 < L) every address is padded.
+template <bool LINEAR>
+__device__ __forceinline__ unsigned pad_at(unsigned p0, unsigned base, unsigned q, unsigned s, unsigned stride)
+{
+    return LINEAR ? p0 + q * stride : pad(base + q * s);
+}
+__device__ __forceinline__ bool pad_linear(unsigned L, unsigned s) { return s >= 64 || L <= 64; }
+__device__ __forceinline__ unsigned pad_stride(unsigned s) { return s >= 64 ? s + 4u * (s >> 6) : s; }
+
 // one in-place pass over the padded shared buffer: sub-length L, radix R, stride s = L / R.
 // forward (DIF): u <- DFT_R(u), u[p] *= W_L^(j p).   inverse (DIT): u[p] *= conj(W_L^(j p)), u <- IDFT_R(u).
-template <int R, bool INV>
-__device__ __forceinline__ void smem_pass(float2* __restrict__ buf, unsigned N, unsigned L, const float2* __restrict__ tw,
-                                          unsigned NT, unsigned tid)
+template <int R, bool INV, bool LINEAR>
+__device__ __forceinline__ void smem_pass_impl(float2* __restrict__ buf, unsigned N, unsigned L, const float2* __restrict__ tw,
+                                               unsigned NT, unsigned tid)
 {
-    const unsigned s = L / R, tws = NT / L;
+    const unsigned s = L / R, tws = NT / L, stride = pad_stride(s);
     for (unsigned t = tid; t < N / R; t += THREADS) {
-        const unsigned j = t & (s - 1), base = (t - j) * R + j;
+        const unsigned j = t & (s - 1), base = (t - j) * R + j, p0 = pad(base);
         float2 u[R], w[R];
 #pragma unroll
-        for (int q = 0; q < R; q++) u[q] = buf[pad(base + q * s)];
+        for (int q = 0; q < R; q++) u[q] = buf[pad_at<LINEAR>(p0, base, q, s, stride)];
         pass_twiddles<R>(tw, j, tws, w);
         if (INV) {
 #pragma unroll
@@ -134,8 +145,15 @@ __device__ __forceinline__ void smem_pass(float2* __restrict__ buf, unsigned N, 
             for (int p = 1; p < R; p++) u[p] = cmul(u[p], w[p]);
         }
 #pragma unroll
-        for (int q = 0; q < R; q++) buf[pad(base + q * s)] = u[q];
+        for (int q = 0; q < R; q++) buf[pad_at<LINEAR>(p0, base, q, s, stride)] = u[q];
     }
+}
+template <int R, bool INV>
+__device__ __forceinline__ void smem_pass(float2* __restrict__ buf, unsigned N, unsigned L, const float2* __restrict__ tw,
+                                          unsigned NT, unsigned tid)
+{
+    if (pad_linear(L, L / R)) smem_pass_impl<R, INV, true>(buf, N, L, tw, NT, tid);
+    else smem_pass_impl<R, INV, false>(buf, N, L, tw, NT, tid);
 }
 
 // first forward pass (L = N) with its inputs read from global memory
@@ -143,7 +161,8 @@ template <int R>
 __device__ __forceinline__ void first_pass_from_global(const float2* __restrict__ x, float2* __restrict__ buf, unsigned N,
                                                        const float2* __restrict__ tw, unsigned NT, unsigned tid)
 {
-    const unsigned s = N / R, tws = NT / N;
+    const unsigned s = N / R, tws = NT / N, stride = pad_stride(s);
+    const bool lin = pad_linear(N, s);
     for (unsigned t = tid; t < s; t += THREADS) {
         float2 u[R], w[R];
 #pragma unroll
@@ -152,8 +171,14 @@ __device__ __forceinline__ void first_pass_from_global(const float2* __restrict_
         dft_r<R, false>(u);
 #pragma unroll
         for (int p = 1; p < R; p++) u[p] = cmul(u[p], w[p]);
+        const unsigned p0 = pad(t);
+        if (lin) {
 #pragma unroll
-        for (int q = 0; q < R; q++) buf[pad(t + q * s)] = u[q];
+            for (int q = 0; q < R; q++) buf[p0 + q * stride] = u[q];
+        } else {
+#pragma unroll
+            for (int q = 0; q < R; q++) buf[pad(t + q * s)] = u[q];
+        }
     }
 }
 
@@ -162,11 +187,18 @@ template <int R>
 __device__ __forceinline__ void last_pass_to_global(float2* __restrict__ buf, float2* __restrict__ y, unsigned N,
                                                     const float2* __restrict__ tw, unsigned NT, float scale, unsigned tid)
 {
-    const unsigned s = N / R, tws = NT / N;
+    const unsigned s = N / R, tws = NT / N, stride = pad_stride(s);
+    const bool lin = pad_linear(N, s);
     for (unsigned t = tid; t < s; t += THREADS) {
         float2 u[R], w[R];
+        const unsigned p0 = pad(t);
+        if (lin) {
 #pragma unroll
-        for (int q = 0; q < R; q++) u[q] = buf[pad(t + q * s)];
+            for (int q = 0; q < R; q++) u[q] = buf[p0 + q * stride];
+        } else {
+#pragma unroll
+            for (int q = 0; q < R; q++) u[q] = buf[pad(t + q * s)];
+        }
         pass_twiddles<R>(tw, t, tws, w);
 #pragma unroll
         for (int p = 1; p < R; p++) u[p] = cmulc(u[p], w[p]);
