@@ -189,4 +189,46 @@ __device__ __forceinline__ float2 nco_mix(float2 x, uint32_t theta, float sign, 
 }
 
 
+// =============================================================================================
+// packed FP32 pairs (sm_100a FFMA2 / FMUL2 / FADD2: fma.rn.f32x2, mul.rn.f32x2, add.rn.f32x2).
+// Each half is an ordinary IEEE-754 round-to-nearest operation, so results are bit-identical to
+// fmaf / __fmul_rn / __fadd_rn on the two components; one issue slot does the work of two.  A
+// complex sample {re, im} that is scaled by a real tap is exactly this shape.
+// =============================================================================================
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pk2(float lo, float hi)
+{
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f32x2_t pk2(float2 v) { return pk2(v.x, v.y); }
+__device__ __forceinline__ float2 unpk2(f32x2_t v)
+{
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c)
+{
+    f32x2_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b)
+{
+    f32x2_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b)
+{
+    f32x2_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// h * {x.re, x.im} + {acc.re, acc.im}
+__device__ __forceinline__ f32x2_t fma2s(float h, f32x2_t x, f32x2_t acc) { return fma2(pk2(h, h), x, acc); }
+
+
 }  // namespace iqgpu

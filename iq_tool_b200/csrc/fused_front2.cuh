@@ -228,17 +228,17 @@ __device__ __forceinline__ void w2_p0(const Fused2Args& A, float2* __restrict__ 
     const long long a0 = tick_start + lane * 16;               // first frame of this lane
     const bool active = (tick_start + W2_T0 > A.n0) && (tick_start < A.N1);
     const bool fast = w2_tick_fast(A, tick_start);
-    float2 x[16];
+    // the lane's 16 frames as packed {re, im} pairs (FMUL2 / FFMA2: one issue slot per complex sample)
+    f32x2_t x[16];
     if (fast && CS16) {
         // sample_convert.c:136-141: x / 32768 * gain (exact power-of-two scale folded into sc)
+        const f32x2_t sc2 = pk2(sc, sc);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const unsigned w[4] = {pre.q[j].x, pre.q[j].y, pre.q[j].z, pre.q[j].w};
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                x[4 * j + k].x = __fmul_rn((float)(short)(w[k] & 0xffffu), sc);
-                x[4 * j + k].y = __fmul_rn((float)(short)(w[k] >> 16), sc);
-            }
+            for (int k = 0; k < 4; k++)
+                x[4 * j + k] = mul2(pk2((float)(short)(w[k] & 0xffffu), (float)(short)(w[k] >> 16)), sc2);
         }
     } else if (fast) {
 #pragma unroll
@@ -246,52 +246,49 @@ __device__ __forceinline__ void w2_p0(const Fused2Args& A, float2* __restrict__ 
             float2 q[4];
             w2_load_quad(fmt, A.raw, (size_t)(a0 - A.n0) + 4 * j, sc, p.gain, q);
 #pragma unroll
-            for (int k = 0; k < 4; k++) x[4 * j + k] = q[k];
+            for (int k = 0; k < 4; k++) x[4 * j + k] = pk2(q[k]);
         }
     } else if (active) {
 #pragma unroll
         for (int k = 0; k < 16; k++) {
             const long long i = a0 + k;
-            x[k] = (i >= A.n0 && i < A.N1) ? w2_load_frame(fmt, A.raw, (size_t)(i - A.n0), sc, p.gain) : make_float2(0.f, 0.f);
+            x[k] = (i >= A.n0 && i < A.N1) ? pk2(w2_load_frame(fmt, A.raw, (size_t)(i - A.n0), sc, p.gain)) : 0ull;
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < 16; k++) x[k] = make_float2(0.f, 0.f);
+        for (int k = 0; k < 16; k++) x[k] = 0ull;
     }
     if (active) {
         if (DC) {
             // DC blocker (dc_block.c:76 -> liquid iirfilt): v[n] = x[n] + c v[n-1], y[n] = x[n] - (1-c) v[n-1].
             // lane-local weighted sum, one warp scan per tick, state at the tick start from the table
             const double2 vt = A.dc_table[(tick_start - A.A0) >> A.dc_table_shift];
-            float pr = x[0].x, pi = x[0].y;
+            const f32x2_t cc = pk2(A.dc.c, A.dc.c), na = pk2(-A.dc.a, -A.dc.a);
+            f32x2_t pr = x[0];
 #pragma unroll
-            for (int k = 1; k < 16; k++) { pr = fmaf(pr, A.dc.c, x[k].x); pi = fmaf(pi, A.dc.c, x[k].y); }
+            for (int k = 1; k < 16; k++) pr = fma2(pr, cc, x[k]);
 #pragma unroll
             for (int s = 0; s < 5; s++) {
                 const int dist = 1 << s;
-                const float qr = __shfl_up_sync(0xffffffffu, pr, dist);
-                const float qi = __shfl_up_sync(0xffffffffu, pi, dist);
-                if (lane >= dist) { pr = fmaf(A.dc.w[s], qr, pr); pi = fmaf(A.dc.w[s], qi, pi); }
+                const f32x2_t q = __shfl_up_sync(0xffffffffu, pr, dist);
+                if (lane >= dist) pr = fma2s(A.dc.w[s], q, pr);
             }
-            float er = __shfl_up_sync(0xffffffffu, pr, 1), ei = __shfl_up_sync(0xffffffffu, pi, 1);
-            if (lane == 0) { er = 0.f; ei = 0.f; }
+            f32x2_t e = __shfl_up_sync(0xffffffffu, pr, 1);
+            if (lane == 0) e = 0ull;
             const float lp = A.dc.lanepow[lane];
-            float wr = fmaf(lp, (float)vt.x, er), wi = fmaf(lp, (float)vt.y, ei);   // v just before the lane's first frame
+            f32x2_t w = fma2s(lp, pk2((float)vt.x, (float)vt.y), e);   // v just before the lane's first frame
 #pragma unroll
             for (int k = 0; k < 16; k++) {
-                const float xr = x[k].x, xi = x[k].y;
-                x[k].x = fmaf(-A.dc.a, wr, xr);
-                x[k].y = fmaf(-A.dc.a, wi, xi);
-                wr = fmaf(A.dc.c, wr, xr);
-                wi = fmaf(A.dc.c, wi, xi);
+                const f32x2_t xk = x[k];
+                x[k] = fma2(na, w, xk);
+                w = fma2(cc, w, xk);
             }
         }
         if (p.iq_enable) {   // iq_correct.c:307-313
 #pragma unroll
             for (int k = 0; k < 16; k++) {
-                const float re = x[k].x;
-                x[k].x = __fmul_rn(re, p.iq_magp1);
-                x[k].y = __fadd_rn(x[k].y, __fmul_rn(p.iq_phase, re));
+                const float2 v = unpk2(x[k]);
+                x[k] = pk2(__fmul_rn(v.x, p.iq_magp1), __fadd_rn(v.y, __fmul_rn(p.iq_phase, v.x)));
             }
         }
         if (p.nco_enable) {  // liquid LIQUID_NCO: 32-bit phase, 1024-entry table, nearest entry
@@ -299,9 +296,9 @@ __device__ __forceinline__ void w2_p0(const Fused2Args& A, float2* __restrict__ 
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 const float2 sc2 = lut2[w2_lut_slot(((th + (1u << 21)) >> 22) & 0x3ffu, A.lut_sh, A.lut_mask)];   // {sign*sin, cos}
-                const float xr = x[k].x, xi = x[k].y;
-                x[k].x = __fsub_rn(__fmul_rn(xr, sc2.y), __fmul_rn(xi, sc2.x));
-                x[k].y = __fadd_rn(__fmul_rn(xr, sc2.x), __fmul_rn(xi, sc2.y));
+                const float2 v = unpk2(x[k]);
+                x[k] = pk2(__fsub_rn(__fmul_rn(v.x, sc2.y), __fmul_rn(v.y, sc2.x)),
+                           __fadd_rn(__fmul_rn(v.x, sc2.x), __fmul_rn(v.y, sc2.y)));
                 th += p.nco_dtheta;
             }
         }
@@ -312,7 +309,7 @@ __device__ __forceinline__ void w2_p0(const Fused2Args& A, float2* __restrict__ 
             for (int k = 0; k < 16; k++) {
                 if (a0 + k < A.n0) {
                     const long long j = a0 + k - (A.n0 - A.H_tail);
-                    x[k] = (j >= 0) ? A.tail_in[j] : make_float2(0.f, 0.f);
+                    x[k] = (j >= 0) ? pk2(A.tail_in[j]) : 0ull;
                 }
             }
         }
@@ -320,14 +317,14 @@ __device__ __forceinline__ void w2_p0(const Fused2Args& A, float2* __restrict__ 
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 const long long j = a0 + k - (A.N1 - A.H_tail);
-                if (j >= 0 && a0 + k < A.N1) A.tail_out[j] = x[k];
+                if (j >= 0 && a0 + k < A.N1) A.tail_out[j] = unpk2(x[k]);
             }
         }
     }
     if (S == 0) {
-        float4* f = reinterpret_cast<float4*>(wsm + P::flat_off + W2_ARB_HIST + 16 * lane);
+        ulonglong2* f = reinterpret_cast<ulonglong2*>(wsm + P::flat_off + W2_ARB_HIST + 16 * lane);
 #pragma unroll
-        for (int j = 0; j < 8; j++) f[j] = make_float4(x[2 * j].x, x[2 * j].y, x[2 * j + 1].x, x[2 * j + 1].y);
+        for (int j = 0; j < 8; j++) f[j] = make_ulonglong2(x[2 * j], x[2 * j + 1]);
     } else {
         // level 0 planes: lane owns plane entries Hh + 8*lane .. +7 = one padded group of 8
         constexpr int c0 = P::Hh(0);
@@ -336,8 +333,8 @@ __device__ __forceinline__ void w2_p0(const Fused2Args& A, float2* __restrict__ 
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int ph = P::phys(0, c0 + 2 * j);
-            *reinterpret_cast<float4*>(E + ph) = make_float4(x[4 * j].x, x[4 * j].y, x[4 * j + 2].x, x[4 * j + 2].y);
-            *reinterpret_cast<float4*>(O + ph) = make_float4(x[4 * j + 1].x, x[4 * j + 1].y, x[4 * j + 3].x, x[4 * j + 3].y);
+            *reinterpret_cast<ulonglong2*>(E + ph) = make_ulonglong2(x[4 * j], x[4 * j + 2]);
+            *reinterpret_cast<ulonglong2*>(O + ph) = make_ulonglong2(x[4 * j + 1], x[4 * j + 3]);
         }
     }
 }
@@ -358,7 +355,9 @@ __device__ __forceinline__ void w2_stage(const Fused2Args& A, float2* __restrict
     constexpr bool VEC = (R >= 4);                    // padded layouts keep even-aligned pairs 16-byte aligned
     const float2* __restrict__ E = wsm + P::e_off(D) + (R + PADD) * lane;
     const float2* __restrict__ O = wsm + P::o_off(D) + (R + PADD) * lane;
-    float2 ent[NE], oc[R];
+    // samples are kept as packed {re, im} pairs: every tap multiplies both halves, so one FFMA2 does the
+    // work of two FFMAs (bit-identical: each half is an IEEE fma)
+    f32x2_t ent[NE], oc[R];
     // even-aligned pairs of a padded plane are 16-byte aligned: one LDS.128 per pair
 #pragma unroll
     for (int e = 0; e < NE; e++) {
@@ -366,10 +365,10 @@ __device__ __forceinline__ void w2_stage(const Fused2Args& A, float2* __restrict
         const bool first = VEC && (c % 2 == 0) && (e + 1 < NE);
         const bool second = VEC && (c % 2 != 0) && (e >= 1);
         if (first) {
-            const float4 v = *reinterpret_cast<const float4*>(E + P::phys(D, c));
-            ent[e] = make_float2(v.x, v.y);
-            ent[e + 1] = make_float2(v.z, v.w);
-        } else if (!second) ent[e] = E[P::phys(D, c)];
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(E + P::phys(D, c));
+            ent[e] = v.x;
+            ent[e + 1] = v.y;
+        } else if (!second) ent[e] = *reinterpret_cast<const f32x2_t*>(E + P::phys(D, c));
     }
 #pragma unroll
     for (int r = 0; r < R; r++) {
@@ -377,35 +376,34 @@ __device__ __forceinline__ void w2_stage(const Fused2Args& A, float2* __restrict
         const bool first = VEC && (c % 2 == 0) && (r + 1 < R);
         const bool second = VEC && (c % 2 != 0) && (r >= 1);
         if (first) {
-            const float4 v = *reinterpret_cast<const float4*>(O + P::phys(D, c));
-            oc[r] = make_float2(v.x, v.y);
-            oc[r + 1] = make_float2(v.z, v.w);
-        } else if (!second) oc[r] = O[P::phys(D, c)];
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(O + P::phys(D, c));
+            oc[r] = v.x;
+            oc[r + 1] = v.y;
+        } else if (!second) oc[r] = *reinterpret_cast<const f32x2_t*>(O + P::phys(D, c));
     }
-    float2 acc[R];
+    f32x2_t acc[R];
 #pragma unroll
-    for (int r = 0; r < R; r++) acc[r] = make_float2(0.f, 0.f);
+    for (int r = 0; r < R; r++) acc[r] = 0ull;
 #pragma unroll
     for (int j = 0; j < 2 * M; j++) {
         const float h = A.taps[P::taps_off(D) + j];
+        const f32x2_t hh = pk2(h, h);
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            acc[r].x = fmaf(h, ent[r + j].x, acc[r].x);
-            acc[r].y = fmaf(h, ent[r + j].y, acc[r].y);
-        }
+        for (int r = 0; r < R; r++) acc[r] = fma2(hh, ent[r + j], acc[r]);
     }
-    float2 v[R];
+    f32x2_t v[R];
+    const f32x2_t zz = pk2(A.zeta, A.zeta);
 #pragma unroll
     for (int r = 0; r < R; r++) {
-        if (D + 1 == S) v[r] = make_float2((oc[r].x + acc[r].x) * A.zeta, (oc[r].y + acc[r].y) * A.zeta);
-        else v[r] = make_float2(oc[r].x + acc[r].x, oc[r].y + acc[r].y);
+        if (D + 1 == S) v[r] = mul2(add2(oc[r], acc[r]), zz);
+        else v[r] = add2(oc[r], acc[r]);
     }
     if (D + 1 == S) {
         float2* f = wsm + P::flat_off + W2_ARB_HIST + R * lane;
         if (R >= 2) {
 #pragma unroll
-            for (int r = 0; r < R; r += 2) *reinterpret_cast<float4*>(f + r) = make_float4(v[r].x, v[r].y, v[r + 1].x, v[r + 1].y);
-        } else f[0] = v[0];
+            for (int r = 0; r < R; r += 2) *reinterpret_cast<ulonglong2*>(f + r) = make_ulonglong2(v[r], v[r + 1]);
+        } else *reinterpret_cast<f32x2_t*>(f) = v[0];
     } else if (R >= 2) {
         constexpr int R2 = R / 2, HN = P::Hh(D + 1), PN = P::PAD(D + 1);
         float2* nE = wsm + P::e_off(D + 1) + (R2 + PN) * lane;
@@ -414,22 +412,22 @@ __device__ __forceinline__ void w2_stage(const Fused2Args& A, float2* __restrict
 #pragma unroll
             for (int i = 0; i < R2; i += 2) {
                 const int ph = P::phys(D + 1, HN + i);
-                *reinterpret_cast<float4*>(nE + ph) = make_float4(v[2 * i].x, v[2 * i].y, v[2 * i + 2].x, v[2 * i + 2].y);
-                *reinterpret_cast<float4*>(nO + ph) = make_float4(v[2 * i + 1].x, v[2 * i + 1].y, v[2 * i + 3].x, v[2 * i + 3].y);
+                *reinterpret_cast<ulonglong2*>(nE + ph) = make_ulonglong2(v[2 * i], v[2 * i + 2]);
+                *reinterpret_cast<ulonglong2*>(nO + ph) = make_ulonglong2(v[2 * i + 1], v[2 * i + 3]);
             }
         } else {
 #pragma unroll
             for (int i = 0; i < R2; i++) {
                 const int ph = P::phys(D + 1, HN + i);
-                nE[ph] = v[2 * i];
-                nO[ph] = v[2 * i + 1];
+                *reinterpret_cast<f32x2_t*>(nE + ph) = v[2 * i];
+                *reinterpret_cast<f32x2_t*>(nO + ph) = v[2 * i + 1];
             }
         }
     } else {
         // R == 1: lane's single output q = lane (+32*half in the consumer's run) -> E'/O' entry q/2
         constexpr int HN = P::Hh(D + 1);
         float2* pl = wsm + ((lane & 1) ? P::o_off(D + 1) : P::e_off(D + 1));
-        pl[HN + 16 * half + (lane >> 1)] = v[0];
+        *reinterpret_cast<f32x2_t*>(pl + HN + 16 * half + (lane >> 1)) = v[0];
     }
 }
 
@@ -487,15 +485,15 @@ __device__ __forceinline__ void w2_arb(const Fused2Args& A, const float2* __rest
         const unsigned idx = (unsigned)(Pp >> 16) & 0xffu;
         const float2* __restrict__ w = flat + rel + (W2_ARB_HIST - 13);
         const float2* __restrict__ b = sbank + w2_bank_row((int)idx);
-        float sr = 0.f, si = 0.f;
+        f32x2_t sacc = 0ull;
 #pragma unroll
         for (int i = 0; i < 7; i++) {
             const float2 h = b[i];
-            const float2 v0 = w[2 * i], v1 = w[2 * i + 1];
-            sr = fmaf(h.x, v0.x, sr); si = fmaf(h.x, v0.y, si);
-            sr = fmaf(h.y, v1.x, sr); si = fmaf(h.y, v1.y, si);
+            const f32x2_t v0 = *reinterpret_cast<const f32x2_t*>(w + 2 * i), v1 = *reinterpret_cast<const f32x2_t*>(w + 2 * i + 1);
+            sacc = fma2s(h.x, v0, sacc);
+            sacc = fma2s(h.y, v1, sacc);
         }
-        A.y[o - A.O0] = make_float2(sr, si);
+        *reinterpret_cast<f32x2_t*>(A.y + (o - A.O0)) = sacc;
     }
 }
 
