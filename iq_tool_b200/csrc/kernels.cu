@@ -789,16 +789,42 @@ struct AgcStep {   // sequential reference step, shared by both paths
         return g;
     }
 };
-// Per tile of AGC_SCAN_TILE chunks: (1) the whole CTA stages the chunk table in shared memory and
-// evaluates everything that is not state dependent in parallel — the running sample counter (block
-// prefix sum) and each chunk's sample-clock time seen/rate (one double division per chunk, off the
-// serial path); (2) one warp walks the tile 32 chunks at a time.  While nothing data dependent
-// happens inside a group all 32 gains come out in one step: scanning (unlocked) groups are a
-// prefix maximum of the peaks, locked groups without a ratchet or creep keep their gain.  A group
-// that contains a lock transition, a ratchet or a creep is replayed chunk by chunk with the
-// reference's sequential step (AgcStep::run), so the results are those of the sequential loop.
+// Chunk-table scan.  Per tile of AGC_SCAN_TILE chunks:
+//  (1) the whole CTA stages the chunk table in shared memory and evaluates everything that is not state
+//      dependent in parallel: the running sample counter (block prefix sum) and each chunk's sample-clock
+//      time seen/rate (one double division per chunk, off the serial path);
+//  (2) "passes": from the current position the CTA evaluates ALL remaining chunks of the tile in parallel under
+//      the hypothesis that no data-dependent event happens (scanning: gains follow the running peak maximum —
+//      a block-wide prefix max; locked: the gain stays put and last_strong follows the latest strong chunk —
+//      a block-wide prefix max of chunk times) and finds the first chunk that breaks the hypothesis (lock
+//      transition, ratchet, creep).  Everything before that chunk is final.  One thread then replays the
+//      reference's sequential step (agc_step_at) from that chunk until a chunk passes without an event (or
+//      AGC_REPLAY_MAX chunks, so that long creep phases amortise the pass), and the next pass starts there.
+// Event-free stretches of any length cost one pass per tile; the results are those of the sequential loop.
 constexpr int AGC_SCAN_TILE = 2048;
 constexpr int AGC_SCAN_THREADS = 512;
+constexpr int AGC_REPLAY_MAX = 256;
+// the reference's sequential step with the chunk's sample-clock time supplied (== (double)s.seen / rate)
+__device__ __forceinline__ float agc_step_at(AgcState& s, float pk, unsigned cnt, float target, float strong_thr, double now, bool& event)
+{
+    float g;
+    event = false;
+    if (!s.locked) {
+        if (pk > s.peak_mem) s.peak_mem = pk;
+        const float safe = (s.peak_mem < 1e-4f) ? 1e-4f : s.peak_mem;
+        g = __fdiv_rn(target, safe);
+        if (now > (double)2.0f) { s.locked = 1; s.gain = g; s.last_strong = now; event = true; }
+    } else {
+        g = s.gain;
+        const float opk = __fmul_rn(pk, g);
+        if (opk > 1.0f) { g = __fdiv_rn(0.99f, pk); s.last_strong = now; event = true; }
+        else if (opk > strong_thr) s.last_strong = now;
+        else if (now - s.last_strong > (double)4.0f) { g = __fmul_rn(g, 1.0005f); event = true; }
+        s.gain = g;
+    }
+    s.seen += cnt;
+    return g;
+}
 __global__ void __launch_bounds__(AGC_SCAN_THREADS) agc_digital_scan_kernel(const uint32_t* __restrict__ seg_start, unsigned nseg,
                                                                             const float* __restrict__ seg_peak, PostParams p,
                                                                             AgcState* __restrict__ st, float* __restrict__ seg_gain)
@@ -808,7 +834,11 @@ __global__ void __launch_bounds__(AGC_SCAN_THREADS) agc_digital_scan_kernel(cons
     __shared__ float s_gain[AGC_SCAN_TILE];
     __shared__ double s_now[AGC_SCAN_TILE];         // seen_before / rate of every chunk
     __shared__ unsigned long long s_warp_tot[AGC_SCAN_THREADS / 32];
+    __shared__ double s_warp_max[AGC_SCAN_THREADS / 32];
     __shared__ AgcState s_state;
+    __shared__ unsigned s_first, s_pos;
+    __shared__ unsigned long long s_sum;
+    __shared__ double s_upd;                        // peak memory / last_strong at the chunk before the first event
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_state = *st;
     __syncthreads();
@@ -819,12 +849,15 @@ __global__ void __launch_bounds__(AGC_SCAN_THREADS) agc_digital_scan_kernel(cons
         const unsigned tn = min((unsigned)AGC_SCAN_TILE, nseg - tile0);
         // ---- (1) parallel part: table, exclusive prefix of the sample counter, chunk times ----
         unsigned cnt[PER_THREAD];
+        float pkv[PER_THREAD];
+        double nowv[PER_THREAD];
         unsigned long long run = 0;
 #pragma unroll
         for (int k = 0; k < PER_THREAD; k++) {
             const unsigned i = tid * PER_THREAD + k;
             cnt[k] = (i < tn) ? (__ldg(seg_start + tile0 + i + 1) - __ldg(seg_start + tile0 + i)) : 0u;
-            if (i < tn) { s_cnt[i] = cnt[k]; s_pk[i] = __ldg(seg_peak + tile0 + i); }
+            pkv[k] = (i < tn) ? __ldg(seg_peak + tile0 + i) : 0.f;
+            if (i < tn) { s_cnt[i] = cnt[k]; s_pk[i] = pkv[k]; }
             run += cnt[k];
         }
         unsigned long long inc = run;
@@ -834,6 +867,7 @@ __global__ void __launch_bounds__(AGC_SCAN_THREADS) agc_digital_scan_kernel(cons
             if (lane >= (unsigned)d) inc += q;
         }
         if (lane == 31) s_warp_tot[warp] = inc;
+        if (tid == 0) s_pos = 0;
         __syncthreads();
         unsigned long long base = s_state.seen;
         for (unsigned w = 0; w < warp; w++) base += s_warp_tot[w];
@@ -841,79 +875,106 @@ __global__ void __launch_bounds__(AGC_SCAN_THREADS) agc_digital_scan_kernel(cons
 #pragma unroll
         for (int k = 0; k < PER_THREAD; k++) {
             const unsigned i = tid * PER_THREAD + k;
-            if (i < tn) s_now[i] = (double)seen_before / p.target_rate;
+            nowv[k] = (double)seen_before / p.target_rate;
+            if (i < tn) s_now[i] = nowv[k];
             seen_before += cnt[k];
         }
         __syncthreads();
-        // ---- (2) serial part: one warp, 32 chunks per step ----
-        if (warp == 0) {
-            AgcState s = s_state;
-            for (unsigned gbase = 0; gbase < tn; gbase += 32) {
-                const unsigned c = gbase + lane;
-                const bool valid = c < tn;
-                const unsigned cn = valid ? s_cnt[c] : 0u;
-                const float pk = valid ? s_pk[c] : 0.f;
-                const double now = valid ? s_now[c] : 0.0;
-                const bool act = cn != 0;                                // agc_apply returns on num_samples == 0
-                unsigned gsum = cn;
+        // ---- (2) passes ----
+        for (;;) {
+            const unsigned pos = s_pos;
+            if (pos >= tn) break;
+            const AgcState s = s_state;
+            if (tid == 0) { s_first = tn; s_sum = 0ull; }
+            // keys: scanning -> peak of the chunk; locked -> time of the chunk if it is "strong" at the current gain
+            double key[PER_THREAD], incl[PER_THREAD];
+            bool actv[PER_THREAD], strong[PER_THREAD], ratchet[PER_THREAD];
+            double trun = -1.0;
 #pragma unroll
-                for (int d = 16; d > 0; d >>= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, d);
-                bool fast = false;
-                float g = 1.0f;
-                if (!s.locked) {
-                    // scanning mode (agc.c:117-160): gain from the running peak maximum; the lock test uses the
-                    // sample count BEFORE the chunk.  Fast when no chunk of the group reaches the lock time.
-                    const bool locks = act && (now > (double)2.0f);
-                    if (!__any_sync(0xffffffffu, locks)) {
-                        float mx = act ? pk : 0.f;
-#pragma unroll
-                        for (int d = 1; d < 32; d <<= 1) {
-                            const float q = __shfl_up_sync(0xffffffffu, mx, d);
-                            if (lane >= (unsigned)d) mx = fmaxf(mx, q);
-                        }
-                        const float mem = fmaxf(s.peak_mem, mx);
-                        const float safe = (mem < 1e-4f) ? 1e-4f : mem;
-                        g = __fdiv_rn(target, safe);
-                        s.peak_mem = __shfl_sync(0xffffffffu, mem, 31);
-                        s.seen += gsum;
-                        fast = true;
-                    }
-                } else {
-                    const float opk = __fmul_rn(pk, s.gain);
-                    const bool ratchet = act && opk > 1.0f;
-                    const bool strong = act && opk > strong_thr;
-                    // time of the latest strong chunk strictly before this lane (chunk times are non-decreasing)
-                    const unsigned smask = __ballot_sync(0xffffffffu, strong);
-                    const unsigned below = smask & ((1u << lane) - 1u);
-                    const int prev = below ? (31 - __clz(below)) : 0;
-                    const double prev_now = __shfl_sync(0xffffffffu, now, prev);
-                    const double ls_excl = below ? fmax(prev_now, s.last_strong) : s.last_strong;
-                    const bool creep = act && !strong && (now - ls_excl > (double)4.0f);
-                    if (!__any_sync(0xffffffffu, ratchet || creep)) {
-                        fast = true;
-                        g = s.gain;
-                        if (smask) {
-                            const double top = __shfl_sync(0xffffffffu, now, 31 - __clz(smask));
-                            s.last_strong = fmax(s.last_strong, top);
-                        }
-                        s.seen += gsum;
-                    }
-                }
-                if (!fast) {
-                    // replay: warp-uniform sequential walk over the group's chunks
-                    for (unsigned k = 0; k < 32 && gbase + k < tn; k++) {
-                        const unsigned ck = __shfl_sync(0xffffffffu, cn, k);
-                        const float pkk = __shfl_sync(0xffffffffu, pk, k);
-                        if (ck == 0) continue;
-                        const float gk = AgcStep::run(s, pkk, ck, target, p.target_rate);
-                        if (lane == k) g = gk;
-                    }
-                }
-                if (valid) s_gain[c] = act ? g : 1.0f;
+            for (int k = 0; k < PER_THREAD; k++) {
+                const unsigned i = tid * PER_THREAD + k;
+                actv[k] = (i >= pos) && (i < tn) && (cnt[k] != 0);            // agc_apply returns on num_samples == 0
+                const float opk = __fmul_rn(pkv[k], s.gain);
+                ratchet[k] = actv[k] && opk > 1.0f;
+                strong[k] = actv[k] && opk > strong_thr;
+                key[k] = !actv[k] ? -1.0 : (s.locked ? (strong[k] ? nowv[k] : -1.0) : (double)pkv[k]);
+                trun = fmax(trun, key[k]);
+                incl[k] = trun;
             }
-            if (lane == 0) s_state = s;
+            double wv = trun;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const double q = __shfl_up_sync(0xffffffffu, wv, d);
+                if (lane >= (unsigned)d) wv = fmax(wv, q);
+            }
+            double tex = __shfl_up_sync(0xffffffffu, wv, 1);
+            if (lane == 0) tex = -1.0;
+            if (lane == 31) s_warp_max[warp] = wv;
+            __syncthreads();
+            for (unsigned w = 0; w < warp; w++) tex = fmax(tex, s_warp_max[w]);   // max of the keys of all chunks before this thread's
+            float g[PER_THREAD];
+            double after[PER_THREAD];                                             // state value once chunk k has been taken
+            unsigned ev = tn;
+#pragma unroll
+            for (int k = 0; k < PER_THREAD; k++) {
+                const unsigned i = tid * PER_THREAD + k;
+                const double ex = (k == 0) ? tex : fmax(tex, incl[k - 1]);
+                const double in = fmax(tex, incl[k]);
+                bool event;
+                if (!s.locked) {
+                    // scanning (agc.c:117-160): gain from the running peak maximum; lock test on the time BEFORE the chunk
+                    const float mem = fmaxf(s.peak_mem, (float)in);
+                    const float safe = (mem < 1e-4f) ? 1e-4f : mem;
+                    g[k] = __fdiv_rn(target, safe);
+                    after[k] = (double)mem;
+                    event = actv[k] && (nowv[k] > (double)2.0f);
+                } else {
+                    const double ls_excl = fmax(s.last_strong, ex);
+                    const bool creep = actv[k] && !strong[k] && (nowv[k] - ls_excl > (double)4.0f);
+                    g[k] = s.gain;
+                    after[k] = fmax(s.last_strong, in);
+                    event = ratchet[k] || creep;
+                }
+                if (event && i < ev) ev = i;
+            }
+            if (ev < tn) atomicMin(&s_first, ev);
+            __syncthreads();
+            const unsigned first = s_first;
+            unsigned long long part = 0;
+#pragma unroll
+            for (int k = 0; k < PER_THREAD; k++) {
+                const unsigned i = tid * PER_THREAD + k;
+                if (i >= pos && i < first) {
+                    s_gain[i] = actv[k] ? g[k] : 1.0f;
+                    part += cnt[k];
+                    if (i + 1 == first) s_upd = after[k];
+                }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+            if (lane == 0 && part) atomicAdd(&s_sum, part);
+            __syncthreads();
+            if (tid == 0) {
+                AgcState t = s;
+                if (first > pos) {
+                    t.seen += s_sum;
+                    if (!t.locked) t.peak_mem = (float)s_upd; else t.last_strong = s_upd;
+                }
+                // sequential replay from the first event until a chunk passes without one
+                unsigned k = first, done = 0;
+                while (k < tn) {
+                    const unsigned ck = s_cnt[k];
+                    if (ck == 0) { s_gain[k] = 1.0f; k++; continue; }
+                    bool event;
+                    s_gain[k] = agc_step_at(t, s_pk[k], ck, target, strong_thr, s_now[k], event);
+                    k++;
+                    if (!event || ++done >= AGC_REPLAY_MAX) break;
+                }
+                s_state = t;
+                s_pos = k;
+            }
+            __syncthreads();
         }
-        __syncthreads();
         for (unsigned i = tid; i < tn; i += AGC_SCAN_THREADS) seg_gain[tile0 + i] = s_gain[i];
         __syncthreads();
     }

@@ -434,3 +434,57 @@ def test_iq_optimizer_pass_matches_reference(gpu, workloads):
     noise = ((rng.standard_normal(1024) + 1j * rng.standard_normal(1024)) * 0.1).astype(np.complex64)
     gm, gp, ga, gr = gpu.iq_optimize(noise, libc_rand_directions(1), 0.01, -0.02)
     assert gr < 20.0 and gm == np.float32(0.01) and gp == np.float32(-0.02)
+
+
+def test_digital_agc_chunk_table_scan_equals_the_sequential_state_machine(gpu):
+    """G2 (agc.c:105-222) over thousands of chunks in ONE train: the GPU evaluates the per-chunk state
+    machine with a parallel scan over the chunk table (event-free stretches in one step, chunks with a lock
+    transition / ratchet / creep replayed sequentially); the oracle walks the chunks one by one on the
+    sample clock.  The amplitude schedule covers scanning with a rising peak memory, the lock, long
+    event-free locked stretches (several scan tiles), isolated and back-to-back ratchets, 'strong'
+    refreshes, and long creep phases."""
+    from oracle import loader
+    rate, chunk = 512.0, 64                      # one chunk = 0.125 s: lock after 17 chunks, creep after 32 weak ones
+    rng = np.random.Generator(np.random.PCG64(77))
+    amps = [0.05, 0.1, 0.2, 0.15, 0.4] + [0.3] * 30                 # scan, lock at chunk 17
+    amps += [0.5, 0.45, 0.44]                                        # ratchet(s)
+    amps += [0.42] * 2500                                            # strong, event free: > one 2048-chunk tile
+    amps += [0.03] * 300                                             # weak: creep starts after 32 chunks
+    amps += [0.9, 0.95, 1.0, 0.2]                                    # ratchets back to back
+    amps += list(rng.choice([0.02, 0.3, 0.45, 0.7], size=1500, p=[0.5, 0.3, 0.15, 0.05]))   # mixed
+    amps += [0.25] * 2200 + [0.6] + [0.01] * 100
+    amps = np.asarray(amps, dtype=np.float32)
+    nchunks = amps.size
+    ph = rng.uniform(0, 2 * np.pi, size=nchunks * chunk)
+    mag = rng.uniform(0.2, 1.0, size=nchunks * chunk)
+    mag[::chunk] = 1.0                                               # every chunk reaches its amplitude
+    x = (np.repeat(amps, chunk) * mag * np.exp(1j * ph)).astype(np.complex64)
+    cfg = ChainConfig(input_format="cf32", output_format="cf32", input_rate_hz=rate, target_rate_hz=rate,
+                      no_resample=True, agc_enable=True, agc_profile=AGC_DIGITAL)
+    lib, pfx = loader.get_lib("oracle")
+    o = CpuChain(cfg, "oracle")
+    ref = np.zeros_like(x)
+    try:
+        for c in range(nchunks):
+            getattr(lib, pfx + "set_fake_clock")(1, c * chunk / rate)
+            ref[c * chunk:(c + 1) * chunk] = o.process(x[c * chunk:(c + 1) * chunk].view(np.float32)).view(np.complex64)
+    finally:
+        getattr(lib, pfx + "set_fake_clock")(0, 0.0)
+    oi = o.info()
+    sizes = np.full(nchunks, chunk, dtype=np.uint32)
+    for pieces in (1, 7):                                            # one train, and ragged trains (state carried)
+        g = gpu.Chain(cfg, 0)
+        outs, edges = [], np.linspace(0, nchunks, pieces + 1).astype(int)
+        for a, b in zip(edges[:-1], edges[1:]):
+            outs.append(g.process(x[a * chunk:b * chunk].view(np.float32), chunk_frames=sizes[a:b]).view(np.complex64))
+        out = np.concatenate(outs)
+        assert out.size == ref.size
+        gi = g.info()
+        assert (gi.agc_locked, gi.agc_samples_seen) == (oi.agc_locked, oi.agc_samples_seen)
+        assert gi.agc_gain == pytest.approx(oi.agc_gain, rel=3e-7) and gi.agc_peak_memory == pytest.approx(oi.agc_peak_memory, rel=3e-7)
+        gain_g = np.abs(out[::chunk]) / amps
+        gain_r = np.abs(ref[::chunk]) / amps
+        assert np.allclose(gain_g, gain_r, rtol=1e-6, atol=0)
+        assert np.allclose(out, ref, rtol=1e-6, atol=1e-9)
+    # the schedule really exercised every branch
+    assert gain_r[40] < gain_r[30] and gain_r[2500 + 38 + 290] > gain_r[2500 + 38 + 10]
