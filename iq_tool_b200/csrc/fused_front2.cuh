@@ -99,6 +99,9 @@ struct W2Plan {
         for (int i = 0; i < d; i++) o += 2 * m(i);
         return o;
     }
+    // first stage straight from the lane's registers (neighbour entries by warp shuffle): cascades whose first
+    // stage has semi-length 3, i.e. S >= 3
+    static constexpr bool reg0 = (S >= 3);
     static constexpr int flat_new = (S == 0) ? W2_T0 : out(S - 1);        // new polyphase inputs per arb run
     static constexpr int flat_off = e_off(S);
     static constexpr int flat_size = (W2_ARB_HIST + flat_new + 3) & ~1;
@@ -219,7 +222,7 @@ __device__ __forceinline__ void w2_prefetch(const Fused2Args& A, long long tick_
 // ------------------------------------------------------------------------------------------------
 template <int S, bool DC, bool CS16>
 __device__ __forceinline__ void w2_p0(const Fused2Args& A, float2* __restrict__ wsm, const float2* __restrict__ lut2,
-                                      long long tick_start, int lane, const W2Raw& pre)
+                                      long long tick_start, int lane, const W2Raw& pre, f32x2_t (&x)[16])
 {
     using P = W2Plan<S>;
     const PreParams& p = A.pre;
@@ -229,7 +232,6 @@ __device__ __forceinline__ void w2_p0(const Fused2Args& A, float2* __restrict__ 
     const bool active = (tick_start + W2_T0 > A.n0) && (tick_start < A.N1);
     const bool fast = w2_tick_fast(A, tick_start);
     // the lane's 16 frames as packed {re, im} pairs (FMUL2 / FFMA2: one issue slot per complex sample)
-    f32x2_t x[16];
     if (fast && CS16) {
         // sample_convert.c:136-141: x / 32768 * gain (exact power-of-two scale folded into sc)
         const f32x2_t sc2 = pk2(sc, sc);
@@ -321,6 +323,7 @@ __device__ __forceinline__ void w2_p0(const Fused2Args& A, float2* __restrict__ 
             }
         }
     }
+    if (P::reg0) return;            // the first halfband stage reads x[] straight from registers (w2_stage0_reg)
     if (S == 0) {
         ulonglong2* f = reinterpret_cast<ulonglong2*>(wsm + P::flat_off + W2_ARB_HIST + 16 * lane);
 #pragma unroll
@@ -337,6 +340,96 @@ __device__ __forceinline__ void w2_p0(const Fused2Args& A, float2* __restrict__ 
             *reinterpret_cast<ulonglong2*>(O + ph) = make_ulonglong2(x[4 * j + 1], x[4 * j + 3]);
         }
     }
+}
+
+// write the R outputs of stage D (lane owns outputs R*lane .. R*lane+R-1 of the run) to the next level's planes,
+// or to the flat polyphase input when D is the last stage
+template <int S, int D>
+__device__ __forceinline__ void w2_stage_store(float2* __restrict__ wsm, int lane, int half, const f32x2_t (&v)[W2Plan<S>::R(D)])
+{
+    using P = W2Plan<S>;
+    constexpr int R = P::R(D);
+    if (D + 1 == S) {
+        float2* f = wsm + P::flat_off + W2_ARB_HIST + R * lane;
+        if (R >= 2) {
+#pragma unroll
+            for (int r = 0; r < R; r += 2) *reinterpret_cast<ulonglong2*>(f + r) = make_ulonglong2(v[r], v[r + 1]);
+        } else *reinterpret_cast<f32x2_t*>(f) = v[0];
+    } else if (R >= 2) {
+        constexpr int R2 = R / 2, HN = P::Hh(D + 1), PN = P::PAD(D + 1);
+        float2* nE = wsm + P::e_off(D + 1) + (R2 + PN) * lane;
+        float2* nO = wsm + P::o_off(D + 1) + (R2 + PN) * lane;
+        if (R2 >= 4 || (R2 == 2 && PN == 2)) {
+#pragma unroll
+            for (int i = 0; i < R2; i += 2) {
+                const int ph = P::phys(D + 1, HN + i);
+                *reinterpret_cast<ulonglong2*>(nE + ph) = make_ulonglong2(v[2 * i], v[2 * i + 2]);
+                *reinterpret_cast<ulonglong2*>(nO + ph) = make_ulonglong2(v[2 * i + 1], v[2 * i + 3]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < R2; i++) {
+                const int ph = P::phys(D + 1, HN + i);
+                *reinterpret_cast<f32x2_t*>(nE + ph) = v[2 * i];
+                *reinterpret_cast<f32x2_t*>(nO + ph) = v[2 * i + 1];
+            }
+        }
+    } else {
+        // R == 1: lane's single output q = lane (+32*half in the consumer's run) -> E'/O' entry q/2
+        constexpr int HN = P::Hh(D + 1);
+        float2* pl = wsm + ((lane & 1) ? P::o_off(D + 1) : P::e_off(D + 1));
+        *reinterpret_cast<f32x2_t*>(pl + HN + 16 * half + (lane >> 1)) = v[0];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// first halfband stage (semi-length 3) straight from registers.  The lane's 16 frames are 8 (E, O) pairs of
+// level 0, i.e. exactly the inputs of its own 8 outputs; the 5 older E entries and 3 older O entries an output
+// window reaches back to belong to the lane below and come by warp shuffle, lane 0 takes them from a 64-byte
+// history that lane 31 left in shared memory one tick earlier.  This replaces the level-0 planes (a 4 KiB
+// store + a 5 KiB load per tick and warp) by 16 shuffles; the arithmetic and its order are those of w2_stage.
+// ------------------------------------------------------------------------------------------------
+template <int S>
+__device__ __forceinline__ void w2_stage0_reg(const Fused2Args& A, float2* __restrict__ wsm, int lane, const f32x2_t (&x)[16])
+{
+    using P = W2Plan<S>;
+    static_assert(P::m(0) == 3 && P::R(0) == 8, "register first stage: semi-length 3, 8 outputs per lane");
+    f32x2_t ent[13], oc[8];
+#pragma unroll
+    for (int k = 0; k < 5; k++) ent[k] = __shfl_up_sync(0xffffffffu, x[6 + 2 * k], 1);      // E[q0-5 .. q0-1]
+#pragma unroll
+    for (int k = 0; k < 3; k++) oc[k] = __shfl_up_sync(0xffffffffu, x[11 + 2 * k], 1);      // O[q0-3 .. q0-1]
+    ulonglong2* hist = reinterpret_cast<ulonglong2*>(wsm + P::e_off(0));                    // level-0 planes are unused
+    if (lane == 0) {
+        const ulonglong2 h0 = hist[0], h1 = hist[1], h2 = hist[2], h3 = hist[3];
+        ent[0] = h0.x; ent[1] = h0.y; ent[2] = h1.x; ent[3] = h1.y; ent[4] = h2.x;
+        oc[0] = h2.y; oc[1] = h3.x; oc[2] = h3.y;
+    }
+    __syncwarp();
+    if (lane == 31) {
+        hist[0] = make_ulonglong2(x[6], x[8]);
+        hist[1] = make_ulonglong2(x[10], x[12]);
+        hist[2] = make_ulonglong2(x[14], x[11]);
+        hist[3] = make_ulonglong2(x[13], x[15]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) ent[5 + k] = x[2 * k];
+#pragma unroll
+    for (int k = 0; k < 5; k++) oc[3 + k] = x[2 * k + 1];
+    f32x2_t acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) acc[r] = 0ull;
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        const float h = A.taps[P::taps_off(0) + j];
+        const f32x2_t hh = pk2(h, h);
+#pragma unroll
+        for (int r = 0; r < 8; r++) acc[r] = fma2(hh, ent[r + j], acc[r]);
+    }
+    f32x2_t v[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[r] = add2(oc[r], acc[r]);
+    w2_stage_store<S, 0>(wsm, lane, 0, v);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -398,37 +491,7 @@ __device__ __forceinline__ void w2_stage(const Fused2Args& A, float2* __restrict
         if (D + 1 == S) v[r] = mul2(add2(oc[r], acc[r]), zz);
         else v[r] = add2(oc[r], acc[r]);
     }
-    if (D + 1 == S) {
-        float2* f = wsm + P::flat_off + W2_ARB_HIST + R * lane;
-        if (R >= 2) {
-#pragma unroll
-            for (int r = 0; r < R; r += 2) *reinterpret_cast<ulonglong2*>(f + r) = make_ulonglong2(v[r], v[r + 1]);
-        } else *reinterpret_cast<f32x2_t*>(f) = v[0];
-    } else if (R >= 2) {
-        constexpr int R2 = R / 2, HN = P::Hh(D + 1), PN = P::PAD(D + 1);
-        float2* nE = wsm + P::e_off(D + 1) + (R2 + PN) * lane;
-        float2* nO = wsm + P::o_off(D + 1) + (R2 + PN) * lane;
-        if (R2 >= 4 || (R2 == 2 && PN == 2)) {
-#pragma unroll
-            for (int i = 0; i < R2; i += 2) {
-                const int ph = P::phys(D + 1, HN + i);
-                *reinterpret_cast<ulonglong2*>(nE + ph) = make_ulonglong2(v[2 * i], v[2 * i + 2]);
-                *reinterpret_cast<ulonglong2*>(nO + ph) = make_ulonglong2(v[2 * i + 1], v[2 * i + 3]);
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < R2; i++) {
-                const int ph = P::phys(D + 1, HN + i);
-                *reinterpret_cast<f32x2_t*>(nE + ph) = v[2 * i];
-                *reinterpret_cast<f32x2_t*>(nO + ph) = v[2 * i + 1];
-            }
-        }
-    } else {
-        // R == 1: lane's single output q = lane (+32*half in the consumer's run) -> E'/O' entry q/2
-        constexpr int HN = P::Hh(D + 1);
-        float2* pl = wsm + ((lane & 1) ? P::o_off(D + 1) : P::e_off(D + 1));
-        *reinterpret_cast<f32x2_t*>(pl + HN + 16 * half + (lane >> 1)) = v[0];
-    }
+    w2_stage_store<S, D>(wsm, lane, half, v);
 }
 
 // move the last Hh entries of both planes of level D to the history slots (all lanes call)
@@ -558,10 +621,17 @@ __global__ void __launch_bounds__(512, 1) fused_front2_kernel(const __grid_const
         const long long tick_start = t * W2_T0;
         const W2Raw cur = nxt;
         if (CS16 && t + 1 < t_end) w2_prefetch(A, tick_start + W2_T0, lane, nxt);
-        w2_p0<S, DC, CS16>(A, wsm, lut2, tick_start, lane, cur);
-        __syncwarp();
+        f32x2_t x[16];
+        w2_p0<S, DC, CS16>(A, wsm, lut2, tick_start, lane, cur, x);
         bool arb_due = true;
-        if constexpr (S > 0) W2Cascade<S, 0>::run(A, wsm, t, lane, arb_due);
+        if constexpr (P::reg0) {
+            w2_stage0_reg<S>(A, wsm, lane, x);
+            __syncwarp();
+            W2Cascade<S, 1>::run(A, wsm, t, lane, arb_due);
+        } else {
+            __syncwarp();
+            if constexpr (S > 0) W2Cascade<S, 0>::run(A, wsm, t, lane, arb_due);
+        }
         if (arb_due) {
             // the new flat entries are the last stage's outputs of this run: absolute decimated index
             const long long kA = ((tick_start + W2_T0) >> S) - P::flat_new;
