@@ -398,7 +398,7 @@ static bool v2_setup(FusedFront* f, const ResamplerDesc& r, bool nco)
     const size_t per_warp = (size_t)f->v2_warp_f2 * sizeof(float2);
     const size_t avail = 227 * 1024 - 1024;
     int warps = (int)((avail - fixed) / per_warp);
-    if (warps > 16) warps = 16;
+    if (warps > W2_MAX_WARPS) warps = W2_MAX_WARPS;
     if (warps < 4) return false;
     f->v2_warps = warps;
     f->v2_smem = fixed + (size_t)warps * per_warp;

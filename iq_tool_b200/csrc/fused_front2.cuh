@@ -26,6 +26,10 @@
 namespace iqgpu {
 
 constexpr int W2_T0 = 512;          // raw frames per warp tick
+#ifndef W2_MAX_WARPS_DEF
+#define W2_MAX_WARPS_DEF 20
+#endif
+constexpr int W2_MAX_WARPS = W2_MAX_WARPS_DEF;   // warps per CTA (one CTA per SM): bounded by 64K registers / (32 x registers per thread)
 constexpr int W2_MAXS = 6;          // deepest cascade with a compiled plan
 constexpr int W2_ARB_HIST = 16;     // >= 13 decimated samples of look-back
 // polyphase bank image in shared memory: row `idx` (14 taps = 7 float2) starts at float2 offset
@@ -86,10 +90,14 @@ struct W2Plan {
     __host__ __device__ static constexpr int entries(int d) { return Hh(d) + out(d); }
     __host__ __device__ static constexpr int phys(int d, int p) { return p + PAD(d) * (p / R(d)); }
     __host__ __device__ static constexpr int plane_size(int d) { return (phys(d, entries(d)) + 3) & ~1; }
+    // first stage straight from the lane's registers (neighbour entries by warp shuffle): cascades whose first
+    // stage has semi-length 3, i.e. S >= 3.  Level 0 then keeps only an 8-entry history instead of its planes.
+    static constexpr bool reg0 = (S >= 3);
+    __host__ __device__ static constexpr int level_size(int d) { return (d == 0 && reg0) ? 8 : 2 * plane_size(d); }
     __host__ __device__ static constexpr int e_off(int d)
     {
         int o = 0;
-        for (int i = 0; i < d; i++) o += 2 * plane_size(i);
+        for (int i = 0; i < d; i++) o += level_size(i);
         return o;
     }
     __host__ __device__ static constexpr int o_off(int d) { return e_off(d) + plane_size(d); }
@@ -99,9 +107,6 @@ struct W2Plan {
         for (int i = 0; i < d; i++) o += 2 * m(i);
         return o;
     }
-    // first stage straight from the lane's registers (neighbour entries by warp shuffle): cascades whose first
-    // stage has semi-length 3, i.e. S >= 3
-    static constexpr bool reg0 = (S >= 3);
     static constexpr int flat_new = (S == 0) ? W2_T0 : out(S - 1);        // new polyphase inputs per arb run
     static constexpr int flat_off = e_off(S);
     static constexpr int flat_size = (W2_ARB_HIST + flat_new + 3) & ~1;
@@ -579,7 +584,7 @@ struct W2Cascade {
 };
 
 template <int S, bool DC, bool CS16>
-__global__ void __launch_bounds__(512, 1) fused_front2_kernel(const __grid_constant__ Fused2Args A, int warps_per_cta)
+__global__ void __launch_bounds__(W2_MAX_WARPS * 32, 1) fused_front2_kernel(const __grid_constant__ Fused2Args A, int warps_per_cta)
 {
     using P = W2Plan<S>;
     extern __shared__ __align__(16) float2 sm2[];
