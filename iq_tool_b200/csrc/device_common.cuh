@@ -145,11 +145,13 @@ struct DcDev16 {
     float c, a;          // pole, 1-pole
     float w[5];          // c^(16*2^s)
     float lanepow[32];   // c^(16*lane)
+    float nac[16];       // -a c^k
 };
 __host__ static inline DcDev16 make_dc_dev16(float c, float a)
 {
     DcDev16 d;
     d.c = c; d.a = a;
+    for (int k = 0; k < 16; k++) d.nac[k] = (float)(-(double)a * pow((double)c, (double)k));
     for (int k = 0; k < 5; k++) d.w[k] = (float)pow((double)c, 16.0 * (double)(1 << k));
     for (int l = 0; l < 32; l++) d.lanepow[l] = (float)pow((double)c, 16.0 * l);
     return d;

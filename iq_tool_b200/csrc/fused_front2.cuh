@@ -270,10 +270,18 @@ __device__ __forceinline__ void w2_p0(const Fused2Args& A, float2* __restrict__ 
             // DC blocker (dc_block.c:76 -> liquid iirfilt): v[n] = x[n] + c v[n-1], y[n] = x[n] - (1-c) v[n-1].
             // lane-local weighted sum, one warp scan per tick, state at the tick start from the table
             const double2 vt = A.dc_table[(tick_start - A.A0) >> A.dc_table_shift];
+            // v just before the lane's frame k is c^k w0 + P(k-1), P = the lane-local running sum, so
+            //   y[k] = (x[k] - a P(k-1)) - (a c^k) w0 :
+            // the first term hangs off the lane-local chain and is independent of the warp scan that delivers w0;
+            // once w0 is known the 16 corrections are independent FMAs (no second serial chain).
             const f32x2_t cc = pk2(A.dc.c, A.dc.c), na = pk2(-A.dc.a, -A.dc.a);
             f32x2_t pr = x[0];
 #pragma unroll
-            for (int k = 1; k < 16; k++) pr = fma2(pr, cc, x[k]);
+            for (int k = 1; k < 16; k++) {
+                const f32x2_t t = fma2(na, pr, x[k]);
+                pr = fma2(pr, cc, x[k]);
+                x[k] = t;
+            }
 #pragma unroll
             for (int s = 0; s < 5; s++) {
                 const int dist = 1 << s;
@@ -283,13 +291,9 @@ __device__ __forceinline__ void w2_p0(const Fused2Args& A, float2* __restrict__ 
             f32x2_t e = __shfl_up_sync(0xffffffffu, pr, 1);
             if (lane == 0) e = 0ull;
             const float lp = A.dc.lanepow[lane];
-            f32x2_t w = fma2s(lp, pk2((float)vt.x, (float)vt.y), e);   // v just before the lane's first frame
+            const f32x2_t w0 = fma2s(lp, pk2((float)vt.x, (float)vt.y), e);   // v just before the lane's first frame
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-                const f32x2_t xk = x[k];
-                x[k] = fma2(na, w, xk);
-                w = fma2(cc, w, xk);
-            }
+            for (int k = 0; k < 16; k++) x[k] = fma2s(A.dc.nac[k], w0, x[k]);
         }
         if (p.iq_enable) {   // iq_correct.c:307-313
 #pragma unroll
@@ -499,27 +503,35 @@ __device__ __forceinline__ void w2_stage(const Fused2Args& A, float2* __restrict
     w2_stage_store<S, D>(wsm, lane, half, v);
 }
 
-// move the last Hh entries of both planes of level D to the history slots (all lanes call)
+// move the last Hh entries of both planes of level D to the history slots (all lanes call).  The loads are
+// issued together with the stage's own loads (the tail is not touched by the stage), the stores after the
+// stage's __syncwarp, so the copy adds no exposed shared-memory round trip.
 template <int S, int D>
-__device__ __forceinline__ void w2_slide(float2* __restrict__ wsm, int lane)
-{
+struct W2Slide {
     using P = W2Plan<S>;
-    constexpr int HH = P::Hh(D), N = P::out(D);
-    float2 t = make_float2(0.f, 0.f);
-    float2* pl = wsm + ((lane < HH) ? P::e_off(D) : P::o_off(D));
-    const int i = (lane < HH) ? lane : lane - HH;
-    const bool act = lane < 2 * HH;
+    static constexpr int HH = P::Hh(D), N = P::out(D);
     static_assert(2 * HH <= 64, "history too long for the two-round slide");
-    float2 t2 = make_float2(0.f, 0.f);
-    float2* pl2 = wsm + ((lane + 32 < HH) ? P::e_off(D) : P::o_off(D));
-    const int i2 = (lane + 32 < HH) ? lane + 32 : lane + 32 - HH;
-    const bool act2 = (2 * HH > 32) && (lane + 32 < 2 * HH);
-    if (act) t = pl[P::phys(D, i + N)];
-    if (act2) t2 = pl2[P::phys(D, i2 + N)];
-    __syncwarp();
-    if (act) pl[P::phys(D, i)] = t;
-    if (act2) pl2[P::phys(D, i2)] = t2;
-}
+    f32x2_t t = 0ull, t2 = 0ull;
+    f32x2_t *pl, *pl2;
+    int i, i2;
+    bool act, act2;
+    __device__ __forceinline__ W2Slide(float2* __restrict__ wsm, int lane)
+    {
+        pl = reinterpret_cast<f32x2_t*>(wsm + ((lane < HH) ? P::e_off(D) : P::o_off(D)));
+        i = (lane < HH) ? lane : lane - HH;
+        act = lane < 2 * HH;
+        pl2 = reinterpret_cast<f32x2_t*>(wsm + ((lane + 32 < HH) ? P::e_off(D) : P::o_off(D)));
+        i2 = (lane + 32 < HH) ? lane + 32 : lane + 32 - HH;
+        act2 = (2 * HH > 32) && (lane + 32 < 2 * HH);
+        if (act) t = pl[P::phys(D, i + N)];
+        if (act2) t2 = pl2[P::phys(D, i2 + N)];
+    }
+    __device__ __forceinline__ void store() const
+    {
+        if (act) pl[P::phys(D, i)] = t;
+        if (act2) pl2[P::phys(D, i2)] = t2;
+    }
+};
 
 // ------------------------------------------------------------------------------------------------
 // polyphase arbitrary-rate stage (liquid resamp_crcf, fixed-point phase) on the new flat entries
@@ -575,9 +587,10 @@ struct W2Cascade {
         if (PER > 1 && ((t & (PER - 1)) != (PER - 1))) { arb_due = false; return; }
         // producer-run parity of this stage inside its consumer's run (levels deeper than 3 take two runs)
         const int half = (D >= 3) ? (int)((t >> (D - 3)) & 1) : 0;
+        const W2Slide<S, D> slide(wsm, lane);
         w2_stage<S, D>(A, wsm, lane, (D + 1 < S && D + 1 >= 4) ? half : 0);
         __syncwarp();
-        w2_slide<S, D>(wsm, lane);
+        slide.store();
         __syncwarp();
         if constexpr (D + 1 < S) W2Cascade<S, D + 1>::run(A, wsm, t, lane, arb_due);
     }
