@@ -26,6 +26,9 @@
 namespace iqgpu {
 
 constexpr int W2_T0 = 512;          // raw frames per warp tick
+#ifndef W2_CAP_DEF
+#define W2_CAP_DEF 0                // 0: per-plan default (W2Plan::CAP)
+#endif
 #ifndef W2_MAX_WARPS_DEF
 #define W2_MAX_WARPS_DEF 20
 #endif
@@ -73,6 +76,7 @@ __host__ static inline void w2_pick_lut_swizzle(uint32_t dtheta, unsigned& sh, u
         if (cost < best - 1e-9) { best = cost; sh = cand_sh[c]; mask = cand_mask[c]; }
     }
 }
+__host__ __device__ constexpr int w2_ilog2(int v) { int l = 0; while ((1 << (l + 1)) <= v) l++; return l; }
 constexpr int W2_BANK_F2 = 2368;    // float2 entries of the image (9*255 + 63 + 7 = 2365, padded to 16 B)
 __host__ __device__ constexpr int w2_bank_row(int idx) { return 9 * idx + (idx >> 2); }
 constexpr int W2_MAX_TAPS = 72;     // sum of 2m over the cascade (6*4 + 10 + 20 = 54 for S = 6)
@@ -83,7 +87,12 @@ constexpr int W2_MAX_TAPS = 72;     // sum of 2m over the cascade (6*4 + 10 + 20
 template <int S>
 struct W2Plan {
     __host__ __device__ static constexpr int m(int d) { return (d == S - 1) ? 10 : ((d == S - 2) ? 5 : 3); }
-    __host__ __device__ static constexpr int out(int d) { return d < 3 ? (256 >> d) : 32; }   // outputs of stage d per run
+    // Stage d makes 256 >> d outputs per tick.  Deep stages would leave a lane with one output per run (21 shared-memory
+    // loads for one output at m = 10: the kernel is bound by the LSU data pipe), so they wait for several ticks and run
+    // on CAP outputs at a time: R = CAP/32 consecutive outputs per lane share one register window.
+    static constexpr int CAP = W2_CAP_DEF ? W2_CAP_DEF : ((S <= 4) ? 128 : 64);
+    __host__ __device__ static constexpr int nat(int d) { return 256 >> d; }
+    __host__ __device__ static constexpr int out(int d) { return nat(d) > CAP ? nat(d) : CAP; }   // outputs of stage d per run
     __host__ __device__ static constexpr int R(int d) { return out(d) / 32; }                 // consecutive outputs per lane
     __host__ __device__ static constexpr int PAD(int d) { return R(d) >= 4 ? 2 : (R(d) == 2 ? 1 : 0); }
     __host__ __device__ static constexpr int Hh(int d) { return ((2 * m(d) - 1 + R(d) - 1) / R(d)) * R(d); }   // history entries per plane
@@ -111,8 +120,10 @@ struct W2Plan {
     static constexpr int flat_off = e_off(S);
     static constexpr int flat_size = (W2_ARB_HIST + flat_new + 3) & ~1;
     static constexpr int warp_f2 = flat_off + flat_size;                 // float2 per warp
-    __host__ __device__ static constexpr int period(int d) { return d <= 3 ? 1 : (1 << (d - 3)); }   // stage d runs every `period` ticks
-    static constexpr int sup = (S > 4) ? (1 << (S - 4)) : 1;             // ticks per super-tick (period of the last stage)
+    __host__ __device__ static constexpr int period(int d) { return nat(d) >= CAP ? 1 : CAP / nat(d); }   // stage d runs every `period` ticks
+    // runs of stage d per run of stage d+1 (1: every run feeds one consumer run; 2: the consumer waits for two)
+    __host__ __device__ static constexpr int ratio(int d) { return 2 * out(d + 1) / out(d); }
+    static constexpr int sup = (S == 0) ? 1 : period(S - 1);             // ticks per super-tick (period of the last stage)
     __host__ __device__ static constexpr long long halo_frames()
     {
         long long h = 0;
@@ -358,14 +369,16 @@ __device__ __forceinline__ void w2_stage_store(float2* __restrict__ wsm, int lan
 {
     using P = W2Plan<S>;
     constexpr int R = P::R(D);
-    if (D + 1 == S) {
+    if constexpr (D + 1 == S) {
         float2* f = wsm + P::flat_off + W2_ARB_HIST + R * lane;
         if (R >= 2) {
 #pragma unroll
             for (int r = 0; r < R; r += 2) *reinterpret_cast<ulonglong2*>(f + r) = make_ulonglong2(v[r], v[r + 1]);
         } else *reinterpret_cast<f32x2_t*>(f) = v[0];
-    } else if (R >= 2) {
+    } else if constexpr (P::ratio(D) == 1) {
+        // the lane's R/2 (E, O) pairs are exactly one register group of the consumer
         constexpr int R2 = R / 2, HN = P::Hh(D + 1), PN = P::PAD(D + 1);
+        static_assert(R2 == P::R(D + 1), "one producer lane feeds one consumer group");
         float2* nE = wsm + P::e_off(D + 1) + (R2 + PN) * lane;
         float2* nO = wsm + P::o_off(D + 1) + (R2 + PN) * lane;
         if (R2 >= 4 || (R2 == 2 && PN == 2)) {
@@ -384,10 +397,27 @@ __device__ __forceinline__ void w2_stage_store(float2* __restrict__ wsm, int lan
             }
         }
     } else {
-        // R == 1: lane's single output q = lane (+32*half in the consumer's run) -> E'/O' entry q/2
-        constexpr int HN = P::Hh(D + 1);
-        float2* pl = wsm + ((lane & 1) ? P::o_off(D + 1) : P::e_off(D + 1));
-        *reinterpret_cast<f32x2_t*>(pl + HN + 16 * half + (lane >> 1)) = v[0];
+        // the consumer takes two runs of this stage (`half` = which one this is): the lane's R/2 pairs are the lower
+        // (even lane) or upper (odd lane) half of consumer group half*16 + lane/2
+        constexpr int R2 = R / 2, RN = P::R(D + 1), HN = P::Hh(D + 1), PN = P::PAD(D + 1);
+        static_assert(P::ratio(D) == 2 && RN == 2 * R2 && R >= 2, "capped stages keep their tile size");
+        const int p0 = HN + half * (P::out(D) / 2) + R2 * lane;        // plane index of the lane's first pair
+        const int ph0 = p0 + PN * (p0 / RN);
+        float2* nE = wsm + P::e_off(D + 1) + ph0;
+        float2* nO = wsm + P::o_off(D + 1) + ph0;
+        if (R2 >= 2 && PN == 2) {
+#pragma unroll
+            for (int i = 0; i < R2; i += 2) {
+                *reinterpret_cast<ulonglong2*>(nE + i) = make_ulonglong2(v[2 * i], v[2 * i + 2]);
+                *reinterpret_cast<ulonglong2*>(nO + i) = make_ulonglong2(v[2 * i + 1], v[2 * i + 3]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < R2; i++) {
+                *reinterpret_cast<f32x2_t*>(nE + i) = v[2 * i];
+                *reinterpret_cast<f32x2_t*>(nO + i) = v[2 * i + 1];
+            }
+        }
     }
 }
 
@@ -585,10 +615,13 @@ struct W2Cascade {
         using P = W2Plan<S>;
         constexpr int PER = P::period(D);
         if (PER > 1 && ((t & (PER - 1)) != (PER - 1))) { arb_due = false; return; }
-        // producer-run parity of this stage inside its consumer's run (levels deeper than 3 take two runs)
-        const int half = (D >= 3) ? (int)((t >> (D - 3)) & 1) : 0;
+        // which of the consumer's two feeding runs this is (stages whose consumer waits for two runs)
+        int half = 0;
+        if constexpr (D + 1 < S) {
+            if (P::ratio(D) == 2) half = (int)((t >> w2_ilog2(PER)) & 1);     // arithmetic shift: t may be negative during warm-up
+        }
         const W2Slide<S, D> slide(wsm, lane);
-        w2_stage<S, D>(A, wsm, lane, (D + 1 < S && D + 1 >= 4) ? half : 0);
+        w2_stage<S, D>(A, wsm, lane, half);
         __syncwarp();
         slide.store();
         __syncwarp();
