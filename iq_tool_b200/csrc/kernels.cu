@@ -601,56 +601,57 @@ __global__ void __launch_bounds__(FIR_THREADS) fir_kernel(const float2* __restri
 constexpr unsigned FIR_PARAM_TAPS = 4096;           // floats (real taps) or 2048 complex taps: 16 KB of parameters
 struct FirTaps { float h[FIR_PARAM_TAPS]; };
 
+// Samples and accumulators are packed {re, im} pairs: a real tap is one FFMA2 per output (tap as a scalar uniform
+// operand), a complex tap two (the second on the swapped pair with {-hi, hi}); each half is the same IEEE fma sequence as
+// the scalar form.  FFMA2 has the FLOP rate of FFMA at half the issue slots, which leaves room for the LDS next to it.
 template <bool CPLX>
 __global__ void __launch_bounds__(FIR_THREADS) fir_param_kernel(const float2* __restrict__ x, size_t n, unsigned ntaps,
                                                                 float2* __restrict__ y, const __grid_constant__ FirTaps T)
 {
     constexpr int WIN = FIR_TILE + FIR_TC;
-    __shared__ float2 sx[WIN + WIN / 8 + 8];
+    __shared__ __align__(16) f32x2_t sx[WIN + WIN / 8 + 8];
     const int t = threadIdx.x;
     const long long tile0 = (long long)blockIdx.x * FIR_TILE;
-    float2 acc[FIR_R];
+    f32x2_t acc[FIR_R];
 #pragma unroll
-    for (int r = 0; r < FIR_R; r++) acc[r] = make_float2(0.f, 0.f);
+    for (int r = 0; r < FIR_R; r++) acc[r] = 0ull;
     for (unsigned c0 = 0; c0 < ntaps; c0 += FIR_TC) {
         const int tc = (ntaps - c0 < (unsigned)FIR_TC) ? (int)(ntaps - c0) : FIR_TC;
         const long long wbase = tile0 - (long long)(ntaps - 1) + c0;
         __syncthreads();
         for (int j = t; j < FIR_TILE + tc - 1; j += FIR_THREADS) {
             const long long g = wbase + j;
-            sx[fir_pad(j)] = (g < (long long)n) ? x[g] : make_float2(0.f, 0.f);
+            sx[fir_pad(j)] = (g < (long long)n) ? *reinterpret_cast<const f32x2_t*>(x + g) : 0ull;
         }
         __syncthreads();
-        float2 win[FIR_R];
-        const int o0 = t * FIR_R;
+        f32x2_t win[FIR_R];
+        const f32x2_t* __restrict__ sp = sx + fir_pad(t * FIR_R);     // o0 and i0 are multiples of 8: pad(o0 + i0 + k) = pad(o0) + 9 i0/8 + k
 #pragma unroll
-        for (int r = 0; r < FIR_R; r++) win[r] = sx[fir_pad(o0 + r)];
+        for (int r = 0; r < FIR_R; r++) win[r] = sp[r];
         for (int i0 = 0; i0 < tc; i0 += FIR_R) {
+            sp += FIR_R + 1;
 #pragma unroll
             for (int u = 0; u < FIR_R; u++) {
                 const float hx = CPLX ? T.h[2 * (c0 + i0 + u)] : T.h[c0 + i0 + u];
                 const float hy = CPLX ? T.h[2 * (c0 + i0 + u) + 1] : 0.f;
+                const f32x2_t hh = pk2(hx, hx), hs = pk2(-hy, hy);
 #pragma unroll
                 for (int r = 0; r < FIR_R; r++) {
-                    const float2 v = win[(r + u) % FIR_R];
-                    if (CPLX) {
-                        acc[r].x = fmaf(hx, v.x, acc[r].x);
-                        acc[r].x = fmaf(-hy, v.y, acc[r].x);
-                        acc[r].y = fmaf(hx, v.y, acc[r].y);
-                        acc[r].y = fmaf(hy, v.x, acc[r].y);
-                    } else {
-                        acc[r].x = fmaf(hx, v.x, acc[r].x);
-                        acc[r].y = fmaf(hx, v.y, acc[r].y);
+                    const f32x2_t v = win[(r + u) % FIR_R];
+                    acc[r] = fma2(hh, v, acc[r]);
+                    if (CPLX) {                                        // (hr + j hi)(vr + j vi)
+                        const float2 f = unpk2(v);
+                        acc[r] = fma2(hs, pk2(f.y, f.x), acc[r]);
                     }
                 }
-                win[u % FIR_R] = sx[fir_pad(o0 + i0 + u + FIR_R)];
+                win[u % FIR_R] = sp[u];
             }
         }
     }
 #pragma unroll
     for (int r = 0; r < FIR_R; r++) {
         const long long o = tile0 + t * FIR_R + r;
-        if (o < (long long)n) y[o] = acc[r];
+        if (o < (long long)n) y[o] = unpk2(acc[r]);
     }
 }
 
