@@ -190,7 +190,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fused", type=int, default=1)
-    ap.add_argument("--subtrain", type=int, default=1 << 28, help="frames per sub-train (kernel launch group) of the HBM-resident leg")
+    ap.add_argument("--dc-overlap", type=int, default=1)
+    ap.add_argument("--subtrain", type=int, default=1 << 30, help="frames per sub-train (kernel launch group) of the HBM-resident leg")
     ap.add_argument("--e2e-subtrain", type=int, default=1 << 25, help="frames per sub-train of the host-buffer leg (H2D/compute/D2H pipeline depth)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -225,7 +226,7 @@ def main():
     # every step (the only collective; no sample data crosses GPUs)
     from iq_tool_b200.shard import ShardedChain
     sc = ShardedChain(cfg, local_rank, shard_frames_hint=n if world > 1 else 0, time_kernels=1, fused=args.fused,
-                      subtrain_frames=args.subtrain)
+                      subtrain_frames=args.subtrain, dc_overlap=args.dc_overlap)
     chain = sc.chain
     info = chain.info()
     replicas = False

@@ -260,6 +260,8 @@ struct iqgpu_chain {
     int run_back(void* d_outp, size_t skip_chunks, size_t* out_frames, cudaStream_t st);
     PreParams pre_params(uint64_t N0) const;
     int prepare_dc(int slot, const void* d_rawp, uint64_t N0, size_t n, cudaStream_t st);
+    bool fir_wrote_output = false;    // this sub-train's FIR epilogue converted and stored the final output
+    bool dc_overlap = true;           // DC pre-pass of sub-train k+1 on the second stream while sub-train k runs
     // pending back half (between process_device_begin and process_device_finish)
     struct Pending {
         bool active = false;
@@ -569,6 +571,7 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
     }
     const size_t total_out = seg[n_chunks];
     launches = 0;
+    fir_wrote_output = false;
 
     // ---------------- K1: pre-processor ----------------
     const PreParams pp = pre_params(N0);
@@ -708,9 +711,15 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
     if (post_filter) {
         span_begin(IQGPU_KCLASS_FILTER, st);
         if (filter_is_fir(filt)) {
+            const int cplx = filt.impl == IQGPU_FILTER_IMPL_FIR_ASYM;
+            // last cf32 stage of the chain (no post shift, no AGC, nobody records the stream, one-phase call): convert in the
+            // filter's epilogue and skip the post kernel
+            fir_wrote_output = phase == 0 && !record_taps && !nco_post && agc_mode == 0 && d_outp && post_n == total_out &&
+                               fir_can_convert_out(cfg.output_format, fir_taps_padded, cplx);
             float2* y = nullptr;
             CK(s_f.begin(post_n, st, &y));
-            CK(launch_fir(post_src, post_n, d_fir_taps, fir_taps_padded, filt.impl == IQGPU_FILTER_IMPL_FIR_ASYM, y, st, h_fir_taps.data()));
+            CK(launch_fir(post_src, post_n, d_fir_taps, fir_taps_padded, cplx, y, st, h_fir_taps.data(),
+                          fir_wrote_output ? cfg.output_format : 0, fir_wrote_output ? d_outp : nullptr));
             launches++;
             s_f.commit(post_n);
             post_src = y;
@@ -782,7 +791,9 @@ int iqgpu_chain::run_back(void* d_outp, size_t skip_chunks, size_t* out_frames, 
         CK(tap[2].append(post_src, post_n, st));
         tap2 = tap[2].p + tap[2].len - post_n;
     }
-    if (post_n) {
+    if (post_n && fir_wrote_output) {
+        fir_wrote_output = false;        // the FIR epilogue already produced the final stream (run_subtrain)
+    } else if (post_n) {
         span_begin(IQGPU_KCLASS_POST, st);
         if (agc_mode == 1) {
             if (skip_chunks) {
@@ -942,6 +953,7 @@ int iqgpu_chain_set_option(iqgpu_chain* c, const char* key, int64_t value)
         return IQGPU_OK;
     }
     if (k == "time_kernels") { c->time_kernels = value != 0; return IQGPU_OK; }
+    if (k == "dc_overlap") { c->dc_overlap = value != 0; return IQGPU_OK; }
     if (k == "subtrain_frames" || k == "chunk_frames") {
         if (c->buffers_ready) return fail(IQGPU_EINVAL, "option must be set before the first process call");
         if (value <= 0) return fail(IQGPU_EINVAL, "value must be positive");
@@ -1075,7 +1087,7 @@ int iqgpu_chain_process_device(iqgpu_chain* c, const void* dev_raw_in, size_t n_
             ci = cj;
         }
     }
-    const bool overlap_dc = c->fused_active && c->dc.enable;
+    const bool overlap_dc = c->fused_active && c->dc.enable && c->dc_overlap;
     const uint64_t base_in = c->n_in;
     auto raw_at = [&](const Sub& sb) { return (const void*)((const char*)dev_raw_in + sb.in_off * c->in_bps); };
     int slot = 0;

@@ -520,6 +520,9 @@ cudaError_t launch_arb(const float2* x, int64_t a0, const float* bank, uint32_t 
     return cudaGetLastError();
 }
 
+template <int FMT> __device__ __forceinline__ void store_out(void* __restrict__ out, size_t i, float2 v);
+template <int FMT> __device__ __forceinline__ void store_out4(void* __restrict__ out, size_t i, size_t n, const float2 (&v)[4], bool vec);
+
 // =============================================================================================
 // K3: tiled time-domain FIR.  reference src/filter.c:449-462 -> liquid firfilt_crcf/cccf
 //   y[n] = sum_{i<N} hrev[i] x[n-(N-1)+i]   (oldest sample first, like liquid's dot product)
@@ -604,9 +607,13 @@ struct FirTaps { float h[FIR_PARAM_TAPS]; };
 // Samples and accumulators are packed {re, im} pairs: a real tap is one FFMA2 per output (tap as a scalar uniform
 // operand), a complex tap two (the second on the swapped pair with {-hi, hi}); each half is the same IEEE fma sequence as
 // the scalar form.  FFMA2 has the FLOP rate of FFMA at half the issue slots, which leaves room for the LDS next to it.
-template <bool CPLX>
+// OUTFMT != 0: the filter is the last cf32 stage of the chain (no post shift, no AGC): the epilogue converts to the
+// output sample format (sample_convert.c:213-306, same code as the post kernel) and writes the final stream, so the
+// filtered cf32 stream is never stored.
+template <bool CPLX, int OUTFMT>
 __global__ void __launch_bounds__(FIR_THREADS) fir_param_kernel(const float2* __restrict__ x, size_t n, unsigned ntaps,
-                                                                float2* __restrict__ y, const __grid_constant__ FirTaps T)
+                                                                float2* __restrict__ y, void* __restrict__ out_conv, bool vec_out,
+                                                                const __grid_constant__ FirTaps T)
 {
     constexpr int WIN = FIR_TILE + FIR_TC;
     __shared__ __align__(16) f32x2_t sx[WIN + WIN / 8 + 8];
@@ -648,6 +655,15 @@ __global__ void __launch_bounds__(FIR_THREADS) fir_param_kernel(const float2* __
             }
         }
     }
+    if (OUTFMT != 0) {
+#pragma unroll
+        for (int q = 0; q < FIR_R; q += 4) {
+            const float2 v[4] = {unpk2(acc[q]), unpk2(acc[q + 1]), unpk2(acc[q + 2]), unpk2(acc[q + 3])};
+            const long long o = tile0 + t * FIR_R + q;
+            if (o < (long long)n) store_out4<OUTFMT == 0 ? IQGPU_FMT_CF32 : OUTFMT>(out_conv, (size_t)o, n, v, vec_out);
+        }
+        return;
+    }
 #pragma unroll
     for (int r = 0; r < FIR_R; r++) {
         const long long o = tile0 + t * FIR_R + r;
@@ -655,17 +671,35 @@ __global__ void __launch_bounds__(FIR_THREADS) fir_param_kernel(const float2* __
     }
 }
 
+bool fir_can_convert_out(int out_format, unsigned ntaps_padded, int complex_taps)
+{
+    const unsigned nfloats = ntaps_padded * (complex_taps ? 2u : 1u);
+    if (nfloats > FIR_PARAM_TAPS || getenv("IQGPU_FIR_SMEM_TAPS") || getenv("IQGPU_FIR_NO_CONVERT")) return false;
+    return out_format == IQGPU_FMT_CS16 || out_format == IQGPU_FMT_CU8 || out_format == IQGPU_FMT_CS8;
+}
+
 cudaError_t launch_fir(const float2* x, size_t n, const float* hrev, unsigned ntaps_padded, int complex_taps,
-                       float2* y, cudaStream_t st, const float* hrev_host)
+                       float2* y, cudaStream_t st, const float* hrev_host, int out_format, void* out_conv)
 {
     if (n == 0) return cudaSuccess;
     const int grid = (int)((n + FIR_TILE - 1) / FIR_TILE);
     const unsigned nfloats = ntaps_padded * (complex_taps ? 2u : 1u);
+    if (out_conv && !(hrev_host && fir_can_convert_out(out_format, ntaps_padded, complex_taps))) return cudaErrorInvalidValue;
     if (hrev_host && nfloats <= FIR_PARAM_TAPS && !getenv("IQGPU_FIR_SMEM_TAPS")) {
         static thread_local FirTaps T;      // 16 KB: copied into the launch's parameter buffer
         memcpy(T.h, hrev_host, nfloats * sizeof(float));
-        if (complex_taps) fir_param_kernel<true><<<grid, FIR_THREADS, 0, st>>>(x, n, ntaps_padded, y, T);
-        else fir_param_kernel<false><<<grid, FIR_THREADS, 0, st>>>(x, n, ntaps_padded, y, T);
+        const bool vo = (reinterpret_cast<size_t>(out_conv) & 15) == 0;
+#define FIR_GO(C, F) fir_param_kernel<C, F><<<grid, FIR_THREADS, 0, st>>>(x, n, ntaps_padded, y, out_conv, vo, T)
+#define FIR_FMT(C)                                                          \
+        do {                                                                \
+            if (!out_conv) FIR_GO(C, 0);                                    \
+            else if (out_format == IQGPU_FMT_CS16) FIR_GO(C, IQGPU_FMT_CS16); \
+            else if (out_format == IQGPU_FMT_CU8) FIR_GO(C, IQGPU_FMT_CU8); \
+            else FIR_GO(C, IQGPU_FMT_CS8);                                  \
+        } while (0)
+        if (complex_taps) FIR_FMT(true); else FIR_FMT(false);
+#undef FIR_FMT
+#undef FIR_GO
         return cudaGetLastError();
     }
     if (complex_taps) fir_kernel<true><<<grid, FIR_THREADS, 0, st>>>(x, n, hrev, ntaps_padded, y);

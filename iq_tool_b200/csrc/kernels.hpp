@@ -61,8 +61,12 @@ cudaError_t launch_arb(const float2* x, int64_t a0, const float* bank, uint32_t 
 // hrev: ntaps_padded complex or real taps, oldest first, zero-padded at the FRONT to a multiple of 8.
 // hrev_host (optional): the same taps in host memory; when they fit the parameter bank (4096 floats) they
 // travel as kernel parameters and are read as constant-bank FFMA operands.
+// out_conv (optional, only when fir_can_convert_out() says so): the filter is the chain's last cf32 stage; the epilogue
+// converts to `out_format` and writes the final output there instead of the cf32 stream y.
 cudaError_t launch_fir(const float2* x, size_t n, const float* hrev, unsigned ntaps_padded,
-                       int complex_taps, float2* y, cudaStream_t st, const float* hrev_host = nullptr);
+                       int complex_taps, float2* y, cudaStream_t st, const float* hrev_host = nullptr,
+                       int out_format = 0, void* out_conv = nullptr);
+bool fir_can_convert_out(int out_format, unsigned ntaps_padded, int complex_taps);
 
 // ---- K4: FFT block filter (overlap-save form of liquid's fftfilt) --------------------------
 // For each block b in [0,nblocks): window = x[(b-1)*B .. (b+1)*B), y[b*B .. (b+1)*B) =

@@ -488,3 +488,21 @@ def test_digital_agc_chunk_table_scan_equals_the_sequential_state_machine(gpu):
         assert np.allclose(out, ref, rtol=1e-6, atol=1e-9)
     # the schedule really exercised every branch
     assert gain_r[40] < gain_r[30] and gain_r[2500 + 38 + 290] > gain_r[2500 + 38 + 10]
+
+
+@pytest.mark.parametrize("out_fmt", ["cs16", "cu8", "cs8"])
+def test_fir_epilogue_conversion_equals_the_post_kernel(out_fmt, gpu, workloads, monkeypatch):
+    """When the FIR is the chain's last cf32 stage its epilogue converts to the output format (C2,
+    sample_convert.c:213-306) instead of a separate post kernel: same bytes either way, ragged length,
+    several sub-trains, and the oracle's +-1 LSB bar."""
+    import dataclasses
+    wl = dataclasses.replace(workloads["cfg2"], dc=0.0)
+    cfg = dataclasses.replace(wl.config, output_format=out_fmt)
+    raw = synth_numpy(wl, (1 << 21) + 4321)
+    a = gpu.Chain(cfg, 0, subtrain_frames=1 << 19).process(raw)
+    monkeypatch.setenv("IQGPU_FIR_NO_CONVERT", "1")
+    b = gpu.Chain(cfg, 0, subtrain_frames=1 << 19).process(raw)
+    monkeypatch.delenv("IQGPU_FIR_NO_CONVERT")
+    assert a.size == b.size and np.array_equal(a, b)
+    ref = CpuChain(cfg, _oracle_kind()).process(raw)
+    assert a.size == ref.size and max_lsb(a, ref) <= INT_LSB_TOL
