@@ -82,30 +82,57 @@ def _all_gather_var(arr: np.ndarray, group, device) -> List[np.ndarray]:
 
     world = dist.get_world_size(group)
     n = torch.tensor([arr.size], dtype=torch.int64, device=device)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
+    got = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(got, n, group=group)
+    sizes = [int(v) for v in torch.cat(got).cpu().tolist()]
     m = max(max(sizes), 1)
-    buf = torch.zeros(m, dtype=torch.int32, device=device)
-    if arr.size:
-        buf[: arr.size] = torch.from_numpy(arr.view(np.int32).copy()).to(device)
-    outs = [torch.zeros_like(buf) for _ in range(world)]
-    dist.all_gather(outs, buf, group=group)
-    return [o[:s].cpu().numpy().view(arr.dtype) for o, s in zip(outs, sizes)]
+    host = np.zeros(m, dtype=np.int32)
+    host[: arr.size] = arr.view(np.int32)
+    out = torch.empty(world * m, dtype=torch.int32, device=device)
+    dist.all_gather_into_tensor(out, torch.from_numpy(host).to(device), group=group)
+    tab = out.cpu().numpy().reshape(world, m)
+    return [tab[r, : sizes[r]].view(arr.dtype) for r in range(world)]
+
+
+def _all_gather_tables(peaks: np.ndarray, counts: np.ndarray, group, device, sizes=None):
+    """all_gather of every rank's (peaks float32[n_r], counts uint32[n_r]) chunk tables in ONE payload collective.
+    `sizes` = the per-rank table lengths when the caller knows them (they follow from the shard plan); otherwise one
+    small all_gather of the lengths comes first."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    if sizes is None:
+        n = torch.tensor([peaks.size], dtype=torch.int64, device=device)
+        got = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(got, n, group=group)
+        sizes = [int(v) for v in torch.cat(got).cpu().tolist()]
+    assert len(sizes) == world and sizes[dist.get_rank(group)] == peaks.size == counts.size
+    m = max(max(sizes), 1)
+    host = np.zeros(2 * m, dtype=np.int32)
+    host[: peaks.size] = peaks.view(np.int32)
+    host[m: m + counts.size] = counts.view(np.int32)
+    buf = torch.from_numpy(host).to(device)
+    out = torch.empty(world * 2 * m, dtype=torch.int32, device=device)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    tab = out.cpu().numpy().reshape(world, 2, m)
+    return ([tab[r, 0, : sizes[r]].view(np.float32) for r in range(world)],
+            [tab[r, 1, : sizes[r]].view(np.uint32) for r in range(world)])
 
 
 def exchange_agc_state(peaks: np.ndarray, counts: np.ndarray, target: float, target_rate_hz: float,
-                       group=None, device="cpu") -> "gpu.AgcStateC":
+                       group=None, device="cpu", sizes=None) -> "gpu.AgcStateC":
     """Digital-AGC state at the start of this rank's shard: all-gather every rank's live per-chunk
     peaks/counts and replay the state machine over the chunks of the ranks below this one."""
     import torch.distributed as dist
 
     rank = dist.get_rank(group)
-    all_peaks = _all_gather_var(np.ascontiguousarray(peaks, dtype=np.float32), group, device)
-    all_counts = _all_gather_var(np.ascontiguousarray(counts, dtype=np.uint32), group, device)
+    all_peaks, all_counts = _all_gather_tables(np.ascontiguousarray(peaks, dtype=np.float32),
+                                               np.ascontiguousarray(counts, dtype=np.uint32), group, device, sizes)
     state = gpu.agc_initial_state()
-    for r in range(rank):
-        gpu.agc_digital_advance(state, target, target_rate_hz, all_peaks[r], all_counts[r])
+    if rank:
+        # one replay over the concatenated tables of the ranks below (the state machine is sequential in the chunks)
+        gpu.agc_digital_advance(state, target, target_rate_hz, np.concatenate(all_peaks[:rank]), np.concatenate(all_counts[:rank]))
     return state
 
 
@@ -130,7 +157,11 @@ class ShardedChain:
         self.target_rate = float(np.float32(cfg.target_rate_hz))
 
     def plan(self, total_frames: int, world: int) -> List[Shard]:
-        return plan_shards(self._probe, total_frames, world, self.halo)
+        shards = plan_shards(self._probe, total_frames, world, self.halo)
+        # live chunks per rank: the lengths of the tables the ranks exchange (no length exchange needed at run time)
+        self._table_sizes = {(s.world, s.rank, s.start, s.frames): [(t.frames + CHUNK_SAMPLES - 1) // CHUNK_SAMPLES for t in shards]
+                             for s in shards}
+        return shards
 
     def process_device(self, shard: Shard, dev_in_ptr: int, dev_out_ptr: int, out_capacity_bytes: int,
                        stream: int = 0, group=None, comm_device="cpu") -> Tuple[int, int]:
@@ -148,8 +179,9 @@ class ShardedChain:
             return ch.process_device(dev_in_ptr, n, dev_out_ptr, out_capacity_bytes, stream), shard.drop
         ch.process_device_begin(dev_in_ptr, n, stream)
         peaks, counts = ch.pending_chunk_peaks()
+        sizes = getattr(self, "_table_sizes", {}).get((shard.world, shard.rank, shard.start, shard.frames))
         state = exchange_agc_state(peaks[shard.skip_chunks:], counts[shard.skip_chunks:], self.agc_target,
-                                   self.target_rate, group, comm_device)
+                                   self.target_rate, group, comm_device, sizes)
         ch.set_agc_state(state)
         produced = ch.process_device_finish(shard.skip_chunks, dev_out_ptr, out_capacity_bytes, stream)
         return produced, shard.drop
