@@ -56,7 +56,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -76,8 +76,8 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons, power = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []                                  # (timestamp, sm clock, max clock, power, reasons)
         for ts, ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
@@ -86,20 +86,30 @@ class ClockSampler:
                 clk, mx = float(f[1]), float(f[2])
             except ValueError:
                 continue
-            smax = mx
-            if t0 - 0.05 <= ts <= t1 + 0.1:
-                sm.append(clk)
-                try:
-                    power.append(float(f[3]))
-                except ValueError:
-                    pass
-                for k, nm in enumerate(names):
-                    if f[5 + k].lower().startswith("active"):
-                        reasons.add(nm)
-        if not sm:  # region shorter than the sampling period: use the nearest samples
-            sm = [float(l.split(",")[1]) for _, l in self.lines[-3:] if len(l.split(",")) > 2] or [0.0]
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(power) if power else None}
+            if clk <= 0:
+                continue
+            try:
+                pw = float(f[3])
+            except ValueError:
+                pw = None
+            rows.append((ts, clk, mx, pw, {nm for k, nm in enumerate(names) if f[5 + k].lower().startswith("active")}))
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no nvidia-smi samples"]}
+        inside = [r for r in rows if t0 - 0.03 <= r[0] <= t1 + 0.03]
+        note = None
+        if not inside:
+            # timed region shorter than the sampling period: the samples nearest to it (the sampler runs from before the
+            # warm-up steps, so these are still samples under load)
+            mid = 0.5 * (t0 + t1)
+            inside = sorted(rows, key=lambda r: abs(r[0] - mid))[:3]
+            note = "timed region shorter than the sampling period: nearest samples"
+        reasons = set().union(*[r[4] for r in inside])
+        power = [r[3] for r in inside if r[3] is not None]
+        out = {"sm_mhz": statistics.median([r[1] for r in inside]), "sm_max_mhz": rows[-1][2], "reasons": sorted(reasons),
+               "samples": len(inside), "power_w_max": max(power) if power else None}
+        if note:
+            out["note"] = note
+        return out
 
 
 # algorithmic bytes per INPUT sample for each kernel class of a workload
@@ -180,7 +190,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2")
@@ -257,15 +267,15 @@ def main():
             return chain.process_device(raw.data_ptr(), n, out.data_ptr(), out.numel(), stream.cuda_stream)
         return sc.process_device(shard, raw.data_ptr(), out.data_ptr(), out.numel(), stream.cuda_stream, None, dev)[0]
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         produced = step()
     chain.kernel_times(reset=True)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.15)
+    time.sleep(0.05)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t0 = time.time()

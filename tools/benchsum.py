@@ -9,6 +9,7 @@ for fn in sys.argv[1:]:
         continue
     r = d.get("roofline") or {}
     e2e = (d.get("e2e") or {}).get("value")
+    d.setdefault("fp32", {"frac_of_nominal": 0.0}); d.setdefault("clocks", {})
     print(f"{fn}: value={d['value']:.0f} ms/step={d['ms_per_step']:.3f} e2e={e2e and round(e2e)} "
           f"roof[{r.get('kernel')}]={r.get('frac', 0):.3f} share={r.get('share_of_step', 0):.2f} "
           f"fp32={d['fp32']['frac_of_nominal']:.3f} sm={d['clocks'].get('sm_mhz')} {d['clocks'].get('reasons')}")
