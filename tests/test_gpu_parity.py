@@ -506,3 +506,47 @@ def test_fir_epilogue_conversion_equals_the_post_kernel(out_fmt, gpu, workloads,
     assert a.size == b.size and np.array_equal(a, b)
     ref = CpuChain(cfg, _oracle_kind()).process(raw)
     assert a.size == ref.size and max_lsb(a, ref) <= INT_LSB_TOL
+
+
+@pytest.mark.parametrize("S", [0, 1, 2, 3, 4, 5, 6])
+def test_fused_front_every_cascade_depth(S, gpu):
+    """Every compiled cascade plan of the warp-streaming fused front (S = 0..6 halfband stages: register first stage
+    for S >= 3, deep stages on 128 / 64 outputs per run) against the stage-by-stage kernels: same FMA order -> same
+    bits; against the oracle: the north_star bar; ragged calls (incl. an empty one) == one call."""
+    rng = np.random.Generator(np.random.PCG64(100 + S))
+    fs = 10e6
+    target = fs * 0.61 / (1 << S)
+    n = 120000 + (40000 << S) + 77
+    t = np.arange(n)
+    x = 0.3 * np.exp(2j * np.pi * (0.11 / (1 << S)) * t) + 0.05 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    raw = np.empty(2 * n, dtype=np.int16)
+    raw[0::2] = np.clip(np.round(x.real * 32767), -32768, 32767)
+    raw[1::2] = np.clip(np.round(x.imag * 32767), -32768, 32767)
+    cfg = ChainConfig(input_format="cs16", output_format="cf32", input_rate_hz=fs, target_rate_hz=target,
+                      freq_shift_hz=-123e3)
+    a = gpu.Chain(cfg, 0, fused=1)
+    b = gpu.Chain(cfg, 0, fused=0)
+    ya, ca = a.process(raw, return_chunk_counts=True)
+    yb, cb = b.process(raw, return_chunk_counts=True)
+    ia = a.info()
+    assert ia.fused_front == 1 and b.info().fused_front == 0 and ia.num_halfband == S
+    assert np.array_equal(ca, cb)
+    assert ya.size == yb.size and np.array_equal(ya.view(np.uint32), yb.view(np.uint32))
+    o = CpuChain(cfg, _oracle_kind())
+    o.trace(n // 16384 + 4)
+    ref = o.process(raw)
+    assert np.array_equal(ca, o.traced())
+    _check_final(cfg, ya, ref)
+    g = gpu.Chain(cfg, 0, fused=1)
+    parts, pos = [], 0
+    for m in (1, 0, 511, 513, 4096 << S, 16385, 100000, n):
+        m = min(m, n - pos)
+        if m == 0 and pos:
+            parts.append(g.process(raw[:0]))
+            continue
+        if m <= 0:
+            break
+        parts.append(g.process(raw[2 * pos:2 * (pos + m)], chunk_frames=[m]))
+        pos += m
+    many = np.concatenate(parts)
+    assert many.size == ya.size and np.array_equal(many.view(np.uint32), ya.view(np.uint32))
