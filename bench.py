@@ -251,7 +251,11 @@ def main():
     raw = synth_torch(wl, shard.read_frames, dev, start=shard.lead)
     out_frames_max = chain.out_capacity_frames(n + halo)
     out = torch.empty(out_frames_max * cfg.out_bytes, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream()
+    # an explicit (non-default) stream: the chain's kernels are launched on it and the timing events are recorded on it
+    # (a NULL stream handle would make the chain use its own internal stream, invisible to torch's events)
+    stream = torch.cuda.Stream(device=dev)
+    stream.wait_stream(torch.cuda.current_stream())
+    torch.cuda.set_stream(stream)
     exchange = bool(sc.digital_agc and world > 1 and not replicas)
 
     def rewind():

@@ -158,7 +158,13 @@ struct iqgpu_chain {
     // second compute stream: the DC pre-pass of sub-train k+1 (HBM bound) runs underneath the fused front
     // kernel of sub-train k (issue bound); ordered with events
     cudaStream_t aux = nullptr;
-    cudaEvent_t ev_pre[2] = {nullptr, nullptr}, ev_front[2] = {nullptr, nullptr}, ev_call = nullptr;
+    cudaEvent_t ev_pre[2] = {nullptr, nullptr}, ev_front[2] = {nullptr, nullptr}, ev_call = nullptr, ev_reset = nullptr;
+    cudaStream_t reset_stream = nullptr;   // stream a not yet consumed reset was queued on
+    int order_after_reset(cudaStream_t st);
+    uint32_t* seg_pin[2] = {nullptr, nullptr};    // pinned staging of the chunk table (digital AGC)
+    size_t seg_pin_cap[2] = {0, 0};
+    cudaEvent_t ev_seg[2] = {nullptr, nullptr};
+    int seg_pin_slot = 0;
     bool front_recorded[2] = {false, false};
     int dc_slot = 0;                    // table slot of the sub-train run_subtrain is about to launch
     bool dc_prepared = false;           // ... and whether its pre-pass was issued on `aux`
@@ -299,6 +305,8 @@ iqgpu_chain::~iqgpu_chain()
         if (ev_front[i]) cudaEventDestroy(ev_front[i]);
     }
     if (ev_call) cudaEventDestroy(ev_call);
+    if (ev_reset) cudaEventDestroy(ev_reset);
+    for (int i = 0; i < 2; i++) { if (ev_seg[i]) cudaEventDestroy(ev_seg[i]); if (seg_pin[i]) cudaFreeHost(seg_pin[i]); }
     if (aux) { cudaStreamSynchronize(aux); cudaStreamDestroy(aux); }
     if (stream) cudaStreamDestroy(stream);
     if (h2d) cudaStreamDestroy(h2d);
@@ -332,6 +340,11 @@ size_t iqgpu_chain::count_outputs(const uint32_t* chunks, size_t n_chunks, uint3
     uint32_t rem = fft_rem;
     uint64_t pos = pre_fft ? n_in - fft_rem : n_in;
     uint64_t before = resampler_outputs_after(rs, pos), total = 0;
+    if (!fft && !per_chunk) {       // only the total is wanted and nothing quantises per chunk: closed form over the whole train
+        uint64_t sum = 0;
+        for (size_t c = 0; c < n_chunks; c++) sum += chunks[c];
+        return (size_t)(resampler_outputs_after(rs, pos + sum) - before);
+    }
     for (size_t c = 0; c < n_chunks; c++) {
         uint32_t f = chunks[c];
         if (pre_fft) { const uint32_t tot = rem + f, b = tot / filt.block; f = b * filt.block; rem = tot - f; }
@@ -357,6 +370,7 @@ int iqgpu_chain::init_device()
     CK(cudaStreamCreateWithFlags(&d2h, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ev_call, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev_reset, cudaEventDisableTiming));
     for (int i = 0; i < 2; i++) {
         CK(cudaEventCreateWithFlags(&ev_pre[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ev_front[i], cudaEventDisableTiming));
@@ -503,28 +517,43 @@ int iqgpu_chain::ensure_buffers()
     return reset_state();
 }
 
+__global__ void agc_state_init_kernel(AgcState* st, AgcState v) { *st = v; }
+
+// Stream discontinuity.  All device state lives behind the stream the chain last ran on, so the reset is QUEUED there
+// (memsets + one tiny kernel, no host synchronisation: the host may go on enqueueing the next train while the previous
+// one still runs); a later call on another stream first waits for ev_reset.
 int iqgpu_chain::reset_state()
 {
     n_in = 0; n_nco_post = 0; n_out = 0; fft_rem = 0;
     if (plan_only || !buffers_ready) return IQGPU_OK;
     CK(cudaSetDevice(device));
-    if (last_stream && last_stream != stream) CK(cudaStreamSynchronize(last_stream));   // queued work still reads the state
-    if (aux) CK(cudaStreamSynchronize(aux));
+    cudaStream_t S = last_stream ? last_stream : stream;
     dc_prepared = false;
-    CK(cudaMemsetAsync(d_dc_carry, 0, sizeof(double2), stream));
+    front_recorded[0] = front_recorded[1] = false;
+    CK(cudaMemsetAsync(d_dc_carry, 0, sizeof(double2), S));
     AgcState a{};
     a.locked = 0; a.gain = 1.0f; a.seen = 0; a.last_strong = 0.0;
     a.peak_mem = (agc_mode == 1) ? 0.05f : 0.001f;   // agc.c:66,78
     a.rms_g = 1.0f; a.rms_y2 = 1.0f;                  // agc.c:58-62 (set_signal_level then set_gain(1))
-    CK(cudaMemcpyAsync(d_agc, &a, sizeof(a), cudaMemcpyHostToDevice, stream));
-    if (fused) CK(fused_reset(fused, stream));
-    if (s_in.base) CK(s_in.reset(stream));
-    if (s_pref.base) CK(s_pref.reset(stream));
-    if (s_arb_in.base) CK(s_arb_in.reset(stream));
-    for (auto& s : s_stage) if (s.base) CK(s.reset(stream));
-    CK(s_rs.reset(stream));
-    if (s_f.base) CK(s_f.reset(stream));
-    CK(cudaStreamSynchronize(stream));
+    agc_state_init_kernel<<<1, 1, 0, S>>>(d_agc, a);
+    CK(cudaGetLastError());
+    if (fused) CK(fused_reset(fused, S));
+    if (s_in.base) CK(s_in.reset(S));
+    if (s_pref.base) CK(s_pref.reset(S));
+    if (s_arb_in.base) CK(s_arb_in.reset(S));
+    for (auto& s : s_stage) if (s.base) CK(s.reset(S));
+    CK(s_rs.reset(S));
+    if (s_f.base) CK(s_f.reset(S));
+    CK(cudaEventRecord(ev_reset, S));
+    reset_stream = S;
+    return IQGPU_OK;
+}
+
+// a call on stream `st` after a reset that was queued on another stream
+int iqgpu_chain::order_after_reset(cudaStream_t st)
+{
+    if (reset_stream && reset_stream != st) CK(cudaStreamWaitEvent(st, ev_reset, 0));
+    reset_stream = nullptr;
     return IQGPU_OK;
 }
 
@@ -760,7 +789,20 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
             CK(cudaMalloc(&d_seg_peak, max_segs * sizeof(float)));
             CK(cudaMalloc(&d_seg_gain, max_segs * sizeof(float)));
         }
-        CK(cudaMemcpyAsync(d_seg_start, seg.data(), (n_chunks + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        {
+            // pinned staging (two slots guarded by events): an async copy from pageable memory would first drain the stream
+            const size_t need = (n_chunks + 1) * sizeof(uint32_t);
+            const int sl = seg_pin_slot ^= 1;
+            if (need > seg_pin_cap[sl]) {
+                if (seg_pin[sl]) { CK(cudaEventSynchronize(ev_seg[sl])); CK(cudaFreeHost(seg_pin[sl])); seg_pin[sl] = nullptr; }
+                CK(cudaMallocHost(&seg_pin[sl], need * 2));
+                seg_pin_cap[sl] = need * 2;
+                if (!ev_seg[sl]) CK(cudaEventCreateWithFlags(&ev_seg[sl], cudaEventDisableTiming));
+            } else CK(cudaEventSynchronize(ev_seg[sl]));
+            memcpy(seg_pin[sl], seg.data(), need);
+            CK(cudaMemcpyAsync(d_seg_start, seg_pin[sl], need, cudaMemcpyHostToDevice, st));
+            CK(cudaEventRecord(ev_seg[sl], st));
+        }
         CK(launch_agc_peaks(post_src, post_n, qp, d_seg_start, n_chunks, d_seg_peak, st));
         span_end(st);
         launches += 1;
@@ -1007,6 +1049,7 @@ int iqgpu_chain_get_info(iqgpu_chain* c, iqgpu_chain_info* o)
     if (!c->plan_only && c->d_agc) {
         AgcState a{};
         cudaSetDevice(c->device);
+        if (c->last_stream) cudaStreamSynchronize(c->last_stream);
         cudaStreamSynchronize(c->stream);
         if (cudaMemcpy(&a, c->d_agc, sizeof(a), cudaMemcpyDeviceToHost) == cudaSuccess) {
             o->agc_locked = a.locked; o->agc_gain = a.gain; o->agc_peak_memory = a.peak_mem; o->agc_samples_seen = a.seen;
@@ -1071,6 +1114,8 @@ int iqgpu_chain_process_device(iqgpu_chain* c, const void* dev_raw_in, size_t n_
         if (f > c->subtrain_frames) return fail(IQGPU_EINVAL, "a chunk exceeds subtrain_frames");
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
     c->last_stream = st;
+    rc = c->order_after_reset(st);
+    if (rc) return rc;
     if (c->count_outputs(chunks.data(), chunks.size(), nullptr) * c->out_bps > out_capacity_bytes)
         return fail(IQGPU_ECAPACITY, "output buffer too small");
     for (auto& t : c->tap) t.len = 0;
@@ -1142,6 +1187,8 @@ int iqgpu_chain_process_device_begin(iqgpu_chain* c, const void* dev_raw_in, siz
         return fail(IQGPU_EINVAL, "a begun call must fit one sub-train (raise the subtrain_frames option)");
     cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : c->stream;
     c->last_stream = st;
+    rc = c->order_after_reset(st);
+    if (rc) return rc;
     for (auto& t : c->tap) t.len = 0;
     size_t produced = 0;
     c->dc_slot = 0; c->dc_prepared = false;
@@ -1283,6 +1330,9 @@ int iqgpu_chain_process(iqgpu_chain* c, const void* raw_in, size_t n_frames, con
         }
         c->d_raw_bytes = raw_need; c->d_out_bytes = out_need;
     }
+    rc = c->order_after_reset(c->stream);
+    if (rc) return rc;
+    c->last_stream = c->stream;
     for (auto& t : c->tap) t.len = 0;
     size_t ci = 0, in_off = 0, out_off = 0, total = 0;
     uint32_t launches = 0;
