@@ -227,6 +227,18 @@ int  iqgpu_chain_process_device_begin(iqgpu_chain *c, const void *dev_raw_in, si
 int  iqgpu_chain_pending_chunk_peaks(iqgpu_chain *c, float *peaks, uint32_t *counts, size_t capacity, size_t *n_chunks);
 int  iqgpu_chain_process_device_finish(iqgpu_chain *c, size_t skip_chunks, void *dev_out, size_t out_capacity_bytes,
                                        size_t *out_frames, uint32_t *per_chunk_out, void *cuda_stream);
+/* Device-side form of the same exchange (no host round trip: the peaks never leave the GPUs).
+ *   iqgpu_chain_pending_chunk_peaks_device  copies the begun call's per-chunk peaks [skip_chunks, n_chunks) into a device
+ *                                           buffer (e.g. the send buffer of an NCCL all-gather), asynchronously on `stream`;
+ *   iqgpu_chain_agc_advance_device          advances the chain's device-resident digital-AGC state over the reference chunks
+ *                                           of input frames [first_frame, first_frame + n_frames) of the capture, whose
+ *                                           per-chunk peaks are in device memory (e.g. a lower rank's slice of the gathered
+ *                                           buffer); the chunks' frame counts are closed form.  Call it once per lower rank,
+ *                                           in rank order, between ..._begin and ..._finish. */
+int  iqgpu_chain_pending_chunk_peaks_device(iqgpu_chain *c, size_t skip_chunks, float *dev_peaks, size_t capacity,
+                                            size_t *n_chunks, void *cuda_stream);
+int  iqgpu_chain_agc_advance_device(iqgpu_chain *c, const float *dev_peaks, uint64_t first_frame, uint64_t n_frames,
+                                    void *cuda_stream);
 int  iqgpu_chain_get_agc_state(iqgpu_chain *c, iqgpu_agc_state *s);
 int  iqgpu_chain_set_agc_state(iqgpu_chain *c, const iqgpu_agc_state *s);
 /* host-only (no device): agc_create's initial state (agc.c:66-80) and the per-chunk state machine */

@@ -1010,7 +1010,8 @@ __global__ void __launch_bounds__(AGC_SCAN_THREADS) agc_digital_scan_kernel(cons
             }
             __syncthreads();
         }
-        for (unsigned i = tid; i < tn; i += AGC_SCAN_THREADS) seg_gain[tile0 + i] = s_gain[i];
+        if (seg_gain)                                     // null: only the state is wanted (chunks of a lower shard)
+            for (unsigned i = tid; i < tn; i += AGC_SCAN_THREADS) seg_gain[tile0 + i] = s_gain[i];
         __syncthreads();
     }
     if (tid == 0) *st = s_state;

@@ -90,6 +90,8 @@ def _load() -> C.CDLL:
     lib.iqgpu_chain_process_device_begin.argtypes = [vp, vp, sz, u32p, sz, vp]
     lib.iqgpu_chain_pending_chunk_peaks.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
     lib.iqgpu_chain_process_device_finish.argtypes = [vp, sz, vp, sz, C.POINTER(sz), u32p, vp]
+    lib.iqgpu_chain_pending_chunk_peaks_device.argtypes = [vp, sz, vp, sz, C.POINTER(sz), vp]
+    lib.iqgpu_chain_agc_advance_device.argtypes = [vp, vp, C.c_uint64, C.c_uint64, vp]
     lib.iqgpu_chain_get_agc_state.argtypes = [vp, C.POINTER(AgcStateC)]
     lib.iqgpu_chain_set_agc_state.argtypes = [vp, C.POINTER(AgcStateC)]
     lib.iqgpu_agc_digital_initial_state.argtypes = [C.POINTER(AgcStateC)]
@@ -111,6 +113,7 @@ def _load() -> C.CDLL:
                  "iqgpu_chain_halo_frames", "iqgpu_chain_resampler_outputs_after",
                  "iqgpu_chain_process_device_begin", "iqgpu_chain_pending_chunk_peaks",
                  "iqgpu_chain_process_device_finish", "iqgpu_chain_get_agc_state", "iqgpu_chain_set_agc_state",
+                 "iqgpu_chain_pending_chunk_peaks_device", "iqgpu_chain_agc_advance_device",
                  "iqgpu_agc_digital_advance", "iqgpu_convert_block_to_cf32",
                  "iqgpu_convert_cf32_to_block", "iqgpu_iq_optimize"):
         getattr(lib, name).restype = C.c_int
@@ -211,6 +214,20 @@ class Chain:
         counts = np.zeros(max(1, n.value), dtype=np.uint32)
         _check(lib.iqgpu_chain_pending_chunk_peaks(self._h, peaks.ctypes.data, counts.ctypes.data, n.value, C.byref(n)))
         return peaks[: n.value], counts[: n.value]
+
+    def pending_chunk_peaks_device(self, skip_chunks: int, dev_peaks_ptr: int, capacity: int, stream: int = 0) -> int:
+        """Copy the begun call's per-chunk peaks [skip_chunks, n_chunks) into device memory (asynchronously); returns
+        the number of peaks."""
+        n = C.c_size_t(0)
+        _check(lib.iqgpu_chain_pending_chunk_peaks_device(self._h, skip_chunks, dev_peaks_ptr, capacity, C.byref(n),
+                                                          C.c_void_p(stream) if stream else None))
+        return n.value
+
+    def agc_advance_device(self, dev_peaks_ptr: int, first_frame: int, n_frames: int, stream: int = 0) -> None:
+        """Advance the device-resident digital-AGC state over the chunks of capture frames
+        [first_frame, first_frame + n_frames) whose peaks are in device memory."""
+        _check(lib.iqgpu_chain_agc_advance_device(self._h, dev_peaks_ptr, first_frame, n_frames,
+                                                  C.c_void_p(stream) if stream else None))
 
     def process_device_finish(self, skip_chunks: int, dev_out_ptr: int, out_capacity_bytes: int, stream: int = 0) -> int:
         nout = C.c_size_t(0)

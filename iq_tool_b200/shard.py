@@ -161,7 +161,35 @@ class ShardedChain:
         # live chunks per rank: the lengths of the tables the ranks exchange (no length exchange needed at run time)
         self._table_sizes = {(s.world, s.rank, s.start, s.frames): [(t.frames + CHUNK_SAMPLES - 1) // CHUNK_SAMPLES for t in shards]
                              for s in shards}
+        self._plans = {(s.world, s.rank, s.start, s.frames): shards for s in shards}
         return shards
+
+    def _finish_device_exchange(self, shard: Shard, shards: List[Shard], dev_out_ptr: int, out_capacity_bytes: int,
+                                stream: int, group, device) -> int:
+        """The digital-AGC exchange without a host round trip: the shard's per-chunk peaks go from the chain into the
+        send buffer of ONE all-gather (NCCL over NVLink), and every rank advances its device-resident AGC state over the
+        lower ranks' slices of the gathered buffer with the chunk-table scan kernel (chunk frame counts are closed
+        form), then finishes its own shard.  Same kernel, same chunks, same order as the single stream -> same bits."""
+        import torch
+        import torch.distributed as dist
+
+        ch = self.chain
+        sizes = [(t.frames + CHUNK_SAMPLES - 1) // CHUNK_SAMPLES for t in shards]
+        m = max(max(sizes), 1)
+        key = (shard.world, m, str(device))
+        bufs = getattr(self, "_xbufs", None)
+        if bufs is None or bufs[0] != key:
+            bufs = (key, torch.zeros(m, dtype=torch.float32, device=device),
+                    torch.zeros(shard.world * m, dtype=torch.float32, device=device))
+            self._xbufs = bufs
+        _, mine, gathered = bufs
+        live = ch.pending_chunk_peaks_device(shard.skip_chunks, mine.data_ptr(), m, stream)
+        assert live == sizes[shard.rank]
+        dist.all_gather_into_tensor(gathered, mine, group=group)          # on torch's current stream == `stream`
+        for r in range(shard.rank):
+            if shards[r].frames:
+                ch.agc_advance_device(gathered.data_ptr() + 4 * r * m, shards[r].start, shards[r].frames, stream)
+        return ch.process_device_finish(shard.skip_chunks, dev_out_ptr, out_capacity_bytes, stream)
 
     def process_device(self, shard: Shard, dev_in_ptr: int, dev_out_ptr: int, out_capacity_bytes: int,
                        stream: int = 0, group=None, comm_device="cpu") -> Tuple[int, int]:
@@ -178,6 +206,9 @@ class ShardedChain:
         if not (self.digital_agc and shard.world > 1):
             return ch.process_device(dev_in_ptr, n, dev_out_ptr, out_capacity_bytes, stream), shard.drop
         ch.process_device_begin(dev_in_ptr, n, stream)
+        plan = getattr(self, "_plans", {}).get((shard.world, shard.rank, shard.start, shard.frames))
+        if plan is not None and str(comm_device).startswith("cuda"):
+            return self._finish_device_exchange(shard, plan, dev_out_ptr, out_capacity_bytes, stream, group, comm_device), shard.drop
         peaks, counts = ch.pending_chunk_peaks()
         sizes = getattr(self, "_table_sizes", {}).get((shard.world, shard.rank, shard.start, shard.frames))
         state = exchange_agc_state(peaks[shard.skip_chunks:], counts[shard.skip_chunks:], self.agc_target,

@@ -131,9 +131,11 @@ def test_agc_exchange_over_gloo_world2_equals_single_stream():
 # ------------------------------------------------------------------------------------------------
 # GPU: shard-stitch parity
 # ------------------------------------------------------------------------------------------------
-def _run_sharded(gpu, wl, raw, world):
+def _run_sharded(gpu, wl, raw, world, device_exchange=False):
     """Process `raw` as `world` shards one after the other on cuda:0 (the data path has no
-    collective, so ranks need not run concurrently; the AGC exchange is replayed in rank order)."""
+    collective, so ranks need not run concurrently; the AGC exchange is replayed in rank order).
+    device_exchange: the peaks stay on the GPU (the all-gather is a set of device buffers here) and the lower
+    shards' chunks are replayed by the scan kernel (iqgpu_chain_agc_advance_device) instead of on the host."""
     import torch
     from iq_tool_b200.shard import ShardedChain
     cfg = wl.config
@@ -149,7 +151,17 @@ def _run_sharded(gpu, wl, raw, world):
         ch.seek(sh.lead)
         out = torch.zeros(ch.out_capacity_frames(sh.read_frames) * cfg.out_bytes, dtype=torch.uint8, device=dev)
         ptr = raw_d.data_ptr() + sh.lead * esz
-        if sc.digital_agc:
+        if sc.digital_agc and device_exchange:
+            ch.process_device_begin(ptr, sh.read_frames)
+            nlive = (sh.frames + CHUNK - 1) // CHUNK
+            mine = torch.zeros(max(nlive, 1), dtype=torch.float32, device=dev)
+            assert ch.pending_chunk_peaks_device(sh.skip_chunks, mine.data_ptr(), mine.numel()) == nlive
+            for q, buf in zip(shards, live_peaks):
+                if q.frames:
+                    ch.agc_advance_device(buf.data_ptr(), q.start, q.frames)
+            live_peaks.append(mine)
+            produced = ch.process_device_finish(sh.skip_chunks, out.data_ptr(), out.numel())
+        elif sc.digital_agc:
             ch.process_device_begin(ptr, sh.read_frames)
             pk, ct = ch.pending_chunk_peaks()
             st = gpu.agc_initial_state()
@@ -181,6 +193,8 @@ def test_sharded_output_equals_single_stream_bit_for_bit(name, chunks, world, gp
     sharded = _run_sharded(gpu, wl, raw, world)
     assert sharded.size == single.size
     assert np.array_equal(sharded, single)
+    on_device = _run_sharded(gpu, wl, raw, world, device_exchange=True)
+    assert np.array_equal(on_device, single)
 
 
 @pytest.mark.gpu
