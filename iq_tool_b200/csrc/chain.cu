@@ -1149,19 +1149,24 @@ int iqgpu_chain_process_device(iqgpu_chain* c, const void* dev_raw_in, size_t n_
     uint32_t launches = 0;
     for (size_t k = 0; k < subs.size(); k++) {
         const Sub& sb = subs[k];
-        if (overlap_dc) {
-            if (k + 1 < subs.size()) {
-                rc = c->prepare_dc(slot ^ 1, raw_at(subs[k + 1]), base_in + subs[k + 1].in_off, subs[k + 1].n, st);
-                if (rc) return rc;
-                launches += 2;
-            }
-            c->dc_slot = slot; c->dc_prepared = true;
-        } else { c->dc_slot = 0; c->dc_prepared = false; }
+        if (overlap_dc) { c->dc_slot = slot; c->dc_prepared = true; }
+        else { c->dc_slot = 0; c->dc_prepared = false; }
         size_t produced = 0;
         rc = c->run_subtrain(raw_at(sb), sb.n, chunks.data() + sb.c0, sb.c1 - sb.c0,
                              (char*)dev_out + out_off, &produced, per_chunk_out ? per_chunk_out + sb.c0 : nullptr, st);
         if (rc) return rc;
         launches += c->launches;
+        if (overlap_dc && k + 1 < subs.size()) {
+            // The pre-pass of the NEXT sub-train (HBM bound, few FMAs) runs on the second stream next to this sub-train's
+            // filter / post kernels (FMA bound, little HBM traffic); it is gated behind this sub-train's fused front kernel,
+            // which it would only slow down (both lean on the LSU pipe; measured).
+            const uint32_t keep = c->launches;
+            CK(cudaStreamWaitEvent(c->aux, c->ev_front[slot], 0));
+            rc = c->prepare_dc(slot ^ 1, raw_at(subs[k + 1]), base_in + subs[k + 1].in_off, subs[k + 1].n, st);
+            if (rc) return rc;
+            c->launches = keep;
+            launches += 2;
+        }
         out_off += produced * c->out_bps; total += produced;
         slot ^= 1;
     }

@@ -904,8 +904,15 @@ __global__ void __launch_bounds__(AGC_SCAN_THREADS) agc_digital_scan_kernel(cons
         if (lane == 31) s_warp_tot[warp] = inc;
         if (tid == 0) s_pos = 0;
         __syncthreads();
-        unsigned long long base = s_state.seen;
-        for (unsigned w = 0; w < warp; w++) base += s_warp_tot[w];
+        // exclusive prefix over the warp totals: every warp scans the 16 totals with shuffles (no serial walk)
+        unsigned long long wt = (lane < AGC_SCAN_THREADS / 32) ? s_warp_tot[lane] : 0ull;
+#pragma unroll
+        for (int d = 1; d < AGC_SCAN_THREADS / 32; d <<= 1) {
+            const unsigned long long q = __shfl_up_sync(0xffffffffu, wt, d);
+            if (lane >= (unsigned)d) wt += q;
+        }
+        const unsigned long long below = __shfl_sync(0xffffffffu, wt, (warp + 31) & 31);     // inclusive total of warp - 1
+        const unsigned long long base = s_state.seen + (warp ? below : 0ull);
         unsigned long long seen_before = base + inc - run;
 #pragma unroll
         for (int k = 0; k < PER_THREAD; k++) {
@@ -946,7 +953,16 @@ __global__ void __launch_bounds__(AGC_SCAN_THREADS) agc_digital_scan_kernel(cons
             if (lane == 0) tex = -1.0;
             if (lane == 31) s_warp_max[warp] = wv;
             __syncthreads();
-            for (unsigned w = 0; w < warp; w++) tex = fmax(tex, s_warp_max[w]);   // max of the keys of all chunks before this thread's
+            {   // max of the keys of all chunks before this thread's: shuffle scan over the 16 warp maxima
+                double wm = (lane < AGC_SCAN_THREADS / 32) ? s_warp_max[lane] : -1.0;
+#pragma unroll
+                for (int d = 1; d < AGC_SCAN_THREADS / 32; d <<= 1) {
+                    const double q = __shfl_up_sync(0xffffffffu, wm, d);
+                    if (lane >= (unsigned)d) wm = fmax(wm, q);
+                }
+                const double wb = __shfl_sync(0xffffffffu, wm, (warp + 31) & 31);
+                if (warp) tex = fmax(tex, wb);
+            }
             float g[PER_THREAD];
             double after[PER_THREAD];                                             // state value once chunk k has been taken
             unsigned ev = tn;
