@@ -140,7 +140,10 @@ def chain_flops_per_sample(cfg, info):
         rate *= 0.5
         fl += rate * (8.0 * m + 2.0)
     fl += info.ratio * 56.0
-    if info.filter_num_taps:
+    if info.filter_num_taps and info.filter_impl in (3, 4):     # FFT block filter: 2 transforms of 2n per n outputs
+        import math
+        fl += info.ratio * (20.0 * math.log2(2.0 * max(1, info.filter_block_size)) + 12.0)
+    elif info.filter_num_taps:
         fl += info.ratio * info.filter_num_taps * (8.0 if info.filter_impl == 2 else 4.0)
     fl += info.ratio * 4.0
     return fl
