@@ -364,6 +364,14 @@ struct FusedFront {
     uint32_t v2_step = 0;
     int H_tail = 0;                     // cf32 tail length of the kernel in use
     float2* d_bank_image = nullptr;     // polyphase bank in the v2 shared-memory layout (w2_bank_row)
+    // local DC state (fused_front2.cuh, DC == 2): per-warp records, per-stretch corrections, row gains of the polyphase stage
+    W2DcStretch* d_dc_stretch = nullptr;
+    W2DcCorr* d_dc_corr = nullptr;
+    size_t dc_stretch_cap = 0;
+    float* d_dc_G = nullptr;
+    float dc_G_for_c = -1.f;            // pole the gains were computed for
+    double dc_atot = 1.0;
+    std::vector<float> h_bank;          // host copy of the 256 x 14 polyphase bank
     uint32_t lut_dtheta = 0;            // NCO table swizzle chosen for this phase increment
     unsigned lut_sh = 4, lut_mask = 0;
     bool lut_picked = false;
@@ -494,6 +502,7 @@ FusedFront* fused_create(int format, const ResamplerDesc& r, bool nco, const flo
             fused_destroy(f);
             return nullptr;
         }
+        f->h_bank = hb;
         for (int idx = 0; idx < 256; idx++)
             for (int i = 0; i < 7; i++) img[w2_bank_row(idx) + i] = make_float2(hb[idx * 14 + 2 * i], hb[idx * 14 + 2 * i + 1]);
         if (cudaMemcpy(f->d_bank_image, img.data(), img.size() * sizeof(float2), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -511,6 +520,7 @@ void fused_destroy(FusedFront* f)
     cudaFree(f->d_taps); cudaFree(f->d_tail[0]); cudaFree(f->d_tail[1]);
     for (int i = 0; i < 2; i++) { cudaFree(f->d_dc_table[i]); cudaFree(f->d_dc_sums[i]); cudaFree(f->d_dc_ws[i]); }
     cudaFree(f->d_bank_image);
+    cudaFree(f->d_dc_stretch); cudaFree(f->d_dc_corr); cudaFree(f->d_dc_G);
     delete f;
 }
 
@@ -591,10 +601,49 @@ static cudaError_t fused_dc_prepass(FusedFront* f, int slot, const void* raw, lo
 
 // DC pre-pass of the sub-train [n0, n0+n) into table slot `slot`, on stream `st` (which may differ from the
 // stream of the front kernel: the caller orders them with events).  fused_launch() then skips its own pre-pass.
+// local DC state + closed-form correction instead of the pre-pass: the blocker must be followed directly by the (real-tap,
+// linear, time-invariant) cascade — no I/Q apply and no table NCO in between
+static bool v2_dc_local(const FusedFront* f, const PreParams& pre)
+{
+    return f->v2 && pre.dc_enable && !pre.nco_enable && !pre.iq_enable && !getenv("IQGPU_DC_TABLE");
+}
+
+// gains of the cascade for the sequence c^n (see fused_front2.cuh): Atot over the halfband stages, G per polyphase row
+static cudaError_t v2_dc_gains(FusedFront* f, float c, cudaStream_t st)
+{
+    if (f->dc_G_for_c == c && f->d_dc_G) return cudaSuccess;
+    double mu = (double)c, atot = 1.0;
+    int k = 0;
+    for (int d = 0; d < f->v2_S; d++) {
+        const int m = (d == f->v2_S - 1) ? 10 : ((d == f->v2_S - 2) ? 5 : 3);
+        double a = pow(mu, (double)(1 - 2 * m));
+        for (int j = 0; j < 2 * m; j++) a += (double)f->v2_taps[k + j] * pow(mu, 2.0 * (double)(j + 1 - 2 * m));
+        k += 2 * m;
+        atot *= a;
+        mu *= mu;
+    }
+    f->dc_atot = atot * (f->v2_S > 0 ? (double)f->v2_zeta : 1.0);
+    std::vector<float> G(256);
+    for (int idx = 0; idx < 256; idx++) {
+        double g = 0.0;
+        for (int i = 0; i < 14; i++) g += (double)f->h_bank[idx * 14 + i] * pow(mu, (double)(i - 13));
+        G[idx] = (float)g;
+    }
+    cudaError_t e = cudaSuccess;
+    if (!f->d_dc_G) e = cudaMalloc(&f->d_dc_G, 256 * sizeof(float));
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(st);           // first use / new pole only
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpy(f->d_dc_G, G.data(), 256 * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) f->dc_G_for_c = c;
+    return e;
+}
+
 cudaError_t fused_prepare_dc(FusedFront* f, int slot, const void* raw, int64_t n0, size_t n, const PreParams& pre,
                              double2* d_dc_carry, uint32_t* launches, cudaStream_t st)
 {
     if (n == 0 || !pre.dc_enable) return cudaSuccess;
+    if (v2_dc_local(f, pre)) return cudaSuccess;        // no pre-pass in this mode
     const long long align = f->v2 ? W2_T0 : 256;
     const long long A0 = (n0 / align) * align;
     cudaError_t e = fused_dc_prepass(f, slot, raw, n0, n0 + (long long)n, pre, d_dc_carry, A0, st);
@@ -605,7 +654,7 @@ cudaError_t fused_prepare_dc(FusedFront* f, int slot, const void* raw, int64_t n
 }
 
 template <int S>
-static cudaError_t launch_v2_s(const FusedFront* f, const Fused2Args& A, int grid, bool dc, bool cs16, cudaStream_t st)
+static cudaError_t launch_v2_s(const FusedFront* f, const Fused2Args& A, int grid, int dc, bool cs16, cudaStream_t st)
 {
     const int threads = f->v2_warps * 32;
     const size_t smem = f->v2_smem;
@@ -615,8 +664,9 @@ static cudaError_t launch_v2_s(const FusedFront* f, const Fused2Args& A, int gri
         if (e_ != cudaSuccess) return e_;                                                                          \
         fused_front2_kernel<S, DCF, C16><<<grid, threads, smem, st>>>(A, f->v2_warps);                              \
     } while (0)
-    if (dc) { if (cs16) V2_LAUNCH(true, true); else V2_LAUNCH(true, false); }
-    else    { if (cs16) V2_LAUNCH(false, true); else V2_LAUNCH(false, false); }
+    if (dc == 2)      { if (cs16) V2_LAUNCH(2, true); else V2_LAUNCH(2, false); }
+    else if (dc == 1) { if (cs16) V2_LAUNCH(1, true); else V2_LAUNCH(1, false); }
+    else              { if (cs16) V2_LAUNCH(0, true); else V2_LAUNCH(0, false); }
 #undef V2_LAUNCH
     return cudaGetLastError();
 }
@@ -666,7 +716,35 @@ static cudaError_t fused_launch_v2(FusedFront* f, const void* raw, int64_t n0, s
                             cudaMemcpyDeviceToDevice, st);
         if (e != cudaSuccess) return e;
     }
-    if (pre.dc_enable) {
+    const bool dc_local = v2_dc_local(f, pre);
+    W2DcGeom geo{};
+    if (dc_local) {
+        e = v2_dc_gains(f, pre.dc_c, st);
+        if (e != cudaSuccess) return e;
+        if ((size_t)warps_needed > f->dc_stretch_cap) {
+            e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) return e;
+            cudaFree(f->d_dc_stretch); cudaFree(f->d_dc_corr);
+            f->d_dc_stretch = nullptr; f->d_dc_corr = nullptr;
+            f->dc_stretch_cap = (size_t)warps_needed + 64;
+            e = cudaMalloc(&f->d_dc_stretch, f->dc_stretch_cap * sizeof(W2DcStretch));
+            if (e != cudaSuccess) return e;
+            e = cudaMalloc(&f->d_dc_corr, f->dc_stretch_cap * sizeof(W2DcCorr));
+            if (e != cudaSuccess) return e;
+        }
+        const double c = (double)pre.dc_c;
+        A.dc_carry = d_dc_carry;
+        A.dc_stretch = f->d_dc_stretch;
+        A.dc_lnc = log(c);
+        A.dc_c512 = pow(c, 512.0);
+        geo.n_stretch = (int)warps_needed;
+        geo.B0 = A.sup_first * sup_frames;
+        geo.L_full = per * sup_frames;
+        geo.L_last = (A.sup_last - (A.sup_first + (warps_needed - 1) * per) + 1) * sup_frames;
+        geo.warm_frames = (long long)f->v2_warm_sup * sup_frames;
+        geo.pad_frames = (A.sup_last + 1) * sup_frames - A.N1;
+        geo.lnc = A.dc_lnc; geo.alpha = (double)pre.dc_a; geo.atot = f->dc_atot;
+    } else if (pre.dc_enable) {
         if (!f->dc_ready[dc_slot]) {
             e = fused_dc_prepass(f, dc_slot, raw, n0, A.N1, pre, d_dc_carry, A.A0, st);
             if (e != cudaSuccess) return e;
@@ -676,7 +754,7 @@ static cudaError_t fused_launch_v2(FusedFront* f, const void* raw, int64_t n0, s
         A.dc_table = f->d_dc_table[dc_slot];
         A.dc_table_shift = 9;
     }
-    const bool dc = pre.dc_enable != 0;
+    const int dc = dc_local ? 2 : (pre.dc_enable ? 1 : 0);
     const bool cs16 = pre.format == IQGPU_FMT_CS16 || pre.format == IQGPU_FMT_SC16Q11;
     switch (f->v2_S) {
         case 0: e = launch_v2_s<0>(f, A, grid, dc, cs16, st); break;
@@ -689,6 +767,15 @@ static cudaError_t fused_launch_v2(FusedFront* f, const void* raw, int64_t n0, s
         default: return cudaErrorInvalidValue;
     }
     if (launches) *launches += 1;
+    if (dc_local && e == cudaSuccess) {
+        w2_dc_scan_kernel<<<1, 1024, 0, st>>>(f->d_dc_stretch, geo, f->d_dc_corr, d_dc_carry);
+        const long long work = (long long)n_out + f->H_tail;
+        const int cgrid = (int)std::min<long long>((work + 255) / 256, 148LL * 16);
+        w2_dc_correct_kernel<<<std::max(cgrid, 1), 256, 0, st>>>(y, A.O0, A.O1, A.step, f->v2_S, geo, f->d_dc_corr, f->d_dc_G,
+                                                               f->d_tail[f->tail_cur ^ 1], A.N1 - f->H_tail, A.n0, A.N1);
+        e = cudaGetLastError();
+        if (launches) *launches += 2;
+    }
     f->tail_cur ^= 1;
     return e;
 }

@@ -132,6 +132,8 @@ struct W2Plan {
     }
 };
 
+struct W2DcStretch { double2 v_emit, v_end; };   // local v at the first frame of the warp's emit range / after its last tick
+
 struct Fused2Args {
     const void* raw;
     long long n0, N1;                   // absolute index range of raw
@@ -143,6 +145,12 @@ struct Fused2Args {
     const double2* dc_table;            // v at absolute multiples of 2^dc_table_shift frames, starting at A0
     int dc_table_shift;                 // 9: per-tick table (dc_tick_sums pre-pass)
     long long A0;
+    // DC == 2 ("local" DC state, no pre-pass): every warp carries v through its own stretch from zero (the warp that holds
+    // n0 from the carried state) and reports v at the start and the end of its emit range; the term it misses is a
+    // decaying exponential, an eigenfunction of the linear cascade, added afterwards in closed form (w2_dc_correct_kernel)
+    const double2* dc_carry;            // device: v just before frame n0
+    W2DcStretch* dc_stretch;            // one record per warp of the launch
+    double dc_c512, dc_lnc;             // c^512 and ln c in double (c = the float pole)
     const float2* bank_image;           // device, W2_BANK_F2 float2 in the w2_bank_row layout
     long long O0, O1;
     float2* y;
@@ -236,9 +244,10 @@ __device__ __forceinline__ void w2_prefetch(const Fused2Args& A, long long tick_
 // ------------------------------------------------------------------------------------------------
 // P0: one tick (512 frames) of the pre-processor chain into level 0 (or the flat level when S == 0)
 // ------------------------------------------------------------------------------------------------
-template <int S, bool DC, bool CS16>
+template <int S, int DC, bool CS16>
 __device__ __forceinline__ void w2_p0(const Fused2Args& A, float2* __restrict__ wsm, const float2* __restrict__ lut2,
-                                      long long tick_start, int lane, const W2Raw& pre, f32x2_t (&x)[16])
+                                      long long tick_start, int lane, const W2Raw& pre, f32x2_t (&x)[16], double2& vloc,
+                                      bool write_tail)
 {
     using P = W2Plan<S>;
     const PreParams& p = A.pre;
@@ -276,11 +285,12 @@ __device__ __forceinline__ void w2_p0(const Fused2Args& A, float2* __restrict__ 
 #pragma unroll
         for (int k = 0; k < 16; k++) x[k] = 0ull;
     }
+    if (DC == 2 && !active) { vloc.x *= A.dc_c512; vloc.y *= A.dc_c512; }     // a tick of zeros
     if (active) {
         if (DC) {
             // DC blocker (dc_block.c:76 -> liquid iirfilt): v[n] = x[n] + c v[n-1], y[n] = x[n] - (1-c) v[n-1].
             // lane-local weighted sum, one warp scan per tick, state at the tick start from the table
-            const double2 vt = A.dc_table[(tick_start - A.A0) >> A.dc_table_shift];
+            const double2 vt = (DC == 2) ? vloc : A.dc_table[(tick_start - A.A0) >> A.dc_table_shift];
             // v just before the lane's frame k is c^k w0 + P(k-1), P = the lane-local running sum, so
             //   y[k] = (x[k] - a P(k-1)) - (a c^k) w0 :
             // the first term hangs off the lane-local chain and is independent of the warp scan that delivers w0;
@@ -301,6 +311,11 @@ __device__ __forceinline__ void w2_p0(const Fused2Args& A, float2* __restrict__ 
             }
             f32x2_t e = __shfl_up_sync(0xffffffffu, pr, 1);
             if (lane == 0) e = 0ull;
+            if (DC == 2) {      // carry the state to the next tick: v' = c^512 v + (weighted sum of the tick)
+                const float2 tot = unpk2(__shfl_sync(0xffffffffu, pr, 31));
+                vloc.x = fma(A.dc_c512, vloc.x, (double)tot.x);
+                vloc.y = fma(A.dc_c512, vloc.y, (double)tot.y);
+            }
             const float lp = A.dc.lanepow[lane];
             const f32x2_t w0 = fma2s(lp, pk2((float)vt.x, (float)vt.y), e);   // v just before the lane's first frame
 #pragma unroll
@@ -335,7 +350,7 @@ __device__ __forceinline__ void w2_p0(const Fused2Args& A, float2* __restrict__ 
                 }
             }
         }
-        if (a0 + 16 > A.N1 - A.H_tail && a0 < A.N1) {
+        if (write_tail && a0 + 16 > A.N1 - A.H_tail && a0 < A.N1) {
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 const long long j = a0 + k - (A.N1 - A.H_tail);
@@ -629,7 +644,7 @@ struct W2Cascade {
     }
 };
 
-template <int S, bool DC, bool CS16>
+template <int S, int DC, bool CS16>
 __global__ void __launch_bounds__(W2_MAX_WARPS * 32, 1) fused_front2_kernel(const __grid_constant__ Fused2Args A, int warps_per_cta)
 {
     using P = W2Plan<S>;
@@ -664,6 +679,13 @@ __global__ void __launch_bounds__(W2_MAX_WARPS * 32, 1) fused_front2_kernel(cons
         const unsigned long long k_emit = (unsigned long long)((t_emit * W2_T0) >> S);
         o_cur = (long long)(((k_emit << 24) + A.step - 1) / A.step);
     }
+    double2 vloc = make_double2(0.0, 0.0);
+    if (DC == 2 && gw == 0) {
+        // the warp that holds n0 starts from the carried state, rewound through the (zero) frames in front of n0
+        const double2 cv = *A.dc_carry;
+        const double f = exp(-(double)(A.n0 - t_begin * W2_T0) * A.dc_lnc);
+        vloc = make_double2(cv.x * f, cv.y * f);
+    }
     W2Raw nxt;
 #pragma unroll
     for (int j = 0; j < 4; j++) nxt.q[j] = make_uint4(0u, 0u, 0u, 0u);
@@ -672,8 +694,11 @@ __global__ void __launch_bounds__(W2_MAX_WARPS * 32, 1) fused_front2_kernel(cons
         const long long tick_start = t * W2_T0;
         const W2Raw cur = nxt;
         if (CS16 && t + 1 < t_end) w2_prefetch(A, tick_start + W2_T0, lane, nxt);
+        if (DC == 2 && t == t_emit && lane == 0) A.dc_stretch[gw].v_emit = vloc;
         f32x2_t x[16];
-        w2_p0<S, DC, CS16>(A, wsm, lut2, tick_start, lane, cur, x);
+        // local DC: the frames of a warm-up tick belong to the emit range of the warp below, which stores them in the tail
+        // with ITS state (warp 0's warm-up frames precede n0: copies of the old tail)
+        w2_p0<S, DC, CS16>(A, wsm, lut2, tick_start, lane, cur, x, vloc, DC != 2 || t >= t_emit || gw == 0);
         bool arb_due = true;
         if constexpr (P::reg0) {
             w2_stage0_reg<S>(A, wsm, lane, x);
@@ -693,6 +718,108 @@ __global__ void __launch_bounds__(W2_MAX_WARPS * 32, 1) fused_front2_kernel(cons
             __syncwarp();
             if (lane < W2_ARB_HIST) flat[lane] = h;
             __syncwarp();
+        }
+    }
+    if (DC == 2 && lane == 0) A.dc_stretch[gw].v_end = vloc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Local DC state (DC == 2): what the warps could not know.
+// Warp w ran its stretch (warm-up from frame s_w = B_w - warm, emit range [B_w, B_w + L_w)) with v = 0 in front of s_w,
+// while the true state there is V0_w.  The blocker is linear, so every frame it produced lacks -a V0_w c^(n - s_w): a
+// decaying exponential.  Each halfband decimator maps kappa mu^n to kappa A(mu) (mu^2)^q and the polyphase stage maps
+// kappa mu^k to kappa mu^k_o G[row_o], so the cascade output lacks  -a V0_w Atot c^(2^S k_o - s_w) G[row_o]  (Atot and the
+// 256 row gains G are computed once on the host in double from the actual taps).  V0_w follows from the records the
+// warps left: v(B_w+1) = a_w v(B_w) + (v_end_w - a_w v_emit_w), a_w = c^L_w — an affine scan over a few thousand stretches.
+// ------------------------------------------------------------------------------------------------
+struct W2DcCorr { float2 c_out, c_pre; };      // -a V0 Atot (cascade output) and -a V0 (cascade input, for the cf32 tail)
+struct W2DcGeom {
+    int n_stretch;
+    long long B0, L_full, L_last, warm_frames, pad_frames;     // pad: zero frames between N1 and the end of the last tick
+    double lnc, alpha, atot;
+};
+
+__global__ void __launch_bounds__(1024) w2_dc_scan_kernel(const W2DcStretch* __restrict__ rec, W2DcGeom g,
+                                                          W2DcCorr* __restrict__ corr, double2* __restrict__ carry)
+{
+    __shared__ double sA[1024], sBx[1024], sBy[1024];
+    const int t = threadIdx.x, n = g.n_stretch;
+    const int G = (n - 1 + 1023) / 1024;                         // stretches 1 .. n-1 in groups of G per thread
+    const int w0 = 1 + t * G, w1 = min(n, w0 + G);
+    const double a_full = exp((double)g.L_full * g.lnc), a_last = exp((double)g.L_last * g.lnc);
+    double A = 1.0, Bx = 0.0, By = 0.0;                          // composite map of this thread's stretches
+    for (int w = w0; w < w1; w++) {
+        const double a = (w == n - 1) ? a_last : a_full;
+        const W2DcStretch r = rec[w];
+        const double bx = r.v_end.x - a * r.v_emit.x, by = r.v_end.y - a * r.v_emit.y;
+        A = a * A; Bx = a * Bx + bx; By = a * By + by;
+    }
+    sA[t] = A; sBx[t] = Bx; sBy[t] = By;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {                         // inclusive scan of the maps (earlier map applied first)
+        double pa = 1.0, pbx = 0.0, pby = 0.0;
+        if (t >= d) { pa = sA[t - d]; pbx = sBx[t - d]; pby = sBy[t - d]; }
+        __syncthreads();
+        if (t >= d) { sBx[t] = sA[t] * pbx + sBx[t]; sBy[t] = sA[t] * pby + sBy[t]; sA[t] = sA[t] * pa; }
+        __syncthreads();
+    }
+    const double2 v1 = rec[0].v_end;                             // stretch 0 ran from the carried state: exact
+    double vx = v1.x, vy = v1.y;
+    if (t > 0) { vx = sA[t - 1] * v1.x + sBx[t - 1]; vy = sA[t - 1] * v1.y + sBy[t - 1]; }
+    const double unwarm = exp(-(double)g.warm_frames * g.lnc);
+    if (t == 0) corr[0] = W2DcCorr{make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    for (int w = w0; w < w1; w++) {
+        const double a = (w == n - 1) ? a_last : a_full;
+        const W2DcStretch r = rec[w];
+        const double v0x = (vx - r.v_emit.x) * unwarm, v0y = (vy - r.v_emit.y) * unwarm;
+        W2DcCorr c;
+        c.c_pre = make_float2((float)(-g.alpha * v0x), (float)(-g.alpha * v0y));
+        c.c_out = make_float2((float)(-g.alpha * v0x * g.atot), (float)(-g.alpha * v0y * g.atot));
+        corr[w] = c;
+        vx = a * vx + (r.v_end.x - a * r.v_emit.x);
+        vy = a * vy + (r.v_end.y - a * r.v_emit.y);
+    }
+    // the state just before N1: the last tick ran pad_frames of zeros beyond it
+    const bool owns_last = (n == 1) ? (t == 0) : (w0 < w1 && w1 == n);
+    if (owns_last) {
+        const double un = exp(-(double)g.pad_frames * g.lnc);
+        *carry = make_double2(vx * un, vy * un);
+    }
+}
+
+// adds the missing term to the outputs [O0, O1) of the launch and to the frames of the cf32 tail it wrote
+__global__ void __launch_bounds__(256) w2_dc_correct_kernel(float2* __restrict__ y, long long O0, long long O1, uint32_t step, int S,
+                                                            W2DcGeom g, const W2DcCorr* __restrict__ corr, const float* __restrict__ G,
+                                                            float2* __restrict__ tail, long long tail_first, long long n0, long long N1)
+{
+    __shared__ float sG[256];
+    sG[threadIdx.x] = G[threadIdx.x];
+    __syncthreads();
+    const float lnc = (float)g.lnc;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long n_out = O1 - O0;
+    const long long t_lo = (tail_first > n0) ? tail_first : n0;
+    const long long n_tail = (N1 > t_lo) ? (N1 - t_lo) : 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_out + n_tail; i += stride) {
+        if (i < n_out) {
+            const unsigned long long Pp = (unsigned long long)(O0 + i) * step;
+            const long long nk = (long long)(Pp >> 24) << S;
+            const long long w = (nk - g.B0) / g.L_full;
+            if (w <= 0) continue;
+            const W2DcCorr c = corr[w];
+            const float e = expf(lnc * (float)(nk - (g.B0 + w * g.L_full - g.warm_frames))) * sG[(unsigned)(Pp >> 16) & 0xffu];
+            float2 v = y[i];
+            v.x = fmaf(c.c_out.x, e, v.x); v.y = fmaf(c.c_out.y, e, v.y);
+            y[i] = v;
+        } else {
+            const long long n = t_lo + (i - n_out);
+            const long long w = (n - g.B0) / g.L_full;
+            if (w <= 0) continue;
+            const W2DcCorr c = corr[w];
+            const float e = expf(lnc * (float)(n - (g.B0 + w * g.L_full - g.warm_frames)));
+            float2 v = tail[n - tail_first];
+            v.x = fmaf(c.c_pre.x, e, v.x); v.y = fmaf(c.c_pre.y, e, v.y);
+            tail[n - tail_first] = v;
         }
     }
 }

@@ -310,7 +310,9 @@ def test_fused_front_is_call_size_invariant(gpu, workloads):
         many = np.concatenate(parts).view(np.complex64)
         assert many.size == one.size
         if cfg.dc_block:
-            assert rel_rms_fullscale(many, one) <= 2e-8
+            # the one-call run evaluates the DC blocker per warp stretch (local state + closed-form correction), the
+            # ragged calls from the carried state: two fp32 evaluation orders of the same arithmetic
+            assert rel_rms_fullscale(many, one) <= 1e-7
         else:
             assert np.array_equal(many.view(np.uint32), one.view(np.uint32))
 
@@ -550,3 +552,29 @@ def test_fused_front_every_cascade_depth(S, gpu):
         pos += m
     many = np.concatenate(parts)
     assert many.size == ya.size and np.array_equal(many.view(np.uint32), ya.view(np.uint32))
+
+
+def test_fused_dc_local_state_equals_the_table_pre_pass(gpu, workloads, monkeypatch):
+    """DC blocker inside the fused front, two evaluations: (a) v at every tick start from a pre-pass over the raw stream
+    (IQGPU_DC_TABLE=1), (b) every warp carries v through its own stretch from zero and the missing decaying exponential —
+    an eigenfunction of the linear cascade — is added to the resampler output in closed form (no second read of the input).
+    Same stream within fp32 round-off, over hundreds of stretches, a DC offset 100x the blocker's usual load, ragged
+    multi-call input (carried state, corrected cf32 tail), and the oracle's bar at the chain output."""
+    import dataclasses
+    wl = dataclasses.replace(workloads["cfg2"], dc=0.2)
+    cfg = dataclasses.replace(wl.config, output_format="cf32", filters=[], filter_taps=0, filter_type_request=0)
+    n = (1 << 23) + 12345
+    raw = synth_numpy(wl, n)
+    a = gpu.Chain(cfg, 0, fused=1, subtrain_frames=1 << 24).process(raw).view(np.complex64)
+    cuts = [0, 3000001, 3000002, 5 << 20, n]
+    g = gpu.Chain(cfg, 0, fused=1, subtrain_frames=1 << 24)
+    parts = [g.process(raw[2 * lo:2 * hi], chunk_frames=[hi - lo]) for lo, hi in zip(cuts[:-1], cuts[1:])]
+    b = np.concatenate(parts).view(np.complex64)
+    monkeypatch.setenv("IQGPU_DC_TABLE", "1")
+    t = gpu.Chain(cfg, 0, fused=1, subtrain_frames=1 << 24).process(raw).view(np.complex64)
+    monkeypatch.delenv("IQGPU_DC_TABLE")
+    assert a.size == t.size == b.size
+    assert rel_rms_fullscale(a, t) <= 1e-7 and np.abs(a - t).max() <= 2e-6
+    assert rel_rms_fullscale(b, t) <= 1e-7 and np.abs(b - t).max() <= 2e-6
+    # the blocker did its job in both: the 0.2 offset is gone from the settled part of the stream
+    assert abs(a[a.size // 2:].mean()) < 2e-3
