@@ -116,8 +116,12 @@ class ClockSampler:
 def class_bytes_per_sample(cfg, info):
     r = info.ratio
     inb, outb = cfg.in_bytes, cfg.out_bytes
+    # DC blocker evaluated with a local state per warp stretch: the fused-front class then also holds the closed-form
+    # correction pass over the resampled stream (read + write, 16 B per output frame) and no pre-pass over the input
+    dc_local = bool(cfg.dc_block and not cfg.iq_correction and not (cfg.freq_shift_hz and not cfg.shift_after_resample)
+                    and info.fused_front)
     return {
-        "fused_front": inb + 8.0 * r,          # raw in, resampled cf32 out
+        "fused_front": inb + 8.0 * r + (16.0 * r if dc_local else 0.0),   # raw in, resampled cf32 out (+ DC correction pass)
         "pre": inb + 8.0,                      # raw in, cf32 out
         "dc_scan": float(inb),                 # raw in
         "resampler": 8.0 + 8.0 * r,            # cf32 in, cf32 out (ideal, no inter-stage traffic)
