@@ -363,7 +363,7 @@ def main():
 
     # ---- roofline of the dominant kernel class ----
     hbm_peak, peak_src, peaks = load_peaks()
-    bps = class_bytes_per_sample(cfg, info)
+    bps = class_bytes_per_sample(cfg, chain.info())       # after the run: fused_front is known
     dom = max(ktimes.items(), key=lambda kv: kv[1][0])[0] if ktimes else None
     roofline = None
     if dom:
