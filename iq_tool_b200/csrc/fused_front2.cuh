@@ -29,6 +29,9 @@ constexpr int W2_T0 = 512;          // raw frames per warp tick
 #ifndef W2_CAP_DEF
 #define W2_CAP_DEF 0                // 0: per-plan default (W2Plan::CAP)
 #endif
+#ifndef W2_REG1_DEF
+#define W2_REG1_DEF 1               // second halfband stage from registers too (S >= 4)
+#endif
 #ifndef W2_MAX_WARPS_DEF
 #define W2_MAX_WARPS_DEF 20
 #endif
@@ -102,7 +105,10 @@ struct W2Plan {
     // first stage straight from the lane's registers (neighbour entries by warp shuffle): cascades whose first
     // stage has semi-length 3, i.e. S >= 3.  Level 0 then keeps only an 8-entry history instead of its planes.
     static constexpr bool reg0 = (S >= 3);
-    __host__ __device__ static constexpr int level_size(int d) { return (d == 0 && reg0) ? 8 : 2 * plane_size(d); }
+    // ... and the second one as well when it also has semi-length 3 (S >= 4): the lane's 8 first-stage outputs are 4 (E, O)
+    // pairs of level 1, the inputs of its own 4 second-stage outputs; older entries come from the two lanes below
+    static constexpr bool reg1 = W2_REG1_DEF && (S >= 4);
+    __host__ __device__ static constexpr int level_size(int d) { return ((d == 0 && reg0) || (d == 1 && reg1)) ? 8 : 2 * plane_size(d); }
     __host__ __device__ static constexpr int e_off(int d)
     {
         int o = 0;
@@ -444,7 +450,8 @@ __device__ __forceinline__ void w2_stage_store(float2* __restrict__ wsm, int lan
 // store + a 5 KiB load per tick and warp) by 16 shuffles; the arithmetic and its order are those of w2_stage.
 // ------------------------------------------------------------------------------------------------
 template <int S>
-__device__ __forceinline__ void w2_stage0_reg(const Fused2Args& A, float2* __restrict__ wsm, int lane, const f32x2_t (&x)[16])
+__device__ __forceinline__ void w2_stage0_reg(const Fused2Args& A, float2* __restrict__ wsm, int lane, const f32x2_t (&x)[16],
+                                              f32x2_t (&v)[8])
 {
     using P = W2Plan<S>;
     static_assert(P::m(0) == 3 && P::R(0) == 8, "register first stage: semi-length 3, 8 outputs per lane");
@@ -480,10 +487,59 @@ __device__ __forceinline__ void w2_stage0_reg(const Fused2Args& A, float2* __res
 #pragma unroll
         for (int r = 0; r < 8; r++) acc[r] = fma2(hh, ent[r + j], acc[r]);
     }
-    f32x2_t v[8];
 #pragma unroll
     for (int r = 0; r < 8; r++) v[r] = add2(oc[r], acc[r]);
-    w2_stage_store<S, 0>(wsm, lane, 0, v);
+    if (!P::reg1) w2_stage_store<S, 0>(wsm, lane, 0, v);
+}
+
+// second halfband stage (semi-length 3, 4 outputs per lane) from the first stage's outputs in registers:
+//   E1[j] = v[2j], O1[j] = v[2j+1] (j < 4) are the lane's level-1 pairs; an output window reaches back 5 E entries (4 from
+//   the lane below, 1 from the lane below that) and 3 O entries (lane below).  Lanes 0 and 1 take theirs from the 64-byte
+//   history lanes 31 and 30 left one tick earlier.  Replaces the level-1 planes by 16 shuffles.
+template <int S>
+__device__ __forceinline__ void w2_stage1_reg(const Fused2Args& A, float2* __restrict__ wsm, int lane, int half, const f32x2_t (&v)[8])
+{
+    using P = W2Plan<S>;
+    static_assert(P::m(1) == 3 && P::R(1) == 4, "register second stage: semi-length 3, 4 outputs per lane");
+    f32x2_t ent[9], oc[4];
+    ent[0] = __shfl_up_sync(0xffffffffu, v[6], 2);                                          // E1[q0-5]
+#pragma unroll
+    for (int k = 0; k < 4; k++) ent[1 + k] = __shfl_up_sync(0xffffffffu, v[2 * k], 1);      // E1[q0-4 .. q0-1]
+#pragma unroll
+    for (int k = 0; k < 3; k++) oc[k] = __shfl_up_sync(0xffffffffu, v[3 + 2 * k], 1);       // O1[q0-3 .. q0-1]
+    ulonglong2* hist = reinterpret_cast<ulonglong2*>(wsm + P::e_off(1));                    // level-1 planes are unused
+    // history: [0..3] = lane 31's E1[0..3], [4..6] = lane 31's O1[1..3], [7] = lane 30's E1[3]
+    if (lane == 0) {
+        const ulonglong2 h0 = hist[0], h1 = hist[1], h2 = hist[2], h3 = hist[3];
+        ent[1] = h0.x; ent[2] = h0.y; ent[3] = h1.x; ent[4] = h1.y;
+        oc[0] = h2.x; oc[1] = h2.y; oc[2] = h3.x; ent[0] = h3.y;
+    }
+    if (lane == 1) ent[0] = reinterpret_cast<const f32x2_t*>(hist)[3];                     // lane 31's E1[3] of the last tick
+    __syncwarp();
+    if (lane == 31) {
+        hist[0] = make_ulonglong2(v[0], v[2]);
+        hist[1] = make_ulonglong2(v[4], v[6]);
+        hist[2] = make_ulonglong2(v[3], v[5]);
+        reinterpret_cast<f32x2_t*>(hist)[6] = v[7];
+    }
+    if (lane == 30) reinterpret_cast<f32x2_t*>(hist)[7] = v[6];
+#pragma unroll
+    for (int k = 0; k < 4; k++) ent[5 + k] = v[2 * k];
+    oc[3] = v[1];
+    f32x2_t acc[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) acc[r] = 0ull;
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        const float h = A.taps[P::taps_off(1) + j];
+        const f32x2_t hh = pk2(h, h);
+#pragma unroll
+        for (int r = 0; r < 4; r++) acc[r] = fma2(hh, ent[r + j], acc[r]);
+    }
+    f32x2_t y[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) y[r] = add2(oc[r], acc[r]);
+    w2_stage_store<S, 1>(wsm, lane, half, y);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -701,9 +757,18 @@ __global__ void __launch_bounds__(W2_MAX_WARPS * 32, 1) fused_front2_kernel(cons
         w2_p0<S, DC, CS16>(A, wsm, lut2, tick_start, lane, cur, x, vloc, DC != 2 || t >= t_emit || gw == 0);
         bool arb_due = true;
         if constexpr (P::reg0) {
-            w2_stage0_reg<S>(A, wsm, lane, x);
-            __syncwarp();
-            W2Cascade<S, 1>::run(A, wsm, t, lane, arb_due);
+            f32x2_t v0[8];
+            w2_stage0_reg<S>(A, wsm, lane, x, v0);
+            if constexpr (P::reg1) {
+                // stage 1 runs every tick; its consumer may wait for two of its runs (capped plans)
+                const int half = (P::ratio(1) == 2) ? (int)(t & 1) : 0;
+                w2_stage1_reg<S>(A, wsm, lane, half, v0);
+                __syncwarp();
+                W2Cascade<S, 2>::run(A, wsm, t, lane, arb_due);
+            } else {
+                __syncwarp();
+                W2Cascade<S, 1>::run(A, wsm, t, lane, arb_due);
+            }
         } else {
             __syncwarp();
             if constexpr (S > 0) W2Cascade<S, 0>::run(A, wsm, t, lane, arb_due);
