@@ -29,6 +29,9 @@ constexpr int W2_T0 = 512;          // raw frames per warp tick
 #ifndef W2_CAP_DEF
 #define W2_CAP_DEF 0                // 0: per-plan default (W2Plan::CAP)
 #endif
+#ifndef W2_REG0_M5_DEF
+#define W2_REG0_M5_DEF 1            // S == 2: first stage (semi-length 5) from registers
+#endif
 #ifndef W2_REG1_DEF
 #define W2_REG1_DEF 1               // second halfband stage from registers too (S >= 4)
 #endif
@@ -104,11 +107,11 @@ struct W2Plan {
     __host__ __device__ static constexpr int plane_size(int d) { return (phys(d, entries(d)) + 3) & ~1; }
     // first stage straight from the lane's registers (neighbour entries by warp shuffle): cascades whose first
     // stage has semi-length 3, i.e. S >= 3.  Level 0 then keeps only an 8-entry history instead of its planes.
-    static constexpr bool reg0 = (S >= 3);
+    static constexpr bool reg0 = (S >= 3) || (S == 2 && W2_REG0_M5_DEF);     // S == 2: first stage of semi-length 5
     // ... and the second one as well when it also has semi-length 3 (S >= 4): the lane's 8 first-stage outputs are 4 (E, O)
     // pairs of level 1, the inputs of its own 4 second-stage outputs; older entries come from the two lanes below
     static constexpr bool reg1 = W2_REG1_DEF && (S >= 4);
-    __host__ __device__ static constexpr int level_size(int d) { return ((d == 0 && reg0) || (d == 1 && reg1)) ? 8 : 2 * plane_size(d); }
+    __host__ __device__ static constexpr int level_size(int d) { return ((d == 0 && reg0) || (d == 1 && reg1)) ? 16 : 2 * plane_size(d); }
     __host__ __device__ static constexpr int e_off(int d)
     {
         int o = 0;
@@ -449,11 +452,64 @@ __device__ __forceinline__ void w2_stage_store(float2* __restrict__ wsm, int lan
 // history that lane 31 left in shared memory one tick earlier.  This replaces the level-0 planes (a 4 KiB
 // store + a 5 KiB load per tick and warp) by 16 shuffles; the arithmetic and its order are those of w2_stage.
 // ------------------------------------------------------------------------------------------------
+// the same for a first stage of semi-length 5 (S == 2): 9 older E entries (8 from the lane below, 1 from the lane below
+// that) and 5 older O entries; lanes 0 and 1 take theirs from the 112-byte history lanes 31 and 30 left one tick earlier
+template <int S>
+__device__ __forceinline__ void w2_stage0_reg_m5(const Fused2Args& A, float2* __restrict__ wsm, int lane, const f32x2_t (&x)[16],
+                                                 f32x2_t (&v)[8])
+{
+    using P = W2Plan<S>;
+    static_assert(P::m(0) == 5 && P::R(0) == 8, "semi-length 5, 8 outputs per lane");
+    f32x2_t ent[17], oc[8];
+    ent[0] = __shfl_up_sync(0xffffffffu, x[14], 2);                                         // E[q0-9]
+#pragma unroll
+    for (int k = 0; k < 8; k++) ent[1 + k] = __shfl_up_sync(0xffffffffu, x[2 * k], 1);      // E[q0-8 .. q0-1]
+#pragma unroll
+    for (int k = 0; k < 5; k++) oc[k] = __shfl_up_sync(0xffffffffu, x[7 + 2 * k], 1);       // O[q0-5 .. q0-1]
+    // history (f32x2 entries): [0..7] lane 31's E[0..7], [8..12] lane 31's O[3..7], [13] lane 30's E[7]
+    ulonglong2* hist = reinterpret_cast<ulonglong2*>(wsm + P::e_off(0));
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const ulonglong2 h = hist[k]; ent[1 + 2 * k] = h.x; ent[2 + 2 * k] = h.y; }
+        const ulonglong2 h4 = hist[4], h5 = hist[5], h6 = hist[6];
+        oc[0] = h4.x; oc[1] = h4.y; oc[2] = h5.x; oc[3] = h5.y; oc[4] = h6.x; ent[0] = h6.y;
+    }
+    if (lane == 1) ent[0] = reinterpret_cast<const f32x2_t*>(hist)[7];                     // lane 31's E[7] of the last tick
+    __syncwarp();
+    if (lane == 31) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) hist[k] = make_ulonglong2(x[4 * k], x[4 * k + 2]);
+        hist[4] = make_ulonglong2(x[7], x[9]);
+        hist[5] = make_ulonglong2(x[11], x[13]);
+        reinterpret_cast<f32x2_t*>(hist)[12] = x[15];
+    }
+    if (lane == 30) reinterpret_cast<f32x2_t*>(hist)[13] = x[14];
+#pragma unroll
+    for (int k = 0; k < 8; k++) ent[9 + k] = x[2 * k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) oc[5 + k] = x[2 * k + 1];
+    f32x2_t acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) acc[r] = 0ull;
+#pragma unroll
+    for (int j = 0; j < 10; j++) {
+        const float h = A.taps[P::taps_off(0) + j];
+        const f32x2_t hh = pk2(h, h);
+#pragma unroll
+        for (int r = 0; r < 8; r++) acc[r] = fma2(hh, ent[r + j], acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[r] = add2(oc[r], acc[r]);
+    w2_stage_store<S, 0>(wsm, lane, 0, v);
+}
+
 template <int S>
 __device__ __forceinline__ void w2_stage0_reg(const Fused2Args& A, float2* __restrict__ wsm, int lane, const f32x2_t (&x)[16],
                                               f32x2_t (&v)[8])
 {
     using P = W2Plan<S>;
+    if constexpr (P::m(0) == 5) { w2_stage0_reg_m5<S>(A, wsm, lane, x, v); return; }
+    else {
     static_assert(P::m(0) == 3 && P::R(0) == 8, "register first stage: semi-length 3, 8 outputs per lane");
     f32x2_t ent[13], oc[8];
 #pragma unroll
@@ -490,6 +546,7 @@ __device__ __forceinline__ void w2_stage0_reg(const Fused2Args& A, float2* __res
 #pragma unroll
     for (int r = 0; r < 8; r++) v[r] = add2(oc[r], acc[r]);
     if (!P::reg1) w2_stage_store<S, 0>(wsm, lane, 0, v);
+    }
 }
 
 // second halfband stage (semi-length 3, 4 outputs per lane) from the first stage's outputs in registers:
