@@ -372,6 +372,10 @@ struct FusedFront {
     float dc_G_for_c = -1.f;            // pole the gains were computed for
     double dc_atot = 1.0;
     std::vector<float> h_bank;          // host copy of the 256 x 14 polyphase bank
+    // polyphase stage variant (one or two outputs per lane: same bits, different shared-memory access pattern).  Which one is
+    // faster depends on the rate of the arbitrary stage (bank conflicts of the window loads), so the first launch that is
+    // large enough times both on its own data — the kernel is idempotent — and the choice sticks.
+    int arb_pairs = -1;
     uint32_t lut_dtheta = 0;            // NCO table swizzle chosen for this phase increment
     unsigned lut_sh = 4, lut_mask = 0;
     bool lut_picked = false;
@@ -756,15 +760,42 @@ static cudaError_t fused_launch_v2(FusedFront* f, const void* raw, int64_t n0, s
     }
     const int dc = dc_local ? 2 : (pre.dc_enable ? 1 : 0);
     const bool cs16 = pre.format == IQGPU_FMT_CS16 || pre.format == IQGPU_FMT_SC16Q11;
-    switch (f->v2_S) {
-        case 0: e = launch_v2_s<0>(f, A, grid, dc, cs16, st); break;
-        case 1: e = launch_v2_s<1>(f, A, grid, dc, cs16, st); break;
-        case 2: e = launch_v2_s<2>(f, A, grid, dc, cs16, st); break;
-        case 3: e = launch_v2_s<3>(f, A, grid, dc, cs16, st); break;
-        case 4: e = launch_v2_s<4>(f, A, grid, dc, cs16, st); break;
-        case 5: e = launch_v2_s<5>(f, A, grid, dc, cs16, st); break;
-        case 6: e = launch_v2_s<6>(f, A, grid, dc, cs16, st); break;
-        default: return cudaErrorInvalidValue;
+    auto go = [&](const Fused2Args& a) -> cudaError_t {
+        switch (f->v2_S) {
+            case 0: return launch_v2_s<0>(f, a, grid, dc, cs16, st);
+            case 1: return launch_v2_s<1>(f, a, grid, dc, cs16, st);
+            case 2: return launch_v2_s<2>(f, a, grid, dc, cs16, st);
+            case 3: return launch_v2_s<3>(f, a, grid, dc, cs16, st);
+            case 4: return launch_v2_s<4>(f, a, grid, dc, cs16, st);
+            case 5: return launch_v2_s<5>(f, a, grid, dc, cs16, st);
+            case 6: return launch_v2_s<6>(f, a, grid, dc, cs16, st);
+            default: return cudaErrorInvalidValue;
+        }
+    };
+    if (const char* force = getenv("IQGPU_ARB_PAIRS")) f->arb_pairs = atoi(force) ? 1 : 0;
+    if (f->arb_pairs < 0 && n >= ((size_t)1 << 22)) {
+        // time both variants on this launch (same inputs, same outputs: the second run overwrites the first with equal bits)
+        cudaEvent_t ev[3];
+        for (auto& x : ev) cudaEventCreate(&x);
+        float ms[2] = {0.f, 0.f};
+        A.arb_pairs = 1; e = go(A);                      // untimed: caches, clocks, TMA descriptors warm for both candidates
+        cudaEventRecord(ev[0], st);
+        if (e == cudaSuccess) { A.arb_pairs = 0; e = go(A); }
+        cudaEventRecord(ev[1], st);
+        if (e == cudaSuccess) { A.arb_pairs = 1; e = go(A); }
+        cudaEventRecord(ev[2], st);
+        if (e == cudaSuccess) e = cudaEventSynchronize(ev[2]);
+        if (e == cudaSuccess) {
+            cudaEventElapsedTime(&ms[0], ev[0], ev[1]);
+            cudaEventElapsedTime(&ms[1], ev[1], ev[2]);
+            f->arb_pairs = (ms[1] < 0.98f * ms[0]) ? 1 : 0;
+            if (getenv("IQGPU_VERBOSE")) fprintf(stderr, "iqgpu: polyphase stage: one output per lane %.3f ms, two %.3f ms -> %s\n", ms[0], ms[1], f->arb_pairs ? "two" : "one");
+        }
+        for (auto& x : ev) cudaEventDestroy(x);
+        if (launches) *launches += 1;
+    } else {
+        A.arb_pairs = f->arb_pairs > 0 ? 1 : 0;
+        e = go(A);
     }
     if (launches) *launches += 1;
     if (dc_local && e == cudaSuccess) {

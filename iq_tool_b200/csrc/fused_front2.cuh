@@ -84,7 +84,8 @@ __host__ static inline void w2_pick_lut_swizzle(uint32_t dtheta, unsigned& sh, u
 }
 __host__ __device__ constexpr int w2_ilog2(int v) { int l = 0; while ((1 << (l + 1)) <= v) l++; return l; }
 constexpr int W2_BANK_F2 = 2368;    // float2 entries of the image (9*255 + 63 + 7 = 2365, padded to 16 B)
-__host__ __device__ constexpr int w2_bank_row(int idx) { return 9 * idx + (idx >> 2); }
+// (two leading float2 of zeros: the second output of a lane reads its taps through a pointer shifted back by up to two floats)
+__host__ __device__ constexpr int w2_bank_row(int idx) { return 9 * idx + (idx >> 2) + 2; }
 constexpr int W2_MAX_TAPS = 72;     // sum of 2m over the cascade (6*4 + 10 + 20 = 54 for S = 6)
 
 // compile-time plan of a cascade of S halfband stages; semi-lengths by execution depth are
@@ -169,6 +170,7 @@ struct Fused2Args {
     uint32_t step;
     float zeta;
     unsigned lut_sh, lut_mask;          // NCO table swizzle (w2_lut_slot)
+    int arb_pairs;                      // polyphase stage: two outputs per lane (1) or one (0); same bits, picked by timing
     float taps[W2_MAX_TAPS];            // h1 by execution depth, concatenated (constant-bank FFMA operands)
 };
 
@@ -717,6 +719,7 @@ __device__ __forceinline__ void w2_arb(const Fused2Args& A, const float2* __rest
     o_cur = ob;
     if (oa < A.O0) oa = A.O0;
     if (ob > A.O1) ob = A.O1;
+    if (!A.arb_pairs) {
     for (long long o = oa + lane; o < ob; o += 32) {
         const unsigned long long Pp = (unsigned long long)o * step;
         const int rel = (int)((long long)(Pp >> 24) - kA);
@@ -732,6 +735,42 @@ __device__ __forceinline__ void w2_arb(const Fused2Args& A, const float2* __rest
             sacc = fma2s(h.y, v1, sacc);
         }
         *reinterpret_cast<f32x2_t*>(A.y + (o - A.O0)) = sacc;
+    }
+        return;
+    }
+    // A lane makes TWO consecutive outputs o, o+1.  Their windows x[k-13 .. k] start d = k(o+1) - k(o) = 1 or 2 entries apart
+    // (the rate of the arbitrary stage lies in [0.5, 1)), so 16 window entries serve both instead of 28; the second
+    // output reads its row from two floats in front of it (rows are separated by >= 4 floats of zeros) and shifts it by d,
+    // which lines its taps up with the shared window: taps that fall outside the row are exact zeros, the order of the
+    // non-zero terms is that of a single output, hence the same bits.
+    for (long long o = oa + 2 * lane; o < ob; o += 64) {
+        const unsigned long long P0 = (unsigned long long)o * step, P1 = P0 + step;
+        const int rel = (int)((long long)(P0 >> 24) - kA);
+        const int d = (int)((P1 >> 24) - (P0 >> 24));
+        const f32x2_t* __restrict__ w = reinterpret_cast<const f32x2_t*>(flat + rel + (W2_ARB_HIST - 13));
+        const float2* __restrict__ b0 = sbank + w2_bank_row((int)((unsigned)(P0 >> 16) & 0xffu));
+        // row of the second output from one float2 (two zeros) in front of it: 8 LDS.64 with the conflict-free pattern of
+        // the first row; the shift by d floats is a select between neighbours
+        const float2* __restrict__ b1 = sbank + w2_bank_row((int)((unsigned)(P1 >> 16) & 0xffu)) - 1;
+        f32x2_t u[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) u[j] = w[j];
+        f32x2_t s0 = 0ull, s1 = 0ull;
+#pragma unroll
+        for (int i = 0; i < 7; i++) {
+            const float2 h = b0[i];
+            s0 = fma2s(h.x, u[2 * i], s0);
+            s0 = fma2s(h.y, u[2 * i + 1], s0);
+        }
+        float f1[17];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { const float2 h = b1[i]; f1[2 * i] = h.x; f1[2 * i + 1] = h.y; }
+        f1[16] = 0.f;
+        const bool d2 = (d == 2);
+#pragma unroll
+        for (int j = 0; j < 16; j++) s1 = fma2s(d2 ? f1[j] : f1[j + 1], u[j], s1);     // tap j - d of the row (zero outside it)
+        *reinterpret_cast<f32x2_t*>(A.y + (o - A.O0)) = s0;
+        if (o + 1 < ob) *reinterpret_cast<f32x2_t*>(A.y + (o + 1 - A.O0)) = s1;
     }
 }
 
