@@ -58,12 +58,13 @@ bool is_complex_format(int fmt) { return fmt >= IQGPU_FMT_CU8 && fmt <= IQGPU_FM
 // previous `hist` samples sit right below it.
 struct DevStream {
     float2* base = nullptr;
-    size_t cap = 0, hist = 0, pos = 0, max_n = 0;
-    int alloc(size_t hist_, size_t max_n_)
+    size_t cap = 0, hist = 0, pos = 0, max_n = 0, slack = 0;   // slack: readable (zeroable) room kept beyond the new data
+    int alloc(size_t hist_, size_t max_n_, size_t slack_ = 0)
     {
         hist = (hist_ + 3) & ~(size_t)3;
         max_n = std::max(max_n_, hist) + 4;
-        cap = hist + 2 * max_n;
+        slack = slack_;
+        cap = hist + 2 * max_n + slack;
         cudaError_t e = cudaMalloc(&base, cap * sizeof(float2));
         if (e != cudaSuccess) return -1;
         return 0;
@@ -78,7 +79,7 @@ struct DevStream {
     cudaError_t begin(size_t n, cudaStream_t st, float2** p)
     {
         if (n > max_n) return cudaErrorInvalidValue;
-        if (pos + n > cap) {
+        if (pos + n + slack > cap) {
             // move the history to the front (ranges cannot overlap: pos - hist >= hist)
             cudaError_t e = cudaMemcpyAsync(base, base + pos - hist, hist * sizeof(float2), cudaMemcpyDeviceToDevice, st);
             if (e != cudaSuccess) return e;
@@ -269,6 +270,10 @@ struct iqgpu_chain {
     PreParams pre_params(uint64_t N0) const;
     int prepare_dc(int slot, const void* d_rawp, uint64_t N0, size_t n, cudaStream_t st);
     bool fir_wrote_output = false;    // this sub-train's FIR epilogue converted and stored the final output
+    // long post-resample FIRs are evaluated by the FFT block filter kernel (overlap-save, same causal convolution): the
+    // time-domain kernel runs at 85 % of FMA peak, so beyond a few hundred taps only fewer FLOPs help
+    bool fir_via_fft = false;
+    unsigned fir_fft_block = 0;
     bool dc_overlap = true;           // DC pre-pass of sub-train k+1 on the second stream while sub-train k runs
     // pending back half (between process_device_begin and process_device_finish)
     struct Pending {
@@ -433,9 +438,15 @@ int iqgpu_chain::init_device()
         CK(cudaMemcpy(d_fir_taps, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
         h_fir_taps = h;
     }
-    if (filter_is_fft(filt)) {
-        if (!fftfilt_supported(filt.block)) return fail(IQGPU_EINVAL, "FFT filter block size not supported by the GPU FFT kernel");
-        const unsigned nfft = 2 * filt.block;
+    if (filter_is_fir(filt) && filt.post_resample && filt.taps.size() >= 512 && filt.taps.size() <= 8192 &&
+        !getenv("IQGPU_FIR_TIME_DOMAIN")) {
+        fir_via_fft = true;
+        fir_fft_block = 8192;
+    }
+    if (filter_is_fft(filt) || fir_via_fft) {
+        const unsigned blk = fir_via_fft ? fir_fft_block : filt.block;
+        if (!fftfilt_supported(blk)) return fail(IQGPU_EINVAL, "FFT filter block size not supported by the GPU FFT kernel");
+        const unsigned nfft = 2 * blk;
         std::vector<float2> tw(nfft), hpad(nfft, make_float2(0.f, 0.f));
         for (unsigned k = 0; k < nfft; k++) {
             double a = -2.0 * M_PI * (double)k / (double)nfft;
@@ -502,9 +513,13 @@ int iqgpu_chain::ensure_buffers()
             rs_max = arb_cnt << S;
         }
     }
+    if (fir_via_fft) {
+        // the block kernel reads one block of history below the first new sample and up to one block (zeroed) beyond the last
+        if (s_rs.alloc(fir_fft_block, rs_max, fir_fft_block) != 0) return fail(IQGPU_ENOMEM, "device allocation failed (s_rs)");
+    } else
     if (s_rs.alloc(post_filter ? filt_hist : 0, rs_max + (post_filter ? filt.block : 0)) != 0)
         return fail(IQGPU_ENOMEM, "device allocation failed (s_rs)");
-    if (post_filter && s_f.alloc(0, rs_max + 2 * (size_t)filt.block) != 0)
+    if (post_filter && s_f.alloc(0, rs_max + 2 * (size_t)std::max<unsigned>(filt.block, fir_fft_block)) != 0)
         return fail(IQGPU_ENOMEM, "device allocation failed (s_f)");
 
     max_runs = n / 128 + 2;
@@ -741,7 +756,27 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
     // ---------------- optional post-resample filter ----------------
     if (post_filter) {
         span_begin(IQGPU_KCLASS_FILTER, st);
-        if (filter_is_fir(filt)) {
+        if (filter_is_fir(filt) && fir_via_fft) {
+            // y[n] = sum_k h[k] x[n-k] by overlap-save blocks of 8192 outputs; the last block is completed with zeros beyond
+            // the newest sample (its outputs past post_n are never read), the history below post_src is the real stream
+            const size_t B = fir_fft_block, blocks = (post_n + B - 1) / B;
+            float2* y = nullptr;
+            CK(s_f.begin(blocks * B, st, &y));
+            if (blocks) {
+                if (blocks * B > post_n)
+                    CK(cudaMemsetAsync(const_cast<float2*>(post_src) + post_n, 0, (blocks * B - post_n) * sizeof(float2), st));
+                const size_t need = fftfilt_scratch_bytes(blocks, (unsigned)B);
+                if (need > fft_scratch_bytes) {
+                    CK(cudaStreamSynchronize(st));
+                    cudaFree(d_fft_scratch); d_fft_scratch = nullptr; fft_scratch_bytes = 0;
+                    CK(cudaMalloc(&d_fft_scratch, need + need / 2));
+                    fft_scratch_bytes = need + need / 2;
+                }
+                CK(launch_fftfilt(post_src, blocks, (unsigned)B, d_fft_H, d_fft_tw, y, d_fft_scratch, &launches, st));
+            }
+            s_f.commit(post_n);
+            post_src = y;
+        } else if (filter_is_fir(filt)) {
             const int cplx = filt.impl == IQGPU_FILTER_IMPL_FIR_ASYM;
             // last cf32 stage of the chain (no post shift, no AGC, nobody records the stream, one-phase call): convert in the
             // filter's epilogue and skip the post kernel

@@ -538,7 +538,7 @@ def test_fused_front_every_cascade_depth(S, gpu):
     o.trace(n // 16384 + 4)
     ref = o.process(raw)
     assert np.array_equal(ca, o.traced())
-    _check_final(cfg, ya, ref)
+    _check_final(cfg, ya.view(np.float32), ref)
     g = gpu.Chain(cfg, 0, fused=1)
     parts, pos = [], 0
     for m in (1, 0, 511, 513, 4096 << S, 16385, 100000, n):
@@ -578,3 +578,35 @@ def test_fused_dc_local_state_equals_the_table_pre_pass(gpu, workloads, monkeypa
     assert rel_rms_fullscale(b, t) <= 1e-7 and np.abs(b - t).max() <= 2e-6
     # the blocker did its job in both: the 0.2 offset is gone from the settled part of the stream
     assert abs(a[a.size // 2:].mean()) < 2e-3
+
+
+def test_long_post_resample_fir_runs_on_the_fft_block_kernel(gpu, workloads, monkeypatch):
+    """A long time-domain FIR (F2, filter.c:449-462) after the resampler is evaluated by the overlap-save FFT kernel — the
+    same causal convolution with ~20x fewer FLOPs.  It must equal the tiled time-domain kernel within fp32 round-off, be
+    independent of how the stream is cut into calls (partial last blocks, history carried in the stream), keep the FIR's
+    output count (no block quantisation), and meet the oracle's bar."""
+    wl = workloads["cfg1"]
+    cfg = ChainConfig(input_format="cs16", output_format="cf32", input_rate_hz=2.4e6, target_rate_hz=1.0e6,
+                      filters=[lowpass(150e3)], filter_taps=1001, filter_type_request=FILTER_REQ_FIR)
+    n = 700001
+    raw = synth_numpy(wl, n)
+    a = gpu.Chain(cfg, 0)
+    ya = a.process(raw).view(np.complex64)
+    assert a.info().filter_post_resample == 1 and a.info().filter_num_taps == 1001
+    g = gpu.Chain(cfg, 0)
+    parts, pos = [], 0
+    for m in (5, 16384, 40000, 300001, n):
+        m = min(m, n - pos)
+        if m <= 0:
+            break
+        parts.append(g.process(raw[2 * pos:2 * (pos + m)], chunk_frames=[m]))
+        pos += m
+    yb = np.concatenate(parts).view(np.complex64)
+    monkeypatch.setenv("IQGPU_FIR_TIME_DOMAIN", "1")
+    yt = gpu.Chain(cfg, 0).process(raw).view(np.complex64)
+    monkeypatch.delenv("IQGPU_FIR_TIME_DOMAIN")
+    assert ya.size == yt.size == yb.size
+    assert rel_rms_fullscale(ya, yt) <= 2e-6 and np.abs(ya - yt).max() <= 2e-5
+    assert rel_rms_fullscale(yb, yt) <= 2e-6
+    ref = CpuChain(cfg, _oracle_kind()).process(raw)
+    _check_final(cfg, ya.view(np.float32), ref)
