@@ -275,6 +275,7 @@ struct iqgpu_chain {
     bool fir_via_fft = false;
     unsigned fir_fft_block = 0;
     bool dc_overlap = true;           // DC pre-pass of sub-train k+1 on the second stream while sub-train k runs
+    uint32_t prepass_launches = 0;
     // pending back half (between process_device_begin and process_device_finish)
     struct Pending {
         bool active = false;
@@ -594,6 +595,7 @@ int iqgpu_chain::prepare_dc(int slot, const void* d_rawp, uint64_t N0, size_t n,
     const PreParams pp = pre_params(N0);
     uint32_t l = 0;
     CK(fused_prepare_dc(fused, slot, d_rawp, (int64_t)N0, n, pp, d_dc_carry, &l, aux));
+    prepass_launches += l;                      // 0 when the front kernel carries the DC state itself (no pre-pass)
     CK(cudaEventRecord(ev_pre[slot], aux));
     return IQGPU_OK;
 }
@@ -1200,13 +1202,12 @@ int iqgpu_chain_process_device(iqgpu_chain* c, const void* dev_raw_in, size_t n_
             rc = c->prepare_dc(slot ^ 1, raw_at(subs[k + 1]), base_in + subs[k + 1].in_off, subs[k + 1].n, st);
             if (rc) return rc;
             c->launches = keep;
-            launches += 2;
         }
         out_off += produced * c->out_bps; total += produced;
         slot ^= 1;
     }
-    if (overlap_dc) launches += 2;   // the first sub-train's pre-pass
-    c->launches = launches;
+    c->launches = launches + c->prepass_launches;   // pre-pass kernels that really ran on the second stream
+    c->prepass_launches = 0;
     *out_frames = total;
     return IQGPU_OK;
 }
