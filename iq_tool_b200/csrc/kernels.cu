@@ -880,6 +880,53 @@ __global__ void __launch_bounds__(AGC_SCAN_THREADS) agc_digital_scan_kernel(cons
     const float target = p.agc_target;
     const float strong_thr = __fmul_rn(target, 0.75f);
     constexpr int PER_THREAD = AGC_SCAN_TILE / AGC_SCAN_THREADS;
+    if (!seg_gain && s_state.locked) {
+        // State only (the chunks of a lower shard) and already locked: the common case is that NOTHING happens in the
+        // whole table — no chunk ratchets (peak * gain <= 1) and every chunk is "strong" (so the creep timer never
+        // runs).  peak -> fl(peak * gain) is monotone, so the largest and the smallest peak decide it: one parallel
+        // reduction instead of a walk.  Then gain stays, last_strong becomes the time of the last chunk.
+        float mx = 0.f, mn = 3.4e38f;
+        unsigned long long total = 0, last_key = 0;            // last_key: (index of the last active chunk + 1) << 32 | its count
+        for (unsigned i = tid; i < nseg; i += AGC_SCAN_THREADS) {
+            const unsigned c = __ldg(seg_start + i + 1) - __ldg(seg_start + i);
+            if (!c) continue;
+            const float pk = __ldg(seg_peak + i);
+            mx = fmaxf(mx, pk); mn = fminf(mn, pk);
+            total += c;
+            const unsigned long long key = ((unsigned long long)(i + 1) << 32) | c;
+            last_key = key > last_key ? key : last_key;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+            total += __shfl_xor_sync(0xffffffffu, total, d);
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, last_key, d);
+            last_key = o > last_key ? o : last_key;
+        }
+        __shared__ float s_mx[AGC_SCAN_THREADS / 32], s_mn[AGC_SCAN_THREADS / 32];
+        __shared__ unsigned long long s_tot[AGC_SCAN_THREADS / 32], s_last[AGC_SCAN_THREADS / 32];
+        __shared__ int s_quiet;
+        if (lane == 0) { s_mx[warp] = mx; s_mn[warp] = mn; s_tot[warp] = total; s_last[warp] = last_key; }
+        __syncthreads();
+        if (tid == 0) {
+            for (unsigned w = 1; w < AGC_SCAN_THREADS / 32; w++) {
+                mx = fmaxf(mx, s_mx[w]); mn = fminf(mn, s_mn[w]); total += s_tot[w];
+                last_key = s_last[w] > last_key ? s_last[w] : last_key;
+            }
+            AgcState s = s_state;
+            const bool quiet = !(__fmul_rn(mx, s.gain) > 1.0f) && (last_key == 0 || __fmul_rn(mn, s.gain) > strong_thr);
+            if (quiet && last_key) {
+                const unsigned long long before_last = s.seen + total - (last_key & 0xffffffffull);
+                s.last_strong = (double)before_last / p.target_rate;
+                s.seen += total;
+                *st = s;
+            }
+            s_quiet = quiet;
+        }
+        __syncthreads();
+        if (s_quiet) return;
+    }
     for (unsigned tile0 = 0; tile0 < nseg; tile0 += AGC_SCAN_TILE) {
         const unsigned tn = min((unsigned)AGC_SCAN_TILE, nseg - tile0);
         // ---- (1) parallel part: table, exclusive prefix of the sample counter, chunk times ----
