@@ -882,50 +882,65 @@ __global__ void __launch_bounds__(AGC_SCAN_THREADS) agc_digital_scan_kernel(cons
     constexpr int PER_THREAD = AGC_SCAN_TILE / AGC_SCAN_THREADS;
     if (!seg_gain && s_state.locked) {
         // State only (the chunks of a lower shard) and already locked: the common case is that NOTHING happens in the
-        // whole table — no chunk ratchets (peak * gain <= 1) and every chunk is "strong" (so the creep timer never
-        // runs).  peak -> fl(peak * gain) is monotone, so the largest and the smallest peak decide it: one parallel
-        // reduction instead of a walk.  Then gain stays, last_strong becomes the time of the last chunk.
-        float mx = 0.f, mn = 3.4e38f;
-        unsigned long long total = 0, last_key = 0;            // last_key: (index of the last active chunk + 1) << 32 | its count
-        for (unsigned i = tid; i < nseg; i += AGC_SCAN_THREADS) {
+        // whole table — no chunk ratchets (peak * gain <= 1) and no weak chunk comes more than 4 s after the latest strong
+        // one (no creep).  That is checked for the whole table in parallel, with the doubles the sequential loop would
+        // compare: every thread walks a contiguous range of chunks; sample counts and "latest strong chunk so far" cross the
+        // ranges through two block scans.  If the table is quiet the gain stays and last_strong becomes the time of the
+        // latest strong chunk; otherwise the tile walk below does the work.
+        unsigned long long* q_tot = reinterpret_cast<unsigned long long*>(s_now);      // the tile arrays are idle here
+        double* q_last = s_now + AGC_SCAN_THREADS;
+        __shared__ int q_event;
+        static_assert(2 * AGC_SCAN_THREADS <= AGC_SCAN_TILE, "scratch fits the chunk-time array");
+        const AgcState s0 = s_state;
+        const unsigned per = (nseg + AGC_SCAN_THREADS - 1) / AGC_SCAN_THREADS;
+        const unsigned i0 = min(nseg, tid * per), i1 = min(nseg, i0 + per);
+        unsigned long long mine = 0;
+        for (unsigned i = i0; i < i1; i++) mine += __ldg(seg_start + i + 1) - __ldg(seg_start + i);
+        q_tot[tid] = mine;
+        if (tid == 0) q_event = 0;
+        __syncthreads();
+        for (unsigned d = 1; d < AGC_SCAN_THREADS; d <<= 1) {             // inclusive scan of the range totals
+            const unsigned long long v = (tid >= d) ? q_tot[tid - d] : 0ull;
+            __syncthreads();
+            q_tot[tid] += v;
+            __syncthreads();
+        }
+        unsigned long long seen = s0.seen + q_tot[tid] - mine;            // samples seen before this thread's first chunk
+        bool event = false;
+        double local_last = -1.0;                                         // time of the latest strong chunk inside the range
+        double weak_before = -1.0;                                        // time of the last weak chunk in front of the first strong one
+        for (unsigned i = i0; i < i1; i++) {
             const unsigned c = __ldg(seg_start + i + 1) - __ldg(seg_start + i);
             if (!c) continue;
-            const float pk = __ldg(seg_peak + i);
-            mx = fmaxf(mx, pk); mn = fminf(mn, pk);
-            total += c;
-            const unsigned long long key = ((unsigned long long)(i + 1) << 32) | c;
-            last_key = key > last_key ? key : last_key;
+            const float opk = __fmul_rn(__ldg(seg_peak + i), s0.gain);
+            const double now = (double)seen / p.target_rate;
+            if (opk > 1.0f) event = true;                                 // ratchet
+            else if (opk > strong_thr) local_last = now;
+            else if (local_last >= 0.0) { if (now - local_last > (double)4.0f) event = true; }   // creep
+            else weak_before = now;
+            seen += c;
         }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-            mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, d));
-            total += __shfl_xor_sync(0xffffffffu, total, d);
-            const unsigned long long o = __shfl_xor_sync(0xffffffffu, last_key, d);
-            last_key = o > last_key ? o : last_key;
-        }
-        __shared__ float s_mx[AGC_SCAN_THREADS / 32], s_mn[AGC_SCAN_THREADS / 32];
-        __shared__ unsigned long long s_tot[AGC_SCAN_THREADS / 32], s_last[AGC_SCAN_THREADS / 32];
-        __shared__ int s_quiet;
-        if (lane == 0) { s_mx[warp] = mx; s_mn[warp] = mn; s_tot[warp] = total; s_last[warp] = last_key; }
+        q_last[tid] = local_last;
         __syncthreads();
-        if (tid == 0) {
-            for (unsigned w = 1; w < AGC_SCAN_THREADS / 32; w++) {
-                mx = fmaxf(mx, s_mx[w]); mn = fminf(mn, s_mn[w]); total += s_tot[w];
-                last_key = s_last[w] > last_key ? s_last[w] : last_key;
-            }
-            AgcState s = s_state;
-            const bool quiet = !(__fmul_rn(mx, s.gain) > 1.0f) && (last_key == 0 || __fmul_rn(mn, s.gain) > strong_thr);
-            if (quiet && last_key) {
-                const unsigned long long before_last = s.seen + total - (last_key & 0xffffffffull);
-                s.last_strong = (double)before_last / p.target_rate;
-                s.seen += total;
+        for (unsigned d = 1; d < AGC_SCAN_THREADS; d <<= 1) {             // inclusive max-scan of the latest strong times
+            const double v = (tid >= d) ? q_last[tid - d] : -1.0;
+            __syncthreads();
+            q_last[tid] = fmax(q_last[tid], v);
+            __syncthreads();
+        }
+        const double before = fmax(s0.last_strong, tid ? q_last[tid - 1] : -1.0);   // latest strong chunk in front of the range
+        if (weak_before >= 0.0 && weak_before - before > (double)4.0f) event = true;
+        if (event) q_event = 1;
+        __syncthreads();
+        if (!q_event) {
+            if (tid == AGC_SCAN_THREADS - 1) {
+                AgcState s = s0;
+                s.seen = s0.seen + q_tot[tid];
+                s.last_strong = fmax(s0.last_strong, q_last[tid]);
                 *st = s;
             }
-            s_quiet = quiet;
+            return;
         }
-        __syncthreads();
-        if (s_quiet) return;
     }
     for (unsigned tile0 = 0; tile0 < nseg; tile0 += AGC_SCAN_TILE) {
         const unsigned tn = min((unsigned)AGC_SCAN_TILE, nseg - tile0);
