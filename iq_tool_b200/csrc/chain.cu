@@ -166,8 +166,10 @@ struct iqgpu_chain {
     size_t seg_pin_cap[2] = {0, 0};
     cudaEvent_t ev_seg[2] = {nullptr, nullptr};
     int seg_pin_slot = 0;
-    uint32_t* d_prefix_seg = nullptr;             // chunk table of a lower shard (iqgpu_chain_agc_advance_device)
-    size_t prefix_seg_cap = 0;
+    // chunk tables of lower shards (iqgpu_chain_agc_advance_device), kept per (first frame, frames): a shard plan is
+    // replayed step after step, and the table is closed form in those two numbers
+    struct PrefixTab { uint64_t first = 0, frames = 0; uint32_t* d_seg = nullptr; size_t nch = 0; };
+    std::vector<PrefixTab> prefix_tabs;
     bool front_recorded[2] = {false, false};
     int dc_slot = 0;                    // table slot of the sub-train run_subtrain is about to launch
     bool dc_prepared = false;           // ... and whether its pre-pass was issued on `aux`
@@ -298,7 +300,8 @@ iqgpu_chain::~iqgpu_chain()
     for (auto* t : d_hb_taps) cudaFree(t);
     cudaFree(d_lut); cudaFree(d_dc_carry); cudaFree(d_run_sums); cudaFree(d_run_start); cudaFree(d_scan_ws); cudaFree(d_bank);
     cudaFree(d_fir_taps); cudaFree(d_fft_H); cudaFree(d_fft_tw); cudaFree(d_fft_scratch); cudaFree(d_agc); cudaFree(d_seg_start);
-    cudaFree(d_seg_peak); cudaFree(d_seg_gain); cudaFree(d_agc_scratch); cudaFree(d_agc_ws); cudaFree(d_prefix_seg);
+    cudaFree(d_seg_peak); cudaFree(d_seg_gain); cudaFree(d_agc_scratch); cudaFree(d_agc_ws);
+    for (auto& t : prefix_tabs) cudaFree(t.d_seg);
     s_in.release(); s_pref.release(); s_arb_in.release(); s_rs.release(); s_f.release();
     for (auto& s : s_stage) s.release();
     for (auto& t : tap) t.release();
@@ -1293,34 +1296,43 @@ int iqgpu_chain_agc_advance_device(iqgpu_chain* c, const float* dev_peaks, uint6
     if (c->last_stream && st != c->last_stream) CK(cudaStreamSynchronize(c->last_stream));
     // the chunks' output frame counts are closed form (pipeline.c:523 via count_outputs' arithmetic)
     const size_t nch = (size_t)((n_frames + c->chunk_frames - 1) / c->chunk_frames);
-    const size_t need = (nch + 1) * sizeof(uint32_t);
-    const int sl = c->seg_pin_slot ^= 1;
-    if (need > c->seg_pin_cap[sl]) {
-        if (c->seg_pin[sl]) { CK(cudaEventSynchronize(c->ev_seg[sl])); CK(cudaFreeHost(c->seg_pin[sl])); c->seg_pin[sl] = nullptr; }
-        CK(cudaMallocHost(&c->seg_pin[sl], need * 2));
-        c->seg_pin_cap[sl] = need * 2;
-        if (!c->ev_seg[sl]) CK(cudaEventCreateWithFlags(&c->ev_seg[sl], cudaEventDisableTiming));
-    } else if (c->ev_seg[sl]) CK(cudaEventSynchronize(c->ev_seg[sl]));
-    uint32_t* seg = c->seg_pin[sl];
-    uint64_t before = resampler_outputs_after(c->rs, first_frame);
-    seg[0] = 0;
-    for (size_t k = 0; k < nch; k++) {
-        const uint64_t end = std::min<uint64_t>(first_frame + n_frames, first_frame + (uint64_t)(k + 1) * c->chunk_frames);
-        const uint64_t after = resampler_outputs_after(c->rs, end);
-        seg[k + 1] = seg[k] + (uint32_t)(after - before);       // the scan uses differences only: wrap-around is harmless
-        before = after;
+    const uint32_t* d_seg = nullptr;
+    for (const auto& t : c->prefix_tabs)
+        if (t.first == first_frame && t.frames == n_frames) { d_seg = t.d_seg; break; }
+    if (!d_seg) {
+        const size_t need = (nch + 1) * sizeof(uint32_t);
+        const int sl = c->seg_pin_slot ^= 1;
+        if (need > c->seg_pin_cap[sl]) {
+            if (c->seg_pin[sl]) { CK(cudaEventSynchronize(c->ev_seg[sl])); CK(cudaFreeHost(c->seg_pin[sl])); c->seg_pin[sl] = nullptr; }
+            CK(cudaMallocHost(&c->seg_pin[sl], need * 2));
+            c->seg_pin_cap[sl] = need * 2;
+            if (!c->ev_seg[sl]) CK(cudaEventCreateWithFlags(&c->ev_seg[sl], cudaEventDisableTiming));
+        } else if (c->ev_seg[sl]) CK(cudaEventSynchronize(c->ev_seg[sl]));
+        uint32_t* seg = c->seg_pin[sl];
+        uint64_t before = resampler_outputs_after(c->rs, first_frame);
+        seg[0] = 0;
+        for (size_t k = 0; k < nch; k++) {
+            const uint64_t end = std::min<uint64_t>(first_frame + n_frames, first_frame + (uint64_t)(k + 1) * c->chunk_frames);
+            const uint64_t after = resampler_outputs_after(c->rs, end);
+            seg[k + 1] = seg[k] + (uint32_t)(after - before);       // the scan uses differences only: wrap-around is harmless
+            before = after;
+        }
+        if (c->prefix_tabs.size() >= 16) {                          // rare: a new plan; drop the oldest table once it is idle
+            CK(cudaStreamSynchronize(st));
+            cudaFree(c->prefix_tabs.front().d_seg);
+            c->prefix_tabs.erase(c->prefix_tabs.begin());
+        }
+        iqgpu_chain::PrefixTab t;
+        t.first = first_frame; t.frames = n_frames; t.nch = nch;
+        CK(cudaMalloc(&t.d_seg, need));
+        CK(cudaMemcpyAsync(t.d_seg, seg, need, cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(c->ev_seg[sl], st));
+        c->prefix_tabs.push_back(t);
+        d_seg = t.d_seg;
     }
-    if (nch + 1 > c->prefix_seg_cap) {
-        CK(cudaStreamSynchronize(st));
-        cudaFree(c->d_prefix_seg);
-        c->prefix_seg_cap = (nch + 1) * 2;
-        CK(cudaMalloc(&c->d_prefix_seg, c->prefix_seg_cap * sizeof(uint32_t)));
-    }
-    CK(cudaMemcpyAsync(c->d_prefix_seg, seg, need, cudaMemcpyHostToDevice, st));
-    CK(cudaEventRecord(c->ev_seg[sl], st));
     PostParams qp{};
     qp.agc_mode = c->agc_mode; qp.agc_target = c->agc_target; qp.agc_alpha = c->agc_alpha; qp.target_rate = c->target_rate;
-    CK(launch_agc_digital_scan(c->d_prefix_seg, nch, dev_peaks, qp, c->d_agc, nullptr, st));
+    CK(launch_agc_digital_scan(d_seg, nch, dev_peaks, qp, c->d_agc, nullptr, st));
     return IQGPU_OK;
 }
 
