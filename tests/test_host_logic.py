@@ -115,3 +115,20 @@ def test_no_cpu_fallback(workloads):
             gpu.Chain(workloads["cfg1"].config, device=0)
         with pytest.raises(gpu.IqGpuError):
             gpu.convert_block_to_cf32(np.zeros(8, dtype=np.int16), 11, 4, 1.0)
+
+
+def test_fused_front_plans_keep_their_invariants(tmp_path):
+    """The compile-time cascade plans of the warp-streaming fused front (S = 0..6): alignment of the per-warp shared-memory
+    regions, whole register tiles, history sizes, run periods and producer/consumer ratios, zero padding around the
+    polyphase rows, >= 16 warps per CTA.  Host-only program, compiled for sm_100a (no GPU needed)."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = tmp_path / "plan_check"
+    subprocess.run([nvcc, "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-I", os.path.join(ROOT, "iq_tool_b200", "csrc"),
+                    "-o", str(exe), os.path.join(ROOT, "tests", "native", "plan_check.cu")], check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout
