@@ -166,7 +166,9 @@ def run_reference(args):
     from oracle.loader import CpuChain, have_ref
     wl = baseline_workloads()[args.workload]
     kind = "ref_fast" if have_ref(fast=True) else "oracle"
-    n = args.cpu_samples
+    # bounded sample: about 25 s of CPU work for the whole run whatever --steps is (the CPU chain does ~50 Msamples/s)
+    n = min(args.cpu_samples, max(1 << 20, int(1.25e9 / max(1, args.steps))))
+    n -= n % 16384
     raw = synth_numpy(wl, n)
     ch = CpuChain(wl.config, kind)
     threaded = kind != "oracle"
