@@ -263,6 +263,72 @@ int         iqgpu_rawfile_run(const iqgpu_chain_config *cfg, int device, const c
                               iqgpu_rawfile_stats *stats /* optional */);
 const char *iqgpu_rawfile_last_error(void);
 
+/* ---- WAV / RF64 containers around the path: the WAV input module
+ *      (src/input_wav.c: wav_initialize :542-632, auxi metadata :146-188,294-441, file-name metadata :190-271,
+ *      --wav-center-target-freq :612-629, reader loop :634-699) and the WAV / RF64 output modules
+ *      (src/output_wav_common.c:54-174, src/output_wav.c, src/output_wav_rf64.c).  The reference parses and
+ *      writes the container with libsndfile and the XML form of the auxi chunk with expat; both are restated
+ *      here in plain C++ (no dependency), the sample payload goes through the same reader / chain / writer
+ *      pass as a raw file. ------------------------------------------------------------------------------- */
+enum { IQGPU_CONTAINER_RAW = 0, IQGPU_CONTAINER_WAV = 1, IQGPU_CONTAINER_RF64 = 2 };
+/* SdrSoftwareType (src/input_wav.c:56-62) */
+enum { IQGPU_SDR_SOFTWARE_UNKNOWN = 0, IQGPU_SDR_CONSOLE, IQGPU_SDR_SHARP, IQGPU_SDR_UNO, IQGPU_SDR_CONNECT };
+
+typedef struct {
+    /* what sf_open + SF_INFO give the reference (src/input_wav.c:552-598) */
+    int32_t  container;             /* IQGPU_CONTAINER_WAV or IQGPU_CONTAINER_RF64 */
+    int32_t  sample_format;         /* IQGPU_FMT_CS16 (PCM_16) or IQGPU_FMT_CU8 (PCM_U8); anything else is refused */
+    int32_t  format_tag;            /* 1 = PCM, 3 = IEEE float, 0xFFFE = extensible (sub-format resolved) ... */
+    int32_t  channels;
+    int32_t  bits_per_sample;
+    int32_t  sample_rate_hz;
+    uint64_t data_offset;           /* file offset of the first sample byte */
+    uint64_t data_bytes;            /* payload length, clipped to the file */
+    uint64_t frames;                /* data_bytes / (channels * bytes per sample) */
+    /* SdrMetadata (src/input_wav.c:64-78) */
+    int32_t  metadata_present;      /* WavPrivateData.sdr_info_present */
+    int32_t  source_software;       /* IQGPU_SDR_* */
+    int32_t  center_freq_hz_present;
+    int32_t  timestamp_unix_present;
+    double   center_freq_hz;
+    int64_t  timestamp_unix;
+    int32_t  timestamp_str_present;
+    int32_t  software_name_present;
+    int32_t  software_version_present;
+    int32_t  radio_model_present;
+    char     timestamp_str[64];
+    char     software_name[64];
+    char     software_version[64];
+    char     radio_model[128];
+} iqgpu_wav_info;
+
+/* wav_initialize up to the shift decision: header, first auxi chunk, then the file name.  Host only (no device).
+ * Fails with IQGPU_EINVAL (message in iqgpu_rawfile_last_error) where the reference log_fatal()s: not a WAV/RF64
+ * file, channels != 2, a PCM subtype other than 16-bit signed / 8-bit unsigned, sample rate <= 0. */
+int  iqgpu_wav_probe(const char *path, iqgpu_wav_info *info);
+/* the two metadata sources on their own (info must be zeroed or hold earlier results; return 1 if anything
+ * new was parsed, 0 if not): an auxi chunk body — XML <Definition .../> attributes first (SDR Console), the
+ * binary SYSTEMTIME + centre-frequency layout second (SDRuno / SDR#) — and the base name of the file. */
+int  iqgpu_wav_parse_auxi(const void *chunk, size_t bytes, iqgpu_wav_info *info);
+int  iqgpu_wav_parse_filename(const char *base_filename, iqgpu_wav_info *info);
+/* --wav-center-target-freq (src/input_wav.c:612-629): nco_shift_hz = centre frequency - (double)target.
+ * IQGPU_EINVAL if a --freq-shift was given as well or the file carries no centre frequency. */
+int  iqgpu_wav_center_target_shift(const iqgpu_wav_info *info, float center_target_hz, double freq_shift_hz_arg,
+                                   double *nco_shift_hz);
+/* the header libsndfile leaves in front of `data_bytes` of 2-channel PCM once the file is closed
+ * (44 bytes for WAV, 80 for RF64: RF64 / ds64 / fmt / data); output_format is CS16 or CU8
+ * (wav_common_validate_options, src/output_wav_common.c:46-52), the rate is (int)target_rate (:96). */
+size_t iqgpu_wav_header_bytes(int container);
+int  iqgpu_wav_build_header(int container, int output_format, int sample_rate_hz, uint64_t data_bytes,
+                            void *header, size_t capacity);
+/* A whole file run: in_container RAW takes format and rate from cfg; WAV / RF64 (either value: the header
+ * decides) take them from the file the way wav_initialize does, and center_target_hz != 0 turns the file's
+ * centre-frequency metadata into the chain's shift.  out_container RAW writes the bare samples, WAV / RF64
+ * the container.  `in_info` (optional) receives the probe result. */
+int  iqgpu_wavfile_run(const iqgpu_chain_config *cfg, int device, const char *in_path, int in_container,
+                       const char *out_path, int out_container, float center_target_hz, size_t train_chunks,
+                       iqgpu_rawfile_stats *stats /* optional */, iqgpu_wav_info *in_info /* optional */);
+
 /* ---- sample_convert.h (include/sample_convert.h:19,35,50) — host buffers ------------- */
 size_t iqgpu_get_bytes_per_sample(int format);
 int    iqgpu_convert_block_to_cf32(const void *in, float *out_cf32, size_t n_frames, int format, float gain);

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "../../include/iqgpu.h"
+#include "stream_io.hpp"
 
 namespace {
 
@@ -75,6 +76,8 @@ thread_local std::string g_io_err;
 
 }  // namespace
 
+void iqio::set_last_error(const std::string& msg) { g_io_err = msg; }
+
 extern "C" {
 
 const char* iqgpu_rawfile_last_error(void) { return g_io_err.c_str(); }
@@ -83,21 +86,36 @@ int iqgpu_rawfile_run(const iqgpu_chain_config* cfg, int device, const char* in_
                       size_t train_chunks, iqgpu_rawfile_stats* stats)
 {
     if (!cfg || !in_path || !out_path) { g_io_err = "null argument"; return IQGPU_EINVAL; }
-    if (train_chunks == 0) train_chunks = 256;
     if (stats) memset(stats, 0, sizeof(*stats));
-    const size_t in_bps = iqgpu_get_bytes_per_sample(cfg->input_format), out_bps = iqgpu_get_bytes_per_sample(cfg->output_format);
-    if (!in_bps || !out_bps) { g_io_err = "unhandled sample format"; return IQGPU_EINVAL; }
+    if (!iqgpu_get_bytes_per_sample(cfg->input_format) || !iqgpu_get_bytes_per_sample(cfg->output_format)) { g_io_err = "unhandled sample format"; return IQGPU_EINVAL; }
 
     iqgpu_chain* chain = nullptr;
     int rc = iqgpu_chain_create(cfg, device, &chain);
     if (rc) { g_io_err = iqgpu_last_error(); return rc; }
-    const size_t train_frames = train_chunks * (size_t)IQGPU_CHUNK_SAMPLES;
-    iqgpu_chain_set_option(chain, "subtrain_frames", (int64_t)std::min<size_t>(train_frames, (size_t)1 << 24));
-
     FILE* fin = fopen(in_path, "rb");
     if (!fin) { g_io_err = std::string("cannot open input file ") + in_path; iqgpu_chain_destroy(chain); return IQGPU_EINVAL; }
     FILE* fout = fopen(out_path, "wb");
     if (!fout) { g_io_err = std::string("cannot open output file ") + out_path; fclose(fin); iqgpu_chain_destroy(chain); return IQGPU_EINVAL; }
+    rc = iqio::run_stream(chain, cfg, fin, UINT64_MAX, fout, train_chunks, stats, g_io_err);
+    fclose(fin);
+    fclose(fout);
+    iqgpu_chain_destroy(chain);
+    return rc;
+}
+
+}  // extern "C"
+
+// One pass of an open input stream through an existing chain into an open output stream: at most `in_limit_bytes`
+// are read from the current position of `fin` (UINT64_MAX = to end of file); the caller owns chain and files.
+int iqio::run_stream(iqgpu_chain* chain, const iqgpu_chain_config* cfg, FILE* fin, uint64_t in_limit_bytes, FILE* fout,
+                     size_t train_chunks, iqgpu_rawfile_stats* stats, std::string& err)
+{
+    if (train_chunks == 0) train_chunks = 256;
+    const size_t in_bps = iqgpu_get_bytes_per_sample(cfg->input_format), out_bps = iqgpu_get_bytes_per_sample(cfg->output_format);
+    if (!in_bps || !out_bps) { err = "unhandled sample format"; return IQGPU_EINVAL; }
+    int rc = IQGPU_OK;
+    const size_t train_frames = train_chunks * (size_t)IQGPU_CHUNK_SAMPLES;
+    iqgpu_chain_set_option(chain, "subtrain_frames", (int64_t)std::min<size_t>(train_frames, (size_t)1 << 24));
 
     // output capacity of one train: closed form for the worst alignment + one FFT block of slack
     iqgpu_chain_info info{};
@@ -114,23 +132,23 @@ int iqgpu_rawfile_run(const iqgpu_chain_config* cfg, int device, const char* in_
     auto cleanup = [&]() {
         for (auto& s : rin.slots) iqgpu_host_free(s.buf);
         for (auto& s : rout.slots) iqgpu_host_free(s.buf);
-        fclose(fin);
-        fclose(fout);
-        iqgpu_chain_destroy(chain);
     };
-    if (!alloc_ok) { g_io_err = "pinned host allocation failed (no CUDA device?)"; cleanup(); return IQGPU_ENOMEM; }
+    if (!alloc_ok) { err = "pinned host allocation failed (no CUDA device?)"; cleanup(); return IQGPU_ENOMEM; }
 
     std::string reader_err, writer_err;
     uint64_t bytes_written = 0;
+    uint64_t remaining = in_limit_bytes;    // touched by the reader thread only
     std::thread reader([&] {
         for (;;) {
             Slot* s = rin.acquire_free();
             if (!s) return;
-            const size_t want = train_frames * in_bps;
-            const size_t got = fread(s->buf, 1, want, fin);
+            const size_t full = train_frames * in_bps;
+            const size_t want = (size_t)std::min<uint64_t>(full, remaining);
+            const size_t got = want ? fread(s->buf, 1, want, fin) : 0;
             if (got < want && ferror(fin)) { reader_err = "read error on the input file"; rin.abort(); return; }
+            remaining -= got;
             s->bytes = got - got % in_bps;      // a trailing partial frame is dropped (input_rawfile.c:236)
-            s->last = got < want;
+            s->last = got < full;
             rin.publish();
             if (s->last) return;
         }
@@ -158,7 +176,7 @@ int iqgpu_rawfile_run(const iqgpu_chain_config* cfg, int device, const char* in_
         size_t produced = 0;
         if (n) {
             rc = iqgpu_chain_process(chain, in->buf, n, nullptr, 0, out->buf, out_cap_frames * out_bps, &produced, nullptr);
-            if (rc) { g_io_err = iqgpu_last_error(); break; }
+            if (rc) { err = iqgpu_last_error(); break; }
         }
         frames_in += n; frames_out += produced; trains++;
         out->bytes = produced * out_bps;
@@ -171,11 +189,10 @@ int iqgpu_rawfile_run(const iqgpu_chain_config* cfg, int device, const char* in_
     if (rc) { rin.abort(); rout.abort(); }
     reader.join();
     writer.join();
-    if (!rc && !reader_err.empty()) { g_io_err = reader_err; rc = IQGPU_EINVAL; }
-    if (!rc && !writer_err.empty()) { g_io_err = writer_err; rc = IQGPU_EINVAL; }
+    // an I/O thread that failed aborted the rings, which is what stopped the loop above: report its message
+    if (!reader_err.empty()) { err = reader_err; rc = IQGPU_EINVAL; }
+    if (!writer_err.empty()) { err = writer_err; rc = IQGPU_EINVAL; }
     if (stats) { stats->frames_in = frames_in; stats->frames_out = frames_out; stats->bytes_written = bytes_written; stats->trains = trains; }
     cleanup();
     return rc;
 }
-
-}  // extern "C"

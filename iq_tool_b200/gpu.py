@@ -54,6 +54,37 @@ class RawfileStatsC(C.Structure):
                 ("trains", C.c_uint64)]
 
 
+class WavInfoC(C.Structure):
+    """iqgpu_wav_info (include/iqgpu.h): SF_INFO + SdrMetadata of src/input_wav.c."""
+    _fields_ = [("container", C.c_int32), ("sample_format", C.c_int32), ("format_tag", C.c_int32),
+                ("channels", C.c_int32), ("bits_per_sample", C.c_int32), ("sample_rate_hz", C.c_int32),
+                ("data_offset", C.c_uint64), ("data_bytes", C.c_uint64), ("frames", C.c_uint64),
+                ("metadata_present", C.c_int32), ("source_software", C.c_int32),
+                ("center_freq_hz_present", C.c_int32), ("timestamp_unix_present", C.c_int32),
+                ("center_freq_hz", C.c_double), ("timestamp_unix", C.c_int64),
+                ("timestamp_str_present", C.c_int32), ("software_name_present", C.c_int32),
+                ("software_version_present", C.c_int32), ("radio_model_present", C.c_int32),
+                ("timestamp_str", C.c_char * 64), ("software_name", C.c_char * 64),
+                ("software_version", C.c_char * 64), ("radio_model", C.c_char * 128)]
+
+    def as_dict(self) -> dict:
+        """The metadata fields that are present, plus the header fields."""
+        d = {k: int(getattr(self, k)) for k in ("container", "sample_format", "format_tag", "channels",
+                                                "bits_per_sample", "sample_rate_hz", "data_offset", "data_bytes",
+                                                "frames", "metadata_present", "source_software")}
+        if self.center_freq_hz_present:
+            d["center_freq_hz"] = float(self.center_freq_hz)
+        if self.timestamp_unix_present:
+            d["timestamp_unix"] = int(self.timestamp_unix)
+        for k in ("timestamp_str", "software_name", "software_version", "radio_model"):
+            if getattr(self, k + "_present"):
+                d[k] = bytes(getattr(self, k)).decode("utf-8", "replace")
+        return d
+
+
+CONTAINER_RAW, CONTAINER_WAV, CONTAINER_RF64 = 0, 1, 2
+
+
 def _load() -> C.CDLL:
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -100,6 +131,18 @@ def _load() -> C.CDLL:
     lib.iqgpu_rawfile_run.restype = C.c_int
     lib.iqgpu_rawfile_run.argtypes = [C.POINTER(ChainConfigC), C.c_int, C.c_char_p, C.c_char_p, sz, C.POINTER(RawfileStatsC)]
     lib.iqgpu_rawfile_last_error.restype = C.c_char_p
+    lib.iqgpu_wav_probe.argtypes = [C.c_char_p, C.POINTER(WavInfoC)]
+    lib.iqgpu_wav_parse_auxi.argtypes = [C.c_char_p, sz, C.POINTER(WavInfoC)]
+    lib.iqgpu_wav_parse_filename.argtypes = [C.c_char_p, C.POINTER(WavInfoC)]
+    lib.iqgpu_wav_center_target_shift.argtypes = [C.POINTER(WavInfoC), C.c_float, C.c_double, C.POINTER(C.c_double)]
+    lib.iqgpu_wav_header_bytes.restype = sz
+    lib.iqgpu_wav_header_bytes.argtypes = [C.c_int]
+    lib.iqgpu_wav_build_header.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint64, vp, sz]
+    lib.iqgpu_wavfile_run.argtypes = [C.POINTER(ChainConfigC), C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int,
+                                      C.c_float, sz, C.POINTER(RawfileStatsC), C.POINTER(WavInfoC)]
+    for name in ("iqgpu_wav_probe", "iqgpu_wav_parse_auxi", "iqgpu_wav_parse_filename",
+                 "iqgpu_wav_center_target_shift", "iqgpu_wav_build_header", "iqgpu_wavfile_run"):
+        getattr(lib, name).restype = C.c_int
     lib.iqgpu_get_bytes_per_sample.restype = sz
     lib.iqgpu_get_bytes_per_sample.argtypes = [C.c_int]
     lib.iqgpu_convert_block_to_cf32.argtypes = [vp, vp, sz, C.c_int, C.c_float]
@@ -364,3 +407,50 @@ def rawfile_run(cfg: ChainConfig, in_path: str, out_path: str, device: int = 0, 
     if rc != 0:
         raise IqGpuError(rc, lib.iqgpu_rawfile_last_error().decode("utf-8", "replace"))
     return st
+
+
+def _io_check(rc: int) -> None:
+    if rc != 0:
+        raise IqGpuError(rc, lib.iqgpu_rawfile_last_error().decode("utf-8", "replace"))
+
+
+def wav_probe(path: str) -> WavInfoC:
+    """wav_initialize's view of a WAV / RF64 capture: header, auxi chunk, file-name metadata (host only)."""
+    info = WavInfoC()
+    _io_check(lib.iqgpu_wav_probe(os.fsencode(path), C.byref(info)))
+    return info
+
+
+def wav_parse_auxi(chunk: bytes, info: WavInfoC | None = None) -> tuple[bool, WavInfoC]:
+    info = info if info is not None else WavInfoC()
+    return bool(lib.iqgpu_wav_parse_auxi(chunk, len(chunk), C.byref(info))), info
+
+
+def wav_parse_filename(base: str, info: WavInfoC | None = None) -> tuple[bool, WavInfoC]:
+    info = info if info is not None else WavInfoC()
+    return bool(lib.iqgpu_wav_parse_filename(os.fsencode(base), C.byref(info))), info
+
+
+def wav_center_target_shift(info: WavInfoC, center_target_hz: float, freq_shift_hz_arg: float = 0.0) -> float:
+    out = C.c_double()
+    _io_check(lib.iqgpu_wav_center_target_shift(C.byref(info), center_target_hz, freq_shift_hz_arg, C.byref(out)))
+    return out.value
+
+
+def wav_build_header(container: int, output_format: int, sample_rate_hz: int, data_bytes: int) -> bytes:
+    n = lib.iqgpu_wav_header_bytes(container)
+    buf = C.create_string_buffer(max(n, 1))
+    _io_check(lib.iqgpu_wav_build_header(container, output_format, sample_rate_hz, data_bytes, buf, n))
+    return buf.raw[:n]
+
+
+def wavfile_run(cfg: ChainConfig, in_path: str, out_path: str, in_container: int = CONTAINER_WAV,
+                out_container: int = CONTAINER_WAV, center_target_hz: float = 0.0, device: int = 0,
+                train_chunks: int = 0) -> tuple[RawfileStatsC, WavInfoC]:
+    """A whole file run with WAV / RF64 containers on either side (format and rate of a WAV input come from its header)."""
+    st, info = RawfileStatsC(), WavInfoC()
+    c = cfg.to_c()
+    rc = lib.iqgpu_wavfile_run(C.byref(c), device, os.fsencode(in_path), in_container, os.fsencode(out_path),
+                               out_container, center_target_hz, train_chunks, C.byref(st), C.byref(info))
+    _io_check(rc)
+    return st, info
