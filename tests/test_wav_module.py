@@ -1,0 +1,130 @@
+"""The drop-in WAV input module (iq_tool_b200/host/input_wav.c: the reference's `get_wav_input_module_api()` /
+`wav_get_cli_options()` without libsndfile or expat) driven through its InputModuleInterface by
+tests/native/wav_module_harness.c the way src/pipeline.c drives an input module: initialize, optional pre-stream
+calibration, start_stream on a reader thread feeding SampleChunks through the reference's own queues, summary,
+cleanup.  CPU only (the module is host code); built by `make -C iq_tool_b200/host wavmodule` where the reference
+headers exist, prebuilt elsewhere."""
+import ctypes as C
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from iq_tool_b200.configs import FORMAT_CODES
+from test_wavfile import SDRC_XML, chunk, fmt_chunk, riff, sdruno_auxi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "tests", "native", "_build", "libwavmodule_harness.so")
+CHUNK = 16384
+
+
+class Result(C.Structure):
+    _fields_ = [("initialized", C.c_int), ("input_format", C.c_int), ("samplerate", C.c_int), ("source_frames", C.c_int64),
+                ("nco_shift_hz", C.c_double), ("total_frames_read", C.c_uint64), ("chunks", C.c_uint64), ("bytes", C.c_uint64),
+                ("largest_chunk_frames", C.c_uint64), ("saw_last_chunk", C.c_int), ("bytes_per_pair", C.c_int),
+                ("has_known_length", C.c_int), ("summary_count", C.c_int), ("summary_label", (C.c_char * 64) * 16),
+                ("summary_value", (C.c_char * 128) * 16)]
+
+    def summary(self) -> dict:
+        return {bytes(self.summary_label[i]).split(b"\0")[0].decode(): bytes(self.summary_value[i]).split(b"\0")[0].decode()
+                for i in range(self.summary_count)}
+
+
+@pytest.fixture(scope="module")
+def mod():
+    if os.path.exists("/root/reference/include/app_context.h"):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "iq_tool_b200", "host"), "wavmodule"], check=True, stdout=subprocess.DEVNULL)
+    if not os.path.exists(LIB):
+        pytest.skip("WAV module harness not built (needs the reference headers)")
+    lib = C.CDLL(LIB)
+    lib.wavmod_run.argtypes = [C.c_char_p, C.c_float, C.c_float, C.c_int, C.c_uint, C.c_uint, C.c_void_p, C.c_size_t, C.POINTER(Result)]
+    lib.wavmod_calibration_block.restype = C.c_long
+    lib.wavmod_calibration_block.argtypes = [C.c_void_p, C.c_size_t]
+    return lib
+
+
+def run(mod, path, target=0.0, shift_arg=0.0, iq=0, pool=4, chunk_frames=CHUNK, cap=1 << 22):
+    sink = np.zeros(cap, dtype=np.uint8)
+    res = Result()
+    rc = mod.wavmod_run(os.fsencode(path), target, shift_arg, iq, pool, chunk_frames, sink.ctypes.data, cap, C.byref(res))
+    return rc, res, sink[:res.bytes].tobytes()
+
+
+def test_module_exports_the_reference_interface(mod):
+    for name in ("get_wav_input_module_api", "wav_get_cli_options", "sf_read_raw", "sf_seek"):
+        assert hasattr(mod, name), name
+
+
+@pytest.mark.parametrize("fmt,bits,frames", [("cs16", 16, 5 * CHUNK + 4321), ("cu8", 8, 3 * CHUNK), ("cs16", 16, 1), ("cs16", 16, 0)])
+def test_reader_thread_delivers_exactly_the_data_chunk(mod, fmt, bits, frames, tmp_path):
+    dt = np.int16 if bits == 16 else np.uint8
+    payload = np.random.default_rng(frames + bits).integers(0, 255, size=2 * frames).astype(dt).tobytes()
+    path = tmp_path / "capture.wav"
+    path.write_bytes(riff(fmt_chunk(2_000_000, bits) + chunk(b"auxi", SDRC_XML) + chunk(b"data", payload + b"\x01" * (1 if frames else 0))
+                          + chunk(b"LIST", b"\x55" * 70_001)))
+    rc, res, got = run(mod, path)
+    assert rc == 0 and res.initialized and res.has_known_length
+    assert (res.input_format, res.samplerate, res.source_frames, res.bytes_per_pair) == (FORMAT_CODES[fmt], 2_000_000, frames, bits // 4)
+    assert got == payload and res.total_frames_read == frames and res.saw_last_chunk
+    assert res.chunks == -(-frames // CHUNK) and res.largest_chunk_frames == min(frames, CHUNK)
+    assert res.nco_shift_hz == 0.0
+
+
+def test_summary_lines_are_the_reference_s(mod, tmp_path):
+    path = tmp_path / "capture.wav"
+    path.write_bytes(riff(fmt_chunk(2_000_000, 16) + chunk(b"auxi", SDRC_XML) + chunk(b"data", b"\0\0\0\0" * 10)))
+    rc, res, _ = run(mod, path)
+    assert rc == 0
+    assert res.summary() == {
+        "Input File": str(path), "Input Format": "16-bit Signed Complex PCM (cs16)", "Input Rate": "2000000 Hz",
+        "Input File Size": res.summary()["Input File Size"], "Timestamp": "2015-08-04 20:56:28 UTC",
+        "Center Frequency": "97300000 Hz", "SDR Software": "SDR Console Version 3.0 build 1", "Radio Model": "Airspy & SpyVerter"}
+    assert res.summary()["Input File Size"].endswith("B") or "bytes" in res.summary()["Input File Size"].lower()
+    plain = tmp_path / "plain.wav"
+    plain.write_bytes(riff(fmt_chunk(48_000, 8) + chunk(b"data", b"\x80\x80" * 10)))
+    rc, res, _ = run(mod, plain)
+    assert rc == 0 and list(res.summary()) == ["Input File", "Input Format", "Input Rate", "Input File Size"]
+    assert res.summary()["Input Format"] == "8-bit Unsigned Complex PCM (cu8)"
+
+
+def test_center_target_option_sets_the_shift_and_its_refusals(mod, tmp_path):
+    path = tmp_path / "SDRuno_20210309_170559Z_14074kHz.wav"
+    path.write_bytes(riff(fmt_chunk(2_000_000, 16) + chunk(b"auxi", sdruno_auxi(freq=14_074_000)) + chunk(b"data", b"\1\0\2\0" * 100)))
+    rc, res, _ = run(mod, path, target=14.1e6)
+    assert rc == 0 and res.nco_shift_hz == 14_074_000.0 - 14_100_000.0
+    assert res.summary()["Center Frequency"] == "14074000 Hz" and res.summary()["SDR Software"].strip() == "SDRuno"
+    rc, res, _ = run(mod, path, target=14.1e6, shift_arg=1000.0)          # --freq-shift given as well
+    assert rc == 1 and not res.initialized
+    bare = tmp_path / "bare.wav"
+    bare.write_bytes(riff(fmt_chunk(2_000_000, 16) + chunk(b"data", b"\1\0\2\0" * 100)))
+    rc, res, _ = run(mod, bare, target=14.1e6)                            # no centre frequency to work from
+    assert rc == 1 and not res.initialized
+    rc, res, _ = run(mod, bare)
+    assert rc == 0 and res.nco_shift_hz == 0.0
+
+
+@pytest.mark.parametrize("blob", [riff(fmt_chunk(48_000, 16, channels=1) + chunk(b"data", b"\0\0" * 8)),
+                                  riff(fmt_chunk(48_000, 24) + chunk(b"data", b"\0" * 12)), b"not a wav file at all"])
+def test_initialize_refuses_what_the_reference_refuses(mod, blob, tmp_path):
+    path = tmp_path / "bad.wav"
+    path.write_bytes(blob)
+    rc, res, _ = run(mod, path)
+    assert rc == 1 and not res.initialized
+    rc, res, _ = run(mod, tmp_path / "missing.wav")
+    assert rc == 1
+
+
+def test_pre_stream_calibration_reads_the_first_block_and_rewinds(mod, tmp_path):
+    frames = 2 * CHUNK + 10
+    payload = np.random.default_rng(5).integers(-3000, 3000, size=2 * frames).astype(np.int16).tobytes()
+    path = tmp_path / "capture.wav"
+    path.write_bytes(riff(fmt_chunk(2_000_000, 16) + chunk(b"data", payload)))
+    rc, res, got = run(mod, path, iq=1)
+    block = np.zeros(8192, dtype=np.uint8)
+    n = mod.wavmod_calibration_block(block.ctypes.data, block.size)
+    assert rc == 0 and n == 4096 and block[:n].tobytes() == payload[:4096]
+    assert got == payload                                                 # the stream still starts at frame 0
+    rc, res, got = run(mod, path, iq=0)
+    assert rc == 0 and mod.wavmod_calibration_block(block.ctypes.data, block.size) == -2      # service not called
