@@ -5,6 +5,8 @@
 
 #include <stdlib.h>
 
+#include "iqgpu.h"
+
 SNDFILE *sfmin_open(const char *path, uint64_t data_offset, uint64_t data_bytes, uint32_t frame_bytes)
 {
     if (!frame_bytes) return NULL;
@@ -52,4 +54,45 @@ sf_count_t sf_seek(SNDFILE *s, sf_count_t frames, int whence)
     if (fseeko(s->file, (off_t)(s->data_offset + (uint64_t)target * s->frame_bytes), SEEK_SET) != 0) return -1;
     s->position = (uint64_t)target * s->frame_bytes;
     return target;
+}
+
+SNDFILE *sfmin_create(const char *path, int container, int sample_format, int sample_rate_hz)
+{
+    unsigned char header[80];
+    const size_t n = iqgpu_wav_header_bytes(container);
+    if (!n || iqgpu_wav_build_header(container, sample_format, sample_rate_hz, 0, header, sizeof(header)) != IQGPU_OK) return NULL;
+    FILE *f = fopen(path, "wb");
+    if (!f) return NULL;
+    SNDFILE *s = (SNDFILE *)calloc(1, sizeof(*s));
+    if (!s || fwrite(header, 1, n, f) != n) { fclose(f); free(s); return NULL; }
+    s->file = f;
+    s->writing = 1;
+    s->container = container;
+    s->sample_format = sample_format;
+    s->sample_rate_hz = sample_rate_hz;
+    return s;
+}
+
+sf_count_t sfmin_write_raw(SNDFILE *s, const void *ptr, sf_count_t bytes)
+{
+    if (!s || !s->writing || bytes < 0) return 0;
+    const size_t done = fwrite(ptr, 1, (size_t)bytes, s->file);
+    s->bytes_written += done;
+    return (sf_count_t)done;
+}
+
+int sfmin_finish(SNDFILE *s)
+{
+    if (!s) return -1;
+    int rc = 0;
+    if (s->writing) {
+        unsigned char header[80];
+        const size_t n = iqgpu_wav_header_bytes(s->container);
+        if (iqgpu_wav_build_header(s->container, s->sample_format, s->sample_rate_hz, s->bytes_written, header, sizeof(header)) != IQGPU_OK ||
+            fseeko(s->file, 0, SEEK_SET) != 0 || fwrite(header, 1, n, s->file) != n)
+            rc = -1;
+    }
+    if (fclose(s->file) != 0) rc = -1;
+    free(s);
+    return rc;
 }

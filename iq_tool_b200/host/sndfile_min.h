@@ -11,12 +11,23 @@
 
 struct SNDFILE_tag {
     FILE    *file;
+    /* reading: a capture positioned on its data chunk */
     uint64_t data_offset;    /* first sample byte */
     uint64_t data_bytes;     /* whole frames only */
     uint64_t position;       /* bytes consumed from the data chunk */
     uint32_t frame_bytes;    /* bytes per I/Q pair */
+    /* writing: a WAV / RF64 file whose header is patched on close */
+    int      writing;
+    int      container;      /* IQGPU_CONTAINER_WAV / _RF64 */
+    int      sample_format;  /* IQGPU_FMT_CS16 / _CU8 */
+    int      sample_rate_hz;
+    uint64_t bytes_written;
 };
 
 SNDFILE *sfmin_open(const char *path, uint64_t data_offset, uint64_t data_bytes, uint32_t frame_bytes);
 void     sfmin_close(SNDFILE *s);
+/* writer side (what SFM_WRITE + sf_write_raw + sf_close amount to for 2-channel PCM) */
+SNDFILE *sfmin_create(const char *path, int container, int sample_format, int sample_rate_hz);
+sf_count_t sfmin_write_raw(SNDFILE *s, const void *ptr, sf_count_t bytes);
+int      sfmin_finish(SNDFILE *s);   /* patches the sizes into the header and closes; 0 on success */
 #endif

@@ -5,6 +5,7 @@
  * The reference's own queue / arena / log / utils / signal sources are compiled in place from /root/reference. */
 #include <pthread.h>
 #include <stdlib.h>
+#include <unistd.h>
 #include <string.h>
 
 #include "app_context.h"
@@ -13,6 +14,9 @@
 #include "iq_correct.h"
 #include "memory_arena.h"
 #include "module.h"
+#include "output_wav.h"
+#include "output_wav_rf64.h"
+#include "ring_buffer.h"
 #include "pipeline_types.h"
 #include "queue.h"
 #include "signal_handler.h"
@@ -141,6 +145,102 @@ int wavmod_run(const char *path, float center_target_hz, float freq_shift_hz_arg
 done:
     api->cleanup(&ctx);
     if (resources->input_module_private_data) rc = rc ? rc : 5;      /* cleanup must drop the private state */
+    mem_arena_destroy(&resources->setup_arena);
+    pthread_mutex_destroy(&resources->progress_mutex);
+    free(config);
+    free(resources);
+    return rc;
+}
+
+/* ---- output side: the reference's own WAV / RF64 wrappers (src/output_wav.c, src/output_wav_rf64.c, compiled in
+ * place) on top of the drop-in output_wav_common.c, driven like the Writer thread side of src/pipeline.c ----------- */
+typedef struct {
+    int       validated, initialized;
+    long long final_output_size_bytes;
+    unsigned long long total_output_frames;
+    unsigned long long progress_calls, progress_last_bytes;
+    int       summary_count;
+    char      summary_label[4][64];
+    char      summary_value[4][128];
+} wavout_result;
+
+static void on_progress(unsigned long long frames, long long total, unsigned long long bytes, void *udata)
+{
+    wavout_result *r = (wavout_result *)udata;
+    (void)frames; (void)total;
+    r->progress_calls++;
+    r->progress_last_bytes = bytes;
+}
+
+static void *writer_main(void *arg)
+{
+    ModuleContext *ctx = (ModuleContext *)((void **)arg)[0];
+    OutputModuleInterface *api = (OutputModuleInterface *)((void **)arg)[1];
+    return api->run_writer(ctx);
+}
+
+/* mode 0: Writer thread fed through the ring buffer in `piece`-byte writes; mode 1: write_chunk called directly */
+int wavout_run(const char *path, int rf64, int output_format, double target_rate, const unsigned char *data, size_t bytes,
+               size_t piece, int mode, wavout_result *out)
+{
+    memset(out, 0, sizeof(*out));
+    reset_shutdown_flag();
+    AppConfig *config = (AppConfig *)calloc(1, sizeof(AppConfig));
+    AppResources *resources = (AppResources *)calloc(1, sizeof(AppResources));
+    if (!config || !resources || !mem_arena_init(&resources->setup_arena, 1u << 20)) return -1;
+    config->effective_output_filename = (char *)path;
+    config->output_format = (format_t)output_format;
+    config->output_sample_format_name = (char *)"as given";
+    config->target_rate = target_rate;
+    pthread_mutex_init(&resources->progress_mutex, NULL);
+    resources->output_bytes_per_sample_pair = output_format == CS16 ? 4 : 2;
+    resources->progress_callback = on_progress;
+    resources->progress_callback_udata = out;
+    resources->expected_total_output_frames = -1;
+
+    ModuleContext ctx = {config, resources};
+    OutputModuleInterface *api = rf64 ? get_wav_rf64_output_module_api() : get_wav_output_module_api();
+    int rc = 0;
+    if (!api->validate_options(config)) { rc = 1; goto done; }
+    out->validated = 1;
+    if (!api->initialize(&ctx)) { rc = 2; goto done; }
+    out->initialized = 1;
+    if (mode == 0) {
+        resources->writer_input_buffer = ring_buffer_create(3u << 20);
+        resources->writer_local_buffer = malloc(IO_OUTPUT_WRITER_CHUNK_SIZE);
+        void *args[2] = {&ctx, api};
+        pthread_t writer;
+        pthread_create(&writer, NULL, writer_main, args);
+        for (size_t off = 0; off < bytes;) {
+            /* ring_buffer_write never blocks: it takes what fits (the reference paces its reader on the fill level) */
+            const size_t n = bytes - off < piece ? bytes - off : piece;
+            const size_t taken = ring_buffer_write(resources->writer_input_buffer, data + off, n);
+            off += taken;
+            if (taken < n) usleep(200);
+        }
+        ring_buffer_signal_end_of_stream(resources->writer_input_buffer);
+        pthread_join(writer, NULL);
+        free(resources->writer_local_buffer);
+        ring_buffer_destroy(resources->writer_input_buffer);
+    } else {
+        for (size_t off = 0; off < bytes;) {
+            const size_t n = bytes - off < piece ? bytes - off : piece;
+            if (api->write_chunk(&ctx, data + off, n) != n) { rc = 3; break; }
+            off += n;
+        }
+    }
+    api->finalize_output(&ctx);
+    out->final_output_size_bytes = resources->final_output_size_bytes;
+    out->total_output_frames = resources->total_output_frames;
+    OutputSummaryInfo summary;
+    memset(&summary, 0, sizeof(summary));
+    api->get_summary_info(&ctx, &summary);
+    out->summary_count = summary.count;
+    for (int i = 0; i < summary.count && i < 4; i++) {
+        strncpy(out->summary_label[i], summary.items[i].label, 63);
+        strncpy(out->summary_value[i], summary.items[i].value, 127);
+    }
+done:
     mem_arena_destroy(&resources->setup_arena);
     pthread_mutex_destroy(&resources->progress_mutex);
     free(config);

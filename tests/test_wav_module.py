@@ -53,7 +53,8 @@ def run(mod, path, target=0.0, shift_arg=0.0, iq=0, pool=4, chunk_frames=CHUNK, 
 
 
 def test_module_exports_the_reference_interface(mod):
-    for name in ("get_wav_input_module_api", "wav_get_cli_options", "sf_read_raw", "sf_seek"):
+    for name in ("get_wav_input_module_api", "wav_get_cli_options", "sf_read_raw", "sf_seek", "wav_common_validate_options",
+                 "wav_common_initialize", "wav_common_run_writer", "wav_common_write_chunk", "wav_common_finalize_output"):
         assert hasattr(mod, name), name
 
 
@@ -128,3 +129,59 @@ def test_pre_stream_calibration_reads_the_first_block_and_rewinds(mod, tmp_path)
     assert got == payload                                                 # the stream still starts at frame 0
     rc, res, got = run(mod, path, iq=0)
     assert rc == 0 and mod.wavmod_calibration_block(block.ctypes.data, block.size) == -2      # service not called
+
+
+# ---------------------------------------------------------------------------------------------- output modules
+class OutResult(C.Structure):
+    _fields_ = [("validated", C.c_int), ("initialized", C.c_int), ("final_output_size_bytes", C.c_longlong),
+                ("total_output_frames", C.c_ulonglong), ("progress_calls", C.c_ulonglong), ("progress_last_bytes", C.c_ulonglong),
+                ("summary_count", C.c_int), ("summary_label", (C.c_char * 64) * 4), ("summary_value", (C.c_char * 128) * 4)]
+
+
+def run_out(mod, path, rf64, fmt, rate, data: bytes, piece, mode):
+    mod.wavout_run.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_char_p, C.c_size_t, C.c_size_t, C.c_int, C.POINTER(OutResult)]
+    res = OutResult()
+    rc = mod.wavout_run(os.fsencode(path), rf64, FORMAT_CODES[fmt], rate, data, len(data), piece, mode, C.byref(res))
+    return rc, res
+
+
+@pytest.mark.parametrize("rf64,fmt,mode,piece", [(0, "cs16", 0, 300_001), (0, "cu8", 0, 1 << 20), (1, "cs16", 0, 77_777), (0, "cs16", 1, 65_536),
+                                                 (1, "cu8", 1, 4096)])
+def test_output_wrappers_of_the_reference_on_the_drop_in_writer(mod, rf64, fmt, mode, piece, tmp_path):
+    """src/output_wav.c / src/output_wav_rf64.c (compiled in place, unmodified) -> drop-in wav_common_*: Writer thread
+    fed through the reference's ring buffer, or direct write_chunk calls; closing patches the header."""
+    import wave
+    from iq_tool_b200 import gpu as G
+    width = 2 if fmt == "cs16" else 1
+    frames = 1_234_567 if mode == 0 else 50_000
+    payload = np.random.default_rng(frames).integers(0, 256, size=2 * width * frames, dtype=np.uint8).tobytes()
+    path = tmp_path / ("out.rf64" if rf64 else "out.wav")
+    rc, res = run_out(mod, path, rf64, fmt, 744187.5, payload, piece, mode)
+    assert rc == 0 and res.validated and res.initialized
+    assert res.final_output_size_bytes == len(payload)
+    blob = path.read_bytes()
+    hb = 80 if rf64 else 44
+    assert blob[hb:] == payload
+    assert blob[:hb] == G.wav_build_header(G.CONTAINER_RF64 if rf64 else G.CONTAINER_WAV, FORMAT_CODES[fmt], 744187, len(payload))
+    info = G.wav_probe(str(path))
+    assert (info.frames, info.sample_rate_hz, info.sample_format) == (frames, 744187, FORMAT_CODES[fmt])
+    if not rf64:
+        with wave.open(str(path), "rb") as w:
+            assert (w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()) == (2, width, 744187, frames)
+    if mode == 0:       # the Writer thread reports progress per 1 MB piece, in frames of the output format
+        assert res.progress_calls >= len(payload) // (1 << 20) and res.progress_last_bytes == len(payload)
+        assert res.total_output_frames == frames
+    label = bytes(res.summary_label[0]).split(b"\0")[0].decode(), bytes(res.summary_value[0]).split(b"\0")[0].decode()
+    assert label[0] == "Output Type" and ("RF64" in label[1]) == bool(rf64)
+
+
+def test_output_module_refusals(mod, tmp_path):
+    rc, res = run_out(mod, tmp_path / "o.wav", 0, "cf32", 48000.0, b"", 1, 1)
+    assert rc == 1 and not res.validated                                   # only cs16 / cu8 go into a WAV container
+    (tmp_path / "dir.wav").mkdir()
+    rc, res = run_out(mod, tmp_path / "dir.wav", 0, "cs16", 48000.0, b"", 1, 1)
+    assert rc == 2 and res.validated and not res.initialized               # exists but is not a regular file
+    rc, res = run_out(mod, tmp_path / "no_dir" / "o.wav", 1, "cs16", 48000.0, b"", 1, 1)
+    assert rc == 2                                                         # cannot be opened
+    rc, res = run_out(mod, tmp_path / "empty.wav", 0, "cu8", 48000.0, b"", 1, 0)
+    assert rc == 0 and (tmp_path / "empty.wav").stat().st_size == 44 and res.final_output_size_bytes == 0
