@@ -10,6 +10,7 @@
 
 #include "app_context.h"
 #include "argparse.h"
+#include "input_rawfile.h"
 #include "input_wav.h"
 #include "iq_correct.h"
 #include "memory_arena.h"
@@ -57,14 +58,16 @@ long wavmod_calibration_block(unsigned char *dst, size_t capacity)
     return g_calibration_bytes;
 }
 
+static InputModuleInterface *g_api;     /* the module under test */
+
 static void *reader_main(void *arg)
 {
     ModuleContext *ctx = (ModuleContext *)arg;
-    return get_wav_input_module_api()->start_stream(ctx);
+    return g_api->start_stream(ctx);
 }
 
-int wavmod_run(const char *path, float center_target_hz, float freq_shift_hz_arg, int iq_correction, unsigned pool_chunks, unsigned chunk_frames,
-               unsigned char *sink, size_t sink_capacity, wavmod_result *out)
+static int drive_input(const char *path, float freq_shift_hz_arg, int iq_correction, unsigned pool_chunks, unsigned chunk_frames,
+                       unsigned char *sink, size_t sink_capacity, wavmod_result *out)
 {
     memset(out, 0, sizeof(*out));
     reset_shutdown_flag();
@@ -78,17 +81,11 @@ int wavmod_run(const char *path, float center_target_hz, float freq_shift_hz_arg
     g_calibration_bytes = -2;
     pthread_mutex_init(&resources->progress_mutex, NULL);
 
-    /* the option reaches the module the way argparse delivers it: through the value pointer of its option table */
-    int n_opts = 0;
-    const struct argparse_option *opts = wav_get_cli_options(&n_opts);
-    for (int i = 0; i < n_opts; i++)
-        if (opts[i].type == ARGPARSE_OPT_FLOAT && opts[i].long_name && strcmp(opts[i].long_name, "wav-center-target-freq") == 0)
-            *(float *)opts[i].value = center_target_hz;
-
     ModuleContext ctx = {config, resources};
-    InputModuleInterface *api = get_wav_input_module_api();
+    InputModuleInterface *api = g_api;
     out->has_known_length = api->has_known_length() ? 1 : 0;
     int rc = 0;
+    if (api->validate_options && !api->validate_options(config)) { rc = 7; goto done; }
     if (!api->initialize(&ctx)) { rc = 1; goto done; }
     out->initialized = 1;
     out->input_format = (int)resources->input_format;
@@ -150,6 +147,38 @@ done:
     free(config);
     free(resources);
     return rc;
+}
+
+/* options reach a module the way argparse delivers them: through the value pointers of its option table */
+static void set_option(const struct argparse_option *opts, int n, const char *long_name, float f, const char *str)
+{
+    for (int i = 0; i < n; i++) {
+        if (!opts[i].long_name || strcmp(opts[i].long_name, long_name) != 0) continue;
+        if (opts[i].type == ARGPARSE_OPT_FLOAT) *(float *)opts[i].value = f;
+        if (opts[i].type == ARGPARSE_OPT_STRING) *(const char **)opts[i].value = str;
+    }
+}
+
+int wavmod_run(const char *path, float center_target_hz, float freq_shift_hz_arg, int iq_correction, unsigned pool_chunks, unsigned chunk_frames,
+               unsigned char *sink, size_t sink_capacity, wavmod_result *out)
+{
+    int n = 0;
+    const struct argparse_option *opts = wav_get_cli_options(&n);
+    set_option(opts, n, "wav-center-target-freq", center_target_hz, NULL);
+    g_api = get_wav_input_module_api();
+    return drive_input(path, freq_shift_hz_arg, iq_correction, pool_chunks, chunk_frames, sink, sink_capacity, out);
+}
+
+/* src/input_rawfile.c's module: rate <= 0 / format NULL = option not given */
+int rawmod_run(const char *path, float rate_hz, const char *format, int iq_correction, unsigned pool_chunks, unsigned chunk_frames,
+               unsigned char *sink, size_t sink_capacity, wavmod_result *out)
+{
+    int n = 0;
+    const struct argparse_option *opts = rawfile_get_cli_options(&n);
+    set_option(opts, n, "raw-file-input-rate", rate_hz, NULL);
+    set_option(opts, n, "raw-file-input-sample-format", 0.0f, format);
+    g_api = get_raw_file_input_module_api();
+    return drive_input(path, 0.0f, iq_correction, pool_chunks, chunk_frames, sink, sink_capacity, out);
 }
 
 /* ---- output side: the reference's own WAV / RF64 wrappers (src/output_wav.c, src/output_wav_rf64.c, compiled in

@@ -185,3 +185,43 @@ def test_output_module_refusals(mod, tmp_path):
     assert rc == 2                                                         # cannot be opened
     rc, res = run_out(mod, tmp_path / "empty.wav", 0, "cu8", 48000.0, b"", 1, 0)
     assert rc == 0 and (tmp_path / "empty.wav").stat().st_size == 44 and res.final_output_size_bytes == 0
+
+
+# ---------------------------------------------------------------------------------------------- raw-file input module
+def run_raw(mod, path, rate, fmt, iq=0, pool=3, chunk_frames=CHUNK, cap=1 << 22):
+    mod.rawmod_run.argtypes = [C.c_char_p, C.c_float, C.c_char_p, C.c_int, C.c_uint, C.c_uint, C.c_void_p, C.c_size_t, C.POINTER(Result)]
+    sink = np.zeros(cap, dtype=np.uint8)
+    res = Result()
+    rc = mod.rawmod_run(os.fsencode(path), rate, fmt.encode() if fmt is not None else None, iq, pool, chunk_frames, sink.ctypes.data, cap, C.byref(res))
+    return rc, res, sink[:res.bytes].tobytes()
+
+
+@pytest.mark.parametrize("fmt,pair,frames,stray", [("cs16", 4, 4 * CHUNK + 99, 3), ("CU8", 2, 2 * CHUNK, 1), ("cf32", 8, CHUNK - 1, 7), ("sc16q11", 4, 10, 0),
+                                                   ("cs8", 2, 0, 1)])
+def test_raw_file_module_reads_whole_frames_in_chunks(mod, fmt, pair, frames, stray, tmp_path):
+    """The drop-in of src/input_rawfile.c (get_raw_file_input_module_api on a plain FILE): format names are matched
+    without regard to case, the length is whole frames, a torn last frame never reaches a chunk."""
+    payload = np.random.default_rng(frames + pair).integers(0, 256, size=frames * pair, dtype=np.uint8).tobytes()
+    path = tmp_path / "capture.raw"
+    path.write_bytes(payload + b"\xee" * stray)
+    rc, res, got = run_raw(mod, path, 2.4e6, fmt)
+    assert rc == 0 and res.initialized and res.has_known_length
+    assert (res.input_format, res.samplerate, res.source_frames, res.bytes_per_pair) == (FORMAT_CODES[fmt.lower()], 2_400_000, frames, pair)
+    assert got == payload and res.total_frames_read == frames and res.saw_last_chunk and res.chunks == -(-frames // CHUNK)
+    s = res.summary()
+    assert list(s) == ["Input File", "Input Type", "Input Format", "Input Rate", "Input File Size"]
+    assert (s["Input Type"], s["Input Format"], s["Input Rate"]) == ("RAW FILE", fmt, "2400000 Hz")
+
+
+def test_raw_file_module_refusals_and_calibration(mod, tmp_path):
+    path = tmp_path / "capture.raw"
+    payload = np.arange(4 * 3000, dtype=np.uint8).tobytes() * 1
+    path.write_bytes(payload)
+    assert run_raw(mod, path, 2.0e6, None)[0] == 7                  # --raw-file-input-sample-format missing
+    assert run_raw(mod, path, 2.0e6, "cs17")[0] == 1                # unknown format name
+    assert run_raw(mod, path, 2.0e6, "cs24")[0] == 1                # not a format the raw reader opens
+    assert run_raw(mod, tmp_path / "missing.raw", 2.0e6, "cs16")[0] == 1
+    rc, res, got = run_raw(mod, path, 2.0e6, "cs16", iq=1)
+    block = np.zeros(8192, dtype=np.uint8)
+    assert rc == 0 and mod.wavmod_calibration_block(block.ctypes.data, block.size) == 4096
+    assert block[:4096].tobytes() == payload[:4096] and got == payload
