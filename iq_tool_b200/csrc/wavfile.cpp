@@ -385,7 +385,7 @@ int probe_stream(FILE* f, const char* path, iqgpu_wav_info* info)
             if (!have_fmt) return fail(std::string("Error opening input file: ") + path + " has its data chunk in front of the fmt chunk");
             if (rf64 && size == 0xFFFFFFFFu && have_ds64) size = ds64_data;
             // a recorder that was stopped hard leaves 0 (or all ones) here: the payload then runs to the end of the file
-            if (body + size > file_len || size == 0xFFFFFFFFu || (size == 0 && (riff_size == 0 || riff_size == 0xFFFFFFFFu || riff_size == 36) && file_len > body))
+            if (size > file_len - body || size == 0xFFFFFFFFu || (size == 0 && (riff_size == 0 || riff_size == 0xFFFFFFFFu || riff_size == 36) && file_len > body))
                 size = file_len - body;
             info->data_offset = body;
             info->data_bytes = size;

@@ -362,3 +362,13 @@ def test_raw_capture_into_a_wav_container(tmp_path, gpu, workloads):
     one = gpu.Chain(cfg, 0).process(raw)
     assert ref["sample_rate_hz"] == int(cfg.target_rate_hz) and ref["frames"] == st.frames_out == one.size // 2
     assert ref["payload"] == one.tobytes()
+
+
+def test_probe_rf64_with_an_absurd_ds64_size_is_clipped_to_the_file(tmp_path):
+    payload = b"\1\0\2\0" * 321
+    ds64 = struct.pack("<QQQI", 2**63, 2**64 - 8, 2**62, 0)
+    blob = riff(chunk(b"ds64", ds64) + fmt_chunk(1_000_000, 16) + b"data" + struct.pack("<I", 0xFFFFFFFF) + payload, magic=b"RF64", size=0xFFFFFFFF)
+    path = tmp_path / "absurd.rf64"
+    path.write_bytes(blob)
+    info = G.wav_probe(str(path))
+    assert (info.frames, info.data_bytes, info.data_offset) == (321, len(payload), len(blob) - len(payload))
