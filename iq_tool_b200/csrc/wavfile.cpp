@@ -11,6 +11,7 @@
 // needs and the two headers are written out in plain C++.  The payload goes through iqio::run_stream
 // (rawfile.cpp) — large pinned reads, one chain call per chunk train, one write per train.  Everything in this
 // file except iqgpu_wavfile_run is host-only and works without a device.
+#include <cctype>
 #include <cerrno>
 #include <cmath>
 #include <cstdint>
@@ -66,9 +67,50 @@ struct XmlStartTag {
     std::vector<std::pair<std::string, std::string>> attrs;
 };
 
-bool is_xml_space(unsigned char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r'; }
-bool is_name_start(unsigned char c) { return (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z') || c == '_' || c == ':' || c >= 0x80; }
-bool is_name_char(unsigned char c) { return is_name_start(c) || (c >= '0' && c <= '9') || c == '-' || c == '.'; }
+// A cursor over the chunk that yields XML characters (UTF-8, or ISO-8859-1 when the declaration says so)
+struct XmlSource {
+    const unsigned char* d;
+    size_t n;
+    bool latin1 = false;
+
+    // code point at i and its byte length; 0 = end of data, malformed UTF-8, or a character XML does not allow
+    int at(size_t i, uint32_t* cp) const
+    {
+        if (i >= n) return 0;
+        const unsigned char c = d[i];
+        uint32_t v;
+        int len;
+        if (c < 0x80 || latin1) { v = c; len = 1; }
+        else if (c >= 0xC2 && c <= 0xDF) { v = c & 0x1F; len = 2; }
+        else if (c >= 0xE0 && c <= 0xEF) { v = c & 0x0F; len = 3; }
+        else if (c >= 0xF0 && c <= 0xF4) { v = c & 0x07; len = 4; }
+        else return 0;
+        if (i + len > n) return 0;
+        for (int k = 1; k < len; k++) {
+            if ((d[i + k] & 0xC0) != 0x80) return 0;
+            v = (v << 6) | (d[i + k] & 0x3F);
+        }
+        if ((len == 3 && v < 0x800) || (len == 4 && (v < 0x10000 || v > 0x10FFFF))) return 0;
+        const bool allowed = v == 0x9 || v == 0xA || v == 0xD || (v >= 0x20 && v <= 0xD7FF) || (v >= 0xE000 && v <= 0xFFFD) || v >= 0x10000;
+        if (!allowed) return 0;
+        *cp = v;
+        return len;
+    }
+};
+
+bool is_xml_space(uint32_t c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r'; }
+// Name characters: exact for ASCII and Latin-1, by block beyond (letters and ideographs in, punctuation / symbols /
+// private use / specials out) — metadata writers use ASCII names
+bool is_name_start(uint32_t c)
+{
+    if (c < 0x80) return (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z') || c == '_' || c == ':';
+    if (c < 0x100) return c >= 0xC0 && c != 0xD7 && c != 0xF7;
+    if (c >= 0x2000 && c <= 0x2FFF) return c == 0x2126 || (c >= 0x212A && c <= 0x212B) || c == 0x212E || (c >= 0x2180 && c <= 0x2182);
+    if (c >= 0x3000 && c <= 0x3006) return false;
+    if (c >= 0xD7A4 && c <= 0xFFFF) return false;
+    return c < 0x10000;
+}
+bool is_name_char(uint32_t c) { return is_name_start(c) || (c >= '0' && c <= '9') || c == '-' || c == '.' || c == 0xB7; }
 
 void append_utf8(std::string& s, uint32_t cp)
 {
@@ -78,125 +120,209 @@ void append_utf8(std::string& s, uint32_t cp)
     else { s += (char)(0xF0 | (cp >> 18)); s += (char)(0x80 | ((cp >> 12) & 0x3F)); s += (char)(0x80 | ((cp >> 6) & 0x3F)); s += (char)(0x80 | (cp & 0x3F)); }
 }
 
-// attribute value with the predefined entities and character references resolved; false = not well formed
-bool decode_attr(const unsigned char* p, size_t n, std::string& out)
+// "&name;" / "&#n;" / "&#xh;" at i (src[i] == '&'): appends the replacement text, returns the byte length or 0
+size_t reference_at(const XmlSource& src, size_t i, std::string* out)
 {
-    for (size_t i = 0; i < n;) {
-        const unsigned char c = p[i];
-        if (c == '<') return false;
-        if (c == '\t' || c == '\n' || c == '\r') { out += ' '; i++; continue; }      // attribute-value normalisation
-        if (c != '&') { out += (char)c; i++; continue; }
-        size_t j = i + 1;
-        while (j < n && p[j] != ';') j++;
-        if (j >= n) return false;
-        const std::string ent((const char*)p + i + 1, j - i - 1);
-        if (ent == "amp") out += '&';
-        else if (ent == "lt") out += '<';
-        else if (ent == "gt") out += '>';
-        else if (ent == "quot") out += '"';
-        else if (ent == "apos") out += '\'';
-        else if (ent.size() > 1 && ent[0] == '#') {
-            char* end = nullptr;
-            const bool hex = ent[1] == 'x';
-            const unsigned long cp = strtoul(ent.c_str() + (hex ? 2 : 1), &end, hex ? 16 : 10);
-            if (!end || *end != '\0' || end == ent.c_str() + (hex ? 2 : 1) || cp == 0 || cp > 0x10FFFF) return false;
-            append_utf8(out, (uint32_t)cp);
-        } else return false;                                                            // undefined entity
-        i = j + 1;
-    }
-    return true;
+    size_t j = i + 1;
+    std::string body;
+    while (j < src.n && src.d[j] != ';' && body.size() < 12) body += (char)src.d[j++];
+    if (j >= src.n || src.d[j] != ';' || body.empty()) return 0;
+    uint32_t cp;
+    if (body == "amp") cp = '&';
+    else if (body == "lt") cp = '<';
+    else if (body == "gt") cp = '>';
+    else if (body == "quot") cp = '"';
+    else if (body == "apos") cp = '\'';
+    else if (body[0] == '#') {
+        const bool hex = body.size() > 1 && body[1] == 'x';
+        const char* digits = body.c_str() + (hex ? 2 : 1);
+        if (!*digits) return 0;
+        for (const char* p = digits; *p; p++)
+            if (!((*p >= '0' && *p <= '9') || (hex && ((*p >= 'a' && *p <= 'f') || (*p >= 'A' && *p <= 'F'))))) return 0;
+        const unsigned long v = strtoul(digits, nullptr, hex ? 16 : 10);
+        const bool allowed = v == 0x9 || v == 0xA || v == 0xD || (v >= 0x20 && v <= 0xD7FF) || (v >= 0xE000 && v <= 0xFFFD) || (v >= 0x10000 && v <= 0x10FFFF);
+        if (!allowed) return 0;
+        cp = (uint32_t)v;
+    } else return 0;                                        // no DTD: any other entity is undefined
+    if (out) append_utf8(*out, cp);
+    return j + 1 - i;
 }
 
-std::vector<XmlStartTag> scan_xml_start_tags(const unsigned char* d, size_t n)
+// a Name at i: its byte length (0 = none), text appended to *out
+size_t name_at(const XmlSource& src, size_t i, std::string* out)
+{
+    uint32_t cp;
+    int len = src.at(i, &cp);
+    if (!len || !is_name_start(cp)) return 0;
+    size_t j = i;
+    while ((len = src.at(j, &cp)) != 0 && is_name_char(cp)) {
+        if (out) append_utf8(*out, cp);
+        j += len;
+    }
+    return j - i;
+}
+
+// every character up to (not including) the terminator string is an allowed XML character; returns the offset of the
+// terminator or npos
+size_t find_terminator(const XmlSource& src, size_t i, const char* term)
+{
+    const size_t tl = strlen(term);
+    while (i < src.n) {
+        if (i + tl <= src.n && memcmp(src.d + i, term, tl) == 0) return i;
+        uint32_t cp;
+        const int len = src.at(i, &cp);
+        if (!len) return (size_t)-1;
+        i += len;
+    }
+    return (size_t)-1;
+}
+
+// <?xml version="1.x" [encoding="..."] [standalone="yes|no"] ?> at the very start; sets latin1; false = malformed / unsupported
+bool xml_declaration(XmlSource& src, size_t i, size_t* end)
+{
+    size_t j = i + 5;
+    const char* expected[] = {"version", "encoding", "standalone"};
+    int next = 0;
+    for (;;) {
+        const size_t before = j;
+        while (j < src.n && is_xml_space(src.d[j])) j++;
+        if (j + 1 < src.n && src.d[j] == '?' && src.d[j + 1] == '>') { *end = j + 2; return next >= 1; }
+        if (j == before) return false;
+        std::string key, value;
+        const size_t kl = name_at(src, j, &key);
+        if (!kl) return false;
+        j += kl;
+        while (j < src.n && is_xml_space(src.d[j])) j++;
+        if (j >= src.n || src.d[j] != '=') return false;
+        j++;
+        while (j < src.n && is_xml_space(src.d[j])) j++;
+        if (j >= src.n || (src.d[j] != '"' && src.d[j] != '\'')) return false;
+        const unsigned char q = src.d[j++];
+        while (j < src.n && src.d[j] != q) value += (char)src.d[j++];
+        if (j >= src.n) return false;
+        j++;
+        while (next < 3 && key != expected[next]) { if (next == 0) return false; next++; }
+        if (next >= 3) return false;
+        if (next == 0) {
+            for (char c : value)           // expat checks the alphabet of the version, not its value
+                if (!isalnum((unsigned char)c) && c != '.' && c != '_' && c != ':' && c != '-') return false;
+        } else if (next == 1) {
+            std::string enc;
+            for (char c : value) enc += (char)tolower((unsigned char)c);
+            if (enc == "iso-8859-1") src.latin1 = true;
+            else if (enc != "utf-8" && enc != "us-ascii") return false;      // UTF-16 and friends: not handled here
+        } else if (value != "yes" && value != "no") return false;
+        next++;
+    }
+}
+
+std::vector<XmlStartTag> scan_xml_start_tags(const unsigned char* data, size_t n)
 {
     std::vector<XmlStartTag> tags;
-    size_t i = 0;
-    int depth = 0;
+    XmlSource src{data, n};
+    std::vector<std::string> open;                         // element stack
     bool root_closed = false;
-    if (n >= 3 && d[0] == 0xEF && d[1] == 0xBB && d[2] == 0xBF) i = 3;                // UTF-8 byte order mark
+    size_t i = 0;
+    if (n >= 3 && data[0] == 0xEF && data[1] == 0xBB && data[2] == 0xBF) i = 3;         // UTF-8 byte order mark
+    if (i + 5 < n && memcmp(data + i, "<?xml", 5) == 0 && is_xml_space(data[i + 5])) {
+        if (!xml_declaration(src, i, &i)) return tags;
+    }
     while (i < n) {
-        if (d[i] != '<') {
-            // character data: only white space is legal outside the root element; control bytes never are
-            const unsigned char c = d[i];
-            if (c < 0x20 && !is_xml_space(c)) return tags;
-            if ((depth == 0) && !is_xml_space(c)) return tags;
-            i++;
+        if (data[i] != '<') {
+            uint32_t cp;
+            const int len = src.at(i, &cp);
+            if (!len) return tags;
+            if (open.empty()) { if (!is_xml_space(cp)) return tags; }                  // only white space outside the root
+            else if (cp == '&') { const size_t r = reference_at(src, i, nullptr); if (!r) return tags; i += r; continue; }
+            else if (cp == ']' && i + 2 < n && data[i + 1] == ']' && data[i + 2] == '>') return tags;
+            i += len;
             continue;
         }
         if (i + 1 >= n) return tags;
-        if (d[i + 1] == '?') {                                                          // declaration / processing instruction
-            size_t j = i + 2;
-            while (j + 1 < n && !(d[j] == '?' && d[j + 1] == '>')) j++;
-            if (j + 1 >= n) return tags;
-            i = j + 2;
+        if (data[i + 1] == '?') {                                                       // processing instruction
+            std::string target;
+            const size_t tl = name_at(src, i + 2, &target);
+            if (!tl) return tags;
+            std::string low;
+            for (char c : target) low += (char)tolower((unsigned char)c);
+            if (low == "xml") return tags;                                              // the declaration is only legal at the start
+            size_t j = i + 2 + tl;
+            if (!(j + 1 < n && data[j] == '?' && data[j + 1] == '>') && !(j < n && is_xml_space(data[j]))) return tags;
+            const size_t e = find_terminator(src, j, "?>");
+            if (e == (size_t)-1) return tags;
+            i = e + 2;
             continue;
         }
-        if (d[i + 1] == '!') {
-            if (i + 3 < n && d[i + 2] == '-' && d[i + 3] == '-') {                      // comment
-                size_t j = i + 4;
-                while (j + 2 < n && !(d[j] == '-' && d[j + 1] == '-' && d[j + 2] == '>')) j++;
-                if (j + 2 >= n) return tags;
-                i = j + 3;
+        if (data[i + 1] == '!') {
+            if (i + 3 < n && data[i + 2] == '-' && data[i + 3] == '-') {                // comment: no "--" inside
+                const size_t e = find_terminator(src, i + 4, "--");
+                if (e == (size_t)-1 || e + 2 >= n || data[e + 2] != '>') return tags;
+                i = e + 3;
                 continue;
             }
-            if (depth > 0 && i + 8 < n && memcmp(d + i, "<![CDATA[", 9) == 0) {
-                size_t j = i + 9;
-                while (j + 2 < n && !(d[j] == ']' && d[j + 1] == ']' && d[j + 2] == '>')) j++;
-                if (j + 2 >= n) return tags;
-                i = j + 3;
+            if (!open.empty() && i + 9 <= n && memcmp(data + i, "<![CDATA[", 9) == 0) {
+                const size_t e = find_terminator(src, i + 9, "]]>");
+                if (e == (size_t)-1) return tags;
+                i = e + 3;
                 continue;
             }
-            size_t j = i + 2;                                                           // <!DOCTYPE ...> without an internal subset
-            while (j < n && d[j] != '>' && d[j] != '[') j++;
-            if (j >= n || d[j] == '[') return tags;
-            i = j + 1;
-            continue;
+            return tags;                                                                // DOCTYPE and the rest: not in metadata chunks
         }
-        if (d[i + 1] == '/') {                                                          // end tag
-            size_t j = i + 2;
-            while (j < n && d[j] != '>') j++;
-            if (j >= n || depth == 0) return tags;
-            if (--depth == 0) root_closed = true;
+        if (data[i + 1] == '/') {                                                       // end tag: must close the innermost element
+            std::string name;
+            const size_t nl = name_at(src, i + 2, &name);
+            size_t j = i + 2 + nl;
+            while (j < n && is_xml_space(data[j])) j++;
+            if (!nl || j >= n || data[j] != '>' || open.empty() || open.back() != name) return tags;
+            open.pop_back();
+            if (open.empty()) root_closed = true;
             i = j + 1;
             continue;
         }
         // start tag
-        if (depth == 0 && root_closed) return tags;                                    // a second root: junk after the document element
-        size_t j = i + 1;
-        if (!is_name_start(d[j])) return tags;
+        if (open.empty() && root_closed) return tags;                                  // junk after the document element
         XmlStartTag tag;
-        while (j < n && is_name_char(d[j])) tag.name += (char)d[j++];
+        const size_t nl = name_at(src, i + 1, &tag.name);
+        if (!nl) return tags;
+        size_t j = i + 1 + nl;
         bool self_closing = false, ok = false;
         while (j < n) {
             const size_t before = j;
-            while (j < n && is_xml_space(d[j])) j++;
+            while (j < n && is_xml_space(data[j])) j++;
             if (j >= n) break;
-            if (d[j] == '>') { ok = true; j++; break; }
-            if (d[j] == '/') { if (j + 1 < n && d[j + 1] == '>') { ok = true; self_closing = true; j += 2; } break; }
-            if (j == before || !is_name_start(d[j])) break;                             // attributes are separated by white space
-            std::string an;
-            while (j < n && is_name_char(d[j])) an += (char)d[j++];
-            while (j < n && is_xml_space(d[j])) j++;
-            if (j >= n || d[j] != '=') break;
+            if (data[j] == '>') { ok = true; j++; break; }
+            if (data[j] == '/') { if (j + 1 < n && data[j + 1] == '>') { ok = true; self_closing = true; j += 2; } break; }
+            if (j == before) break;                                                     // attributes are separated by white space
+            std::string an, av;
+            const size_t al = name_at(src, j, &an);
+            if (!al) break;
+            j += al;
+            while (j < n && is_xml_space(data[j])) j++;
+            if (j >= n || data[j] != '=') break;
             j++;
-            while (j < n && is_xml_space(d[j])) j++;
-            if (j >= n || (d[j] != '"' && d[j] != '\'')) break;
-            const unsigned char q = d[j++];
-            const size_t v0 = j;
-            while (j < n && d[j] != q) j++;
-            if (j >= n) break;
-            std::string av;
-            if (!decode_attr(d + v0, j - v0, av)) break;
-            j++;
+            while (j < n && is_xml_space(data[j])) j++;
+            if (j >= n || (data[j] != '"' && data[j] != '\'')) break;
+            const unsigned char q = data[j++];
+            bool closed = false;
+            while (j < n) {
+                if (data[j] == q) { closed = true; j++; break; }
+                uint32_t cp;
+                const int len = src.at(j, &cp);
+                if (!len || cp == '<') break;
+                if (cp == '&') { const size_t r = reference_at(src, j, &av); if (!r) break; j += r; continue; }
+                if (cp == '\t' || cp == '\n' || cp == '\r') av += ' '; else append_utf8(av, cp);   // attribute-value normalisation
+                j += len;
+            }
+            if (!closed) break;
             bool dup = false;
             for (auto& a : tag.attrs) dup |= a.first == an;
             if (dup) break;
             tag.attrs.emplace_back(std::move(an), std::move(av));
         }
         if (!ok) return tags;
+        if (!self_closing) open.push_back(tag.name);
+        else if (open.empty()) root_closed = true;
         tags.push_back(std::move(tag));
-        if (!self_closing) depth++;
-        else if (depth == 0) root_closed = true;
         i = j;
     }
     return tags;

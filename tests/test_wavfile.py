@@ -175,6 +175,14 @@ AUXI_CASES = {
     "undefined_entity": b'<r><Definition RadioModel="&nbsp;"/></r>',
     "wrong_element": b'<r><definition RadioCenterFreq="5"/></r>',
     "time_only_string": b'<r><Definition CurrentTimeUTC="not a time"/></r>',
+    "latin1_declared": b'<?xml version="1.0" encoding="ISO-8859-1"?><r><Definition RadioModel="caf\xe9 \xb5" RadioCenterFreq="7"/></r>',
+    "latin1_undeclared": b'<r><Definition RadioModel="caf\xe9" RadioCenterFreq="7"/></r>',
+    "utf8_declared_standalone": b'<?xml version="1.0" encoding="UTF-8" standalone="yes"?><r><Definition RadioModel="caf\xc3\xa9"/></r>',
+    "utf16_declared_in_bytes": b'<?xml version="1.0" encoding="UTF-16"?><r><Definition RadioCenterFreq="7"/></r>',
+    "declaration_not_first": b' <?xml version="1.0"?><r><Definition RadioCenterFreq="7"/></r>',
+    "mismatched_end_tag": b'<r><a></b><Definition RadioCenterFreq="7"/></r>',
+    "comment_with_double_dash": b'<r><!-- a -- b --><Definition RadioCenterFreq="7"/></r>',
+    "non_ascii_names": b'<r \xc3\xa9l\xc3\xa9ment="1"><Definition RadioCenterFreq="7" \xc3\x97="bad"/></r>',
     "sdruno_binary": sdruno_auxi(),
     "binary_no_freq": sdruno_auxi(freq=0),
     "binary_short": sdruno_auxi()[:35],
@@ -372,3 +380,33 @@ def test_probe_rf64_with_an_absurd_ds64_size_is_clipped_to_the_file(tmp_path):
     path.write_bytes(blob)
     info = G.wav_probe(str(path))
     assert (info.frames, info.data_bytes, info.data_offset) == (321, len(payload), len(blob) - len(payload))
+
+
+def test_xml_scanner_against_expat_on_mutated_documents():
+    """Differential check of the product's XML scanner against pyexpat (the reference's parser): 5000 seeded
+    mutations of an SDR Console chunk — byte flips, deletions, insertions of markup characters / NULs / broken
+    UTF-8, spliced elements, comments, references, CDATA, processing instructions, byte-order marks."""
+    import random
+    rng = random.Random(20261017)
+    alphabet = b"<>&;\"'=/ ?!-[]ab1#x\0\n\t" + bytes([0xC3, 0xA9, 0xFF])
+    fragments = [b'<Definition RadioCenterFreq="5"/>', b"<!-- x -->", b"&amp;", b"&#x41;", b'<a b="c">', b"</a>", b"<?p?>",
+                 b"<![CDATA[z]]>", b' RadioModel="Q"', b"\xef\xbb\xbf", b'<?xml version="1.0" encoding="ISO-8859-1"?>', b"\xe9"]
+    for it in range(5000):
+        b = bytearray(SDRC_XML)
+        for _ in range(rng.randint(1, 3)):
+            op, pos = rng.randint(0, 3), rng.randrange(len(b))
+            if op == 0:
+                b[pos] = rng.choice(alphabet)
+            elif op == 1:
+                del b[pos:pos + rng.randint(1, 6)]
+            elif op == 2:
+                b.insert(pos, rng.choice(alphabet))
+            else:
+                b[pos:pos] = rng.choice(fragments)
+            if not b:
+                b = bytearray(b"<")
+        blob = bytes(b)
+        md = O.new_metadata()
+        want = O.parse_auxi(blob, md)
+        got, info = G.wav_parse_auxi(blob)
+        assert got == want and md_of(info) == md, (it, blob)
