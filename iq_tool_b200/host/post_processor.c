@@ -17,27 +17,34 @@
 #include "sample_convert.h"
 #include "signal_handler.h"
 
+/* EAGER mode: one module-level GPU chain per stage on the chunk's host buffers.  `at` follows the samples through the
+ * ping-pong pair: a stage that works out of place leaves them in the other buffer. */
+static complex_float_t *other_of(const SampleChunk *item, const complex_float_t *buf)
+{
+    return buf == item->complex_sample_buffer_a ? item->complex_sample_buffer_b : item->complex_sample_buffer_a;
+}
+
 static void post_eager(AppResources *resources, SampleChunk *item)
 {
-    AppConfig *config = (AppConfig *)resources->config;
-    if (item->frames_to_write == 0) return;
-    complex_float_t *cur = item->current_input_buffer;
-    if (resources->user_filter_object && config->apply_user_filter_post_resample) {
-        const bool fft = resources->user_filter_type_actual == FILTER_IMPL_FFT_SYMMETRIC ||
-                         resources->user_filter_type_actual == FILTER_IMPL_FFT_ASYMMETRIC;
+    const AppConfig *config = resources->config;
+    if (!item->frames_to_write) return;
+    complex_float_t *at = item->current_input_buffer;
+    const bool filter_here = resources->user_filter_object != NULL && config->apply_user_filter_post_resample;
+    if (filter_here) {
+        const FilterImplementationType impl = resources->user_filter_type_actual;
         item->frames_to_write = filter_apply(resources, item, true);
-        if (fft) cur = item->current_output_buffer;
+        /* the FFT forms write whole blocks into the chunk's output buffer, the FIR forms work in place */
+        if (impl == FILTER_IMPL_FFT_SYMMETRIC || impl == FILTER_IMPL_FFT_ASYMMETRIC) at = item->current_output_buffer;
     }
     if (resources->post_resample_nco) {
-        complex_float_t *dst = (cur == item->complex_sample_buffer_a) ? item->complex_sample_buffer_b : item->complex_sample_buffer_a;
-        freq_shift_apply(resources->post_resample_nco, resources->nco_shift_hz, cur, dst, item->frames_to_write);
-        cur = dst;
+        complex_float_t *mixed = other_of(item, at);
+        freq_shift_apply(resources->post_resample_nco, resources->nco_shift_hz, at, mixed, item->frames_to_write);
+        at = mixed;
     }
-    agc_apply(resources, cur, item->frames_to_write);
-    if (!convert_cf32_to_block(cur, item->final_output_data, item->frames_to_write, config->output_format)) {
-        handle_fatal_thread_error("Post-Processor: Failed to convert samples.", resources);
-        item->frames_to_write = 0;
-    }
+    agc_apply(resources, at, item->frames_to_write);
+    if (convert_cf32_to_block(at, item->final_output_data, item->frames_to_write, config->output_format)) return;
+    handle_fatal_thread_error("Post-Processor: Failed to convert samples.", resources);
+    item->frames_to_write = 0;
 }
 
 void post_processor_apply_chain(AppResources *resources, SampleChunk *item)
