@@ -64,6 +64,16 @@ def _timegm(year, month, day, hour, minute, sec):
     return None if ts == -1 else ts
 
 
+def _sscanf_ints(text: str, fmt: bytes, n: int):
+    """libc sscanf of n ints — the reference's own parser for its two time patterns, signs / spaces / short fields included."""
+    raw = text.encode("utf-8", "surrogateescape")
+    if b"\0" in raw:
+        raw = raw.split(b"\0")[0]
+    vals = [ctypes.c_int(0) for _ in range(n)]
+    got = _libc.sscanf(ctypes.c_char_p(raw), ctypes.c_char_p(fmt), *[ctypes.byref(v) for v in vals])
+    return got, [v.value for v in vals]
+
+
 def new_metadata() -> dict:
     """SdrMetadata after init_sdr_metadata (:140-144); keys appear only once they are 'present'."""
     return {"source_software": SDR_SOFTWARE_UNKNOWN}
@@ -89,9 +99,8 @@ def parse_auxi_xml(chunk: bytes, md: dict) -> bool:
                     md["timestamp_unix"] = int(v)
             elif k == "CurrentTimeUTC":
                 md["timestamp_str"] = v.encode("utf-8")[:63].decode("utf-8", "ignore")
-                m = re.match(r"\s*([+-]?\d+)-\s*([+-]?\d+)-\s*([+-]?\d+) \s*([+-]?\d+):\s*([+-]?\d+):\s*([+-]?\d+)", v)
-                if m:
-                    day, month, year, hour, minute, sec = (int(g) for g in m.groups())
+                got, (day, month, year, hour, minute, sec) = _sscanf_ints(v, b"%d-%d-%d %d:%d:%d", 6)
+                if got == 6:
                     ts = _timegm(year, month, day, hour, minute, sec)
                     if ts is not None:
                         md["timestamp_unix"] = ts
@@ -148,10 +157,11 @@ def parse_filename(base: str, md: dict) -> bool:
     if "timestamp_unix" not in md:
         for m in re.finditer(r"_", base):
             s = base[m.start():]
-            mm = re.match(r"_(\d{4})(\d{2})(\d{2})_(\d{2})(\d{2})(\d{2})Z", s)
-            if not mm:
+            if len(s.encode("utf-8", "surrogateescape")) < 17 or s[9:10] != "_" or s[16:17] != "Z":
                 continue
-            y, mo, d, h, mi, se = (int(g) for g in mm.groups())
+            got, (y, mo, d, h, mi, se) = _sscanf_ints(s, b"_%4d%2d%2d_%2d%2d%2dZ", 6)
+            if got != 6:
+                continue
             ts = _timegm(y, mo, d, h, mi, se)
             if ts is None or ts == -1:
                 continue

@@ -410,3 +410,22 @@ def test_xml_scanner_against_expat_on_mutated_documents():
         want = O.parse_auxi(blob, md)
         got, info = G.wav_parse_auxi(blob)
         assert got == want and md_of(info) == md, (it, blob)
+
+
+def test_filename_parser_against_the_restated_reference_on_random_names():
+    """4000 seeded names from the alphabet the two patterns care about (digits, '_', 'Z', 'Hz' in both cases, signs,
+    blanks, exponents), with valid fragments spliced in; the oracle scans with libc's sscanf / strtod / timegm."""
+    import random
+    rng = random.Random(7)
+    alphabet = "0123456789__ZzHh.e+- k"
+    pieces = ["_20150804_205628Z", "_97300000Hz", "SDRuno_", "SDRconnect_", "_1.0905e9hz", "_20201301_256199Z", "_IQ", ".wav", "_+2015-804_ 5 628Z"]
+    for it in range(4000):
+        n = rng.randint(0, 30)
+        name = "".join(rng.choice(alphabet) for _ in range(n))
+        for _ in range(rng.randint(0, 2)):
+            pos = rng.randint(0, len(name))
+            name = name[:pos] + rng.choice(pieces) + name[pos:]
+        md = O.new_metadata()
+        want = O.parse_filename(name, md)
+        got, info = G.wav_parse_filename(name)
+        assert got == want and md_of(info) == md, (it, name)
