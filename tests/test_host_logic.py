@@ -132,3 +132,19 @@ def test_fused_front_plans_keep_their_invariants(tmp_path):
                    stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout
+
+
+@pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+def test_closed_form_counts_at_maximum_sizes(name, workloads):
+    """The 64-bit closed form ceil(floor(N / 2^S) * 2^24 / step) of the product's host side against Python's big
+    integers, from one frame to 2^60 frames (a capture of centuries): no overflow anywhere on the way (the
+    intermediate product needs more than 64 bits from N = 2^(40+S) on)."""
+    g = gpu.Chain(workloads[name].config, device=-1)
+    info = g.info()
+    S, step = info.num_halfband, info.arb_step
+    assert step > 0
+    rng = np.random.Generator(np.random.PCG64(11))
+    sizes = [0, 1, 16383, 16384, 10**6, 10**9, 2**36 + 12345, 2**40 + 7, 10**13, 2**44 + 1, 2**52 + 5, 2**60 + 11]
+    sizes += [int(rng.integers(1, 2**62)) for _ in range(200)]
+    for n in sizes:
+        assert g.resampler_outputs_after(n) == -((-((n >> S) << 24)) // step), n
