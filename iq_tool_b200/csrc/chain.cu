@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <exception>
 #include <vector>
 
 #include "../../include/iqgpu.h"
@@ -1103,19 +1104,30 @@ int iqgpu_chain_get_info(iqgpu_chain* c, iqgpu_chain_info* o)
 static int build_chunks(iqgpu_chain* c, size_t n_frames, const uint32_t* chunk_frames, size_t n_chunks,
                         std::vector<uint32_t>& chunks)
 {
-    if (chunk_frames) {
-        size_t sum = 0;
-        chunks.assign(chunk_frames, chunk_frames + n_chunks);
-        for (auto f : chunks) sum += f;
-        if (sum != n_frames) return fail(IQGPU_EINVAL, "chunk lengths do not add up to n_frames");
-    } else {
-        chunks.clear();
-        size_t left = n_frames;
-        while (left) {
-            uint32_t f = (uint32_t)std::min<size_t>(left, c->chunk_frames);
-            chunks.push_back(f);
-            left -= f;
+    // the chunk table is host memory (4 B per chunk): a train beyond 2^30 chunks (1.7e13 frames) is refused rather than
+    // allowed to exhaust it, and no allocation failure may leave the C ABI as a C++ exception
+    constexpr size_t kMaxTrainChunks = (size_t)1 << 30;
+    try {
+        if (chunk_frames) {
+            if (n_chunks > kMaxTrainChunks) return fail(IQGPU_EINVAL, "train too long: more than 2^30 chunks in one call");
+            size_t sum = 0;
+            chunks.assign(chunk_frames, chunk_frames + n_chunks);
+            for (auto f : chunks) sum += f;
+            if (sum != n_frames) return fail(IQGPU_EINVAL, "chunk lengths do not add up to n_frames");
+        } else {
+            const size_t per = std::max<uint32_t>(1, c->chunk_frames);
+            if (n_frames / per >= kMaxTrainChunks) return fail(IQGPU_EINVAL, "train too long: more than 2^30 chunks in one call");
+            chunks.clear();
+            chunks.reserve(n_frames / per + 1);
+            size_t left = n_frames;
+            while (left) {
+                uint32_t f = (uint32_t)std::min<size_t>(left, per);
+                chunks.push_back(f);
+                left -= f;
+            }
         }
+    } catch (const std::exception&) {
+        return fail(IQGPU_ENOMEM, "out of host memory for the chunk table");
     }
     return IQGPU_OK;
 }

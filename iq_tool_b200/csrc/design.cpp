@@ -233,8 +233,8 @@ bool design_resampler(float r, float as, bool passthrough, ResamplerPlan& p, std
 uint64_t arb_outputs_after(uint64_t pushes, uint32_t step)
 {
     // ceil(pushes * 2^24 / step); 64-bit arithmetic while it fits (the per-chunk bookkeeping calls this once per chunk),
-    // 128-bit intermediate beyond 2^40 pushes
-    if (pushes < (1ull << 40)) return ((pushes << 24) + step - 1) / step;
+    // 128-bit intermediate from 2^39 pushes on (pushes * 2^24 + step - 1 must stay below 2^64, and step < 2^32)
+    if (pushes < (1ull << 39)) return ((pushes << 24) + step - 1) / step;
     unsigned __int128 num = (unsigned __int128)pushes << 24;
     return (uint64_t)((num + step - 1) / step);
 }

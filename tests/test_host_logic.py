@@ -146,5 +146,13 @@ def test_closed_form_counts_at_maximum_sizes(name, workloads):
     rng = np.random.Generator(np.random.PCG64(11))
     sizes = [0, 1, 16383, 16384, 10**6, 10**9, 2**36 + 12345, 2**40 + 7, 10**13, 2**44 + 1, 2**52 + 5, 2**60 + 11]
     sizes += [int(rng.integers(1, 2**62)) for _ in range(200)]
+    # the hand-over from 64-bit to 128-bit arithmetic: pushes = N >> S around 2^39 and 2^40
+    sizes += [((2**k + d) << S) + e for k in (39, 40) for d in (-2, -1, 0, 1) for e in (0, (1 << S) - 1)]
     for n in sizes:
         assert g.resampler_outputs_after(n) == -((-((n >> S) << 24)) // step), n
+    # a train the host cannot tabulate (more than 2^30 chunks) is refused, not attempted
+    assert g.predict_output(10**9 + 1) > 0
+    with pytest.raises(gpu.IqGpuError, match="train too long"):
+        g.predict_output(2**44)
+    with pytest.raises(gpu.IqGpuError, match="train too long"):
+        g.predict_output(2**63)
