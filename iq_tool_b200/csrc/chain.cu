@@ -15,6 +15,7 @@
 #include <cstring>
 #include <string>
 #include <exception>
+#include <new>
 #include <vector>
 
 #include "../../include/iqgpu.h"
@@ -940,7 +941,7 @@ void* iqgpu_host_alloc(size_t bytes)
 void iqgpu_host_free(void* p) { if (p) cudaFreeHost(p); }
 size_t iqgpu_get_bytes_per_sample(int format) { return bytes_per_sample(format); }
 
-int iqgpu_chain_create(const iqgpu_chain_config* cfgp, int device, iqgpu_chain** out)
+static int chain_create_impl(const iqgpu_chain_config* cfgp, int device, iqgpu_chain** out, iqgpu_chain*& in_flight)
 {
     if (!cfgp || !out) return fail(IQGPU_EINVAL, "null argument");
     *out = nullptr;
@@ -950,6 +951,7 @@ int iqgpu_chain_create(const iqgpu_chain_config* cfgp, int device, iqgpu_chain**
     if (!is_complex_format(g.output_format) || !bytes_per_sample(g.output_format))
         return fail(IQGPU_EINVAL, "unhandled output format");      // sample_convert.c:304
     iqgpu_chain* c = new iqgpu_chain();
+    in_flight = c;                  // the caller frees it if a design step throws
     c->cfg = g;
     c->device = device;
     c->plan_only = device < 0;
@@ -958,7 +960,7 @@ int iqgpu_chain_create(const iqgpu_chain_config* cfgp, int device, iqgpu_chain**
     c->in_bps = bytes_per_sample(g.input_format);
     c->out_bps = bytes_per_sample(g.output_format);
     std::string err;
-    auto bail = [&](int code, const std::string& m) { delete c; return fail(code, m); };
+    auto bail = [&](int code, const std::string& m) { in_flight = nullptr; delete c; return fail(code, m); };
     if (c->in_rate <= 0) return bail(IQGPU_EINVAL, "input sample rate must be positive");
     // setup.c:91-113
     if (g.no_resample) c->target_rate = (double)c->in_rate;
@@ -1009,10 +1011,29 @@ int iqgpu_chain_create(const iqgpu_chain_config* cfgp, int device, iqgpu_chain**
     }
     if (!c->plan_only) {
         int rc = c->init_device();
-        if (rc != IQGPU_OK) { std::string m = g_err; delete c; return fail(rc, m); }
+        if (rc != IQGPU_OK) { std::string m = g_err; in_flight = nullptr; delete c; return fail(rc, m); }
     }
+    in_flight = nullptr;
     *out = c;
     return IQGPU_OK;
+}
+
+// No C++ exception may cross the C ABI: a configuration whose design cannot be carried out (a tap count that does not
+// fit memory, a length that went negative before its cast ...) is refused like any other invalid configuration.
+int iqgpu_chain_create(const iqgpu_chain_config* cfgp, int device, iqgpu_chain** out)
+{
+    iqgpu_chain* in_flight = nullptr;
+    try {
+        return chain_create_impl(cfgp, device, out, in_flight);
+    } catch (const std::bad_alloc&) {
+        delete in_flight;
+        if (out) *out = nullptr;
+        return fail(IQGPU_ENOMEM, "out of host memory while designing the chain");
+    } catch (const std::exception& e) {
+        delete in_flight;
+        if (out) *out = nullptr;
+        return fail(IQGPU_EINVAL, std::string("configuration cannot be designed: ") + e.what());
+    }
 }
 
 void iqgpu_chain_destroy(iqgpu_chain* c) { delete c; }
