@@ -112,16 +112,21 @@ class ClockSampler:
         return out
 
 
-# algorithmic bytes per INPUT sample for each kernel class of a workload
+def dc_local_state(cfg, info):
+    """DC blocker evaluated with a local state per warp stretch (no pre-pass over the input; a closed-form correction pass
+    over the resampled stream instead)."""
+    return bool(cfg.dc_block and not cfg.iq_correction and not (cfg.freq_shift_hz and not cfg.shift_after_resample)
+                and info.fused_front)
+
+
+# ALGORITHMIC bytes per INPUT sample for each kernel class of a workload (SURVEY 8(d) / DESIGN.md Kernels): what an ideal
+# implementation must move.  Passes an implementation adds on top (the DC correction pass of the fused front: 16 r) show up
+# in `traffic` and in the time, never here.
 def class_bytes_per_sample(cfg, info):
     r = info.ratio
     inb, outb = cfg.in_bytes, cfg.out_bytes
-    # DC blocker evaluated with a local state per warp stretch: the fused-front class then also holds the closed-form
-    # correction pass over the resampled stream (read + write, 16 B per output frame) and no pre-pass over the input
-    dc_local = bool(cfg.dc_block and not cfg.iq_correction and not (cfg.freq_shift_hz and not cfg.shift_after_resample)
-                    and info.fused_front)
     return {
-        "fused_front": inb + 8.0 * r + (16.0 * r if dc_local else 0.0),   # raw in, resampled cf32 out (+ DC correction pass)
+        "fused_front": inb + 8.0 * r,          # raw in, resampled cf32 out
         "pre": inb + 8.0,                      # raw in, cf32 out
         "dc_scan": float(inb),                 # raw in
         "resampler": 8.0 + 8.0 * r,            # cf32 in, cf32 out (ideal, no inter-stage traffic)
@@ -188,12 +193,144 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores,
                          "kind": "reference" if kind != "oracle" else "port",
                          "sample": f"{n} input frames per step; reference stage sources (-O3 -ffast-math) on the "
-                                   f"restated liquid layer, pre/resampler/post stage threads as in pipeline.c:99-116"},
+                                   f"restated liquid layer (SCALAR dot products: a floor for a real AVX libliquid, not its "
+                                   f"speed), pre/resampler/post stage threads as in pipeline.c:99-116"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host_cpus": os.cpu_count(),
     }
     print(json.dumps(line))
     return 0
+
+
+class WorkloadRun:
+    """One workload on this rank: the HBM-resident capture (one time shard of it when world > 1), the chain, and the
+    step the bench times — `restart` (or closed-form seek to the shard lead) + one device-resident pass over the capture."""
+
+    def __init__(self, name, args, world, rank, local_rank, dev, stream, samples=0):
+        import torch
+        from iq_tool_b200 import baseline_workloads, gpu
+        from iq_tool_b200.configs import stage_workloads
+        from iq_tool_b200.shard import ShardedChain
+        from iq_tool_b200.synth import synth_torch
+        self.gpu, self.torch = gpu, torch
+        self.args, self.world, self.rank, self.local_rank, self.dev, self.stream = args, world, rank, local_rank, dev, stream
+        self.wl = {**baseline_workloads(), **stage_workloads()}[name]
+        self.cfg = self.wl.config
+        n = samples or self.wl.throughput_samples
+        self.n = n - n % 16384
+        # N > 1: the capture of world*n frames is time-sharded (iq_tool_b200/shard.py): closed-form seek, halo in front of
+        # the shard, and — for digital-AGC chains — the per-chunk peak exchange inside every step (the only collective; no
+        # sample data crosses GPUs)
+        self.sc = ShardedChain(self.cfg, local_rank, shard_frames_hint=self.n if world > 1 else 0, time_kernels=1,
+                               fused=args.fused, subtrain_frames=args.subtrain, dc_overlap=args.dc_overlap)
+        self.chain = self.sc.chain
+        self.info = self.chain.info()
+        self.replicas = False
+        if world > 1:
+            try:
+                self.chain.seek(0)
+            except gpu.IqGpuError:
+                self.replicas = True   # FFT-filter / RMS-AGC chains are not exactly shardable (DESIGN.md 5): N independent replicas
+        single = world == 1 or self.replicas
+        self.single = single
+        self.shard = self.sc.plan(self.n, 1)[0] if single else self.sc.plan(world * self.n, world)[rank]
+        self.halo = self.shard.start - self.shard.lead
+        self.raw = synth_torch(self.wl, self.shard.read_frames, dev, start=self.shard.lead)
+        self.out = torch.empty(self.chain.out_capacity_frames(self.n + self.halo) * self.cfg.out_bytes, dtype=torch.uint8, device=dev)
+        self.exchange = bool(self.sc.digital_agc and world > 1 and not self.replicas)
+        self.produced = 0
+
+    def step(self):
+        st = self.stream.cuda_stream
+        if self.single:
+            self.chain.restart()
+            self.produced = self.chain.process_device(self.raw.data_ptr(), self.n, self.out.data_ptr(), self.out.numel(), st)
+        else:
+            self.produced = self.sc.process_device(self.shard, self.raw.data_ptr(), self.out.data_ptr(), self.out.numel(), st,
+                                                   None, self.dev)[0]
+        return self.produced
+
+    def timed(self, steps, warmup, sampler=None, min_seconds=0.0):
+        """K steps (or, with min_seconds, as many whole batches of K as it takes) bracketed by CUDA events on the launch
+        stream, barrier + synchronize on both sides, max over ranks.  Returns (ms total, steps run, t0, t1 wall)."""
+        import torch.distributed as dist
+        torch = self.torch
+        for _ in range(warmup):
+            self.step()
+        self.chain.kernel_times(reset=True)
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        time.sleep(0.05)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        e0.record(self.stream)
+        done = 0
+        while True:
+            for _ in range(steps):
+                self.step()
+            done += steps
+            if min_seconds <= 0:
+                break
+            # the host runs far ahead of the device (no sync inside a batch): decide on the device's progress
+            e1.record(self.stream)
+            e1.synchronize()
+            el = e0.elapsed_time(e1)
+            if self.world > 1:          # every rank must take the same decision (the steps may hold a collective)
+                t = torch.tensor([el], device=self.dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                el = float(t.item())
+            if el >= 1e3 * min_seconds:
+                break
+        e1.record(self.stream)
+        torch.cuda.synchronize()
+        t1 = time.time()
+        if self.world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, done, t0, t1
+
+    def sharding_text(self):
+        if self.world == 1:
+            return "single stream"
+        if self.replicas:
+            return "replicas only (chain not exactly shardable)"
+        if self.exchange:
+            return "time shards; all-gather of per-chunk AGC peaks (4 B / 16384 frames), no sample data exchanged"
+        return "time shards, no collective"
+
+
+def pcie_probe(world, dev, nbytes=1 << 30, reps=3):
+    """Plain pinned-host -> device copies, all ranks at once: the platform's ceiling for the end-to-end leg, per rank.
+    (SCALE_r01's box shows every GPU behind one NUMA node, `nvidia-smi topo`: CPU affinity 0-31, NUMA 0 — there is no
+    placement to choose; this records what the host side of each GPU delivers when all of them pull together.)"""
+    import torch
+    import torch.distributed as dist
+    host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    host.zero_()
+    devb = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    devb.copy_(host, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        devb.copy_(host, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    gbs = reps * nbytes / (e0.elapsed_time(e1) / 1e3) / 1e9
+    if world > 1:
+        t = torch.zeros(world, device=dev, dtype=torch.float64)
+        t[dist.get_rank()] = gbs
+        dist.all_reduce(t)
+        return [round(float(v), 2) for v in t.cpu().tolist()]
+    return [round(gbs, 2)]
 
 
 def main():
@@ -212,6 +349,11 @@ def main():
     ap.add_argument("--dc-overlap", type=int, default=1)
     ap.add_argument("--subtrain", type=int, default=1 << 30, help="frames per sub-train (kernel launch group) of the HBM-resident leg")
     ap.add_argument("--e2e-subtrain", type=int, default=1 << 25, help="frames per sub-train of the host-buffer leg (H2D/compute/D2H pipeline depth)")
+    ap.add_argument("--sustained-seconds", type=float, default=2.0, help="second timed leg: back-to-back steps for at least this long (0 = off)")
+    ap.add_argument("--sharded-capture", default="cfg5",
+                    help="second workload measured in the same run and reported as `sharded_capture` (BASELINE.json configs[4], the "
+                         "multi-GPU configuration: time shards + the AGC peak all-gather); '' = off")
+    ap.add_argument("--no-pcie-probe", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -221,99 +363,59 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from iq_tool_b200 import baseline_workloads, gpu
-    from iq_tool_b200.synth import synth_torch
+    from iq_tool_b200 import gpu
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if gpu.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device; iq_tool_b200 has no CPU fallback")
+    # one rank = one GPU = its own share of the host cores (the staging threads of the end-to-end leg stay put)
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        if world > 1 and len(cpus) >= 2 * world:
+            per = len(cpus) // world
+            os.sched_setaffinity(0, set(cpus[local_rank * per:(local_rank + 1) * per]))
+    except (AttributeError, OSError):
+        pass
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-
-    from iq_tool_b200.configs import stage_workloads
-    wl = {**baseline_workloads(), **stage_workloads()}[args.workload]
-    cfg = wl.config
-    n = args.samples or wl.throughput_samples
-    n -= n % 16384
-
-    # N > 1: the capture of world*n frames is time-sharded (iq_tool_b200/shard.py): closed-form seek,
-    # halo in front of the shard, and — for digital-AGC chains — the per-chunk peak exchange inside
-    # every step (the only collective; no sample data crosses GPUs)
-    from iq_tool_b200.shard import ShardedChain
-    sc = ShardedChain(cfg, local_rank, shard_frames_hint=n if world > 1 else 0, time_kernels=1, fused=args.fused,
-                      subtrain_frames=args.subtrain, dc_overlap=args.dc_overlap)
-    chain = sc.chain
-    info = chain.info()
-    replicas = False
-    if world > 1:
-        try:
-            chain.seek(0)
-        except gpu.IqGpuError:
-            replicas = True       # FFT-filter / RMS-AGC chains are not exactly shardable: N independent replicas
-    shard = sc.plan(n, 1)[0] if (world == 1 or replicas) else sc.plan(world * n, world)[rank]
-    halo = shard.start - shard.lead
-    shard_start = shard.start
-    raw = synth_torch(wl, shard.read_frames, dev, start=shard.lead)
-    out_frames_max = chain.out_capacity_frames(n + halo)
-    out = torch.empty(out_frames_max * cfg.out_bytes, dtype=torch.uint8, device=dev)
     # an explicit (non-default) stream: the chain's kernels are launched on it and the timing events are recorded on it
     # (a NULL stream handle would make the chain use its own internal stream, invisible to torch's events)
     stream = torch.cuda.Stream(device=dev)
     stream.wait_stream(torch.cuda.current_stream())
     torch.cuda.set_stream(stream)
-    exchange = bool(sc.digital_agc and world > 1 and not replicas)
 
-    def rewind():
-        # single stream: plain reset (works for every chain); shards: closed-form seek to the shard lead
-        if world == 1 or replicas:
-            chain.reset()
-        else:
-            chain.seek(shard.lead)
-
-    def step():
-        if world == 1 or replicas:
-            chain.reset()
-            return chain.process_device(raw.data_ptr(), n, out.data_ptr(), out.numel(), stream.cuda_stream)
-        return sc.process_device(shard, raw.data_ptr(), out.data_ptr(), out.numel(), stream.cuda_stream, None, dev)[0]
+    run = WorkloadRun(args.workload, args, world, rank, local_rank, dev, stream, args.samples)
+    wl, cfg, chain, n, halo = run.wl, run.cfg, run.chain, run.n, run.halo
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for _ in range(args.warmup):
-        produced = step()
-    chain.kernel_times(reset=True)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    time.sleep(0.05)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    t0 = time.time()
-    e0.record(stream)
-    for _ in range(args.steps):
-        produced = step()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    t1 = time.time()
-    if world > 1:
-        dist.barrier()
+    ms, steps_done, t0, t1 = run.timed(args.steps, args.warmup)
     clocks = sampler.stop(t0, t1)
-    ms = e0.elapsed_time(e1)
     ktimes = chain.kernel_times(reset=True)
     launches_per_step = chain.info().kernel_launches
-    if world > 1:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    produced = run.produced
     value = world * n * args.steps / (ms / 1e3) / 1e6
+
+    # ---- sustained leg: the same step back to back for >= 2 s (power / clock behaviour of a long run) ----
+    sustained = None
+    if args.sustained_seconds > 0:
+        s2 = ClockSampler(local_rank)
+        s2.start()
+        sms, sdone, st0, st1 = run.timed(args.steps, 1, min_seconds=args.sustained_seconds)
+        sclk = s2.stop(st0, st1)
+        chain.kernel_times(reset=True)
+        sustained = {"value": world * n * sdone / (sms / 1e3) / 1e6, "unit": UNIT, "seconds": sms / 1e3, "steps": sdone,
+                     "ms_per_step": sms / sdone, "clocks": sclk}
 
     # ---- end-to-end: host buffers through the C ABI (pinned host memory, H2D + D2H inside) ----
     e2e = None
     if args.e2e_steps > 0:
         import ctypes as C
+        raw, out, shard, sc, exchange = run.raw, run.out, run.shard, run.sc, run.exchange
         nbytes = (n + halo) * cfg.in_bytes
         hin = gpu.lib.iqgpu_host_alloc(nbytes)
         hout = gpu.lib.iqgpu_host_alloc(out.numel())
@@ -335,8 +437,8 @@ def main():
                     torch.cuda.synchronize()
                     nout.value = k
                     return
-                if world == 1 or replicas:
-                    e2e_chain.reset()
+                if run.single:
+                    e2e_chain.restart()
                 else:
                     e2e_chain.seek(shard.lead)
                 gpu._check(gpu.lib.iqgpu_chain_process(e2e_chain._h, hin, n + halo, None, 0, hout, out.numel(),
@@ -347,16 +449,44 @@ def main():
             tt0 = time.perf_counter()
             for _ in range(args.e2e_steps):
                 e2e_step()
-            dt = time.perf_counter() - tt0
+            dt_own = time.perf_counter() - tt0
+            dt = dt_own
+            per_rank_s = [dt_own]
             if world > 1:
-                t = torch.tensor([dt], device=dev, dtype=torch.float64)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                dt = float(t.item())
+                t = torch.zeros(world, device=dev, dtype=torch.float64)
+                t[rank] = dt_own
+                dist.all_reduce(t)
+                per_rank_s = [float(v) for v in t.cpu().tolist()]
+                dt = max(per_rank_s)
             e2e = {"value": world * n * args.e2e_steps / dt / 1e6, "unit": UNIT,
                    "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(nout.value * cfg.out_bytes),
-                   "steps": args.e2e_steps, "host_memory": "pinned (iqgpu_host_alloc)"}
+                   "steps": args.e2e_steps, "host_memory": "pinned (iqgpu_host_alloc)",
+                   "per_rank_gbs_h2d": [round(nbytes * args.e2e_steps / s_ / 1e9, 2) for s_ in per_rank_s]}
             gpu.lib.iqgpu_host_free(hin)
             gpu.lib.iqgpu_host_free(hout)
+            if not exchange:
+                e2e_chain.close()
+        if not args.no_pcie_probe:
+            probe = pcie_probe(world, dev)
+            if e2e is not None:
+                # what plain pinned copies reach on the same box with every rank copying at once: the leg's ceiling
+                e2e["pcie_probe_gbs_h2d_per_rank"] = probe
+                e2e["fraction_of_probe_min_rank"] = round(min(e2e["per_rank_gbs_h2d"]) / max(min(probe), 1e-9), 3)
+
+    # ---- BASELINE.json configs[4], the multi-GPU configuration, in the same run: cfg5 time-sharded with the peak exchange ----
+    sharded = None
+    if args.sharded_capture and args.sharded_capture != args.workload:
+        del run.raw, run.out
+        run2 = WorkloadRun(args.sharded_capture, args, world, rank, local_rank, dev, stream)
+        k2 = max(5, min(args.steps, 20))
+        ms2, _, _, _ = run2.timed(k2, 3)
+        kt2 = run2.chain.kernel_times(reset=True)
+        sharded = {"workload": f"{run2.wl.name}: {run2.wl.description}", "value": world * run2.n * k2 / (ms2 / 1e3) / 1e6,
+                   "unit": UNIT, "n_gpus": world, "steps": k2, "ms_per_step": ms2 / k2, "frames_per_gpu_per_step": run2.n,
+                   "halo_frames": run2.halo, "sharding": run2.sharding_text(), "scaling": "weak",
+                   "kernel_ms_per_step": {k: v[0] / k2 for k, v in kt2.items()},
+                   "note": "efficiency at N = value(N) / (N * value(1)) of THIS object across the per-N lines"}
+        del run2
 
     if rank != 0:
         if world > 1:
@@ -384,21 +514,33 @@ def main():
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                     "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                     "launch_ms": per_launch_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                    "algorithmic_bytes_per_input_frame": bps.get(dom, 0.0),
                     "share_of_step": dom_ms / (ms if world == 1 else sum(v[0] for v in ktimes.values()))}
-    flops = chain_flops_per_sample(cfg, info)
-    sm_mhz = clocks.get("sm_mhz") or 1965.0
+        if dom == "fused_front" and dc_local_state(cfg, chain.info()):
+            roofline["note"] = ("launch_ms spans the front kernel, the DC stretch scan and the closed-form DC correction pass over "
+                                "the resampled stream; that pass's own read + write (16 r bytes per input frame) is NOT counted "
+                                "as algorithmic traffic (SURVEY 8(d): input + 8 r)")
+    flops = chain_flops_per_sample(cfg, run.info)
     fp32_peak_nominal = 148 * 128 * 2 * 1.965e9 / 1e12
-    fp32 = {"achieved_tflops": flops * value * 1e6 / world / 1e12, "peak_tflops_nominal": fp32_peak_nominal,
-            "frac_of_nominal": flops * value * 1e6 / world / 1e12 / fp32_peak_nominal,
-            "flops_per_input_sample": flops, "peak_tflops_at_observed_clock": 148 * 128 * 2 * sm_mhz * 1e6 / 1e12}
+    try:
+        fp32_measured = gpu.fp32_peak_tflops(local_rank)
+    except gpu.IqGpuError:
+        fp32_measured = None
+    ach = flops * value * 1e6 / world / 1e12
+    fp32 = {"achieved_tflops": ach, "peak_tflops_measured": fp32_measured,
+            "frac_of_measured": (ach / fp32_measured) if fp32_measured else None,
+            "peak_source": "FFMA2 micro-benchmark in libiqgpu.so (iqgpu_ubench_fp32_peak), this run",
+            "peak_tflops_nominal": fp32_peak_nominal, "frac_of_nominal": ach / fp32_peak_nominal,
+            "flops_per_input_sample": flops}
 
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ----
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
+        from iq_tool_b200.synth import synth_torch
         from oracle.loader import CpuChain, have_ref
         kind = "ref_fast" if have_ref(fast=True) else "oracle"
         m = min(n, 8 * args.cpu_samples)          # about 10 s of CPU work at ~50 Msamples/s
-        sample = raw[: 2 * m].cpu().numpy()
+        sample = synth_torch(wl, m, dev).cpu().numpy()
         ch = CpuChain(cfg, kind)
         ch.process(sample[: 2 * (1 << 20)], threaded=(kind != "oracle"))
         ch = CpuChain(cfg, kind)
@@ -408,8 +550,8 @@ def main():
         cpu = {"value": m / dt / 1e6, "unit": UNIT, "cores": 3 if kind != "oracle" else 1,
                "kind": "reference" if kind != "oracle" else "port",
                "sample": f"first {m} frames of the same capture; reference stage sources on the restated liquid "
-                         f"layer, one thread per stage (pre/resampler/post) as pipeline.c:99-116; host has "
-                         f"{os.cpu_count()} cpus"}
+                         f"layer (SCALAR dot products: a floor for a real AVX libliquid, not its speed), one thread per "
+                         f"stage (pre/resampler/post) as pipeline.c:99-116; host has {os.cpu_count()} cpus"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -417,12 +559,11 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{wl.name}: {wl.description}", "frames_per_gpu_per_step": n, "halo_frames": halo,
                    "output_frames_per_step": int(produced), "l2_policy": "inputs larger than L2 (no flush needed)",
-                   "sharding": ("single stream" if world == 1 else "replicas only (chain not exactly shardable)" if replicas else
-                                "time shards; all-gather of per-chunk AGC peaks (4 B / 16384 frames), no sample data exchanged"
-                                if exchange else "time shards, no collective"),
+                   "sharding": run.sharding_text(),
                    "fused_front": int(chain.info().fused_front),
                    "chunk_frames": 16384},
-        "roofline": roofline, "fp32": fp32, "cpu_baseline": cpu, "e2e": e2e,
+        "roofline": roofline, "fp32": fp32, "cpu_baseline": cpu, "e2e": e2e, "sustained": sustained,
+        "sharded_capture": sharded,
         "gpu_launches": int(launches_per_step) * args.steps, "clocks": clocks,
         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items()},
     }

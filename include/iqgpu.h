@@ -142,11 +142,18 @@ void        iqgpu_host_free(void *p);
 int  iqgpu_chain_create(const iqgpu_chain_config *cfg, int device, iqgpu_chain **out);
 void iqgpu_chain_destroy(iqgpu_chain *c);
 /* stream discontinuity: pre_processor_reset + resampler_reset + post_processor_reset
- * (include/pre_processor.h:34, include/resampler.h:43, include/post_processor.h:34) */
+ * (include/pre_processor.h:34, include/resampler.h:43, include/post_processor.h:34).  As in the reference, filter_reset
+ * (src/filter.c:417-436) clears the FFT filter's overlap state but NOT the count of frames waiting for a full block: with
+ * an FFT filter those frames re-enter the new stream in front of its first chunk. */
 int  iqgpu_chain_reset(iqgpu_chain *c);
+/* the state right after iqgpu_chain_create (nothing of the old stream survives): rewinding a benchmark or a test */
+int  iqgpu_chain_restart(iqgpu_chain *c);
 int  iqgpu_chain_get_info(iqgpu_chain *c, iqgpu_chain_info *info);
 /* runtime knobs: "fused" (0/1), "subtrain_frames", "chunk_frames", "record_taps" (0/1),
- * "time_kernels" (0/1: bracket every kernel class with CUDA events on the launch stream) */
+ * "time_kernels" (0/1: bracket every kernel class with CUDA events on the launch stream),
+ * "dc_mode" (0 = DC blocker in exact arithmetic, the chunk-train default; 1 = the reference's fp32 direct-form-II state
+ * rounding of liquid's iirfilt_crcf (src/dc_block.c:76-85), evaluated serially: what the module-level dc_block_apply
+ * drop-in uses on its 16384-frame chunks — set before the first process call) */
 int  iqgpu_chain_set_option(iqgpu_chain *c, const char *key, int64_t value);
 /* kernel classes for iqgpu_chain_get_kernel_times */
 enum {
@@ -341,6 +348,11 @@ int    iqgpu_convert_cf32_to_block(const float *in_cf32, void *out, size_t n_fra
  * stores them. */
 int  iqgpu_iq_optimize(const float *block1024_cf32, const float *directions50,
                        float *mag, float *phase, float *avg_power, float *power_range);
+
+/* ---- diagnostics (not on the data path) --------------------------------------------------------------------------
+ * FP32 FMA peak of `device` in TFLOP/s, measured with the instruction the kernels spend their FLOPs in (packed FFMA2 with
+ * a warp-uniform tap): the denominator of the FP32 roofline bench.py reports (BASELINE.md asks for the measured figure). */
+int  iqgpu_ubench_fp32_peak(int device, double *tflops, double *kernel_ms /* optional */);
 
 #ifdef __cplusplus
 }

@@ -77,6 +77,9 @@ class ChainConfig:
     iq_mag: float = 0.0
     iq_phase: float = 0.0
     freq_shift_hz: float = 0.0
+    # False: --freq-shift, a float CLI argument (argparse.c:110); True: the double AppResources.nco_shift_hz that the WAV
+    # input derives from centre-frequency metadata (input_wav.c:614-628), generally not a float
+    freq_shift_is_double: bool = False
     shift_after_resample: bool = False
     no_resample: bool = False
     # (type, freq1_hz, freq2_hz) as built by reference src/config.c:192-216
@@ -115,7 +118,7 @@ class ChainConfig:
         c.iq_correction_enable = int(self.iq_correction)
         c.iq_mag, c.iq_phase = self.iq_mag, self.iq_phase
         c.shift_after_resample = int(self.shift_after_resample)
-        c.freq_shift_hz = f32(self.freq_shift_hz)
+        c.freq_shift_hz = float(self.freq_shift_hz) if self.freq_shift_is_double else f32(self.freq_shift_hz)
         c.no_resample = int(self.no_resample)
         c.num_filter_requests = len(self.filters)
         for i, (t, a, b) in enumerate(self.filters):

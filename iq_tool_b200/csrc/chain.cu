@@ -77,6 +77,12 @@ struct DevStream {
         pos = hist;
         return hist ? cudaMemsetAsync(base, 0, hist * sizeof(float2), st) : cudaSuccess;
     }
+    // stream discontinuity that keeps the newest `keep` samples where they are and clears the history below them
+    cudaError_t reset_keep_tail(cudaStream_t st, size_t keep)
+    {
+        if (keep >= hist) return cudaSuccess;
+        return cudaMemsetAsync(base + pos - hist, 0, (hist - keep) * sizeof(float2), st);
+    }
     // make room for n new samples; returns pointer to the first new sample
     cudaError_t begin(size_t n, cudaStream_t st, float2** p)
     {
@@ -144,6 +150,9 @@ struct iqgpu_chain {
     size_t subtrain_frames = (size_t)1 << 22;
     uint32_t chunk_frames = IQGPU_CHUNK_SAMPLES;
     bool want_fused = true;
+    // 0: DC blocker in exact arithmetic (blocked affine scan, double carries); 1: the reference's fp32 direct-form-II state
+    // rounding, evaluated serially (launch_dc_reference) — module-level dc_block_apply and parity tests
+    int dc_mode = 0;
     bool record_taps = false;
     bool record_tap0 = false;   // tap 0 (pre-processor output) only exists on the unfused path
     bool fused_used = false;
@@ -154,6 +163,10 @@ struct iqgpu_chain {
     uint64_t n_nco_post = 0;  // samples that went through the post NCO
     uint64_t n_out = 0;
     uint32_t fft_rem = 0;     // FFT filter remainder length (frames waiting for a full block)
+    // F5: filter_reset (src/filter.c:417-436) clears the liquid object but NOT pre/post_fft_remainder_len, so the frames that
+    // were waiting for a full block re-enter the new stream in front of its first chunk.  A pre-resample remainder then
+    // counts as resampler input of the new stream: fft_rem_carry = its length at the reset.
+    uint32_t fft_rem_carry = 0;
     uint32_t launches = 0;
 
     // ---- device state ----
@@ -178,6 +191,7 @@ struct iqgpu_chain {
     cudaStream_t last_stream = nullptr;   // stream of the most recent process call
     float* d_lut = nullptr;
     double2* d_dc_carry = nullptr;
+    float2* d_dc_ref = nullptr;          // dc_mode 1: liquid's v0 {re, im} in fp32
     double2 *d_run_sums = nullptr, *d_run_start = nullptr;
     double* d_scan_ws = nullptr;
     size_t max_runs = 0;
@@ -262,7 +276,8 @@ struct iqgpu_chain {
     ~iqgpu_chain();
     int init_device();
     int ensure_buffers();
-    int reset_state();
+    // keep_fft_remainder: the reference's stream-discontinuity semantics (F5); false = the state right after create
+    int reset_state(bool keep_fft_remainder = false);
     size_t max_out_for(size_t n_frames) const;
     // closed-form per-chunk output frame counts from the current position (no state change)
     size_t count_outputs(const uint32_t* chunks, size_t n_chunks, uint32_t* per_chunk) const;
@@ -300,7 +315,7 @@ iqgpu_chain::~iqgpu_chain()
     collect_spans();
     for (auto e : ev_pool) cudaEventDestroy(e);
     for (auto* t : d_hb_taps) cudaFree(t);
-    cudaFree(d_lut); cudaFree(d_dc_carry); cudaFree(d_run_sums); cudaFree(d_run_start); cudaFree(d_scan_ws); cudaFree(d_bank);
+    cudaFree(d_lut); cudaFree(d_dc_carry); cudaFree(d_dc_ref); cudaFree(d_run_sums); cudaFree(d_run_start); cudaFree(d_scan_ws); cudaFree(d_bank);
     cudaFree(d_fir_taps); cudaFree(d_fft_H); cudaFree(d_fft_tw); cudaFree(d_fft_scratch); cudaFree(d_agc); cudaFree(d_seg_start);
     cudaFree(d_seg_peak); cudaFree(d_seg_gain); cudaFree(d_agc_scratch); cudaFree(d_agc_ws);
     for (auto& t : prefix_tabs) cudaFree(t.d_seg);
@@ -351,7 +366,7 @@ size_t iqgpu_chain::count_outputs(const uint32_t* chunks, size_t n_chunks, uint3
     const bool fft = filter_is_fft(filt);
     const bool pre_fft = fft && !filt.post_resample, post_fft = fft && filt.post_resample;
     uint32_t rem = fft_rem;
-    uint64_t pos = pre_fft ? n_in - fft_rem : n_in;
+    uint64_t pos = pre_fft ? n_in + fft_rem_carry - fft_rem : n_in;
     uint64_t before = resampler_outputs_after(rs, pos), total = 0;
     if (!fft && !per_chunk) {       // only the total is wanted and nothing quantises per chunk: closed form over the whole train
         uint64_t sum = 0;
@@ -399,6 +414,7 @@ int iqgpu_chain::init_device()
     CK(cudaMalloc(&d_lut, sizeof(lut)));
     CK(cudaMemcpy(d_lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
     CK(cudaMalloc(&d_dc_carry, sizeof(double2)));
+    CK(cudaMalloc(&d_dc_ref, sizeof(float2)));
     CK(cudaMalloc(&d_agc, sizeof(AgcState)));
     if (!rs.passthrough) {
         d_hb_taps.resize(rs.num_halfband, nullptr);
@@ -481,7 +497,7 @@ int iqgpu_chain::ensure_buffers()
     const bool post_filter = filt.impl != IQGPU_FILTER_IMPL_NONE && filt.post_resample;
     const size_t filt_hist = filter_is_fir(filt) ? fir_taps_padded : (filter_is_fft(filt) ? 2 * (size_t)filt.block : 0);
 
-    fused_active = fused && want_fused && !record_tap0;
+    fused_active = fused && want_fused && !record_tap0 && !(dc.enable && dc_mode == 1);
     // s_in: consumer is the pre-filter, else the first resampler stage, else nothing
     size_t in_hist = 0;
     if (pre_filter) in_hist = filt_hist;
@@ -545,15 +561,19 @@ __global__ void agc_state_init_kernel(AgcState* st, AgcState v) { *st = v; }
 // Stream discontinuity.  All device state lives behind the stream the chain last ran on, so the reset is QUEUED there
 // (memsets + one tiny kernel, no host synchronisation: the host may go on enqueueing the next train while the previous
 // one still runs); a later call on another stream first waits for ev_reset.
-int iqgpu_chain::reset_state()
+int iqgpu_chain::reset_state(bool keep_fft_remainder)
 {
-    n_in = 0; n_nco_post = 0; n_out = 0; fft_rem = 0;
+    const bool pre_fft = filter_is_fft(filt) && !filt.post_resample, post_fft = filter_is_fft(filt) && filt.post_resample;
+    const uint32_t keep = (keep_fft_remainder && (pre_fft || post_fft)) ? fft_rem : 0;
+    n_in = 0; n_nco_post = 0; n_out = 0; fft_rem = keep;
+    fft_rem_carry = pre_fft ? keep : 0;
     if (plan_only || !buffers_ready) return IQGPU_OK;
     CK(cudaSetDevice(device));
     cudaStream_t S = last_stream ? last_stream : stream;
     dc_prepared = false;
     front_recorded[0] = front_recorded[1] = false;
     CK(cudaMemsetAsync(d_dc_carry, 0, sizeof(double2), S));
+    CK(cudaMemsetAsync(d_dc_ref, 0, sizeof(float2), S));
     AgcState a{};
     a.locked = 0; a.gain = 1.0f; a.seen = 0; a.last_strong = 0.0;
     a.peak_mem = (agc_mode == 1) ? 0.05f : 0.001f;   // agc.c:66,78
@@ -561,11 +581,11 @@ int iqgpu_chain::reset_state()
     agc_state_init_kernel<<<1, 1, 0, S>>>(d_agc, a);
     CK(cudaGetLastError());
     if (fused) CK(fused_reset(fused, S));
-    if (s_in.base) CK(s_in.reset(S));
+    if (s_in.base) CK((keep && pre_fft) ? s_in.reset_keep_tail(S, keep) : s_in.reset(S));
     if (s_pref.base) CK(s_pref.reset(S));
     if (s_arb_in.base) CK(s_arb_in.reset(S));
     for (auto& s : s_stage) if (s.base) CK(s.reset(S));
-    CK(s_rs.reset(S));
+    CK((keep && post_fft) ? s_rs.reset_keep_tail(S, keep) : s_rs.reset(S));
     if (s_f.base) CK(s_f.reset(S));
     CK(cudaEventRecord(ev_reset, S));
     reset_stream = S;
@@ -651,6 +671,26 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
         uint32_t rows = (uint32_t)((n + 127) / 128), rpr = 1;
         while (rpr < 32 && rows / rpr > 16384) rpr <<= 1;
         const uint32_t run_len = 128 * rpr;
+        if (dc.enable && dc_mode == 1) {
+            // reference rounding: convert, then liquid's fp32 recurrence literally (serial), then I/Q apply + NCO in place
+            PreParams p1 = pp;
+            p1.dc_enable = 0; p1.iq_enable = 0; p1.nco_enable = 0;
+            span_begin(IQGPU_KCLASS_PRE, st);
+            CK(launch_pre(d_rawp, n, p1, run_len, nullptr, x_in, st));
+            span_end(st);
+            span_begin(IQGPU_KCLASS_DC_SCAN, st);
+            CK(launch_dc_reference(x_in, n, dc.c, d_dc_ref, st));
+            span_end(st);
+            launches += 2;
+            if (pp.iq_enable || pp.nco_enable) {
+                PreParams p2 = pp;
+                p2.format = IQGPU_FMT_CF32; p2.gain = 1.0f; p2.dc_enable = 0;
+                span_begin(IQGPU_KCLASS_PRE, st);
+                CK(launch_pre(x_in, n, p2, run_len, nullptr, x_in, st));
+                span_end(st);
+                launches++;
+            }
+        } else {
         if (dc.enable) {
             const size_t n_runs = (n + run_len - 1) / run_len;
             if (n_runs > max_runs) return fail(IQGPU_EINVAL, "internal: run table too small");
@@ -664,6 +704,7 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
         CK(launch_pre(d_rawp, n, pp, run_len, d_run_start, x_in, st));
         span_end(st);
         launches++;
+        }
         s_in.commit(n);
         if (record_tap0) CK(tap[0].append(x_in, n, st));
 
@@ -688,7 +729,7 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
                     CK(launch_fftfilt(x_in - fft_rem, blocks, filt.block, d_fft_H, d_fft_tw, y, d_fft_scratch, &launches, st));
                 }
                 s_pref.commit((size_t)blocks * filt.block);
-                rs_pos0 = N0 - fft_rem;
+                rs_pos0 = N0 + fft_rem_carry - fft_rem;
                 fft_rem = tot - blocks * filt.block;
                 rs_src = y; rs_n = (size_t)blocks * filt.block;
             }
@@ -971,7 +1012,9 @@ static int chain_create_impl(const iqgpu_chain_config* cfgp, int device, iqgpu_c
     if (g.dc_block_enable && c->dc.alpha <= 0.0f) return bail(IQGPU_EINVAL, "DC block alpha invalid");
     c->iq_mag = g.iq_mag; c->iq_phase = g.iq_phase;
     // frequency_shift.c:24-84
-    const double shift = (double)(float)g.freq_shift_hz;
+    // AppResources.nco_shift_hz is a double (frequency_shift.c:32-33 widens the float CLI argument, input_wav.c:614-628
+    // stores centre - (double)target): no float round trip here, callers that emulate --freq-shift cast themselves
+    const double shift = g.freq_shift_hz;
     if (g.shift_after_resample && std::fabs(shift) < 1e-9)
         return bail(IQGPU_EINVAL, "--shift-after-resample used without an effective frequency shift");
     if (std::fabs(shift) >= 1e-9) {
@@ -1041,7 +1084,13 @@ void iqgpu_chain_destroy(iqgpu_chain* c) { delete c; }
 int iqgpu_chain_reset(iqgpu_chain* c)
 {
     if (!c) return fail(IQGPU_EINVAL, "null chain");
-    return c->reset_state();
+    return c->reset_state(true);
+}
+
+int iqgpu_chain_restart(iqgpu_chain* c)
+{
+    if (!c) return fail(IQGPU_EINVAL, "null chain");
+    return c->reset_state(false);
 }
 
 int iqgpu_chain_set_option(iqgpu_chain* c, const char* key, int64_t value)
@@ -1051,6 +1100,12 @@ int iqgpu_chain_set_option(iqgpu_chain* c, const char* key, int64_t value)
     if (k == "fused") {
         if (c->buffers_ready) return fail(IQGPU_EINVAL, "option must be set before the first process call");
         c->want_fused = value != 0;
+        return IQGPU_OK;
+    }
+    if (k == "dc_mode") {
+        if (c->buffers_ready) return fail(IQGPU_EINVAL, "option must be set before the first process call");
+        if (value != 0 && value != 1) return fail(IQGPU_EINVAL, "dc_mode: 0 (exact arithmetic) or 1 (reference fp32 state rounding)");
+        c->dc_mode = (int)value;
         return IQGPU_OK;
     }
     if (k == "record_taps") {

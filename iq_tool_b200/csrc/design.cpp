@@ -226,6 +226,13 @@ bool design_resampler(float r, float as, bool passthrough, ResamplerPlan& p, std
         }
         halo += (uint64_t)(p.arb_sub_len) << S;
         p.halo_input_frames = halo;
+    } else {
+        // interpolation: the arbitrary stage runs first, at the input rate, over a window of 2*7 input frames; interpolator s
+        // (design index s, input rate rate_arb * 2^s > 2^s input rates) looks back 2 m_s samples of its own input, i.e. fewer
+        // than 2 m_s / 2^s input frames; two frames of slack per stage for the rounding of the mapped-back positions
+        uint64_t halo = p.arb_sub_len;
+        for (unsigned s = 0; s < S; s++) halo += ((uint64_t)(2 * p.stages[s].m) + ((1ull << s) - 1)) / (1ull << s) + 2;
+        p.halo_input_frames = halo;
     }
     return true;
 }

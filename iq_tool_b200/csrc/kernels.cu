@@ -414,6 +414,50 @@ cudaError_t launch_pre(const void* raw, size_t n, const PreParams& p, uint32_t r
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// DC blocker, REFERENCE ROUNDING (dc_mode 1): liquid's iirfilt_crcf in direct form II keeps the integrator state
+// v ~ dc / alpha in fp32 and rounds it twice per sample (dc_block.c:76-85 -> iirfilt_crcf_execute_block):
+//     v0 = x - a1 * v1 ;  y = (0 + b0 * v0) + b1 * v1      a1 = -1 + alpha, b = {1, -1}
+// That rounding sequence is a property of the serial evaluation and only a serial evaluation reproduces it: one thread per
+// component walks the stream (8 dependent cycles per sample, ~250 Msamples/s).  It exists for the module-level
+// dc_block_apply drop-in (16384-frame chunks, where it costs what a launch costs) and for the parity tests; the chunk-train
+// path evaluates the same difference equation in exact arithmetic (DC blocker).
+// ---------------------------------------------------------------------------------------------
+constexpr int DCREF_TILE = 2048;
+__global__ void __launch_bounds__(256, 1) dc_reference_kernel(float2* __restrict__ x, size_t n, float a1, float2* __restrict__ state)
+{
+    __shared__ float tile[2 * DCREF_TILE];
+    const int t = threadIdx.x;
+    float v = 0.f;
+    if (t < 2) v = reinterpret_cast<const float*>(state)[t];
+    for (size_t base = 0; base < n; base += DCREF_TILE) {
+        const size_t cnt = (n - base < (size_t)DCREF_TILE) ? n - base : (size_t)DCREF_TILE;
+        float* g = reinterpret_cast<float*>(x + base);
+        for (size_t i = t; i < 2 * cnt; i += 256) tile[i] = g[i];
+        __syncthreads();
+        if (t < 2) {
+#pragma unroll 8
+            for (size_t k = 0; k < cnt; k++) {
+                const float xin = tile[2 * k + t];
+                const float v1 = v;
+                v = __fsub_rn(xin, __fmul_rn(a1, v1));
+                tile[2 * k + t] = __fadd_rn(__fadd_rn(0.f, __fmul_rn(1.0f, v)), __fmul_rn(-1.0f, v1));
+            }
+        }
+        __syncthreads();
+        for (size_t i = t; i < 2 * cnt; i += 256) g[i] = tile[i];
+        __syncthreads();
+    }
+    if (t < 2) reinterpret_cast<float*>(state)[t] = v;
+}
+
+cudaError_t launch_dc_reference(float2* x, size_t n, float dc_c, float2* state, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    dc_reference_kernel<<<1, 256, 0, st>>>(x, n, -dc_c, state);
+    return cudaGetLastError();
+}
+
 // =============================================================================================
 // K2 (unfused building blocks): liquid msresamp_crcf pieces, reference src/resampler.c:49
 // =============================================================================================

@@ -43,6 +43,10 @@ size_t dc_scan_workspace_doubles(size_t n_runs);
 cudaError_t launch_pre(const void* raw, size_t n, const PreParams& p, uint32_t run_len,
                        const double2* run_start, float2* out, cudaStream_t st);
 
+// DC blocker with the reference's fp32 state rounding (liquid iirfilt_crcf, direct form II), serial, in place on a cf32
+// stream; state = v0 {re, im} carried across calls (device memory)
+cudaError_t launch_dc_reference(float2* x, size_t n, float dc_c, float2* state, cudaStream_t st);
+
 // ---- K2: resampler building blocks (unfused) -------------------------------------------------
 // x points at the stream sample with absolute index a0 (history lies at negative offsets).
 // Produces outputs k in [k0, k0+count): y[k-k0].  h1: 2m taps, oldest first.

@@ -658,6 +658,8 @@ int iqgpu_wavfile_run(const iqgpu_chain_config* cfg_in, int device, const char* 
         fclose(fin);
         return fail("Option --wav-center-target-freq needs a WAV input");
     }
+    // setup.c:99: with --no-resample the target rate IS the source rate (known only now for a WAV input)
+    if (cfg.no_resample) cfg.target_rate_hz = (double)(int)cfg.input_rate_hz;
     // output side: wav_common_validate_options + wav_common_initialize (src/output_wav_common.c:46-118)
     unsigned char header[80];
     const size_t header_bytes = iqgpu_wav_header_bytes(out_container);

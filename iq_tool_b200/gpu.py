@@ -103,6 +103,7 @@ def _load() -> C.CDLL:
     lib.iqgpu_chain_create.argtypes = [C.POINTER(ChainConfigC), C.c_int, C.POINTER(vp)]
     lib.iqgpu_chain_destroy.argtypes = [vp]
     lib.iqgpu_chain_reset.argtypes = [vp]
+    lib.iqgpu_chain_restart.argtypes = [vp]
     lib.iqgpu_chain_get_info.argtypes = [vp, C.POINTER(ChainInfoC)]
     lib.iqgpu_chain_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     lib.iqgpu_chain_set_iq_factors.argtypes = [vp, C.c_float, C.c_float]
@@ -143,13 +144,15 @@ def _load() -> C.CDLL:
     for name in ("iqgpu_wav_probe", "iqgpu_wav_parse_auxi", "iqgpu_wav_parse_filename",
                  "iqgpu_wav_center_target_shift", "iqgpu_wav_build_header", "iqgpu_wavfile_run"):
         getattr(lib, name).restype = C.c_int
+    lib.iqgpu_ubench_fp32_peak.restype = C.c_int
+    lib.iqgpu_ubench_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.iqgpu_get_bytes_per_sample.restype = sz
     lib.iqgpu_get_bytes_per_sample.argtypes = [C.c_int]
     lib.iqgpu_convert_block_to_cf32.argtypes = [vp, vp, sz, C.c_int, C.c_float]
     lib.iqgpu_convert_cf32_to_block.argtypes = [vp, vp, sz, C.c_int]
     lib.iqgpu_iq_optimize.argtypes = [vp, vp, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                       C.POINTER(C.c_float), C.POINTER(C.c_float)]
-    for name in ("iqgpu_chain_reset", "iqgpu_chain_get_info", "iqgpu_chain_set_option",
+    for name in ("iqgpu_chain_reset", "iqgpu_chain_restart", "iqgpu_chain_get_info", "iqgpu_chain_set_option",
                  "iqgpu_chain_set_iq_factors", "iqgpu_chain_process", "iqgpu_chain_process_device",
                  "iqgpu_chain_predict_output", "iqgpu_chain_read_tap", "iqgpu_chain_get_filter_taps",
                  "iqgpu_chain_get_halfband_taps", "iqgpu_chain_get_arb_taps", "iqgpu_chain_seek",
@@ -173,6 +176,13 @@ def _check(rc: int) -> None:
 
 def device_count() -> int:
     return lib.iqgpu_device_count()
+
+
+def fp32_peak_tflops(device: int = 0) -> float:
+    """Measured FP32 FMA peak (packed FFMA2 micro-benchmark inside the library), TFLOP/s."""
+    t = C.c_double(0.0)
+    _check(lib.iqgpu_ubench_fp32_peak(device, C.byref(t), None))
+    return t.value
 
 
 class Chain:
@@ -207,7 +217,12 @@ class Chain:
         _check(lib.iqgpu_chain_set_iq_factors(self._h, mag, phase))
 
     def reset(self) -> None:
+        """Stream discontinuity with the reference's semantics (an FFT filter's waiting frames survive, filter.c:417-436)."""
         _check(lib.iqgpu_chain_reset(self._h))
+
+    def restart(self) -> None:
+        """Back to the state right after create."""
+        _check(lib.iqgpu_chain_restart(self._h))
 
     def info(self) -> ChainInfoC:
         o = ChainInfoC()

@@ -167,6 +167,10 @@ iqgpu_chain *iqgpu_dropin_module(IqGpuDropin *d, int stage)
             log_fatal("GPU chain: module-level chain (stage %d) failed: %s", stage, iqgpu_last_error());
             *slot = NULL;
         }
+        /* the module-level DC blocker reproduces liquid's fp32 state rounding (serial evaluation: on one 16384-frame
+         * chunk it costs what a kernel launch costs); IQGPU_DC_EXACT=1 selects the exact-arithmetic scan instead */
+        const char *ex = getenv("IQGPU_DC_EXACT");
+        if (*slot && stage == IQGPU_STAGE_DC && !(ex && *ex && *ex != '0')) iqgpu_chain_set_option(*slot, "dc_mode", 1);
     }
     return *slot;
 }
@@ -192,6 +196,10 @@ static bool ensure_fused(IqGpuDropin *d)
     if (!iqgpu_dropin_configure(d)) return false;
     if (d->fused) return true;
     if (iqgpu_chain_create(&d->cfg, d->device, &d->fused) != IQGPU_OK) { d->fused = NULL; return false; }
+    /* chunk trains evaluate the DC blocker in exact arithmetic (DC blocker); IQGPU_DC_REFERENCE=1 trades the
+     * fused front for liquid's literal fp32 recurrence (serial, ~250 Msamples/s) when bit-level agreement matters more */
+    const char *lit = getenv("IQGPU_DC_REFERENCE");
+    if (lit && *lit && *lit != '0') iqgpu_chain_set_option(d->fused, "dc_mode", 1);
     return true;
 }
 

@@ -164,32 +164,66 @@ class ShardedChain:
         self._plans = {(s.world, s.rank, s.start, s.frames): shards for s in shards}
         return shards
 
+    def _exchange_buffers(self, world: int, m: int, device):
+        import torch
+        key = (world, m, str(device))
+        bufs = getattr(self, "_xbufs", None)
+        if bufs is None or bufs[0] != key:
+            bufs = (key, torch.zeros(m, dtype=torch.float32, device=device),
+                    torch.zeros(world * m, dtype=torch.float32, device=device))
+            self._xbufs = bufs
+        return bufs[1], bufs[2]
+
+    @staticmethod
+    def _on_stream(stream: int):
+        """torch's current stream must be the stream the chain runs on: the copy of the peaks into the send buffer, the
+        all-gather and the scan kernel that reads the gathered buffer are ordered by that one stream."""
+        import torch
+        if not stream:
+            raise ValueError("the device-side AGC exchange needs an explicit CUDA stream (stream=0 would leave the chain on "
+                             "its private stream and the collective on torch's: unordered)")
+        return torch.cuda.stream(torch.cuda.ExternalStream(stream))
+
     def _finish_device_exchange(self, shard: Shard, shards: List[Shard], dev_out_ptr: int, out_capacity_bytes: int,
                                 stream: int, group, device) -> int:
         """The digital-AGC exchange without a host round trip: the shard's per-chunk peaks go from the chain into the
         send buffer of ONE all-gather (NCCL over NVLink), and every rank advances its device-resident AGC state over the
         lower ranks' slices of the gathered buffer with the chunk-table scan kernel (chunk frame counts are closed
-        form), then finishes its own shard.  Same kernel, same chunks, same order as the single stream -> same bits."""
-        import torch
+        form), then finishes its own shard.  Same kernel, same chunks, same order as the single stream -> same bits.
+
+        A rank whose shard is empty (more ranks than chunks) takes part in the same collective with a zero-filled send
+        buffer, so that every rank issues the same sequence of collectives."""
         import torch.distributed as dist
 
         ch = self.chain
         sizes = [(t.frames + CHUNK_SAMPLES - 1) // CHUNK_SAMPLES for t in shards]
         m = max(max(sizes), 1)
-        key = (shard.world, m, str(device))
-        bufs = getattr(self, "_xbufs", None)
-        if bufs is None or bufs[0] != key:
-            bufs = (key, torch.zeros(m, dtype=torch.float32, device=device),
-                    torch.zeros(shard.world * m, dtype=torch.float32, device=device))
-            self._xbufs = bufs
-        _, mine, gathered = bufs
-        live = ch.pending_chunk_peaks_device(shard.skip_chunks, mine.data_ptr(), m, stream)
-        assert live == sizes[shard.rank]
-        dist.all_gather_into_tensor(gathered, mine, group=group)          # on torch's current stream == `stream`
-        for r in range(shard.rank):
-            if shards[r].frames:
-                ch.agc_advance_device(gathered.data_ptr() + 4 * r * m, shards[r].start, shards[r].frames, stream)
-        return ch.process_device_finish(shard.skip_chunks, dev_out_ptr, out_capacity_bytes, stream)
+        mine, gathered = self._exchange_buffers(shard.world, m, device)
+        with self._on_stream(stream):
+            if shard.read_frames:
+                live = ch.pending_chunk_peaks_device(shard.skip_chunks, mine.data_ptr(), m, stream)
+                assert live == sizes[shard.rank]
+            else:
+                mine.zero_()
+            dist.all_gather_into_tensor(gathered, mine, group=group)
+            if not shard.read_frames:
+                return 0
+            # lower shards, in rank order.  The first one holds the scan-to-lock transition (a tile walk); the others are
+            # usually quiet at the locked gain and, when their tables are full (sizes == m) and whole chunks, contiguous in
+            # the gathered buffer: ONE scan launch covers all of them (the quiet test is a parallel pass over the table).
+            lower = [r for r in range(shard.rank) if shards[r].frames]
+            while lower:
+                r0 = lower[0]
+                run = [r0]
+                if r0 != 0:
+                    while (len(run) < len(lower) and lower[len(run)] == run[-1] + 1 and sizes[run[-1]] == m and
+                           shards[run[-1]].frames % CHUNK_SAMPLES == 0 and
+                           shards[run[-1]].start + shards[run[-1]].frames == shards[lower[len(run)]].start):
+                        run.append(lower[len(run)])
+                ch.agc_advance_device(gathered.data_ptr() + 4 * r0 * m, shards[r0].start,
+                                      sum(shards[r].frames for r in run), stream)
+                lower = lower[len(run):]
+            return ch.process_device_finish(shard.skip_chunks, dev_out_ptr, out_capacity_bytes, stream)
 
     def process_device(self, shard: Shard, dev_in_ptr: int, dev_out_ptr: int, out_capacity_bytes: int,
                        stream: int = 0, group=None, comm_device="cpu") -> Tuple[int, int]:
@@ -198,19 +232,24 @@ class ShardedChain:
         out_lead = ch.seek(shard.lead)
         assert out_lead == shard.out_lead
         n = shard.read_frames
+        exchange = self.digital_agc and shard.world > 1
+        plan = getattr(self, "_plans", {}).get((shard.world, shard.rank, shard.start, shard.frames))
+        sizes = getattr(self, "_table_sizes", {}).get((shard.world, shard.rank, shard.start, shard.frames))
+        on_device = exchange and plan is not None and str(comm_device).startswith("cuda")
         if n == 0:
-            if self.digital_agc and shard.world > 1:
+            # an empty shard (more ranks than chunks) still takes part in the exchange, in the form its peers use
+            if on_device:
+                self._finish_device_exchange(shard, plan, dev_out_ptr, out_capacity_bytes, stream, group, comm_device)
+            elif exchange:
                 exchange_agc_state(np.zeros(0, np.float32), np.zeros(0, np.uint32), self.agc_target,
-                                   self.target_rate, group, comm_device)
+                                   self.target_rate, group, comm_device, sizes)
             return 0, 0
-        if not (self.digital_agc and shard.world > 1):
+        if not exchange:
             return ch.process_device(dev_in_ptr, n, dev_out_ptr, out_capacity_bytes, stream), shard.drop
         ch.process_device_begin(dev_in_ptr, n, stream)
-        plan = getattr(self, "_plans", {}).get((shard.world, shard.rank, shard.start, shard.frames))
-        if plan is not None and str(comm_device).startswith("cuda"):
+        if on_device:
             return self._finish_device_exchange(shard, plan, dev_out_ptr, out_capacity_bytes, stream, group, comm_device), shard.drop
         peaks, counts = ch.pending_chunk_peaks()
-        sizes = getattr(self, "_table_sizes", {}).get((shard.world, shard.rank, shard.start, shard.frames))
         state = exchange_agc_state(peaks[shard.skip_chunks:], counts[shard.skip_chunks:], self.agc_target,
                                    self.target_rate, group, comm_device, sizes)
         ch.set_agc_state(state)

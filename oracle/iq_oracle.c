@@ -711,7 +711,9 @@ void *iqo_create(const iq_chain_cfg *cfg)
         c->iq_mag = cfg->iq_mag; c->iq_phase = cfg->iq_phase;
     }
     /* N1: one NCO, pre at Fs_in or post at target rate     reference src/frequency_shift.c:24-84 */
-    c->shift_hz = (double)(float)cfg->freq_shift_hz;
+    /* AppResources.nco_shift_hz is a double: a float CLI argument arrives widened (frequency_shift.c:32-33),
+     * a WAV centre-target shift does not fit a float at all (input_wav.c:614-628) */
+    c->shift_hz = cfg->freq_shift_hz;
     if (cfg->shift_after_resample && fabs(c->shift_hz) < 1e-9) goto fail;
     if (fabs(c->shift_hz) >= 1e-9) {
         double rate = cfg->shift_after_resample ? c->target_rate : (double)c->in_rate;

@@ -173,7 +173,9 @@ void *iqref_create(const iq_chain_cfg *c)
         r->iq_correction.factors_buffer[0].phase = c->iq_phase;
         r->iq_correction.factors_buffer[1] = r->iq_correction.factors_buffer[0];
     }
-    r->nco_shift_hz = 0.0;
+    /* a shift that is not a float (WAV centre-target metadata, input_wav.c:614-628) arrives in nco_shift_hz itself;
+     * a float --freq-shift is widened by freq_shift_create (frequency_shift.c:32-33) */
+    r->nco_shift_hz = ((double)(float)c->freq_shift_hz != c->freq_shift_hz) ? c->freq_shift_hz : 0.0;
     if (!freq_shift_create(&h->config, r)) goto fail;
     r->resampler = create_resampler(&h->config, r, ratio);
     if (!r->resampler && !r->is_passthrough) goto fail;

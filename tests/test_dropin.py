@@ -118,7 +118,16 @@ def test_dropin_fused_equals_direct_chain_and_reference(name, n, gpu, workloads)
     # stream discontinuity (pre/resampler/post resets as the marker flows through): stream restarts
     d2.reset()
     head = raw[: 2 * 5 * 16384]
-    assert np.array_equal(d2.process(head), gpu.Chain(wl.config, 0).process(head))
+    after = d2.process(head)
+    if wl.config.filters and wl.config.filter_taps == 4095:
+        # FFT filter: the frames that were waiting for a full block survive filter_reset (filter.c:417-436, F5) and lead
+        # the new stream — the reference does exactly that, so the reference after the same reset is the yardstick
+        r2 = CpuChain(wl.config, "ref" if have_ref() else "oracle")
+        r2.process(raw)
+        r2.reset()
+        _tolerance_check(wl.config, after, r2.process(head))
+    else:
+        assert np.array_equal(after, gpu.Chain(wl.config, 0).process(head))
 
 
 @pytest.mark.gpu
@@ -127,11 +136,8 @@ def test_dropin_fused_equals_direct_chain_and_reference(name, n, gpu, workloads)
 def test_dropin_eager_module_api_matches_reference(name, n, gpu, workloads, monkeypatch):
     """EAGER mode: every module function (convert, dc_block_apply, iq_correct_apply, freq_shift_apply,
     resampler_execute, filter_apply, agc_apply, convert) does its own work on host buffers."""
-    import dataclasses
-    wl = workloads[name]
-    if wl.config.dc_block:
-        wl = dataclasses.replace(wl, dc=0.0)               # DC-blocker exception, see test_gpu_parity
-    raw = synth_numpy(wl, n)
+    wl = workloads[name]                                   # as specified: cfg4 keeps its DC offset and I/Q imbalance
+    raw = synth_numpy(wl, n)                               # (the module-level dc_block_apply reproduces liquid's fp32 rounding)
     monkeypatch.setenv("IQGPU_DROPIN_EAGER", "1")
     d = CpuChain(wl.config, "dropin")
     d.capture(0, n + 16)
@@ -143,11 +149,9 @@ def test_dropin_eager_module_api_matches_reference(name, n, gpu, workloads, monk
     ref = r.process(raw)
     assert rel_rms_fullscale(d.captured(0), r.captured(0)) <= 1e-5     # pre-processor output (buffer A on the host)
     assert rel_rms_fullscale(d.captured(1), r.captured(1)) <= 1e-5     # resampler output
-    if wl.config.agc_enable and wl.config.output_format == "cf32":
-        a, b = out.view(np.complex64), ref.view(np.complex64)
-        assert rel_rms_fullscale(a, b) <= 3e-5 and snr_db(a, b) >= 97.0
-    else:
-        _tolerance_check(wl.config, out, ref)
+    from helpers import parity_metrics, record_parity
+    record_parity(f"dropin_eager/{name}", parity_metrics(wl.config, out, ref))
+    _tolerance_check(wl.config, out, ref)
 
 
 @pytest.mark.gpu

@@ -24,6 +24,12 @@ pytestmark = pytest.mark.gpu
 CF32_RMS_TOL = 1e-5     # of full scale (north_star)
 CF32_SNR_DB = 100.0
 INT_LSB_TOL = 1
+# The documented exception (DC blocker): measured deviation of the exact-arithmetic DC blocker from the
+# reference's fp32 state rounding on the as-specified inputs, plus margin.  Measured values: profiles/r02_parity.md.
+CFG2_DC_EXCEPTION_MAX_LSB = 6
+CFG2_DC_EXCEPTION_RMS_LSB = 1.0
+CFG4_DC_EXCEPTION_REL_RMS = 1e-4
+CFG4_DC_EXCEPTION_SNR_DB = 80.0
 
 
 def _oracle_kind():
@@ -95,6 +101,8 @@ def test_cfg2_chain_without_dc_offset_meets_the_bar(gpu, workloads):
     assert np.array_equal(counts, o.traced())
     assert rel_rms_fullscale(g.read_tap(0), o.captured(0)) <= CF32_RMS_TOL
     assert snr_db(g.read_tap(1), o.captured(1)) >= CF32_SNR_DB
+    from helpers import parity_metrics, record_parity
+    record_parity("cfg2/dc_offset_removed/dc_mode=0", parity_metrics(wl.config, out, ref))
     _check_final(wl.config, out, ref)
 
 
@@ -140,19 +148,97 @@ def test_dc_block_is_exact_arithmetic_and_reference_differs_only_by_its_state_ro
     assert rel_rms_fullscale(y2, gpu_y) <= 2e-8
 
 
-@pytest.mark.parametrize("name,n", [("cfg2", (1 << 22) + 333)])
-def test_baseline_config_parity_with_dc(name, n, gpu, workloads):
-    """cfg2 as specified (dc = 0.02): counts exact; outputs within the bound the reference's own
-    integrator rounding allows (see the test above): 3 ulp(v_max) of full scale, in cs16 LSBs."""
-    wl = workloads[name]
+# ---------------------------------------------------------------------------------------------
+# cfg2 / cfg4 AS SPECIFIED (BASELINE.json: dc = 0.02 / 0.03, cfg4 with its I/Q imbalance and pinned factors), at
+# SURVEY 8(d)'s parity sizes, against the reference's own stage code.  Two evaluations of the DC blocker:
+#   dc_mode 1  liquid's fp32 direct-form-II recurrence, literally (serial kernel): the whole chain must meet the
+#              north_star bar as written — this pins every other stage of the two configs on their specified inputs;
+#   dc_mode 0  the chunk-train default (exact arithmetic, fused front): what it differs by is the reference's own state
+#              rounding noise; the deviation is MEASURED, recorded (gpurun_out/parity_r02.jsonl -> profiles/) and bounded
+#              by that measurement plus a small margin — the one documented exception (DC blocker).
+# ---------------------------------------------------------------------------------------------
+def _as_specified(gpu, wl, n, **opts):
     raw = synth_numpy(wl, n)
-    g, o, out, ref, counts = _run_pair(gpu, wl.config, raw)
-    assert np.array_equal(counts, o.traced())
-    x = raw.astype(np.float64).view(np.complex128) / 32768.0
-    _, vmax = _dc_reference_f64(x, wl.config.input_rate_hz)
-    bound_lsb = int(np.ceil(3.0 * float(np.spacing(np.float32(vmax))) * 32767.0)) + 1
+    o = CpuChain(wl.config, _oracle_kind())
+    o.trace(n // 16384 + 4)
+    ref = o.process(raw)
+    g = gpu.Chain(wl.config, 0, **opts)
+    out, counts = g.process(raw, return_chunk_counts=True)
+    assert np.array_equal(counts, o.traced())               # per-chunk frames_to_write: exact
     assert out.size == ref.size
-    assert max_lsb(out, ref) <= bound_lsb
+    return g, out, ref
+
+
+def test_cfg2_as_specified_with_reference_dc_rounding_meets_the_bar(gpu, workloads):
+    from helpers import parity_metrics, record_parity
+    wl = workloads["cfg2"]
+    g, out, ref = _as_specified(gpu, wl, wl.parity_samples, dc_mode=1)
+    m = parity_metrics(wl.config, out, ref)
+    record_parity("cfg2/as_specified/dc_mode=1", m)
+    assert g.info().fused_front == 0
+    assert m["max_lsb"] <= INT_LSB_TOL, m
+
+
+def test_cfg2_as_specified_default_path_measured_deviation(gpu, workloads):
+    """The headline bench configuration on its specified input through the path the bench times (fused front, local DC
+    state).  Measured on B200 (profiles/r02_parity.md): see the bound below."""
+    from helpers import error_spectrum_db, parity_metrics, record_parity
+    wl = workloads["cfg2"]
+    g, out, ref = _as_specified(gpu, wl, wl.parity_samples)
+    assert g.info().fused_front == 1
+    m = parity_metrics(wl.config, out, ref)
+    sp = error_spectrum_db(out, ref, wl.config)
+    if sp is not None:
+        m["err_spectrum_db_fs_per_bin"] = {"min": float(sp.min()), "median": float(np.median(sp)), "max": float(sp.max())}
+    record_parity("cfg2/as_specified/dc_mode=0", m)
+    # reference integrator noise: ulp(v) = 4.9e-4 at v ~ dc/alpha = 6.4e3, white over 20 MHz, cascade keeps 0.37 MHz of it
+    assert m["max_lsb"] <= CFG2_DC_EXCEPTION_MAX_LSB and m["rms_lsb"] <= CFG2_DC_EXCEPTION_RMS_LSB, m
+
+
+def test_cfg4_as_specified_with_reference_dc_rounding_meets_the_bar(gpu, workloads):
+    from helpers import parity_metrics, record_parity
+    wl = workloads["cfg4"]
+    g, out, ref = _as_specified(gpu, wl, wl.parity_samples, dc_mode=1)
+    m = parity_metrics(wl.config, out, ref)
+    record_parity("cfg4/as_specified/dc_mode=1", m)
+    assert m["rel_rms"] <= CF32_RMS_TOL and m["snr_db"] >= CF32_SNR_DB, m
+
+
+def test_cfg4_as_specified_default_path_measured_deviation(gpu, workloads):
+    from helpers import error_spectrum_db, parity_metrics, record_parity
+    wl = workloads["cfg4"]
+    g, out, ref = _as_specified(gpu, wl, wl.parity_samples)
+    assert g.info().fused_front == 1
+    m = parity_metrics(wl.config, out, ref)
+    sp = error_spectrum_db(out, ref, wl.config)
+    if sp is not None:
+        m["err_spectrum_db_fs_per_bin"] = {"min": float(sp.min()), "median": float(np.median(sp)), "max": float(sp.max())}
+    record_parity("cfg4/as_specified/dc_mode=0", m)
+    assert m["rel_rms"] <= CFG4_DC_EXCEPTION_REL_RMS and m["snr_db"] >= CFG4_DC_EXCEPTION_SNR_DB, m
+
+
+def test_dc_reference_mode_is_bit_exact_and_call_size_invariant(gpu, workloads):
+    """dc_mode 1 at the blocker's output: the same bits as liquid's recurrence in the reference build, however the stream
+    is cut into calls (fp32 state carried on the device)."""
+    wl = workloads["cfg2"]
+    cfg = ChainConfig(input_format="cs16", output_format="cf32", input_rate_hz=wl.config.input_rate_hz,
+                      target_rate_hz=wl.config.input_rate_hz, no_resample=True, dc_block=True)
+    n = (1 << 20) + 1234
+    raw = synth_numpy(wl, n)
+    ref = CpuChain(cfg, _oracle_kind()).process(raw)
+    one = gpu.Chain(cfg, 0, dc_mode=1).process(raw)
+    assert np.array_equal(one.view(np.uint32), ref.view(np.uint32))
+    g2 = gpu.Chain(cfg, 0, dc_mode=1)
+    parts, pos = [], 0
+    for m in (1, 127, 2048, 2049, 100000, n):
+        m = min(m, n - pos)
+        if m <= 0:
+            break
+        parts.append(g2.process(raw[2 * pos:2 * (pos + m)], chunk_frames=[m]))
+        pos += m
+    assert np.array_equal(np.concatenate(parts).view(np.uint32), ref.view(np.uint32))
+    g2.reset()
+    assert np.array_equal(g2.process(raw[: 2 * 5000]).view(np.uint32), ref[: 2 * 5000].view(np.uint32))
 
 
 def test_fir_filter_stage_parity(gpu):
@@ -189,10 +275,10 @@ def test_cfg4_full_chain_without_dc_offset(gpu, workloads):
     g, o, out, ref, counts = _run_pair(gpu, wl.config, raw)
     assert np.array_equal(counts, o.traced())
     assert rel_rms_fullscale(g.read_tap(1), o.captured(1)) <= CF32_RMS_TOL
-    a, b = out.view(np.complex64), ref.view(np.complex64)
-    # the AGC normalises to unit power: compare relative to the output RMS
-    assert rel_rms_fullscale(a, b) <= CF32_RMS_TOL * 3.0
-    assert snr_db(a, b) >= CF32_SNR_DB - 3.0
+    from helpers import parity_metrics, record_parity
+    m = parity_metrics(wl.config, out, ref)
+    record_parity("cfg4/dc_offset_removed/dc_mode=0", m)
+    assert m["rel_rms"] <= CF32_RMS_TOL and m["snr_db"] >= CF32_SNR_DB, m
 
 
 def test_chunk_train_invariance(gpu, workloads):
@@ -610,3 +696,71 @@ def test_long_post_resample_fir_runs_on_the_fft_block_kernel(gpu, workloads, mon
     assert rel_rms_fullscale(yb, yt) <= 2e-6
     ref = CpuChain(cfg, _oracle_kind()).process(raw)
     _check_final(cfg, ya.view(np.float32), ref)
+
+
+# ---------------------------------------------------------------------------------------------
+# interpolation (r > 1): arbitrary stage first, then halfband interpolators (msresamp_crcf INTERP, resampler.c:49)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["interp_1p5", "interp_6", "upsample_prefilter"])
+def test_interpolating_resampler_parity(name, gpu):
+    """r = 1.5 (S = 0), r = 6 (S = 2: arbitrary stage at 1.5, two halfband interpolators) and an up-sampling chain whose
+    user filter therefore stays pre-resample (filter.c:43-92): output counts exact, resampler stream <= 1e-6 / >= 120 dB,
+    final stream at the north_star bar, ragged calls == one call bit for bit."""
+    from test_host_logic import EXTRA
+    cfg = EXTRA[name]
+    rng = np.random.Generator(np.random.PCG64(61))
+    n = 12 * 16384 + 777
+    t = np.arange(n)
+    x = 0.3 * np.exp(2j * np.pi * 0.037 * t) + 0.1 * np.exp(-2j * np.pi * 0.11 * t) + \
+        0.02 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    if cfg.input_format == "cf32":
+        raw = x.astype(np.complex64).view(np.float32)
+    else:
+        raw = np.empty(2 * n, dtype=np.int16)
+        raw[0::2] = np.clip(np.rint(x.real * 32767), -32768, 32767)
+        raw[1::2] = np.clip(np.rint(x.imag * 32767), -32768, 32767)
+    g, o, out, ref, counts = _run_pair(gpu, cfg, raw)
+    gi = g.info()
+    assert gi.is_interp == 1 and gi.fused_front == 0
+    assert np.array_equal(counts, o.traced())
+    assert rel_rms_fullscale(g.read_tap(1), o.captured(1)) <= 1e-6 and snr_db(g.read_tap(1), o.captured(1)) >= 120.0
+    _check_final(cfg, out, ref)
+    g2 = gpu.Chain(cfg, 0)
+    parts, pos = [], 0
+    for m in (1, 2, 127, 4097, 16384, 50001, n):
+        m = min(m, n - pos)
+        if m <= 0:
+            break
+        parts.append(g2.process(raw[2 * pos:2 * (pos + m)], chunk_frames=[m]))
+        pos += m
+    many = np.concatenate(parts)
+    assert many.size == out.size and np.array_equal(many.view(np.uint8), out.view(np.uint8))
+
+
+def test_fft_filter_remainder_survives_a_stream_discontinuity_like_the_reference(gpu):
+    """filter_reset (filter.c:417-436) clears liquid's overlap state but not post/pre_fft_remainder_len, so
+    after a discontinuity the frames that were waiting for a full block are filtered in front of the new stream (with an
+    empty overlap).  iqgpu_chain_reset reproduces that, post- and pre-resample; iqgpu_chain_restart is a fresh chain."""
+    from iq_tool_b200.configs import FILTER_REQ_FFT
+    rng = np.random.Generator(np.random.PCG64(71))
+    n1, n2 = 3 * 16384 + 1500, 2 * 16384 + 4000
+    x = ((rng.standard_normal(n1 + n2) + 1j * rng.standard_normal(n1 + n2)) * 0.2).astype(np.complex64).view(np.float32)
+    for rates in ((2e6, 1e6), (1e6, 1e6)):                 # post-resample filter (decimation) / pre-resample (no_resample)
+        cfg = ChainConfig(input_format="cf32", output_format="cf32", input_rate_hz=rates[0], target_rate_hz=rates[1],
+                          no_resample=(rates[0] == rates[1]), filters=[lowpass(100e3)], filter_taps=301,
+                          filter_type_request=FILTER_REQ_FFT, filter_fft_size=2048)
+        g = gpu.Chain(cfg, 0)
+        o = CpuChain(cfg, _oracle_kind())
+        a1, b1 = g.process(x[: 2 * n1]), o.process(x[: 2 * n1])
+        assert a1.size == b1.size and a1.size % (2 * 1024) == 0
+        waiting = (n1 if cfg.no_resample else g.resampler_outputs_after(n1)) - a1.size // 2
+        assert 0 < waiting < 1024                          # the case under test: frames are waiting at the discontinuity
+        g.reset()
+        o.reset()
+        a2, b2 = g.process(x[2 * n1:]), o.process(x[2 * n1:])
+        assert a2.size == b2.size                          # the waiting frames count towards the new stream's blocks
+        _check_final(cfg, a2, b2)
+        fresh = gpu.Chain(cfg, 0).process(x[2 * n1:])
+        assert fresh.size != a2.size or not np.array_equal(fresh, a2)
+        g.restart()
+        assert np.array_equal(g.process(x[2 * n1:]).view(np.uint32), fresh.view(np.uint32))

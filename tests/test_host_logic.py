@@ -73,6 +73,26 @@ def test_host_design_equals_oracle_bit_exact(name, workloads):
     assert np.array_equal(g.filter_taps().view(np.uint32), o.filter_taps().view(np.uint32))
 
 
+def test_nco_increment_for_a_shift_that_is_not_a_float():
+    """AppResources.nco_shift_hz is a double (frequency_shift.c:32-33; input_wav.c:614-628 stores centre - target):
+    the 32-bit phase increment must come from the double, not from its float rounding."""
+    from oracle.loader import have_ref
+    kinds = ["oracle"] + (["ref"] if have_ref() else [])
+    rng = np.random.Generator(np.random.PCG64(11))
+    differ = 0
+    for _ in range(60):
+        shift = float(rng.uniform(2.0 ** 24, 4.9e7)) * (1 if rng.random() < 0.5 else -1) + 1.0 / 3.0
+        cfg = ChainConfig(input_format="cs16", output_format="cs16", input_rate_hz=10e6, target_rate_hz=5e6,
+                          freq_shift_hz=shift, freq_shift_is_double=True)
+        as_float = ChainConfig(input_format="cs16", output_format="cs16", input_rate_hz=10e6, target_rate_hz=5e6,
+                               freq_shift_hz=shift)
+        g = gpu.Chain(cfg, device=-1).info().nco_dtheta
+        differ += g != gpu.Chain(as_float, device=-1).info().nco_dtheta
+        for k in kinds:
+            assert g == CpuChain(cfg, k).info().nco_dtheta, (k, shift)
+    assert differ > 5       # the float round trip would have changed the increment in a good share of these
+
+
 @pytest.mark.parametrize("name", ["cfg1", "cfg2", "cfg3", "cfg5", "interp_1p5", "notch_fft"])
 def test_closed_form_output_counts_equal_reference_chunk_loop(name, workloads):
     """iqgpu_chain_predict_output (pure integer arithmetic) == frames the oracle's chunk loop emits."""

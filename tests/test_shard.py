@@ -212,3 +212,72 @@ def test_sharded_cfg2_with_dc_block_halo_meets_the_bar(gpu, workloads):
     assert sharded.size == single.size
     d = np.abs(sharded.astype(np.int32) - single.astype(np.int32))
     assert d.max() <= 1 and (d > 0).mean() < 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 5])
+def test_sharded_interpolating_chain_equals_single_stream(world, gpu):
+    """r = 6 (arbitrary stage at 1.5, two halfband interpolators) with a pre-resample shift: the halo covers the
+    arbitrary stage's 14-frame window plus the interpolators' histories mapped back to input frames (it used
+    to be 0 for interpolating chains), so the stitched shards equal the single stream bit for bit."""
+    import types
+    cfg = ChainConfig(input_format="cs16", output_format="cs16", input_rate_hz=250e3, target_rate_hz=1.5e6,
+                      freq_shift_hz=-20e3)
+    probe = gpu.Chain(cfg, -1)
+    assert probe.info().is_interp == 1 and probe.halo_frames() >= 14
+    rng = np.random.default_rng(5)
+    n = 23 * CHUNK + 4321
+    t = np.arange(n)
+    x = 0.4 * np.exp(2j * np.pi * 0.05 * t) + 0.05 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    raw = np.empty(2 * n, dtype=np.int16)
+    raw[0::2] = np.clip(np.rint(x.real * 32767), -32768, 32767)
+    raw[1::2] = np.clip(np.rint(x.imag * 32767), -32768, 32767)
+    wl = types.SimpleNamespace(config=cfg)
+    single = gpu.Chain(cfg, 0).process(raw)
+    sharded = _run_sharded(gpu, wl, raw, world)
+    assert sharded.size == single.size and np.array_equal(sharded, single)
+
+
+@pytest.mark.gpu
+def test_shard_stitch_at_2_pow_28_frames(gpu, workloads):
+    """shard-stitch parity of cfg5 on 2^28 input frames (1 GiB of cs16, generated in HBM): eight time shards
+    with halo, closed-form seek and the device-side AGC peak exchange == the single stream, byte for byte."""
+    import torch
+    from iq_tool_b200.shard import ShardedChain
+    from iq_tool_b200.synth import synth_torch
+    wl = workloads["cfg5"]
+    cfg = wl.config
+    total = 1 << 28
+    dev = torch.device("cuda", 0)
+    raw = synth_torch(wl, total, dev)
+    h = total // 2                                    # a loud stretch so that the AGC ratchets inside a later shard
+    raw[2 * h: 2 * (h + 8 * CHUNK)] = torch.clamp(raw[2 * h: 2 * (h + 8 * CHUNK)].to(torch.int32) * 3, -32768, 32767).to(torch.int16)
+    single_chain = gpu.Chain(cfg, 0, subtrain_frames=1 << 30)
+    out1 = torch.zeros(single_chain.out_capacity_frames(total) * cfg.out_bytes, dtype=torch.uint8, device=dev)
+    n1 = single_chain.process_device(raw.data_ptr(), total, out1.data_ptr(), out1.numel())
+    torch.cuda.synchronize()
+    sc = ShardedChain(cfg, 0, shard_frames_hint=total // 8 + (1 << 20))
+    shards = sc.plan(total, 8)
+    stitched = torch.zeros_like(out1)
+    live, pos = [], 0
+    for sh in shards:
+        ch = sc.chain
+        ch.seek(sh.lead)
+        out = torch.zeros(ch.out_capacity_frames(sh.read_frames) * cfg.out_bytes, dtype=torch.uint8, device=dev)
+        ch.process_device_begin(raw.data_ptr() + sh.lead * 4, sh.read_frames)
+        nlive = (sh.frames + CHUNK - 1) // CHUNK
+        mine = torch.zeros(max(nlive, 1), dtype=torch.float32, device=dev)
+        assert ch.pending_chunk_peaks_device(sh.skip_chunks, mine.data_ptr(), mine.numel()) == nlive
+        for q, buf in zip(shards, live):
+            if q.frames:
+                ch.agc_advance_device(buf.data_ptr(), q.start, q.frames)
+        live.append(mine)
+        produced = ch.process_device_finish(sh.skip_chunks, out.data_ptr(), out.numel())
+        torch.cuda.synchronize()
+        assert produced - sh.drop == sh.out_frames
+        k = sh.out_frames * cfg.out_bytes
+        stitched[pos: pos + k] = out[sh.drop * cfg.out_bytes: produced * cfg.out_bytes]
+        pos += k
+    assert pos == n1 * cfg.out_bytes
+    assert torch.equal(stitched[:pos], out1[:pos])
+    assert single_chain.info().agc_locked == 1

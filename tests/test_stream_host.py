@@ -131,3 +131,19 @@ def test_wav_stream_of_a_raw_capture_and_the_shift_option(stub, tmp_path):
     # a centre target needs a WAV input with the metadata; nothing is written when it is refused
     assert stub.iqgpu_wavfile_run(C.byref(c), 0, os.fsencode(src), 0, os.fsencode(tmp_path / "x.wav"), 1, C.c_float(1e6), C.c_size_t(0), None, None) != 0
     assert b"needs a WAV input" in stub.iqgpu_rawfile_last_error() and not (tmp_path / "x.wav").exists()
+
+
+def test_wav_to_wav_without_resampling_takes_the_header_rate_from_the_file(stub, tmp_path):
+    """--no-resample: setup.c:99 makes the source rate the target rate; for a WAV input that rate is only known after the
+    probe, so the output header must carry the FILE's rate, not the configuration's target."""
+    raw = np.arange(2 * 640, dtype=np.int16)
+    src, dst = tmp_path / "in.wav", tmp_path / "out.wav"
+    src.write_bytes(riff(fmt_chunk(1_234_567, 16) + chunk(b"data", raw.tobytes())))
+    c = cfg_c()
+    c.no_resample = 1
+    c.target_rate_hz = 0.0                      # unset on the command line when --no-resample is given
+    st = RawfileStatsC()
+    rc = stub.iqgpu_wavfile_run(C.byref(c), 0, os.fsencode(src), 1, os.fsencode(dst), 1, C.c_float(0.0), C.c_size_t(0), C.byref(st), None)
+    assert rc == 0, stub.iqgpu_rawfile_last_error()
+    with wave.open(str(dst), "rb") as w:
+        assert w.getframerate() == 1_234_567

@@ -17,14 +17,14 @@ ch = gpu.Chain(cfg, 0, subtrain_frames=1 << 30)
 out = torch.empty(ch.out_capacity_frames(n) * cfg.out_bytes, dtype=torch.uint8, device=dev)
 st = torch.cuda.current_stream().cuda_stream
 for _ in range(3):
-    ch.reset(); ch.process_device(raw.data_ptr(), n, out.data_ptr(), out.numel(), st)
+    ch.restart(); ch.process_device(raw.data_ptr(), n, out.data_ptr(), out.numel(), st)
 torch.cuda.synchronize()
 K = 20
 host = []
 t0 = time.perf_counter()
 for _ in range(K):
     a = time.perf_counter()
-    ch.reset()
+    ch.restart()
     b = time.perf_counter()
     ch.process_device(raw.data_ptr(), n, out.data_ptr(), out.numel(), st)
     c = time.perf_counter()
