@@ -398,6 +398,39 @@ template <int S> static void v2_fill(FusedFront* f)
     f->v2_warm_sup = (int)((warm_ticks + W2Plan<S>::sup - 1) / W2Plan<S>::sup);
     f->H_tail = (f->v2_warm_sup + 1) * W2Plan<S>::sup * W2_T0;
 }
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder()
+{
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        if (getenv("IQGPU_NO_RAW_TMA")) return nullptr;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q{};
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+// the raw cs16 capture of one call as rows of 128 bytes; a tick is a {32 x u32, 16 rows} box, 128-byte swizzle
+static bool encode_raw_map(CUtensorMap* map, const void* raw, size_t n_frames)
+{
+    EncodeTiledFn enc = tensor_map_encoder();
+    const cuuint64_t rows = (cuuint64_t)(n_frames * 4 / 128);
+    if (!enc || rows < 16) return false;
+    const cuuint64_t dims[2] = {32, rows};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {32, 16};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(raw), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static bool v2_setup(FusedFront* f, const ResamplerDesc& r, bool nco)
 {
     if (getenv("IQGPU_FUSED_V1")) return false;
@@ -406,9 +439,11 @@ static bool v2_setup(FusedFront* f, const ResamplerDesc& r, bool nco)
     V2_TRY(0) V2_TRY(1) V2_TRY(2) V2_TRY(3) V2_TRY(4) V2_TRY(5) V2_TRY(6)
 #undef V2_TRY
     if (!ok) return false;
-    const size_t fixed = (size_t)W2_BANK_F2 * sizeof(float2) + (nco ? 1024 * sizeof(float2) : 0);
-    const size_t per_warp = (size_t)f->v2_warp_f2 * sizeof(float2);
-    const size_t avail = 227 * 1024 - 1024;
+    const bool cs16 = f->format == IQGPU_FMT_CS16 || f->format == IQGPU_FMT_SC16Q11;
+    // cs16 kernels: a 2 KiB raw tick buffer per warp in front of everything else, 1 KiB aligned (up to 1 KiB of slack)
+    const size_t fixed = (size_t)W2_BANK_F2 * sizeof(float2) + (nco ? 1024 * sizeof(float2) : 0) + (cs16 ? 1024 : 0);
+    const size_t per_warp = (size_t)f->v2_warp_f2 * sizeof(float2) + (cs16 ? (size_t)W2_RAW_TICK_BYTES : 0);
+    const size_t avail = 227 * 1024 - 2048;      // static shared memory (barriers) and the driver's reserve stay clear
     int warps = (int)((avail - fixed) / per_warp);
     if (warps > W2_MAX_WARPS) warps = W2_MAX_WARPS;
     if (warps < 4) return false;
@@ -713,6 +748,10 @@ static cudaError_t fused_launch_v2(FusedFront* f, const void* raw, int64_t n0, s
     const long long warps_needed = (nsup + per - 1) / per;
     const int grid = (int)((warps_needed + f->v2_warps - 1) / f->v2_warps);
     A.raw_aligned = ((reinterpret_cast<size_t>(raw) & 15) == 0) && (n0 % 4 == 0);
+    // ticks start at absolute multiples of 512 frames: they are whole 128-byte rows of this call's buffer iff n0 is a multiple of 32
+    A.raw_tma = 0;
+    if ((pre.format == IQGPU_FMT_CS16 || pre.format == IQGPU_FMT_SC16Q11) && A.raw_aligned && n0 % 32 == 0)
+        A.raw_tma = encode_raw_map(&A.raw_map, raw, n) ? 1 : 0;
     cudaError_t e;
     if ((long long)n < f->H_tail) {
         const size_t keep = (size_t)f->H_tail - n;

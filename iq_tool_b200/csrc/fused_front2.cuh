@@ -20,6 +20,7 @@
 //     the stage-by-stage kernels; all indices are absolute, so results do not depend on how the
 //     host cuts the stream into calls.
 #pragma once
+#include <cuda.h>          // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include "device_common.cuh"
 #include "kernels.hpp"
 
@@ -172,7 +173,15 @@ struct Fused2Args {
     unsigned lut_sh, lut_mask;          // NCO table swizzle (w2_lut_slot)
     int arb_pairs;                      // polyphase stage: two outputs per lane (1) or one (0); same bits, picked by timing
     float taps[W2_MAX_TAPS];            // h1 by execution depth, concatenated (constant-bank FFMA operands)
+    // raw staging by TMA (cs16): the capture seen as rows of 128 bytes (32 frames); a tick is a box of 16 rows that one
+    // cp.async.bulk.tensor per warp drops into the warp's 2 KiB buffer with the 128-byte swizzle, so that the lanes' 64-byte
+    // runs (16 consecutive frames each) come out with four conflict-free LDS.128 — instead of four LDG.128 whose 32 lanes
+    // touch 16 different cache lines each (64 LSU wavefronts per tick, a quarter of the kernel's LSU traffic in
+    // profiles/r01j_fused_front2_full_cfg2.md)
+    int raw_tma;                        // 0: the map is not valid (unaligned call): ticks load with LDG
+    alignas(64) CUtensorMap raw_map;
 };
+constexpr int W2_RAW_TICK_BYTES = W2_T0 * 4;     // cs16 tick
 
 // ------------------------------------------------------------------------------------------------
 // TMA bulk copy global -> shared with mbarrier completion (cp.async.bulk, sm_90+/sm_100a)
@@ -188,6 +197,13 @@ __device__ __forceinline__ void w2_tma_load(void* smem_dst, const void* gmem_src
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(w2_smem_u32(bar)), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(w2_smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(w2_smem_u32(bar)) : "memory");
+}
+// one tick of raw cs16 frames: box {32 x u32, 16 rows} at row `row` of the capture -> 2 KiB of shared memory (128B swizzle)
+__device__ __forceinline__ void w2_tma_load_tick(void* smem_dst, const CUtensorMap* map, int row, uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(w2_smem_u32(bar)), "r"(W2_RAW_TICK_BYTES) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(w2_smem_u32(smem_dst)), "l"(map), "r"(0), "r"(row), "r"(w2_smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void w2_mbar_wait(uint64_t* bar, unsigned parity)
 {
@@ -800,14 +816,26 @@ template <int S, int DC, bool CS16>
 __global__ void __launch_bounds__(W2_MAX_WARPS * 32, 1) fused_front2_kernel(const __grid_constant__ Fused2Args A, int warps_per_cta)
 {
     using P = W2Plan<S>;
-    extern __shared__ __align__(16) float2 sm2[];
+    extern __shared__ __align__(16) float2 sm2_base[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // shared tables: polyphase bank image (TMA bulk copy), NCO table {sign*sin, cos}[1024]
     __shared__ __align__(8) uint64_t tma_bar;
+    __shared__ __align__(8) uint64_t raw_bar[W2_MAX_WARPS];
+    // per-warp raw tick buffers first (the 128-byte swizzle repeats every 1 KiB: 1 KiB-aligned), cs16 kernels only
+    unsigned char* dyn = reinterpret_cast<unsigned char*>(sm2_base);
+    unsigned char* rawbuf = nullptr;
+    if (CS16) {
+        const unsigned a = w2_smem_u32(dyn);
+        dyn += ((a + 1023u) & ~1023u) - a;
+        rawbuf = dyn + warp * W2_RAW_TICK_BYTES;
+        dyn += warps_per_cta * W2_RAW_TICK_BYTES;
+    }
+    float2* sm2 = reinterpret_cast<float2*>(dyn);
     float2* sbank = sm2;
     float2* lut2 = sm2 + W2_BANK_F2;
     float2* wsm = lut2 + (A.pre.nco_enable ? 1024 : 0) + warp * P::warp_f2;
     if (tid == 0) w2_mbar_init(&tma_bar, 1);
+    if (CS16 && lane == 0) w2_mbar_init(&raw_bar[warp], 1);
     __syncthreads();
     if (tid == 0) w2_tma_load(sbank, A.bank_image, W2_BANK_F2 * sizeof(float2), &tma_bar);
     if (A.pre.nco_enable)
@@ -838,19 +866,48 @@ __global__ void __launch_bounds__(W2_MAX_WARPS * 32, 1) fused_front2_kernel(cons
         const double f = exp(-(double)(A.n0 - t_begin * W2_T0) * A.dc_lnc);
         vloc = make_double2(cv.x * f, cv.y * f);
     }
-    W2Raw nxt;
-#pragma unroll
-    for (int j = 0; j < 4; j++) nxt.q[j] = make_uint4(0u, 0u, 0u, 0u);
-    if (CS16) w2_prefetch(A, t_begin * W2_T0, lane, nxt);
+    // raw frames of a fast cs16 tick: staged one tick ahead by TMA (A.raw_tma) into the warp's buffer
+    const bool use_tma = CS16 && A.raw_tma;
+    bool staged = false;                    // a TMA load for the tick about to run is in flight / has landed (warp-uniform)
+    unsigned raw_phase = 0;
+    if (use_tma && w2_tick_fast(A, t_begin * W2_T0)) {
+        if (lane == 0) w2_tma_load_tick(rawbuf, &A.raw_map, (int)((t_begin * W2_T0 - A.n0) >> 5), &raw_bar[warp]);
+        staged = true;
+    }
+    // the lane's four 16-byte chunks of its 64-byte run: chunk u = 4*lane + j sits in row u >> 3 at 16-byte slot (u & 7) ^ (row & 7)
+    const unsigned raw_row = w2_smem_u32(rawbuf) + 128u * (unsigned)(lane >> 1);
+    const unsigned raw_sw = (unsigned)(lane >> 1) & 7u, raw_c0 = 4u * (unsigned)(lane & 1);
     for (long long t = t_begin; t < t_end; t++) {
         const long long tick_start = t * W2_T0;
-        const W2Raw cur = nxt;
-        if (CS16 && t + 1 < t_end) w2_prefetch(A, tick_start + W2_T0, lane, nxt);
+        W2Raw cur;
+        if (CS16) {
+            if (staged) {
+                w2_mbar_wait(&raw_bar[warp], raw_phase);
+                raw_phase ^= 1u;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const unsigned addr = raw_row + 16u * ((raw_c0 + (unsigned)j) ^ raw_sw);
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(cur.q[j].x), "=r"(cur.q[j].y), "=r"(cur.q[j].z), "=r"(cur.q[j].w) : "r"(addr));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) cur.q[j] = make_uint4(0u, 0u, 0u, 0u);
+                w2_prefetch(A, tick_start, lane, cur);          // unaligned call: plain loads, no look-ahead
+            }
+        }
         if (DC == 2 && t == t_emit && lane == 0) A.dc_stretch[gw].v_emit = vloc;
         f32x2_t x[16];
         // local DC: the frames of a warm-up tick belong to the emit range of the warp below, which stores them in the tail
         // with ITS state (warp 0's warm-up frames precede n0: copies of the old tail)
         w2_p0<S, DC, CS16>(A, wsm, lut2, tick_start, lane, cur, x, vloc, DC != 2 || t >= t_emit || gw == 0);
+        if (use_tma) {
+            // every lane has consumed its chunks (the conversions in w2_p0 depend on them): the buffer may be refilled
+            __syncwarp();
+            staged = (t + 1 < t_end) && w2_tick_fast(A, tick_start + W2_T0);
+            if (staged && lane == 0)
+                w2_tma_load_tick(rawbuf, &A.raw_map, (int)((tick_start + W2_T0 - A.n0) >> 5), &raw_bar[warp]);
+        }
         bool arb_due = true;
         if constexpr (P::reg0) {
             f32x2_t v0[8];
