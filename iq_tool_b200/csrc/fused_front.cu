@@ -364,6 +364,9 @@ struct FusedFront {
     uint32_t v2_step = 0;
     int H_tail = 0;                     // cf32 tail length of the kernel in use
     float2* d_bank_image = nullptr;     // polyphase bank in the v2 shared-memory layout (w2_bank_row)
+    float2* d_bank_image_q = nullptr;   // ... and in the layout of the four-output variant (w2_qbank_chunk, rotation arb_tz)
+    int arb_tz = 0, arb_b2 = 0, arb_b3 = 0;
+    bool arb_quad_ok = false;
     // local DC state (fused_front2.cuh, DC == 2): per-warp records, per-stretch corrections, row gains of the polyphase stage
     W2DcStretch* d_dc_stretch = nullptr;
     W2DcCorr* d_dc_corr = nullptr;
@@ -549,6 +552,24 @@ FusedFront* fused_create(int format, const ResamplerDesc& r, bool nco, const flo
             fused_destroy(f);
             return nullptr;
         }
+        // four-output variant: rows of 16 floats, rotated / chunk-permuted for this rate (fused_front2.cuh)
+        f->arb_b2 = (int)((2ull * r.step) >> 24);
+        f->arb_b3 = (int)((3ull * r.step) >> 24);
+        f->arb_quad_ok = (f->arb_b2 == 2 && (f->arb_b3 == 3 || f->arb_b3 == 4)) || (f->arb_b2 == 3 && (f->arb_b3 == 4 || f->arb_b3 == 5));
+        if (f->arb_quad_ok) {
+            f->arb_tz = (int)w2_pick_qbank_tz(r.step);
+            std::vector<float> q((size_t)W2_BANK_F2 * 2, 0.f);
+            for (unsigned idx = 0; idx < 256; idx++)
+                for (unsigned j = 0; j < 4; j++)
+                    for (unsigned t = 0; t < 4; t++)
+                        if (4 * j + t < 14) q[w2_qbank_chunk(idx, (unsigned)f->arb_tz, j) + t] = hb[idx * 14 + 4 * j + t];
+            if (cudaMalloc(&f->d_bank_image_q, q.size() * sizeof(float)) != cudaSuccess ||
+                cudaMemcpy(f->d_bank_image_q, q.data(), q.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+                err = "fused front: bank image upload failed";
+                fused_destroy(f);
+                return nullptr;
+            }
+        }
     }
     return f;
 }
@@ -559,6 +580,7 @@ void fused_destroy(FusedFront* f)
     cudaFree(f->d_taps); cudaFree(f->d_tail[0]); cudaFree(f->d_tail[1]);
     for (int i = 0; i < 2; i++) { cudaFree(f->d_dc_table[i]); cudaFree(f->d_dc_sums[i]); cudaFree(f->d_dc_ws[i]); }
     cudaFree(f->d_bank_image);
+    cudaFree(f->d_bank_image_q);
     cudaFree(f->d_dc_stretch); cudaFree(f->d_dc_corr); cudaFree(f->d_dc_G);
     delete f;
 }
@@ -811,29 +833,41 @@ static cudaError_t fused_launch_v2(FusedFront* f, const void* raw, int64_t n0, s
             default: return cudaErrorInvalidValue;
         }
     };
-    if (const char* force = getenv("IQGPU_ARB_PAIRS")) f->arb_pairs = atoi(force) ? 1 : 0;
+    A.arb_tz = f->arb_tz; A.arb_b2 = f->arb_b2; A.arb_b3 = f->arb_b3;
+    auto set_mode = [&](int m) { A.arb_pairs = m; A.bank_image = (m == 2) ? f->d_bank_image_q : f->d_bank_image; };
+    if (const char* force = getenv("IQGPU_ARB_PAIRS")) {
+        f->arb_pairs = std::max(0, std::min(2, atoi(force)));
+        if (f->arb_pairs == 2 && !f->arb_quad_ok) f->arb_pairs = 1;
+    }
     if (f->arb_pairs < 0 && n >= ((size_t)1 << 22)) {
-        // time both variants on this launch (same inputs, same outputs: the second run overwrites the first with equal bits)
-        cudaEvent_t ev[3];
+        // time the variants on this launch (same inputs, same outputs: every run overwrites the last with equal bits)
+        const int nmodes = f->arb_quad_ok ? 3 : 2;
+        cudaEvent_t ev[4];
         for (auto& x : ev) cudaEventCreate(&x);
-        float ms[2] = {0.f, 0.f};
-        A.arb_pairs = 1; e = go(A);                      // untimed: caches, clocks, TMA descriptors warm for both candidates
+        float ms[3] = {0.f, 0.f, 0.f};
+        set_mode(1); e = go(A);                          // untimed: caches, clocks, TMA descriptors warm for all candidates
         cudaEventRecord(ev[0], st);
-        if (e == cudaSuccess) { A.arb_pairs = 0; e = go(A); }
-        cudaEventRecord(ev[1], st);
-        if (e == cudaSuccess) { A.arb_pairs = 1; e = go(A); }
-        cudaEventRecord(ev[2], st);
-        if (e == cudaSuccess) e = cudaEventSynchronize(ev[2]);
+        for (int m = 0; m < nmodes && e == cudaSuccess; m++) {
+            set_mode(m); e = go(A);
+            cudaEventRecord(ev[m + 1], st);
+        }
+        if (e == cudaSuccess) e = cudaEventSynchronize(ev[nmodes]);
         if (e == cudaSuccess) {
-            cudaEventElapsedTime(&ms[0], ev[0], ev[1]);
-            cudaEventElapsedTime(&ms[1], ev[1], ev[2]);
-            f->arb_pairs = (ms[1] < 0.98f * ms[0]) ? 1 : 0;
-            if (getenv("IQGPU_VERBOSE")) fprintf(stderr, "iqgpu: polyphase stage: one output per lane %.3f ms, two %.3f ms -> %s\n", ms[0], ms[1], f->arb_pairs ? "two" : "one");
+            int best = 0;
+            for (int m = 0; m < nmodes; m++) {
+                cudaEventElapsedTime(&ms[m], ev[m], ev[m + 1]);
+                if (ms[m] < 0.98f * ms[best]) best = m;
+            }
+            f->arb_pairs = best;
+            if (getenv("IQGPU_VERBOSE"))
+                fprintf(stderr, "iqgpu: polyphase stage: one output per lane %.3f ms, two %.3f ms, four %.3f ms -> mode %d (tz %d, B2 %d, B3 %d)\n",
+                        ms[0], ms[1], ms[2], best, f->arb_tz, f->arb_b2, f->arb_b3);
         }
         for (auto& x : ev) cudaEventDestroy(x);
-        if (launches) *launches += 1;
+        if (launches) *launches += (uint32_t)nmodes;
+        if (e == cudaSuccess && A.arb_pairs != f->arb_pairs) { set_mode(f->arb_pairs); e = go(A); if (launches) *launches += 1; }
     } else {
-        A.arb_pairs = f->arb_pairs > 0 ? 1 : 0;
+        set_mode(f->arb_pairs > 0 ? f->arb_pairs : 0);
         e = go(A);
     }
     if (launches) *launches += 1;

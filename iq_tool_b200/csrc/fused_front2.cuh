@@ -129,7 +129,9 @@ struct W2Plan {
     }
     static constexpr int flat_new = (S == 0) ? W2_T0 : out(S - 1);        // new polyphase inputs per arb run
     static constexpr int flat_off = e_off(S);
-    static constexpr int flat_size = (W2_ARB_HIST + flat_new + 3) & ~1;
+    // + 8: the four-output polyphase variant reads up to 6 entries beyond the newest one (they meet zero taps; the slack is
+    // zeroed once and never written, so the products are exact zeros)
+    static constexpr int flat_size = (W2_ARB_HIST + flat_new + 8 + 1) & ~1;
     static constexpr int warp_f2 = flat_off + flat_size;                 // float2 per warp
     __host__ __device__ static constexpr int period(int d) { return nat(d) >= CAP ? 1 : CAP / nat(d); }   // stage d runs every `period` ticks
     // runs of stage d per run of stage d+1 (1: every run feeds one consumer run; 2: the consumer waits for two)
@@ -171,7 +173,8 @@ struct Fused2Args {
     uint32_t step;
     float zeta;
     unsigned lut_sh, lut_mask;          // NCO table swizzle (w2_lut_slot)
-    int arb_pairs;                      // polyphase stage: two outputs per lane (1) or one (0); same bits, picked by timing
+    int arb_pairs;                      // polyphase stage: one output per lane (0), two (1) or four (2); same bits, picked by timing
+    int arb_tz, arb_b2, arb_b3;         // four-output variant: row rotation of the bank image; floor(2/rate), floor(3/rate)
     float taps[W2_MAX_TAPS];            // h1 by execution depth, concatenated (constant-bank FFMA operands)
     // raw staging by TMA (cs16): the capture seen as rows of 128 bytes (32 frames); a tick is a box of 16 rows that one
     // cp.async.bulk.tensor per warp drops into the warp's 2 KiB buffer with the 128-byte swizzle, so that the lanes' 64-byte
@@ -411,7 +414,29 @@ __device__ __forceinline__ void w2_stage_store(float2* __restrict__ wsm, int lan
 {
     using P = W2Plan<S>;
     constexpr int R = P::R(D);
-    if constexpr (D + 1 == S) {
+    if constexpr (D + 1 == S && R == 8) {
+        // 64 contiguous bytes per lane: four STS.128 in lane order would put the 8 lanes of a quarter warp on two bank groups
+        // (4-way conflict, 48 excess wavefronts per tick on cfg1).  Every lane starts with a different chunk instead — chunk
+        // (j + rot) & 3 in instruction j, rot = (lane >> 1) & 3 — which covers all eight groups; the rotation of the register
+        // chunks is a two-level select.
+        float2* f = wsm + P::flat_off + W2_ARB_HIST + R * lane;
+        const unsigned rot = ((unsigned)lane >> 1) & 3u;
+        const bool r1 = rot & 1u, r2 = rot & 2u;
+        f32x2_t a[8], b[8];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            a[2 * c] = r1 ? v[(2 * c + 2) & 7] : v[2 * c];
+            a[2 * c + 1] = r1 ? v[(2 * c + 3) & 7] : v[2 * c + 1];
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            b[2 * c] = r2 ? a[(2 * c + 4) & 7] : a[2 * c];
+            b[2 * c + 1] = r2 ? a[(2 * c + 5) & 7] : a[2 * c + 1];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            *reinterpret_cast<ulonglong2*>(f + 2 * (((unsigned)j + rot) & 3u)) = make_ulonglong2(b[2 * j], b[2 * j + 1]);
+    } else if constexpr (D + 1 == S) {
         float2* f = wsm + P::flat_off + W2_ARB_HIST + R * lane;
         if (R >= 2) {
 #pragma unroll
@@ -710,6 +735,109 @@ struct W2Slide {
 };
 
 // ------------------------------------------------------------------------------------------------
+// polyphase stage, FOUR consecutive outputs per lane (arb_pairs == 2).  The stage is bound by the LSU data pipe (97 % of its
+// wavefront peak on cfg1, profiles/r02a_fused_front2_cfg1.md): one output per lane loads 14 window entries (LDS.64 whose lanes
+// are 1.3 .. 1.7 entries apart: 2 x the ideal wavefronts) and 14 taps (7 LDS.64 from rows a configuration-dependent stride
+// apart: another 2 x).  Here the windows of outputs o .. o+3 start k_q - k_0 = 0, {1,2}, {B2, B2+1}, {B3, B3+1} entries apart
+// (rate in [0.5, 1)), so ONE register window of 15 + B3 entries serves all four, and the rows come as four LDS.128 each from
+// an image in which row r sits at rotr8(r, tz) with its four 16-byte chunks XOR-permuted — tz chosen on the host so that the
+// eight lanes of a quarter warp, whose rows advance by (4 step >> 16) mod 256, fall into eight different bank groups.
+// Output q reads its taps shifted by e_q = (k_q - k_0) - Bq in {0, 1} through a select (T[j] = e ? f[j-1] : f[j]; the taps
+// that fall outside the row are exact zeros, the non-zero terms keep the reference's order: same bits as one output per lane).
+// ------------------------------------------------------------------------------------------------
+constexpr int W2_QBANK_ROW_F = 16;            // floats per row of the image: 14 taps + 2 zeros
+__host__ __device__ constexpr unsigned w2_qbank_rot(unsigned r, unsigned tz) { return ((r >> tz) | (r << (8u - tz))) & 255u; }
+// float offset of logical chunk j (4 floats) of row r
+__host__ __device__ constexpr unsigned w2_qbank_chunk(unsigned r, unsigned tz, unsigned j)
+{
+    return 16u * w2_qbank_rot(r, tz) + 4u * (j ^ ((w2_qbank_rot(r, tz) >> 1) & 3u));
+}
+__host__ static inline unsigned w2_pick_qbank_tz(uint32_t step)
+{
+    unsigned best_tz = 0;
+    double best = 1e30;
+    for (unsigned tz = 0; tz < 8; tz++) {
+        double cost = 0;
+        for (unsigned trial = 0; trial < 256; trial++) {
+            const unsigned long long o0 = 4ull * (trial * 977ull + 13ull);
+            for (int quarter = 0; quarter < 4; quarter++)
+                for (int q = 0; q < 4; q++)
+                    for (unsigned j = 0; j < 4; j++) {
+                        int hits[8] = {0};
+                        unsigned seen[8];
+                        int deg = 0;
+                        for (int l = 0; l < 8; l++) {
+                            const unsigned long long o = o0 + 4ull * (unsigned)(8 * quarter + l) + (unsigned)q;
+                            const unsigned r = (unsigned)((o * step) >> 16) & 255u;
+                            const unsigned off = w2_qbank_chunk(r, tz, j);
+                            seen[l] = off;
+                            bool dup = false;
+                            for (int m = 0; m < l; m++) dup |= (seen[m] == off);
+                            if (dup) continue;
+                            const unsigned slot = (off >> 2) & 7u;
+                            if (++hits[slot] > deg) deg = hits[slot];
+                        }
+                        cost += deg;
+                    }
+        }
+        if (cost < best - 1e-9) { best = cost; best_tz = tz; }
+    }
+    return best_tz;
+}
+
+template <int B2, int B3>
+__device__ __forceinline__ void w2_arb_quad(const Fused2Args& A, const float2* __restrict__ flat, const float2* __restrict__ sbank,
+                                            long long kA, long long oa, long long ob, int lane)
+{
+    const unsigned long long step = A.step;
+    const unsigned tz = (unsigned)A.arb_tz;
+    const float* __restrict__ bank = reinterpret_cast<const float*>(sbank);
+    constexpr int NU = 15 + B3;                         // window entries: output 3 reaches index B3 + 1 + 13
+    for (long long o = oa + 4 * lane; o < ob; o += 128) {
+        const unsigned long long P0 = (unsigned long long)o * step, P1 = P0 + step, P2 = P1 + step, P3 = P2 + step;
+        const long long k0 = (long long)(P0 >> 24);
+        const int rel = (int)(k0 - kA);
+        const bool e1 = ((long long)(P1 >> 24) - k0) != 1;
+        const bool e2 = ((long long)(P2 >> 24) - k0) != B2;
+        const bool e3 = ((long long)(P3 >> 24) - k0) != B3;
+        const f32x2_t* __restrict__ w = reinterpret_cast<const f32x2_t*>(flat + rel + (W2_ARB_HIST - 13));
+        f32x2_t u[NU];
+#pragma unroll
+        for (int j = 0; j < NU; j++) u[j] = w[j];
+        f32x2_t s[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const unsigned long long Pq = (q == 0) ? P0 : (q == 1 ? P1 : (q == 2 ? P2 : P3));
+            const unsigned r = (unsigned)(Pq >> 16) & 255u;
+            const unsigned pr = w2_qbank_rot(r, tz);
+            const float* __restrict__ row = bank + 16u * pr;
+            const unsigned sw = (pr >> 1) & 3u;
+            float f[17];
+            f[0] = 0.f;                                     // f[1 + i] = tap i; f[15], f[16] = the row's zero padding
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float4 c = *reinterpret_cast<const float4*>(row + 4u * ((unsigned)j ^ sw));
+                f[1 + 4 * j] = c.x; f[2 + 4 * j] = c.y; f[3 + 4 * j] = c.z; f[4 + 4 * j] = c.w;
+            }
+            f32x2_t acc = 0ull;
+            if (q == 0) {
+#pragma unroll
+                for (int i = 0; i < 14; i++) acc = fma2s(f[1 + i], u[i], acc);
+            } else {
+                const bool e = (q == 1) ? e1 : (q == 2 ? e2 : e3);
+                const int base = (q == 1) ? 1 : (q == 2 ? B2 : B3);
+#pragma unroll
+                for (int j = 0; j < 15; j++) acc = fma2s(e ? f[j] : f[j + 1], u[base + j], acc);   // tap j - e of the row
+            }
+            s[q] = acc;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (o + q < ob) *reinterpret_cast<f32x2_t*>(A.y + (o + q - A.O0)) = s[q];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // polyphase arbitrary-rate stage (liquid resamp_crcf, fixed-point phase) on the new flat entries
 //   output o: P = o*step, k = P >> 24, bank row = (P >> 16) & 255, y = sum_{i<14} row[i] * x[k-13+i]
 // ------------------------------------------------------------------------------------------------
@@ -735,6 +863,16 @@ __device__ __forceinline__ void w2_arb(const Fused2Args& A, const float2* __rest
     o_cur = ob;
     if (oa < A.O0) oa = A.O0;
     if (ob > A.O1) ob = A.O1;
+    if (A.arb_pairs == 2) {
+        if (A.arb_b2 == 2) {
+            if (A.arb_b3 == 3) w2_arb_quad<2, 3>(A, flat, sbank, kA, oa, ob, lane);
+            else w2_arb_quad<2, 4>(A, flat, sbank, kA, oa, ob, lane);
+        } else {
+            if (A.arb_b3 == 4) w2_arb_quad<3, 4>(A, flat, sbank, kA, oa, ob, lane);
+            else w2_arb_quad<3, 5>(A, flat, sbank, kA, oa, ob, lane);
+        }
+        return;
+    }
     if (!A.arb_pairs) {
     for (long long o = oa + lane; o < ob; o += 32) {
         const unsigned long long Pp = (unsigned long long)o * step;

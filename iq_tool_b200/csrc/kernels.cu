@@ -15,6 +15,7 @@
 
 #include "../../include/iqgpu.h"
 #include "device_common.cuh"
+#include "agc_math.h"
 
 namespace cg = cooperative_groups;
 
@@ -1182,7 +1183,11 @@ __device__ __forceinline__ double agc_exp_small(double t)   // |t| <= 0.5 (t = -
     return fma(p, t, 1.0);
 }
 
+__constant__ AgcLogEntry agc_log_tab_c[AGC_LOG_N];
+__constant__ double agc_coef_c[AGC_NCOEF] = AGC_COEF_LIST;
+
 __device__ __forceinline__ float2 agc_rms_step(float2 v, size_t i, const PostParams& p, const float* __restrict__ lut,
+                                               const AgcLogEntry* __restrict__ ltab,
                                                float alpha, double oma, float mha, float& g, float& y2p)
 {
     if (p.nco_enable) v = nco_mix(v, p.nco_theta0 + (uint32_t)i * p.nco_dtheta, p.nco_sign, lut);
@@ -1191,58 +1196,90 @@ __device__ __forceinline__ float2 agc_rms_step(float2 v, size_t i, const PostPar
     y2p = (float)(oma * (double)y2p + (double)__fmul_rn(alpha, y2));
     if (y2p > 1e-6f) {
         // logf/expf evaluated in double and rounded once: matches a correctly rounded libm
-        const float lf = (float)agc_log_pos(y2p);
+        // (agc_math.h: table log + Estrin polynomials, ~12 dependent double operations instead of ~35)
+        const float lf = (float)agc_log_fast(y2p, ltab, agc_coef_c);
         const float tt = __fmul_rn(mha, lf);
-        const float ex = (fabsf(tt) <= 0.5f) ? (float)agc_exp_small((double)tt) : (float)exp((double)tt);
+        float ex;
+        if (fabsf(tt) <= 0.125f) ex = (float)agc_exp_tiny((double)tt, agc_coef_c);
+        else ex = (fabsf(tt) <= 0.5f) ? (float)agc_exp_small((double)tt) : (float)exp((double)tt);
         g = __fmul_rn(g, ex);
     }
     if (g > 1e6f) g = 1e6f;
     return make_float2(yr, yi);
 }
 
-// one block of the recurrence; samples are fetched eight at a time ahead of the serial chain so that memory
-// latency stays off the critical path (a thread's samples are contiguous, lanes are a whole block apart)
-__device__ __forceinline__ void agc_rms_block(const float2* __restrict__ x, size_t i0, size_t i1, const PostParams& p,
-                                              const float* __restrict__ lut, float& g, float& y2p, float2* __restrict__ y)
+// one block of the recurrence.  Samples are fetched eight at a time, one group AHEAD of the serial chain (a thread's samples
+// are contiguous, lanes are a whole block apart: every group is a DRAM access of its own, ~1 us — hidden behind the ~2000
+// cycles the chain spends on the previous group).
+// Checkpoints: every AGC_CK samples the state (g, y2') is compared with / written to the block's checkpoint row.  A block
+// that is run AGAIN (its start state changed) stops as soon as its state equals the one its previous run had at the same
+// sample: from there on the two trajectories are the same bits, so the outputs and the end state already in memory stand.
+// Returns true when the run stopped that way.
+constexpr int AGC_CK = 256;
+__device__ __forceinline__ bool agc_rms_block(const float2* __restrict__ x, size_t i0, size_t i1, const PostParams& p,
+                                              const float* __restrict__ lut, const AgcLogEntry* __restrict__ ltab,
+                                              float& g, float& y2p, float2* __restrict__ y, float2* __restrict__ ck, bool compare)
 {
     const float alpha = p.agc_alpha;
     const double oma = 1.0 - (double)alpha;
     const float mha = __fmul_rn(-0.5f, alpha);
     size_t i = i0;
+    float2 nx[8];
+    if (i + 8 <= i1) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) nx[k] = x[i + k];
+    }
     for (; i + 8 <= i1; i += 8) {
+        if (((i - i0) & (AGC_CK - 1)) == 0) {
+            float2* c = ck + ((i - i0) / AGC_CK);
+            if (compare) {
+                const float2 o = *c;
+                if (__float_as_uint(o.x) == __float_as_uint(g) && __float_as_uint(o.y) == __float_as_uint(y2p)) return true;
+            }
+            *c = make_float2(g, y2p);
+        }
         float2 v[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = x[i + k];
+        for (int k = 0; k < 8; k++) v[k] = nx[k];
+        if (i + 16 <= i1) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = agc_rms_step(v[k], i + k, p, lut, alpha, oma, mha, g, y2p);
+            for (int k = 0; k < 8; k++) nx[k] = x[i + 8 + k];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = agc_rms_step(v[k], i + k, p, lut, ltab, alpha, oma, mha, g, y2p);
 #pragma unroll
         for (int k = 0; k < 8; k++) y[i + k] = v[k];
     }
-    for (; i < i1; i++) y[i] = agc_rms_step(x[i], i, p, lut, alpha, oma, mha, g, y2p);
+    for (; i < i1; i++) y[i] = agc_rms_step(x[i], i, p, lut, ltab, alpha, oma, mha, g, y2p);
+    return false;
 }
 
 constexpr int AGC_RMS_THREADS = 128;
 __global__ void __launch_bounds__(AGC_RMS_THREADS) agc_rms_parallel_kernel(const float2* __restrict__ x, size_t n, PostParams p,
                                                                             AgcState* __restrict__ st, float2* __restrict__ y,
                                                                             size_t B, unsigned nblocks, float2* __restrict__ fin,
-                                                                            unsigned* __restrict__ flags)
+                                                                            unsigned* __restrict__ flags, float2* __restrict__ ckpt,
+                                                                            unsigned ck_per_block)
 {
     cg::grid_group grid = cg::this_grid();
     __shared__ float lut[1024];
+    __shared__ AgcLogEntry ltab[AGC_LOG_N];
     if (p.nco_enable)
         for (int i = threadIdx.x; i < 1024; i += blockDim.x) lut[i] = p.nco_table[i];
+    for (int i = threadIdx.x; i < AGC_LOG_N; i += blockDim.x) ltab[i] = agc_log_tab_c[i];
     __syncthreads();
     const unsigned b = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = b < nblocks;
     const size_t i0 = (size_t)b * B, i1 = (i0 + B < n) ? i0 + B : n;
     const float2 carried = make_float2(st->rms_g, st->rms_y2);
     float2 start = carried;            // block 0: exact; others: first guess
+    float2* ck = ckpt + (size_t)b * ck_per_block;
     bool run = true;
     for (unsigned it = 0; it <= nblocks; it++) {
         if (active && run) {
             float g = start.x, y2p = start.y;
-            agc_rms_block(x, i0, i1, p, lut, g, y2p, y);
-            fin[b] = make_float2(g, y2p);
+            const bool merged = agc_rms_block(x, i0, i1, p, lut, ltab, g, y2p, y, ck, it > 0);
+            if (!merged) fin[b] = make_float2(g, y2p);
         }
         grid.sync();
         run = false;
@@ -1437,7 +1474,8 @@ static void agc_rms_plan(size_t n, float alpha, size_t& B, unsigned& nblocks)
     // blocks of ~20 time constants the second sweep already starts every block within ~e^-20 of the truth, so two
     // or three full sweeps plus a short tail of partial ones reach the fixed point; shorter blocks need one full
     // sweep per block length of convergence (measured: 25 sweeps at 493 samples, alpha = 1e-2).
-    const size_t floorB = (size_t)std::min(65536.0, std::max(256.0, 40.0 / std::max((double)alpha, 1e-6)));
+    static const double tc = getenv("IQGPU_AGC_BLOCK_TC") ? atof(getenv("IQGPU_AGC_BLOCK_TC")) : 40.0;
+    const size_t floorB = (size_t)std::min(65536.0, std::max(256.0, tc / std::max((double)alpha, 1e-6)));
     if (B < floorB) B = floorB;
     nblocks = (unsigned)((n + B - 1) / B);
 }
@@ -1445,12 +1483,28 @@ size_t agc_rms_workspace_bytes(size_t n, float alpha)
 {
     size_t B; unsigned nb;
     agc_rms_plan(n, alpha, B, nb);
-    return (size_t)nb * sizeof(float2) + ((size_t)nb + 2) * sizeof(unsigned);
+    const size_t ckb = (B + AGC_CK - 1) / AGC_CK;
+    // end states, sweep flags (rounded up so that the checkpoint rows stay 8-byte aligned), checkpoint rows
+    return (size_t)nb * sizeof(float2) + (((size_t)nb + 2 + 1) & ~(size_t)1) * sizeof(unsigned) + (size_t)nb * ckb * sizeof(float2);
 }
 cudaError_t launch_agc_rms(const float2* x, size_t n, const PostParams& p, AgcState* state, float2* y, void* ws,
                            cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
+    {   // the log table, once per device
+        static bool up[64] = {false};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !up[dev]) {
+            AgcLogEntry tab[AGC_LOG_N];
+            agc_log_table(tab);
+            cudaError_t e0 = cudaMemcpyToSymbolAsync(agc_log_tab_c, tab, sizeof(tab), 0, cudaMemcpyHostToDevice, st);
+            if (e0 != cudaSuccess) return e0;
+            e0 = cudaStreamSynchronize(st);          // `tab` is on this stack frame
+            if (e0 != cudaSuccess) return e0;
+            if (dev >= 0 && dev < 64) up[dev] = true;
+        }
+    }
     size_t B; unsigned nb;
     agc_rms_plan(n, p.agc_alpha, B, nb);
     float2* fin = reinterpret_cast<float2*>(ws);
@@ -1458,7 +1512,10 @@ cudaError_t launch_agc_rms(const float2* x, size_t n, const PostParams& p, AgcSt
     cudaError_t e = cudaMemsetAsync(flags, 0, ((size_t)nb + 2) * sizeof(unsigned), st);
     if (e != cudaSuccess) return e;
     PostParams pp = p;
-    void* args[] = {(void*)&x, (void*)&n, (void*)&pp, (void*)&state, (void*)&y, (void*)&B, (void*)&nb, (void*)&fin, (void*)&flags};
+    float2* ckpt = reinterpret_cast<float2*>(flags + (((size_t)nb + 2 + 1) & ~(size_t)1));
+    unsigned ckb = (unsigned)((B + AGC_CK - 1) / AGC_CK);
+    void* args[] = {(void*)&x, (void*)&n, (void*)&pp, (void*)&state, (void*)&y, (void*)&B, (void*)&nb, (void*)&fin, (void*)&flags,
+                    (void*)&ckpt, (void*)&ckb};
     const unsigned grid = (nb + AGC_RMS_THREADS - 1) / AGC_RMS_THREADS;
     e = cudaLaunchCooperativeKernel((void*)agc_rms_parallel_kernel, dim3(grid), dim3(AGC_RMS_THREADS), args, 0, st);
     if (e == cudaSuccess && getenv("IQGPU_DEBUG_AGC")) {
