@@ -170,6 +170,16 @@ enum {
 int  iqgpu_chain_get_kernel_times(iqgpu_chain *c, double *ms, uint32_t *launches, int reset);
 /* live update of the I/Q correction factors (iq_correct.c:206-216 double-buffer swap) */
 int  iqgpu_chain_set_iq_factors(iqgpu_chain *c, float mag, float phase);
+/* In-chain I/Q optimiser (option "iq_optimize" = 1; "iq_optimize_interval_ms", default 500 = IQ_CORRECTION_INTERVAL_MS;
+ * "iq_optimize_seed"): replaces the side thread of src/utility_threads.c:35-47 and the probe copy of src/pipeline.c:468-476.
+ * For every chunk of >= 1024 frames that starts at least the interval after the last probed one — on the SAMPLE clock,
+ * input frames / input rate — the chain takes the first 1024 pre-processed frames and runs one pass of
+ * iq_correct_run_optimization (src/iq_correct.c:154-235) on the device, with +-1 directions from a counter-based generator
+ * (the reference uses wall time and rand()); the factors a sub-train's passes leave are applied from the next
+ * sub-train on.  get_iq_state returns the factors in force and the number of successful passes / probed blocks. */
+int  iqgpu_chain_get_iq_state(iqgpu_chain *c, float *mag, float *phase, uint64_t *passes, uint64_t *attempts);
+/* the generator behind the in-chain optimiser's directions (host; lets a test or a host-side optimiser reproduce them) */
+float iqgpu_iq_direction(uint32_t seed, uint64_t attempt, uint32_t k);
 
 /* Process a train of n_frames input frames held in HOST memory.  The train is cut into
  * reference chunks of IQGPU_CHUNK_SAMPLES frames (last one short) unless chunk_frames/n_chunks

@@ -213,6 +213,22 @@ struct iqgpu_chain {
         if (e == cudaSuccess) fft_scratch_bytes = need + need / 2;
         return e;
     }
+    // in-chain I/Q optimiser: gate on the sample clock, passes on the device, factors applied from the
+    // next sub-train on
+    bool iq_optimize = false;
+    double iq_interval_ms = 500.0;          // IQ_CORRECTION_INTERVAL_MS, include/constants.h:159
+    uint32_t iq_seed = 20261017u;
+    double iq_last_attempt_s = -1e18;       // sample-clock time of the last probe
+    IqOptState* d_iq_state = nullptr;
+    IqOptState* h_iq_state = nullptr;       // pinned
+    float2* d_iq_probe = nullptr;
+    size_t iq_probe_cap = 0;
+    cudaEvent_t ev_iq = nullptr, ev_iq_probe = nullptr;
+    bool iq_pending = false;
+    int iq_sync_state();
+    int iq_push_state(cudaStream_t st);
+    int iq_run_probes(const void* d_rawp, const float2* pre_out, uint64_t N0, const uint32_t* chunks, size_t n_chunks, int slot,
+                      cudaStream_t st);
     AgcState* d_agc = nullptr;
     uint32_t* d_seg_start = nullptr;
     float *d_seg_peak = nullptr, *d_seg_gain = nullptr;
@@ -318,6 +334,10 @@ iqgpu_chain::~iqgpu_chain()
     cudaFree(d_lut); cudaFree(d_dc_carry); cudaFree(d_dc_ref); cudaFree(d_run_sums); cudaFree(d_run_start); cudaFree(d_scan_ws); cudaFree(d_bank);
     cudaFree(d_fir_taps); cudaFree(d_fft_H); cudaFree(d_fft_tw); cudaFree(d_fft_scratch); cudaFree(d_agc); cudaFree(d_seg_start);
     cudaFree(d_seg_peak); cudaFree(d_seg_gain); cudaFree(d_agc_scratch); cudaFree(d_agc_ws);
+    cudaFree(d_iq_state); cudaFree(d_iq_probe);
+    if (h_iq_state) cudaFreeHost(h_iq_state);
+    if (ev_iq) cudaEventDestroy(ev_iq);
+    if (ev_iq_probe) cudaEventDestroy(ev_iq_probe);
     for (auto& t : prefix_tabs) cudaFree(t.d_seg);
     s_in.release(); s_pref.release(); s_arb_in.release(); s_rs.release(); s_f.release();
     for (auto& s : s_stage) s.release();
@@ -566,6 +586,7 @@ int iqgpu_chain::reset_state(bool keep_fft_remainder)
     const bool pre_fft = filter_is_fft(filt) && !filt.post_resample, post_fft = filter_is_fft(filt) && filt.post_resample;
     const uint32_t keep = (keep_fft_remainder && (pre_fft || post_fft)) ? fft_rem : 0;
     n_in = 0; n_nco_post = 0; n_out = 0; fft_rem = keep;
+    iq_last_attempt_s = -1e18;              // the sample clock restarts with the stream
     fft_rem_carry = pre_fft ? keep : 0;
     if (plan_only || !buffers_ready) return IQGPU_OK;
     CK(cudaSetDevice(device));
@@ -626,6 +647,91 @@ int iqgpu_chain::prepare_dc(int slot, const void* d_rawp, uint64_t N0, size_t n,
 }
 
 // ---------------------------------------------------------------------------------------------
+// in-chain I/Q optimiser.  Reference: the pre thread copies the first 1024 frames of every pre-processed chunk to a side
+// queue (src/pipeline.c:468-476), a side thread runs iq_correct_run_optimization on them at most every 500 ms of WALL time
+// with rand() directions (src/utility_threads.c:35-47, src/iq_correct.c:154-235).  Here (deliberate): the
+// gate runs on the SAMPLE clock (input frames / input rate; an attempt on a weak block also restarts it), the directions
+// come from a counter-based generator, the passes of a sub-train run back to back on the device behind the front kernel, and
+// the factors they leave are applied from the next sub-train on (the reference's apply sees them one chunk later).
+// ---------------------------------------------------------------------------------------------
+int iqgpu_chain::iq_sync_state()
+{
+    if (!iq_pending) return IQGPU_OK;
+    CK(cudaEventSynchronize(ev_iq));
+    iq_pending = false;
+    iq_mag = h_iq_state->mag; iq_phase = h_iq_state->phase;
+    return IQGPU_OK;
+}
+
+int iqgpu_chain::iq_push_state(cudaStream_t st)
+{
+    if (!d_iq_state) {
+        CK(cudaMalloc(&d_iq_state, sizeof(IqOptState)));
+        CK(cudaMallocHost(&h_iq_state, sizeof(IqOptState)));
+        CK(cudaEventCreateWithFlags(&ev_iq, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_iq_probe, cudaEventDisableTiming));
+        memset(h_iq_state, 0, sizeof(IqOptState));
+        h_iq_state->seed = iq_seed;
+    }
+    { int rc_ = iq_sync_state(); if (rc_) return rc_; }
+    h_iq_state->mag = iq_mag; h_iq_state->phase = iq_phase; h_iq_state->seed = iq_seed;
+    CK(cudaMemcpyAsync(d_iq_state, h_iq_state, sizeof(IqOptState), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));          // h_iq_state is also the read-back buffer
+    return IQGPU_OK;
+}
+
+// pre_out: the pre-processor output of this sub-train when it exists in memory (unfused path), else nullptr: the probe
+// blocks are then re-computed from the raw frames (convert, DC from the tick table, I/Q apply, NCO — the K1 kernel on 1024
+// frames per eligible chunk)
+int iqgpu_chain::iq_run_probes(const void* d_rawp, const float2* pre_out, uint64_t N0, const uint32_t* chunks, size_t n_chunks,
+                               int slot, cudaStream_t st)
+{
+    if (!iq_optimize || !cfg.iq_correction_enable) return IQGPU_OK;
+    std::vector<uint64_t> pos_list;
+    uint64_t pos = N0;
+    for (size_t c = 0; c < n_chunks; c++) {
+        const double t = (double)pos / (double)in_rate;
+        if (chunks[c] >= 1024 && (t - iq_last_attempt_s) * 1000.0 >= iq_interval_ms) {       // pipeline.c:469, iq_correct.c:157-162
+            bool ok = true;
+            if (!pre_out && dc.enable && !fused_dc_state_at(fused, slot, (int64_t)N0, (int64_t)pos)) ok = false;
+            if (ok) { pos_list.push_back(pos); iq_last_attempt_s = t; }
+        }
+        pos += chunks[c];
+    }
+    if (pos_list.empty()) return IQGPU_OK;
+    if (!d_iq_state) { int rc_ = iq_push_state(st); if (rc_) return rc_; }
+    if (pos_list.size() > iq_probe_cap) {
+        CK(cudaStreamSynchronize(st));
+        if (aux) CK(cudaStreamSynchronize(aux));
+        cudaFree(d_iq_probe);
+        iq_probe_cap = pos_list.size() * 2 + 8;
+        CK(cudaMalloc(&d_iq_probe, iq_probe_cap * 1024 * sizeof(float2)));
+    }
+    if (iq_pending) CK(cudaStreamWaitEvent(st, ev_iq, 0));      // the previous train's passes still read the probe buffer
+    for (size_t i = 0; i < pos_list.size(); i++) {
+        const uint64_t p0 = pos_list[i];
+        float2* dst = d_iq_probe + i * 1024;
+        if (pre_out) {
+            CK(cudaMemcpyAsync(dst, pre_out + (p0 - N0), 1024 * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+        } else {
+            const PreParams pp = pre_params(p0);
+            const double2* v = dc.enable ? fused_dc_state_at(fused, slot, (int64_t)N0, (int64_t)p0) : nullptr;
+            CK(launch_pre(reinterpret_cast<const char*>(d_rawp) + (p0 - N0) * in_bps, 1024, pp, 1024, v, dst, st));
+            launches++;
+        }
+    }
+    // the passes themselves run on the second stream: the post kernels of this sub-train do not wait for them
+    CK(cudaEventRecord(ev_iq_probe, st));
+    CK(cudaStreamWaitEvent(aux, ev_iq_probe, 0));
+    CK(launch_iq_optimize_train(d_iq_probe, (int)pos_list.size(), d_iq_state, aux));
+    launches++;
+    CK(cudaMemcpyAsync(h_iq_state, d_iq_state, sizeof(IqOptState), cudaMemcpyDeviceToHost, aux));
+    CK(cudaEventRecord(ev_iq, aux));
+    iq_pending = true;
+    return IQGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // one sub-train on the device
 // ---------------------------------------------------------------------------------------------
 int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chunks, size_t n_chunks, void* d_outp,
@@ -645,6 +751,7 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
     const size_t total_out = seg[n_chunks];
     launches = 0;
     fir_wrote_output = false;
+    if (iq_optimize) { int rc_iq = iq_sync_state(); if (rc_iq) return rc_iq; }      // factors the last train's passes left
 
     // ---------------- K1: pre-processor ----------------
     const PreParams pp = pre_params(N0);
@@ -660,6 +767,7 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
         span_begin(IQGPU_KCLASS_FUSED_FRONT, st);
         CK(fused_launch(fused, d_rawp, (int64_t)N0, n, pp, d_dc_carry, (int64_t)O0, (size_t)(O1 - O0), y_rs, &launches, dc_slot, st));
         span_end(st);
+        { int rc_iq = iq_run_probes(d_rawp, nullptr, N0, chunks, n_chunks, dc_slot, st); if (rc_iq) return rc_iq; }
         if (dc.enable) { CK(cudaEventRecord(ev_front[dc_slot], st)); front_recorded[dc_slot] = true; }
         dc_prepared = false;
         s_rs.commit((size_t)(O1 - O0));
@@ -707,6 +815,7 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
         }
         s_in.commit(n);
         if (record_tap0) CK(tap[0].append(x_in, n, st));
+        if (!(pre_filter && filter_is_fir(filt))) { int rc_iq = iq_run_probes(d_rawp, x_in, N0, chunks, n_chunks, 0, st); if (rc_iq) return rc_iq; }
 
         // ---------------- optional pre-resample filter ----------------
         const float2* rs_src = x_in;     // stream feeding the resampler (first new sample)
@@ -720,6 +829,8 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
                 launches++;
                 s_pref.commit(n);
                 rs_src = y;
+                // the reference probes buffer A after the whole pre chain, i.e. behind a pre-resample FIR (pipeline.c:466-472)
+                { int rc_iq = iq_run_probes(d_rawp, y, N0, chunks, n_chunks, 0, st); if (rc_iq) return rc_iq; }
             } else {
                 const uint32_t tot = fft_rem + (uint32_t)n, blocks = tot / filt.block;
                 float2* y = nullptr;
@@ -1102,6 +1213,9 @@ int iqgpu_chain_set_option(iqgpu_chain* c, const char* key, int64_t value)
         c->want_fused = value != 0;
         return IQGPU_OK;
     }
+    if (k == "iq_optimize") { c->iq_optimize = value != 0; return IQGPU_OK; }
+    if (k == "iq_optimize_interval_ms") { if (value < 0) return fail(IQGPU_EINVAL, "negative interval"); c->iq_interval_ms = (double)value; return IQGPU_OK; }
+    if (k == "iq_optimize_seed") { c->iq_seed = (uint32_t)value; if (c->d_iq_state) return c->iq_push_state(c->last_stream ? c->last_stream : c->stream); return IQGPU_OK; }
     if (k == "dc_mode") {
         if (c->buffers_ready) return fail(IQGPU_EINVAL, "option must be set before the first process call");
         if (value != 0 && value != 1) return fail(IQGPU_EINVAL, "dc_mode: 0 (exact arithmetic) or 1 (reference fp32 state rounding)");
@@ -1140,7 +1254,24 @@ int iqgpu_chain_get_kernel_times(iqgpu_chain* c, double* ms, uint32_t* launches,
 int iqgpu_chain_set_iq_factors(iqgpu_chain* c, float mag, float phase)
 {
     if (!c) return fail(IQGPU_EINVAL, "null chain");
+    if (c->d_iq_state) {
+        int rc = c->iq_sync_state();
+        if (rc) return rc;
+        c->iq_mag = mag; c->iq_phase = phase;
+        return c->iq_push_state(c->last_stream ? c->last_stream : c->stream);
+    }
     c->iq_mag = mag; c->iq_phase = phase;
+    return IQGPU_OK;
+}
+
+int iqgpu_chain_get_iq_state(iqgpu_chain* c, float* mag, float* phase, uint64_t* passes, uint64_t* attempts)
+{
+    if (!c) return fail(IQGPU_EINVAL, "null chain");
+    if (!c->plan_only) { CK(cudaSetDevice(c->device)); int rc = c->iq_sync_state(); if (rc) return rc; }
+    if (mag) *mag = c->iq_mag;
+    if (phase) *phase = c->iq_phase;
+    if (passes) *passes = c->h_iq_state ? c->h_iq_state->passes : 0;
+    if (attempts) *attempts = c->h_iq_state ? c->h_iq_state->attempts : 0;
     return IQGPU_OK;
 }
 
@@ -1678,6 +1809,8 @@ int iqgpu_convert_cf32_to_block(const float* in_cf32, void* out, size_t n, int f
     if (!is_complex_format(format)) return fail(IQGPU_EINVAL, "Unhandled output format");
     return convert_common(in_cf32, out, n, IQGPU_FMT_CF32, format, 1.0f);
 }
+
+float iqgpu_iq_direction(uint32_t seed, uint64_t attempt, uint32_t k) { return iq_direction_host(seed, attempt, k); }
 
 int iqgpu_iq_optimize(const float* block1024_cf32, const float* directions50, float* mag, float* phase,
                       float* avg_power, float* power_range)

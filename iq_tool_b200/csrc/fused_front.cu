@@ -365,7 +365,7 @@ struct FusedFront {
     int H_tail = 0;                     // cf32 tail length of the kernel in use
     float2* d_bank_image = nullptr;     // polyphase bank in the v2 shared-memory layout (w2_bank_row)
     float2* d_bank_image_q = nullptr;   // ... and in the layout of the four-output variant (w2_qbank_chunk, rotation arb_tz)
-    int arb_tz = 0, arb_b2 = 0, arb_b3 = 0;
+    int arb_tz = 0, arb_b2 = 0, arb_b3 = 0, arb_skew_sh = 31;
     bool arb_quad_ok = false;
     // local DC state (fused_front2.cuh, DC == 2): per-warp records, per-stretch corrections, row gains of the polyphase stage
     W2DcStretch* d_dc_stretch = nullptr;
@@ -555,9 +555,11 @@ FusedFront* fused_create(int format, const ResamplerDesc& r, bool nco, const flo
         // four-output variant: rows of 16 floats, rotated / chunk-permuted for this rate (fused_front2.cuh)
         f->arb_b2 = (int)((2ull * r.step) >> 24);
         f->arb_b3 = (int)((3ull * r.step) >> 24);
-        f->arb_quad_ok = (f->arb_b2 == 2 && (f->arb_b3 == 3 || f->arb_b3 == 4)) || (f->arb_b2 == 3 && (f->arb_b3 == 4 || f->arb_b3 == 5));
+        f->arb_quad_ok = f->v2_S <= 2 &&        // W2Plan<S>::quad
+                         ((f->arb_b2 == 2 && (f->arb_b3 == 3 || f->arb_b3 == 4)) || (f->arb_b2 == 3 && (f->arb_b3 == 4 || f->arb_b3 == 5)));
         if (f->arb_quad_ok) {
             f->arb_tz = (int)w2_pick_qbank_tz(r.step);
+            f->arb_skew_sh = getenv("IQGPU_ARB_SKEW") ? atoi(getenv("IQGPU_ARB_SKEW")) : w2_pick_flat_skew(r.step);
             std::vector<float> q((size_t)W2_BANK_F2 * 2, 0.f);
             for (unsigned idx = 0; idx < 256; idx++)
                 for (unsigned j = 0; j < 4; j++)
@@ -599,6 +601,18 @@ uint32_t fused_halo_frames(const FusedFront* f)
     return f->v2 ? (uint32_t)(f->v2_warm_sup * f->v2_sup * W2_T0) : (uint32_t)(f->plan.warm_blocks * f->plan.B0);
 }
 int fused_version(const FusedFront* f) { return f->v2 ? 2 : 1; }
+
+// DC blocker state v just before absolute frame `pos` of the sub-train that fused_launch() last ran from frame n0 with table
+// slot `slot` (device pointer into the tick table), or nullptr when the launch kept no table entry for that frame (local DC
+// state, v1 kernel, frame not on a tick boundary)
+const double2* fused_dc_state_at(const FusedFront* f, int slot, int64_t n0, int64_t pos)
+{
+    if (!f->v2 || slot < 0 || slot > 1 || !f->d_dc_table[slot] || pos < n0) return nullptr;
+    const int64_t A0 = (n0 / W2_T0) * W2_T0;
+    if ((pos - A0) % W2_T0) return nullptr;
+    const size_t idx = (size_t)((pos - A0) / W2_T0);
+    return idx < f->dc_cap[slot] ? f->d_dc_table[slot] + idx : nullptr;
+}
 
 // DC pre-pass on the virtual range [A0, N1): frames below n0 read as zero, the carry is rewound to A0
 static cudaError_t fused_dc_prepass(FusedFront* f, int slot, const void* raw, long long n0, long long N1, const PreParams& pre,
@@ -748,6 +762,7 @@ static cudaError_t fused_launch_v2(FusedFront* f, const void* raw, int64_t n0, s
     A.O0 = O0; A.O1 = O0 + (long long)n_out; A.y = y;
     A.step = f->v2_step; A.zeta = f->v2_zeta;
     A.lut_sh = 4; A.lut_mask = 0;
+    A.arb_skew_sh = 31;
     if (pre.nco_enable) {
         if (f->lut_dtheta != pre.nco_dtheta || !f->lut_picked) {
             w2_pick_lut_swizzle(pre.nco_dtheta, f->lut_sh, f->lut_mask);
@@ -834,7 +849,11 @@ static cudaError_t fused_launch_v2(FusedFront* f, const void* raw, int64_t n0, s
         }
     };
     A.arb_tz = f->arb_tz; A.arb_b2 = f->arb_b2; A.arb_b3 = f->arb_b3;
-    auto set_mode = [&](int m) { A.arb_pairs = m; A.bank_image = (m == 2) ? f->d_bank_image_q : f->d_bank_image; };
+    auto set_mode = [&](int m) {
+        A.arb_pairs = m;
+        A.bank_image = (m == 2) ? f->d_bank_image_q : f->d_bank_image;
+        A.arb_skew_sh = (m == 2) ? f->arb_skew_sh : 31;
+    };
     if (const char* force = getenv("IQGPU_ARB_PAIRS")) {
         f->arb_pairs = std::max(0, std::min(2, atoi(force)));
         if (f->arb_pairs == 2 && !f->arb_quad_ok) f->arb_pairs = 1;
@@ -860,8 +879,8 @@ static cudaError_t fused_launch_v2(FusedFront* f, const void* raw, int64_t n0, s
             }
             f->arb_pairs = best;
             if (getenv("IQGPU_VERBOSE"))
-                fprintf(stderr, "iqgpu: polyphase stage: one output per lane %.3f ms, two %.3f ms, four %.3f ms -> mode %d (tz %d, B2 %d, B3 %d)\n",
-                        ms[0], ms[1], ms[2], best, f->arb_tz, f->arb_b2, f->arb_b3);
+                fprintf(stderr, "iqgpu: polyphase stage: one output per lane %.3f ms, two %.3f ms, four %.3f ms -> mode %d (tz %d, B2 %d, B3 %d, skew %d)\n",
+                        ms[0], ms[1], ms[2], best, f->arb_tz, f->arb_b2, f->arb_b3, f->arb_skew_sh);
         }
         for (auto& x : ev) cudaEventDestroy(x);
         if (launches) *launches += (uint32_t)nmodes;

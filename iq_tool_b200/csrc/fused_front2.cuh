@@ -83,6 +83,7 @@ __host__ static inline void w2_pick_lut_swizzle(uint32_t dtheta, unsigned& sh, u
         if (cost < best - 1e-9) { best = cost; sh = cand_sh[c]; mask = cand_mask[c]; }
     }
 }
+__host__ __device__ constexpr int w2_flat_phys(int e, int sh) { return e + ((e >> sh) << 1); }
 __host__ __device__ constexpr int w2_ilog2(int v) { int l = 0; while ((1 << (l + 1)) <= v) l++; return l; }
 constexpr int W2_BANK_F2 = 2368;    // float2 entries of the image (9*255 + 63 + 7 = 2365, padded to 16 B)
 // (two leading float2 of zeros: the second output of a lane reads its taps through a pointer shifted back by up to two floats)
@@ -131,7 +132,13 @@ struct W2Plan {
     static constexpr int flat_off = e_off(S);
     // + 8: the four-output polyphase variant reads up to 6 entries beyond the newest one (they meet zero taps; the slack is
     // zeroed once and never written, so the products are exact zeros)
-    static constexpr int flat_size = (W2_ARB_HIST + flat_new + 8 + 1) & ~1;
+    // (+ 1/8 on top: room for the skew of the four-output variant, 2 entries per 16)
+    // The four-output variant exists for the shallow cascades, where the polyphase stage is most of the kernel (S <= 2: one
+    // output per lane spends 60 % of cfg1's LSU wavefronts there); deeper cascades keep the smaller level — on S = 4 the extra
+    // 220 bytes per warp would cost the CTA its 20th warp
+    static constexpr bool quad = (S <= 2);
+    static constexpr int flat_lin = W2_ARB_HIST + flat_new + (quad ? 8 : 0);
+    static constexpr int flat_size = quad ? ((flat_lin + flat_lin / 8 + 2 + 1) & ~1) : ((flat_lin + 3) & ~1);
     static constexpr int warp_f2 = flat_off + flat_size;                 // float2 per warp
     __host__ __device__ static constexpr int period(int d) { return nat(d) >= CAP ? 1 : CAP / nat(d); }   // stage d runs every `period` ticks
     // runs of stage d per run of stage d+1 (1: every run feeds one consumer run; 2: the consumer waits for two)
@@ -175,6 +182,10 @@ struct Fused2Args {
     unsigned lut_sh, lut_mask;          // NCO table swizzle (w2_lut_slot)
     int arb_pairs;                      // polyphase stage: one output per lane (0), two (1) or four (2); same bits, picked by timing
     int arb_tz, arb_b2, arb_b3;         // four-output variant: row rotation of the bank image; floor(2/rate), floor(3/rate)
+    // skew of the polyphase input level: entry e sits at e + 2 * (e >> arb_skew_sh) (31: none).  The four-output variant's
+    // window loads start 4 / rate entries apart from lane to lane; at rates where three such strides come to ~16 entries
+    // (cfg1: 16.13) the lanes of a half warp pile onto three bank groups — two entries of padding per 16 (or 32) spread them
+    int arb_skew_sh;
     float taps[W2_MAX_TAPS];            // h1 by execution depth, concatenated (constant-bank FFMA operands)
     // raw staging by TMA (cs16): the capture seen as rows of 128 bytes (32 frames); a tick is a box of 16 rows that one
     // cp.async.bulk.tensor per warp drops into the warp's 2 KiB buffer with the 128-byte swizzle, so that the lanes' 64-byte
@@ -390,7 +401,7 @@ __device__ __forceinline__ void w2_p0(const Fused2Args& A, float2* __restrict__ 
     }
     if (P::reg0) return;            // the first halfband stage reads x[] straight from registers (w2_stage0_reg)
     if (S == 0) {
-        ulonglong2* f = reinterpret_cast<ulonglong2*>(wsm + P::flat_off + W2_ARB_HIST + 16 * lane);
+        ulonglong2* f = reinterpret_cast<ulonglong2*>(wsm + P::flat_off + w2_flat_phys(W2_ARB_HIST + 16 * lane, A.arb_skew_sh));
 #pragma unroll
         for (int j = 0; j < 8; j++) f[j] = make_ulonglong2(x[2 * j], x[2 * j + 1]);
     } else {
@@ -410,7 +421,8 @@ __device__ __forceinline__ void w2_p0(const Fused2Args& A, float2* __restrict__ 
 // write the R outputs of stage D (lane owns outputs R*lane .. R*lane+R-1 of the run) to the next level's planes,
 // or to the flat polyphase input when D is the last stage
 template <int S, int D>
-__device__ __forceinline__ void w2_stage_store(float2* __restrict__ wsm, int lane, int half, const f32x2_t (&v)[W2Plan<S>::R(D)])
+__device__ __forceinline__ void w2_stage_store(float2* __restrict__ wsm, int lane, int half, const f32x2_t (&v)[W2Plan<S>::R(D)],
+                                               int skew_sh = 31)
 {
     using P = W2Plan<S>;
     constexpr int R = P::R(D);
@@ -419,8 +431,9 @@ __device__ __forceinline__ void w2_stage_store(float2* __restrict__ wsm, int lan
         // (4-way conflict, 48 excess wavefronts per tick on cfg1).  Every lane starts with a different chunk instead — chunk
         // (j + rot) & 3 in instruction j, rot = (lane >> 1) & 3 — which covers all eight groups; the rotation of the register
         // chunks is a two-level select.
-        float2* f = wsm + P::flat_off + W2_ARB_HIST + R * lane;
-        const unsigned rot = ((unsigned)lane >> 1) & 3u;
+        if (!P::quad) skew_sh = 31;
+        float2* f = wsm + P::flat_off + w2_flat_phys(W2_ARB_HIST + R * lane, skew_sh);
+        const unsigned rot = (skew_sh == 31) ? (((unsigned)lane >> 1) & 3u) : 0u;      // a skewed level is conflict free as it is
         const bool r1 = rot & 1u, r2 = rot & 2u;
         f32x2_t a[8], b[8];
 #pragma unroll
@@ -437,7 +450,8 @@ __device__ __forceinline__ void w2_stage_store(float2* __restrict__ wsm, int lan
         for (int j = 0; j < 4; j++)
             *reinterpret_cast<ulonglong2*>(f + 2 * (((unsigned)j + rot) & 3u)) = make_ulonglong2(b[2 * j], b[2 * j + 1]);
     } else if constexpr (D + 1 == S) {
-        float2* f = wsm + P::flat_off + W2_ARB_HIST + R * lane;
+        if (!P::quad) skew_sh = 31;
+        float2* f = wsm + P::flat_off + w2_flat_phys(W2_ARB_HIST + R * lane, skew_sh);
         if (R >= 2) {
 #pragma unroll
             for (int r = 0; r < R; r += 2) *reinterpret_cast<ulonglong2*>(f + r) = make_ulonglong2(v[r], v[r + 1]);
@@ -543,7 +557,7 @@ __device__ __forceinline__ void w2_stage0_reg_m5(const Fused2Args& A, float2* __
     }
 #pragma unroll
     for (int r = 0; r < 8; r++) v[r] = add2(oc[r], acc[r]);
-    w2_stage_store<S, 0>(wsm, lane, 0, v);
+    w2_stage_store<S, 0>(wsm, lane, 0, v, A.arb_skew_sh);
 }
 
 template <int S>
@@ -588,7 +602,7 @@ __device__ __forceinline__ void w2_stage0_reg(const Fused2Args& A, float2* __res
     }
 #pragma unroll
     for (int r = 0; r < 8; r++) v[r] = add2(oc[r], acc[r]);
-    if (!P::reg1) w2_stage_store<S, 0>(wsm, lane, 0, v);
+    if (!P::reg1) w2_stage_store<S, 0>(wsm, lane, 0, v, A.arb_skew_sh);
     }
 }
 
@@ -639,7 +653,7 @@ __device__ __forceinline__ void w2_stage1_reg(const Fused2Args& A, float2* __res
     f32x2_t y[4];
 #pragma unroll
     for (int r = 0; r < 4; r++) y[r] = add2(oc[r], acc[r]);
-    w2_stage_store<S, 1>(wsm, lane, half, y);
+    w2_stage_store<S, 1>(wsm, lane, half, y, A.arb_skew_sh);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -701,7 +715,7 @@ __device__ __forceinline__ void w2_stage(const Fused2Args& A, float2* __restrict
         if (D + 1 == S) v[r] = mul2(add2(oc[r], acc[r]), zz);
         else v[r] = add2(oc[r], acc[r]);
     }
-    w2_stage_store<S, D>(wsm, lane, half, v);
+    w2_stage_store<S, D>(wsm, lane, half, v, A.arb_skew_sh);
 }
 
 // move the last Hh entries of both planes of level D to the history slots (all lanes call).  The loads are
@@ -785,6 +799,39 @@ __host__ static inline unsigned w2_pick_qbank_tz(uint32_t step)
     return best_tz;
 }
 
+// shared-memory wavefronts of the four-output variant's window loads (LDS.64, half warps of 16 lanes) for a given skew
+__host__ static inline double w2_window_cost(uint32_t step, int sh)
+{
+    double cost = 0;
+    for (unsigned trial = 0; trial < 128; trial++) {
+        const unsigned long long o0 = 4ull * (trial * 7919ull + 5ull);
+        const long long kbase = (long long)((o0 * step) >> 24);
+        for (int half = 0; half < 2; half++) {
+            int cnt[32] = {0};
+            int deg = 0;
+            for (int l = 0; l < 16; l++) {
+                const unsigned long long o = o0 + 4ull * (unsigned)(16 * half + l);
+                const int e = (int)((long long)((o * step) >> 24) - kbase) + 3;
+                const int ph = w2_flat_phys(e, sh);
+                for (int w = 0; w < 2; w++) { const int b = (2 * ph + w) & 31; if (++cnt[b] > deg) deg = cnt[b]; }
+            }
+            cost += deg;
+        }
+    }
+    return cost;
+}
+__host__ static inline int w2_pick_flat_skew(uint32_t step)
+{
+    const int cand[3] = {31, 4, 5};
+    int best = 31;
+    double bc = 1e30;
+    for (int c = 0; c < 3; c++) {
+        const double k = w2_window_cost(step, cand[c]);
+        if (k < bc * 0.97) { bc = k; best = cand[c]; }       // a skew has to pay for its address arithmetic
+    }
+    return best;
+}
+
 template <int B2, int B3>
 __device__ __forceinline__ void w2_arb_quad(const Fused2Args& A, const float2* __restrict__ flat, const float2* __restrict__ sbank,
                                             long long kA, long long oa, long long ob, int lane)
@@ -800,10 +847,11 @@ __device__ __forceinline__ void w2_arb_quad(const Fused2Args& A, const float2* _
         const bool e1 = ((long long)(P1 >> 24) - k0) != 1;
         const bool e2 = ((long long)(P2 >> 24) - k0) != B2;
         const bool e3 = ((long long)(P3 >> 24) - k0) != B3;
-        const f32x2_t* __restrict__ w = reinterpret_cast<const f32x2_t*>(flat + rel + (W2_ARB_HIST - 13));
+        const f32x2_t* __restrict__ w = reinterpret_cast<const f32x2_t*>(flat);
+        const int e0 = rel + (W2_ARB_HIST - 13), ssh = A.arb_skew_sh;
         f32x2_t u[NU];
 #pragma unroll
-        for (int j = 0; j < NU; j++) u[j] = w[j];
+        for (int j = 0; j < NU; j++) u[j] = w[w2_flat_phys(e0 + j, ssh)];
         f32x2_t s[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -863,7 +911,7 @@ __device__ __forceinline__ void w2_arb(const Fused2Args& A, const float2* __rest
     o_cur = ob;
     if (oa < A.O0) oa = A.O0;
     if (ob > A.O1) ob = A.O1;
-    if (A.arb_pairs == 2) {
+    if (P::quad && A.arb_pairs == 2) {
         if (A.arb_b2 == 2) {
             if (A.arb_b3 == 3) w2_arb_quad<2, 3>(A, flat, sbank, kA, oa, ob, lane);
             else w2_arb_quad<2, 4>(A, flat, sbank, kA, oa, ob, lane);
@@ -1070,9 +1118,10 @@ __global__ void __launch_bounds__(W2_MAX_WARPS * 32, 1) fused_front2_kernel(cons
             if (t >= t_emit) w2_arb<S>(A, flat, sbank, kA, o_cur, lane);
             __syncwarp();
             float2 h = make_float2(0.f, 0.f);
-            if (lane < W2_ARB_HIST) h = flat[lane + P::flat_new];
+            const int ssh = P::quad ? A.arb_skew_sh : 31;
+            if (lane < W2_ARB_HIST) h = flat[w2_flat_phys(lane + P::flat_new, ssh)];
             __syncwarp();
-            if (lane < W2_ARB_HIST) flat[lane] = h;
+            if (lane < W2_ARB_HIST) flat[w2_flat_phys(lane, ssh)] = h;
             __syncwarp();
         }
     }

@@ -61,80 +61,139 @@ __device__ void iq_power_spectrum(const float2* __restrict__ x, const float* __r
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(IQ_THREADS) iq_optimize_kernel(const float2* __restrict__ block, const float* __restrict__ dirs,
-                                                                 float mag_in, float phase_in, IqOptResult* __restrict__ out)
+// +-1 step directions of the in-chain optimiser: a counter-based generator (the reference draws them from
+// rand() seeded with time(); here pass number and seed decide, so a run can be repeated)
+__host__ __device__ inline float iq_direction(unsigned seed, unsigned long long pass, unsigned k)
 {
-    __shared__ float2 x[IQ_NFFT], buf[IQ_NFFT], tw[IQ_NFFT];
-    __shared__ float win[IQ_NFFT], spec[IQ_NFFT];
-    __shared__ float s_metric;
-    __shared__ float s_avg, s_range;
-    const int t = threadIdx.x;
-    for (int i = t; i < IQ_NFFT; i += IQ_THREADS) {
-        x[i] = block[i];
+    unsigned long long z = ((unsigned long long)seed << 32) ^ (pass * 0x9E3779B97F4A7C15ull) ^ ((unsigned long long)k * 0xBF58476D1CE4E5B9ull);
+    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+    z ^= z >> 27; z *= 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (z & 1ull) ? 1.0f : -1.0f;
+}
+
+struct IqShared {
+    float2 x[IQ_NFFT], buf[IQ_NFFT], tw[IQ_NFFT];
+    float win[IQ_NFFT], spec[IQ_NFFT];
+    float metric, avg, range;
+};
+
+__device__ void iq_tables(IqShared& sh)
+{
+    for (int i = threadIdx.x; i < IQ_NFFT; i += IQ_THREADS) {
         float s, c;
         sincospif(-2.0f * (float)i / (float)IQ_NFFT, &s, &c);
-        tw[i] = make_float2(c, s);
+        sh.tw[i] = make_float2(c, s);
         // iq_correct.c:121-123 Hamming window, evaluated in float like the reference
-        win[i] = __fsub_rn(0.54f, __fmul_rn(0.46f, cosf(__fdiv_rn(__fmul_rn(__fmul_rn(2.0f, 3.14159265358979323846f), (float)i), (float)(IQ_NFFT - 1)))));
+        sh.win[i] = __fsub_rn(0.54f, __fmul_rn(0.46f, cosf(__fdiv_rn(__fmul_rn(__fmul_rn(2.0f, 3.14159265358979323846f), (float)i), (float)(IQ_NFFT - 1)))));
     }
-    __syncthreads();
+}
+
+// one optimisation pass on the block in sh.x (iq_correct_run_optimization, :154-235).  dirs != nullptr: caller-supplied
+// directions (function-level entry point); otherwise iq_direction(seed, pass_no, k).  All threads return the same result.
+__device__ IqOptResult iq_pass(IqShared& sh, const float* __restrict__ dirs, unsigned seed, unsigned long long pass_no,
+                               float mag_in, float phase_in)
+{
+    const int t = threadIdx.x;
     const int half = IQ_NFFT / 2;
     const int lo = (int)(0.05f * half), hi = (int)(0.95f * half);
-
     // ---- _estimate_power (:361-389)
-    iq_power_spectrum(x, win, tw, buf, spec, 0.0f, 0.0f);
+    iq_power_spectrum(sh.x, sh.win, sh.tw, sh.buf, sh.spec, 0.0f, 0.0f);
     if (t == 0) {
         float mx = -1000.0f;
         double sum = 0.0;
         int count = 0;
         for (int i = lo; i < hi; i++) {
-            const float pn = spec[i], pp = spec[IQ_NFFT - 1 - i];
+            const float pn = sh.spec[i], pp = sh.spec[IQ_NFFT - 1 - i];
             if (pp > mx) mx = pp;
             if (pn > mx) mx = pn;
             sum += (double)__fadd_rn(pp, pn);
             count += 2;
         }
-        s_avg = count ? (float)(sum / count) : 0.0f;
-        s_range = count ? __fsub_rn(mx, s_avg) : 0.0f;
+        sh.avg = count ? (float)(sum / count) : 0.0f;
+        sh.range = count ? __fsub_rn(mx, sh.avg) : 0.0f;
     }
     __syncthreads();
-    if (s_range < 20.0f) {                                  // IQ_CORRECTION_POWER_THRESHOLD_DB (:168)
-        if (t == 0) *out = IqOptResult{mag_in, phase_in, s_avg, s_range, 0};
-        return;
-    }
+    const float avg = sh.avg, range = sh.range;
+    if (range < 20.0f) return IqOptResult{mag_in, phase_in, avg, range, 0};   // IQ_CORRECTION_POWER_THRESHOLD_DB (:168)
     // ---- hill climb (:177-201); the metric sum runs sequentially in float like the reference
     float cur_g = mag_in, cur_p = phase_in, best = 0.f;
     for (int pass = -1; pass < IQ_PASSES; pass++) {
         float cg = cur_g, cp = cur_p;
         if (pass >= 0) {
-            cg = __fadd_rn(cur_g, __fmul_rn(0.0001f, dirs[2 * pass]));
-            cp = __fadd_rn(cur_p, __fmul_rn(0.0001f, dirs[2 * pass + 1]));
+            const float d0 = dirs ? dirs[2 * pass] : iq_direction(seed, pass_no, 2u * (unsigned)pass);
+            const float d1 = dirs ? dirs[2 * pass + 1] : iq_direction(seed, pass_no, 2u * (unsigned)pass + 1u);
+            cg = __fadd_rn(cur_g, __fmul_rn(0.0001f, d0));
+            cp = __fadd_rn(cur_p, __fmul_rn(0.0001f, d1));
         }
-        iq_power_spectrum(x, win, tw, buf, spec, cg, cp);
+        iq_power_spectrum(sh.x, sh.win, sh.tw, sh.buf, sh.spec, cg, cp);
         if (t == 0) {
             float total = 0.0f;
             for (int i = lo; i < hi; i++) {
-                const float pn = spec[i], pp = spec[IQ_NFFT - 1 - i];
+                const float pn = sh.spec[i], pp = sh.spec[IQ_NFFT - 1 - i];
                 if (pp > -80.0f || pn > -80.0f) {
                     const float d = __fsub_rn(pp, pn);
                     total = __fadd_rn(total, __fmul_rn(d, d));
                 }
             }
-            s_metric = total;
+            sh.metric = total;
         }
         __syncthreads();
-        const float m = s_metric;
+        const float m = sh.metric;
         if (pass < 0) best = m;
         else if (m > best) { best = m; cur_g = cg; cur_p = cp; }   // keeps a candidate when the metric INCREASES (:196, quirk B8)
         __syncthreads();
     }
-    if (t == 0) {
-        // 5 % smoothing into the inactive slot (:206-216)
-        const float sg = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, 0.05f), mag_in), __fmul_rn(0.05f, cur_g));
-        const float sp = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, 0.05f), phase_in), __fmul_rn(0.05f, cur_p));
-        *out = IqOptResult{sg, sp, s_avg, s_range, 1};
-    }
+    // 5 % smoothing into the inactive slot (:206-216)
+    const float sg = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, 0.05f), mag_in), __fmul_rn(0.05f, cur_g));
+    const float sp = __fadd_rn(__fmul_rn(__fsub_rn(1.0f, 0.05f), phase_in), __fmul_rn(0.05f, cur_p));
+    return IqOptResult{sg, sp, avg, range, 1};
 }
+
+__global__ void __launch_bounds__(IQ_THREADS) iq_optimize_kernel(const float2* __restrict__ block, const float* __restrict__ dirs,
+                                                                 float mag_in, float phase_in, IqOptResult* __restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char iq_smem[];
+    IqShared& sh = *reinterpret_cast<IqShared*>(iq_smem);
+    for (int i = threadIdx.x; i < IQ_NFFT; i += IQ_THREADS) sh.x[i] = block[i];
+    iq_tables(sh);
+    __syncthreads();
+    const IqOptResult r = iq_pass(sh, dirs, 0u, 0ull, mag_in, phase_in);
+    if (threadIdx.x == 0) *out = r;
+}
+
+// In-chain optimiser (reference src/utility_threads.c:35-47 + src/pipeline.c:468-476): the passes of one
+// train, in stream order, on the probe blocks the chain extracted (first 1024 pre-processed frames of every eligible chunk).
+// The factors live in device memory; every pass starts from what the previous one left (iq_correct.c:183-186 reads the
+// active slot), weak blocks leave them alone (:168-171).
+__global__ void __launch_bounds__(IQ_THREADS) iq_optimize_train_kernel(const float2* __restrict__ probes, int n_probes,
+                                                                       IqOptState* __restrict__ state)
+{
+    extern __shared__ __align__(16) unsigned char iq_smem[];
+    IqShared& sh = *reinterpret_cast<IqShared*>(iq_smem);
+    iq_tables(sh);
+    IqOptState st = *state;
+    for (int b = 0; b < n_probes; b++) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < IQ_NFFT; i += IQ_THREADS) sh.x[i] = probes[(size_t)b * IQ_NFFT + i];
+        __syncthreads();
+        const IqOptResult r = iq_pass(sh, nullptr, st.seed, st.attempts, st.mag, st.phase);
+        st.attempts++;
+        st.avg_power = r.avg_power; st.power_range = r.power_range;
+        if (r.optimized) { st.mag = r.mag; st.phase = r.phase; st.passes++; }
+    }
+    if (threadIdx.x == 0) *state = st;
+}
+
+cudaError_t launch_iq_optimize_train(const float2* probes, int n_probes, IqOptState* state, cudaStream_t st)
+{
+    if (n_probes <= 0) return cudaSuccess;
+    static_assert(sizeof(IqShared) <= 48 * 1024, "fits the default dynamic shared memory limit");
+    iq_optimize_train_kernel<<<1, IQ_THREADS, sizeof(IqShared), st>>>(probes, n_probes, state);
+    return cudaGetLastError();
+}
+
+float iq_direction_host(unsigned seed, unsigned long long pass, unsigned k) { return iq_direction(seed, pass, k); }
 
 cudaError_t iq_optimize_device(const float* host_block1024, const float* host_dirs50, float* mag, float* phase,
                                float* avg_power, float* power_range, int* optimized)
@@ -150,7 +209,7 @@ cudaError_t iq_optimize_device(const float* host_block1024, const float* host_di
     e = cudaMemcpy(d_block, host_block1024, IQ_NFFT * sizeof(float2), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d_dirs, host_dirs50, 2 * IQ_PASSES * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
-        iq_optimize_kernel<<<1, IQ_THREADS>>>(d_block, d_dirs, *mag, *phase, d_out);
+        iq_optimize_kernel<<<1, IQ_THREADS, sizeof(IqShared)>>>(d_block, d_dirs, *mag, *phase, d_out);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpy(&r, d_out, sizeof(r), cudaMemcpyDeviceToHost);

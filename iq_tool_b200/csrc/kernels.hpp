@@ -129,6 +129,12 @@ cudaError_t launch_convert_out(const float2* x, size_t n, int format, void* out,
 cudaError_t iq_optimize_device(const float* host_block1024, const float* host_dirs50, float* mag, float* phase,
                                float* avg_power, float* power_range, int* optimized);
 
+// in-chain form: the optimiser's factors and counters in device memory; one launch runs the passes of a train over
+// n_probes blocks of 1024 frames (stream order), +-1 directions from a counter-based generator (seed, attempt number)
+struct IqOptState { float mag, phase, avg_power, power_range; unsigned long long passes, attempts; unsigned seed, pad; };
+cudaError_t launch_iq_optimize_train(const float2* probes, int n_probes, IqOptState* state, cudaStream_t st);
+float iq_direction_host(unsigned seed, unsigned long long pass, unsigned k);
+
 // ---- fused front: raw -> [convert, DC, I/Q, NCO] -> halfband cascade -> polyphase stage -------
 constexpr int FUSED_MAX_STAGES = 10;
 struct ResamplerDesc {
@@ -145,6 +151,7 @@ void fused_destroy(FusedFront* f);
 cudaError_t fused_reset(FusedFront* f, cudaStream_t st);
 uint32_t fused_halo_frames(const FusedFront* f);
 int fused_version(const FusedFront* f);   // 1 = block-synchronous kernel, 2 = warp-streaming kernel
+const double2* fused_dc_state_at(const FusedFront* f, int slot, int64_t n0, int64_t pos);
 // raw[0] has absolute index n0; produces outputs [O0, O0+n_out) into y; d_dc_carry is the DC state at n0
 // (updated to the state at n0+n).  *launches is incremented by the kernels launched.
 // dc_slot (0/1): DC table slot; if fused_prepare_dc() filled it (possibly on another stream, ordered by

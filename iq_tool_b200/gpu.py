@@ -107,6 +107,10 @@ def _load() -> C.CDLL:
     lib.iqgpu_chain_get_info.argtypes = [vp, C.POINTER(ChainInfoC)]
     lib.iqgpu_chain_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     lib.iqgpu_chain_set_iq_factors.argtypes = [vp, C.c_float, C.c_float]
+    lib.iqgpu_chain_get_iq_state.restype = C.c_int
+    lib.iqgpu_chain_get_iq_state.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.iqgpu_iq_direction.restype = C.c_float
+    lib.iqgpu_iq_direction.argtypes = [C.c_uint32, C.c_uint64, C.c_uint32]
     lib.iqgpu_chain_get_kernel_times.restype = C.c_int
     lib.iqgpu_chain_get_kernel_times.argtypes = [vp, C.POINTER(C.c_double), u32p, C.c_int]
     lib.iqgpu_chain_process.argtypes = [vp, vp, sz, u32p, sz, vp, sz, C.POINTER(sz), u32p]
@@ -215,6 +219,13 @@ class Chain:
 
     def set_iq_factors(self, mag: float, phase: float) -> None:
         _check(lib.iqgpu_chain_set_iq_factors(self._h, mag, phase))
+
+    def iq_state(self):
+        """(mag, phase, successful passes, probed blocks) of the in-chain I/Q optimiser."""
+        m, p = C.c_float(0), C.c_float(0)
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        _check(lib.iqgpu_chain_get_iq_state(self._h, C.byref(m), C.byref(p), C.byref(a), C.byref(b)))
+        return m.value, p.value, a.value, b.value
 
     def reset(self) -> None:
         """Stream discontinuity with the reference's semantics (an FFT filter's waiting frames survive, filter.c:417-436)."""

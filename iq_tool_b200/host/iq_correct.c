@@ -37,7 +37,7 @@ bool iq_correct_init(AppConfig *config, AppResources *resources, MemoryArena *ar
     resources->iq_correction.average_power = 0.0f;
     resources->iq_correction.power_range = 0.0f;
     resources->iq_correction.samples_in_accum = 0;
-    resources->iq_correction.last_optimization_time = 0.0;
+    resources->iq_correction.last_optimization_time = -1e9;     /* sample clock starts at 0: the first probe passes the gate, as in the reference */
     log_info("I/Q Correction enabled");
     return true;
 }
@@ -61,11 +61,22 @@ void iq_correct_run_optimization(AppResources *resources, const complex_float_t 
 {
     if (!resources->config->iq_correction.enable || !resources->iq_correction.fft_plan) return;
     IqCorrectionResources *q = &resources->iq_correction;
-    const double now = get_monotonic_time_sec();
-    if ((now - q->last_optimization_time) * 1000.0 < IQ_CORRECTION_INTERVAL_MS) return;   /* :157-162 */
+    IqGpuDropin *d = (IqGpuDropin *)q->fft_plan;
+    /* :157-162 paces the passes with the wall clock and :391 draws the step directions from rand() seeded with time(): the
+     * result then depends on how fast the machine is and on when it was started.  Deliberate divergence:
+     * the clock is the SAMPLE clock — frames that have entered the pre-processor stage / input rate — and the directions
+     * come from a counter-based generator (seed: IQGPU_IQ_SEED), so a capture gives the same factors every time. */
+    const double rate = (double)resources->source_info.samplerate;
+    const double now = rate > 0.0 ? (double)__atomic_load_n(&d->frames_pre_total, __ATOMIC_RELAXED) / rate : 0.0;
+    if ((now - q->last_optimization_time) * 1000.0 < IQ_CORRECTION_INTERVAL_MS) return;
 
     float dirs[2 * IQ_MAX_PASSES];
-    for (int i = 0; i < 2 * IQ_MAX_PASSES; i++) dirs[i] = (rand() > (RAND_MAX / 2)) ? 1.0f : -1.0f;   /* :391 */
+    const uint64_t attempt = d->iq_attempts++;
+    /* IQGPU_IQ_LIBC_RAND=1: the reference's own source of directions (rand(), :391) — for parity runs against it */
+    const char *libc_rand = getenv("IQGPU_IQ_LIBC_RAND");
+    const int use_rand = libc_rand && *libc_rand && *libc_rand != '0';
+    for (int i = 0; i < 2 * IQ_MAX_PASSES; i++)
+        dirs[i] = use_rand ? ((rand() > (RAND_MAX / 2)) ? 1.0f : -1.0f) : iqgpu_iq_direction(d->iq_seed, attempt, (uint32_t)i);
     pthread_mutex_lock(&q->iq_factors_mutex);
     const int active = q->active_buffer_idx;
     float mag = q->factors_buffer[active].mag, phase = q->factors_buffer[active].phase;
@@ -133,7 +144,7 @@ bool iq_correct_run_initial_calibration(ModuleContext *ctx, SNDFILE *infile)
         pre_processor_reset(resources);                      /* the probe block must leave no state behind */
         resources->iq_correction.last_optimization_time = -1e9;
         iq_correct_run_optimization(resources, cf);
-        resources->iq_correction.last_optimization_time = get_monotonic_time_sec();
+        resources->iq_correction.last_optimization_time = 0.0;          /* sample clock: the stream starts here */
         if (sf_seek(infile, 0, SEEK_SET) < 0) { log_fatal("Failed to rewind input file after I/Q calibration."); ok = false; }
         else log_info("Initial I/Q calibration complete.");
     }

@@ -46,6 +46,8 @@ IqGpuDropin *iqgpu_dropin_get(AppResources *res)
     d->eager = (e && *e && *e != '0');
     const char *dev = getenv("IQGPU_DEVICE");
     d->device = dev ? atoi(dev) : 0;
+    const char *seed = getenv("IQGPU_IQ_SEED");
+    d->iq_seed = seed ? (uint32_t)strtoul(seed, NULL, 0) : 20261017u;
     pthread_mutex_init(&d->mu, NULL);
     pthread_cond_init(&d->room, NULL);
     pthread_mutex_lock(&g_reg_mu);

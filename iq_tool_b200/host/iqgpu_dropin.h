@@ -79,6 +79,11 @@ typedef struct IqGpuDropin {
     size_t         out_n, out_next;
     size_t         out_off_bytes;
     float          probe[2 * 1024]; /* I/Q optimiser probe block */
+    /* I/Q optimiser pacing and directions (sample clock and a seeded generator instead of the reference's
+     * wall clock and rand()): frames that have entered the pre stage, probed blocks so far, generator seed */
+    volatile uint64_t frames_pre_total;
+    uint64_t       iq_attempts;
+    uint32_t       iq_seed;
 } IqGpuDropin;
 
 IqGpuDropin *iqgpu_dropin_get(AppResources *res);         /* creates on first use, never NULL unless OOM */

@@ -65,6 +65,7 @@ void pre_processor_apply_chain(AppResources *resources, SampleChunk *item)
         item->frames_read = 0;
         return;
     }
+    if (item->frames_read > 0) __atomic_fetch_add(&d->frames_pre_total, (uint64_t)item->frames_read, __ATOMIC_RELAXED);   /* the sample clock */
     if (d->eager) { iqgpu_dropin_pre_eager(resources, item); return; }
     item->current_input_buffer = item->complex_sample_buffer_a;
     item->current_output_buffer = item->complex_sample_buffer_a;

@@ -779,3 +779,52 @@ def test_fft_filter_remainder_survives_a_stream_discontinuity_like_the_reference
         assert fresh.size != a2.size or not np.array_equal(fresh, a2)
         g.restart()
         assert np.array_equal(g.process(x[2 * n1:]).view(np.uint32), fresh.view(np.uint32))
+
+
+def test_in_chain_iq_optimizer_equals_function_level_passes(gpu, workloads):
+    """the optimiser inside the chain (sample-clocked gate, counter-based directions, passes on the
+    device, factors applied from the next train) == the function-level pass (iq_correct_run_optimization, K6) applied by
+    hand to the same probe blocks with the same directions.  cfg4's chain, unfused so that the pre-processor output the
+    probes are cut from can be read back; then the fused path (probe blocks re-computed from the raw frames)."""
+    import ctypes as C
+    wl = workloads["cfg4"]
+    cfg = wl.config
+    chunk, rate = 16384, int(cfg.input_rate_hz)
+    trains = [40, 45, 100]                                   # chunks per call; 500 ms = 73.2 chunks at 2.4 Msps
+    raw = synth_numpy(wl, sum(trains) * chunk)
+    seed = 1234
+    g = gpu.Chain(cfg, 0, fused=0, record_taps=2, iq_optimize=1, iq_optimize_seed=seed, subtrain_frames=1 << 22)
+    mag, phase = np.float32(cfg.iq_mag), np.float32(cfg.iq_phase)
+    applied = [(float(mag), float(phase))]
+    last_t, attempts, passes, pos = -1e18, 0, 0, 0
+    for n_chunks in trains:
+        lo, hi = pos * 2, (pos + n_chunks * chunk) * 2
+        g.process(raw[lo:hi])
+        tap0 = g.read_tap(0)                                 # accumulates over the calls
+        for c in range(n_chunks):
+            p0 = pos + c * chunk
+            t = p0 / rate
+            if (t - last_t) * 1000.0 >= 500.0:
+                last_t = t
+                blk = tap0[p0:p0 + 1024]
+                dirs = np.array([gpu.lib.iqgpu_iq_direction(seed, attempts, k) for k in range(50)], dtype=np.float32)
+                m2, p2, _, rng_db = gpu.iq_optimize(blk, dirs, float(mag), float(phase))
+                attempts += 1
+                if rng_db >= 20.0:
+                    mag, phase, passes = np.float32(m2), np.float32(p2), passes + 1
+        pos += n_chunks * chunk
+        gm, gp, gpasses, gattempts = g.iq_state()
+        assert (gattempts, gpasses) == (attempts, passes)
+        assert np.float32(gm) == mag and np.float32(gp) == phase, (gm, mag, gp, phase)
+        applied.append((gm, gp))
+    assert attempts == 3 and passes >= 1 and applied[-1] != applied[0]
+    # fused front: same gate, same generator; the probe blocks come from a second evaluation of the pre-processor chain
+    # (fp32 round-off in the DC state: a metric comparison may tip the other way once, i.e. one step of 0.05 * 1e-4)
+    f = gpu.Chain(cfg, 0, fused=1, iq_optimize=1, iq_optimize_seed=seed, subtrain_frames=1 << 22)
+    pos = 0
+    for n_chunks in trains:
+        f.process(raw[pos * 2:(pos + n_chunks * chunk) * 2])
+        pos += n_chunks * chunk
+    fm, fp_, fpasses, fattempts = f.iq_state()
+    assert f.info().fused_front == 1 and (fattempts, fpasses) == (attempts, passes)
+    assert abs(fm - float(mag)) <= 3.3e-5 and abs(fp_ - float(phase)) <= 3.3e-5
