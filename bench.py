@@ -169,7 +169,7 @@ def run_reference(args):
     from iq_tool_b200 import baseline_workloads
     from iq_tool_b200.synth import synth_numpy
     from oracle.loader import CpuChain, have_ref
-    wl = baseline_workloads()[args.workload]
+    wl = baseline_workloads()[args.workload.split(":", 1)[-1]]      # file:<cfg> times the same chain
     kind = "ref_fast" if have_ref(fast=True) else "oracle"
     # bounded sample: about 25 s of CPU work for the whole run whatever --steps is (the CPU chain does ~50 Msamples/s)
     n = min(args.cpu_samples, max(1 << 20, int(1.25e9 / max(1, args.steps))))
@@ -305,6 +305,79 @@ class WorkloadRun:
         return "time shards, no collective"
 
 
+def run_file_bench(args):
+    """--workload file:<cfg>: SURVEY 8(f) rank 2 — a raw capture on tmpfs through iqgpu_rawfile_run (reader thread -> chunk
+    trains -> chain -> writer thread, pinned rings) into a raw file on tmpfs, timed by the wall clock like the reference's own
+    run summary (src/main.c:286-306).  `value` and `e2e` are the same number here (the path is host to host by nature);
+    cpu_baseline = the reference's stage code fed by read() / write() of the same file on a bounded prefix."""
+    import numpy as np
+    from iq_tool_b200 import baseline_workloads, gpu
+    from iq_tool_b200.synth import synth_numpy
+    name = args.workload.split(":", 1)[1]
+    wl = baseline_workloads()[name]
+    cfg = wl.config
+    if gpu.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; iq_tool_b200 has no CPU fallback")
+    n = args.samples or (1 << 28)
+    n -= n % 16384
+    tmp = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+    src, dst = os.path.join(tmp, f"iqgpu_bench_{os.getpid()}_in.raw"), os.path.join(tmp, f"iqgpu_bench_{os.getpid()}_out.raw")
+    block = synth_numpy(wl, min(n, 1 << 24)).tobytes()
+    nbytes = n * cfg.in_bytes
+    with open(src, "wb") as f:
+        left = nbytes
+        while left:
+            k = min(left, len(block))
+            f.write(block[:k])
+            left -= k
+    steps = max(1, min(args.steps, 5))
+    try:
+        sampler = ClockSampler(0)
+        sampler.start()
+        for _ in range(max(1, min(args.warmup, 2))):
+            st = gpu.rawfile_run(cfg, src, dst, 0, args.train_chunks)
+        t0 = time.time()
+        p0 = time.perf_counter()
+        for _ in range(steps):
+            st = gpu.rawfile_run(cfg, src, dst, 0, args.train_chunks)
+        dt = time.perf_counter() - p0
+        clocks = sampler.stop(t0, time.time())
+        out_bytes = os.path.getsize(dst)
+        value = n * steps / dt / 1e6
+        cpu = None
+        if not args.no_cpu_baseline:
+            from oracle.loader import CpuChain, have_ref
+            kind = "ref_fast" if have_ref(fast=True) else "oracle"
+            m = min(n, args.cpu_samples * 4)
+            ch = CpuChain(cfg, kind)
+            c0 = time.perf_counter()
+            raw = np.fromfile(src, dtype=np.int16 if cfg.in_bytes == 4 else np.uint8, count=2 * m)
+            out = ch.process(raw, threaded=(kind != "oracle"))
+            out.tofile(dst + ".cpu")
+            cdt = time.perf_counter() - c0
+            os.remove(dst + ".cpu")
+            cpu = {"value": m / cdt / 1e6, "unit": UNIT, "cores": 3 if kind != "oracle" else 1,
+                   "kind": "reference" if kind != "oracle" else "port",
+                   "sample": f"first {m} frames of the same file, read() -> reference stage code on the restated liquid layer "
+                             f"(scalar dot products) -> write(); host has {os.cpu_count()} cpus"}
+    finally:
+        for pth in (src, dst):
+            if os.path.exists(pth):
+                os.remove(pth)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"file:{wl.name}: raw file on {tmp} -> iqgpu_rawfile_run -> raw file; {wl.description}",
+                       "frames_per_step": n, "output_frames_per_step": int(st.frames_out), "train_chunks": int(args.train_chunks or 256),
+                       "trains_per_step": int(st.trains), "timing": "wall clock around the whole file run (open .. close)"},
+            "roofline": None, "cpu_baseline": cpu,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(out_bytes),
+                    "read_gbs": nbytes * steps / dt / 1e9},
+            "gpu_launches": None, "clocks": clocks}
+    print(json.dumps(line))
+    return 0
+
+
 def pcie_probe(world, dev, nbytes=1 << 30, reps=3):
     """Plain pinned-host -> device copies, all ranks at once: the platform's ceiling for the end-to-end leg, per rank.
     (SCALE_r01's box shows every GPU behind one NUMA node, `nvidia-smi topo`: CPU affinity 0-31, NUMA 0 — there is no
@@ -354,10 +427,13 @@ def main():
                     help="second workload measured in the same run and reported as `sharded_capture` (BASELINE.json configs[4], the "
                          "multi-GPU configuration: time shards + the AGC peak all-gather); '' = off")
     ap.add_argument("--no-pcie-probe", action="store_true")
+    ap.add_argument("--train-chunks", type=int, default=2048, help="file workloads: reference chunks per chain call")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload.startswith("file:"):
+        return run_file_bench(args)
 
     import numpy as np
     import torch
@@ -481,10 +557,28 @@ def main():
         k2 = max(5, min(args.steps, 20))
         ms2, _, _, _ = run2.timed(k2, 3)
         kt2 = run2.chain.kernel_times(reset=True)
+        # where the exchange's time goes (a few extra steps with CUDA events around its three parts, per rank)
+        exch = None
+        if run2.exchange:
+            run2.sc.exchange_marks = []
+            for _ in range(5):
+                run2.step()
+            torch.cuda.synchronize()
+            marks = [m for m in run2.sc.exchange_marks if len(m) == 4]
+            run2.sc.exchange_marks = None
+            if marks:
+                mine_ms = [sum(m[i].elapsed_time(m[i + 1]) for m in marks) / len(marks) for i in range(3)]
+                t = torch.zeros(world * 3, device=dev, dtype=torch.float64)
+                t[3 * rank: 3 * rank + 3] = torch.tensor(mine_ms, dtype=torch.float64)
+                dist.all_reduce(t)
+                tt = t.cpu().tolist()
+                exch = {"per_rank_ms": {"all_gather_incl_wait": [round(tt[3 * r], 4) for r in range(world)],
+                                        "advance_over_lower_shards": [round(tt[3 * r + 1], 4) for r in range(world)],
+                                        "own_scan_scale_convert": [round(tt[3 * r + 2], 4) for r in range(world)]}}
         sharded = {"workload": f"{run2.wl.name}: {run2.wl.description}", "value": world * run2.n * k2 / (ms2 / 1e3) / 1e6,
                    "unit": UNIT, "n_gpus": world, "steps": k2, "ms_per_step": ms2 / k2, "frames_per_gpu_per_step": run2.n,
                    "halo_frames": run2.halo, "sharding": run2.sharding_text(), "scaling": "weak",
-                   "kernel_ms_per_step": {k: v[0] / k2 for k, v in kt2.items()},
+                   "kernel_ms_per_step": {k: v[0] / k2 for k, v in kt2.items()}, "exchange": exch,
                    "note": "efficiency at N = value(N) / (N * value(1)) of THIS object across the per-N lines"}
         del run2
 

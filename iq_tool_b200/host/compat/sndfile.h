@@ -1,8 +1,7 @@
-/* compat/sndfile.h — the sliver of <sndfile.h> that iq_tool's sources need once the WAV modules are served by
- * libiqgpu's host-only container code (host/input_wav.c, host/output_wav_common.c, host/sndfile_min.c): the
- * SNDFILE / sf_count_t types, the two raw calls the calibration service makes on an input handle, and the
- * container / subtype constants the output wrappers (src/output_wav.c, src/output_wav_rf64.c) pass down.
- * Put this directory on the include path ONLY in a build that does not link libsndfile. */
+/* compat/sndfile.h — the sliver of <sndfile.h> the drop-in translation units need to compile without libsndfile
+ * installed: the SNDFILE / sf_count_t types and the two raw calls iq_correct_run_initial_calibration makes on an input
+ * handle (include/iq_correct.h:76).  A build that links the real libsndfile (the reference's normal build) uses its own
+ * header instead; this directory goes on the include path only where the library is absent (the test harness). */
 #ifndef IQGPU_COMPAT_SNDFILE_H
 #define IQGPU_COMPAT_SNDFILE_H
 #include <stdint.h>

@@ -199,13 +199,26 @@ class ShardedChain:
         sizes = [(t.frames + CHUNK_SAMPLES - 1) // CHUNK_SAMPLES for t in shards]
         m = max(max(sizes), 1)
         mine, gathered = self._exchange_buffers(shard.world, m, device)
+        marks = getattr(self, "exchange_marks", None)        # optional: CUDA events around the exchange (bench diagnostics)
+
+        def mark():
+            if marks is not None:
+                import torch
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(torch.cuda.current_stream())
+                marks[-1].append(ev)
+
         with self._on_stream(stream):
+            if marks is not None:
+                marks.append([])
+            mark()                                            # front + peaks queued before this point
             if shard.read_frames:
                 live = ch.pending_chunk_peaks_device(shard.skip_chunks, mine.data_ptr(), m, stream)
                 assert live == sizes[shard.rank]
             else:
                 mine.zero_()
             dist.all_gather_into_tensor(gathered, mine, group=group)
+            mark()                                            # all-gather done (includes waiting for the slowest rank)
             if not shard.read_frames:
                 return 0
             # lower shards, in rank order.  The first one holds the scan-to-lock transition (a tile walk); the others are
@@ -223,7 +236,10 @@ class ShardedChain:
                 ch.agc_advance_device(gathered.data_ptr() + 4 * r0 * m, shards[r0].start,
                                       sum(shards[r].frames for r in run), stream)
                 lower = lower[len(run):]
-            return ch.process_device_finish(shard.skip_chunks, dev_out_ptr, out_capacity_bytes, stream)
+            mark()                                            # state advanced over the lower shards
+            produced = ch.process_device_finish(shard.skip_chunks, dev_out_ptr, out_capacity_bytes, stream)
+            mark()                                            # own scan + scale + convert
+            return produced
 
     def process_device(self, shard: Shard, dev_in_ptr: int, dev_out_ptr: int, out_capacity_bytes: int,
                        stream: int = 0, group=None, comm_device="cpu") -> Tuple[int, int]:

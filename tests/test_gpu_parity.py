@@ -800,13 +800,13 @@ def test_in_chain_iq_optimizer_equals_function_level_passes(gpu, workloads):
     for n_chunks in trains:
         lo, hi = pos * 2, (pos + n_chunks * chunk) * 2
         g.process(raw[lo:hi])
-        tap0 = g.read_tap(0)                                 # accumulates over the calls
+        tap0 = g.read_tap(0)                                 # the pre-processor output of THIS call
         for c in range(n_chunks):
             p0 = pos + c * chunk
             t = p0 / rate
             if (t - last_t) * 1000.0 >= 500.0:
                 last_t = t
-                blk = tap0[p0:p0 + 1024]
+                blk = tap0[c * chunk:c * chunk + 1024]
                 dirs = np.array([gpu.lib.iqgpu_iq_direction(seed, attempts, k) for k in range(50)], dtype=np.float32)
                 m2, p2, _, rng_db = gpu.iq_optimize(blk, dirs, float(mag), float(phase))
                 attempts += 1
