@@ -235,6 +235,8 @@ struct iqgpu_chain {
     size_t max_segs = 0;
     float2* d_agc_scratch = nullptr;
     size_t agc_scratch_cap = 0;
+    void* d_agc_quiet = nullptr;        // digital AGC: workspace of the grid-wide quiet test (state-only advance)
+    size_t agc_quiet_bytes = 0;
     void* d_agc_ws = nullptr;           // RMS-AGC time-parallel workspace (block end states + sweep flags)
     size_t agc_ws_bytes = 0;
     // streams: s_in = pre output; s_stage[d] = output of executed halfband stage d; s_rs = resampler
@@ -334,7 +336,7 @@ iqgpu_chain::~iqgpu_chain()
     cudaFree(d_lut); cudaFree(d_dc_carry); cudaFree(d_dc_ref); cudaFree(d_run_sums); cudaFree(d_run_start); cudaFree(d_scan_ws); cudaFree(d_bank);
     cudaFree(d_fir_taps); cudaFree(d_fft_H); cudaFree(d_fft_tw); cudaFree(d_fft_scratch); cudaFree(d_agc); cudaFree(d_seg_start);
     cudaFree(d_seg_peak); cudaFree(d_seg_gain); cudaFree(d_agc_scratch); cudaFree(d_agc_ws);
-    cudaFree(d_iq_state); cudaFree(d_iq_probe);
+    cudaFree(d_iq_state); cudaFree(d_iq_probe); cudaFree(d_agc_quiet);
     if (h_iq_state) cudaFreeHost(h_iq_state);
     if (ev_iq) cudaEventDestroy(ev_iq);
     if (ev_iq_probe) cudaEventDestroy(ev_iq_probe);
@@ -1551,7 +1553,15 @@ int iqgpu_chain_agc_advance_device(iqgpu_chain* c, const float* dev_peaks, uint6
     }
     PostParams qp{};
     qp.agc_mode = c->agc_mode; qp.agc_target = c->agc_target; qp.agc_alpha = c->agc_alpha; qp.target_rate = c->target_rate;
-    CK(launch_agc_digital_scan(d_seg, nch, dev_peaks, qp, c->d_agc, nullptr, st));
+    const size_t qneed = agc_quiet_workspace_bytes(nch);
+    if (qneed > c->agc_quiet_bytes) {
+        CK(cudaStreamSynchronize(st));
+        cudaFree(c->d_agc_quiet);
+        c->d_agc_quiet = nullptr; c->agc_quiet_bytes = 0;
+        CK(cudaMalloc(&c->d_agc_quiet, qneed * 2));
+        c->agc_quiet_bytes = qneed * 2;
+    }
+    CK(launch_agc_digital_scan(d_seg, nch, dev_peaks, qp, c->d_agc, nullptr, st, c->d_agc_quiet));
     return IQGPU_OK;
 }
 

@@ -264,23 +264,8 @@ __device__ __forceinline__ void w2_load_quad(int fmt, const void* __restrict__ r
     }
 }
 
-// a tick is "fast" when all of its 512 frames come straight from this call's raw buffer with aligned
-// vector loads and none of them belongs to the cf32 tail kept for the next call
-__device__ __forceinline__ bool w2_tick_fast(const Fused2Args& A, long long tick_start)
-{
-    return A.raw_aligned && (tick_start >= A.n0) && (tick_start + W2_T0 <= A.N1 - A.H_tail);
-}
-// software prefetch (cs16 fast path): the lane's 64 raw bytes of the NEXT tick are requested one
-// whole tick ahead and sit in 16 registers while the cascade of the current tick runs
+// raw frames of one tick and one lane (cs16 fast path): four 16-byte chunks
 struct W2Raw { uint4 q[4]; };
-__device__ __forceinline__ void w2_prefetch(const Fused2Args& A, long long tick_start, int lane, W2Raw& r)
-{
-    if (w2_tick_fast(A, tick_start)) {
-        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(A.raw) + (tick_start - A.n0 + lane * 16) * 4);
-#pragma unroll
-        for (int j = 0; j < 4; j++) r.q[j] = __ldg(src + j);
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // P0: one tick (512 frames) of the pre-processor chain into level 0 (or the flat level when S == 0)
@@ -288,15 +273,15 @@ __device__ __forceinline__ void w2_prefetch(const Fused2Args& A, long long tick_
 template <int S, int DC, bool CS16>
 __device__ __forceinline__ void w2_p0(const Fused2Args& A, float2* __restrict__ wsm, const float2* __restrict__ lut2,
                                       long long tick_start, int lane, const W2Raw& pre, f32x2_t (&x)[16], double2& vloc,
-                                      bool write_tail)
+                                      bool write_tail, bool active, bool fast)
 {
+    // active: the tick holds frames of this call; fast: all of them come from this call's raw buffer with aligned vector
+    // loads and none belongs to the cf32 tail (both decided by the caller from per-warp tick ranges)
     using P = W2Plan<S>;
     const PreParams& p = A.pre;
     const int fmt = CS16 ? IQGPU_FMT_CS16 : p.format;
     const float sc = CS16 ? p.gain * ((p.format == IQGPU_FMT_SC16Q11) ? (1.0f / 2048.0f) : (1.0f / 32768.0f)) : w2_scale(fmt, p.gain);
     const long long a0 = tick_start + lane * 16;               // first frame of this lane
-    const bool active = (tick_start + W2_T0 > A.n0) && (tick_start < A.N1);
-    const bool fast = w2_tick_fast(A, tick_start);
     // the lane's 16 frames as packed {re, im} pairs (FMUL2 / FFMA2: one issue slot per complex sample)
     if (fast && CS16) {
         // sample_convert.c:136-141: x / 32768 * gain (exact power-of-two scale folded into sc)
@@ -1052,19 +1037,38 @@ __global__ void __launch_bounds__(W2_MAX_WARPS * 32, 1) fused_front2_kernel(cons
         const double f = exp(-(double)(A.n0 - t_begin * W2_T0) * A.dc_lnc);
         vloc = make_double2(cv.x * f, cv.y * f);
     }
+    // Per-tick bookkeeping in 32-bit tick numbers relative to t_begin (the 64-bit range tests of every tick were 8 % of the
+    // kernel's instructions in profiles/r02f_fused_front2_cfg2.md): ticks [fast_lo, fast_hi) are "fast", [act_lo, act_hi) hold
+    // frames of this call, emission starts at emit_r.
+    const int n_ticks = (int)(t_end - t_begin), emit_r = (int)(t_emit - t_begin);
+    int fast_lo = 0, fast_hi = 0, act_lo, act_hi;
+    {
+        const long long lo = (A.n0 + W2_T0 - 1) / W2_T0, hi = (A.N1 - A.H_tail) / W2_T0;      // tick_start >= n0, tick end <= N1 - H_tail
+        if (A.raw_aligned && hi > lo) {
+            fast_lo = (int)max(0LL, min((long long)n_ticks, lo - t_begin));
+            fast_hi = (int)max(0LL, min((long long)n_ticks, hi - t_begin));
+        }
+        const long long alo = A.n0 / W2_T0, ahi = (A.N1 + W2_T0 - 1) / W2_T0;                 // tick end > n0, tick_start < N1
+        act_lo = (int)max(0LL, min((long long)n_ticks, alo - t_begin));
+        act_hi = (int)max(0LL, min((long long)n_ticks, ahi - t_begin));
+    }
+    const unsigned fast_len = (unsigned)max(0, fast_hi - fast_lo), act_len = (unsigned)max(0, act_hi - act_lo);
     // raw frames of a fast cs16 tick: staged one tick ahead by TMA (A.raw_tma) into the warp's buffer
     const bool use_tma = CS16 && A.raw_tma;
     bool staged = false;                    // a TMA load for the tick about to run is in flight / has landed (warp-uniform)
     unsigned raw_phase = 0;
-    if (use_tma && w2_tick_fast(A, t_begin * W2_T0)) {
-        if (lane == 0) w2_tma_load_tick(rawbuf, &A.raw_map, (int)((t_begin * W2_T0 - A.n0) >> 5), &raw_bar[warp]);
+    const int row0 = (int)((t_begin * W2_T0 - A.n0) >> 5);       // 128-byte row of tick 0 (meaningful for fast ticks only)
+    if (use_tma && (unsigned)(0 - fast_lo) < fast_len) {
+        if (lane == 0) w2_tma_load_tick(rawbuf, &A.raw_map, row0, &raw_bar[warp]);
         staged = true;
     }
     // the lane's four 16-byte chunks of its 64-byte run: chunk u = 4*lane + j sits in row u >> 3 at 16-byte slot (u & 7) ^ (row & 7)
     const unsigned raw_row = w2_smem_u32(rawbuf) + 128u * (unsigned)(lane >> 1);
     const unsigned raw_sw = (unsigned)(lane >> 1) & 7u, raw_c0 = 4u * (unsigned)(lane & 1);
-    for (long long t = t_begin; t < t_end; t++) {
+    long long t = t_begin;
+    for (int tr = 0; tr < n_ticks; tr++, t++) {
         const long long tick_start = t * W2_T0;
+        const bool fast = (unsigned)(tr - fast_lo) < fast_len, active = (unsigned)(tr - act_lo) < act_len;
         W2Raw cur;
         if (CS16) {
             if (staged) {
@@ -1079,20 +1083,23 @@ __global__ void __launch_bounds__(W2_MAX_WARPS * 32, 1) fused_front2_kernel(cons
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; j++) cur.q[j] = make_uint4(0u, 0u, 0u, 0u);
-                w2_prefetch(A, tick_start, lane, cur);          // unaligned call: plain loads, no look-ahead
+                if (fast) {                                       // unaligned call: plain loads, no look-ahead
+                    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(A.raw) + (tick_start - A.n0 + lane * 16) * 4);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) cur.q[j] = __ldg(src + j);
+                }
             }
         }
-        if (DC == 2 && t == t_emit && lane == 0) A.dc_stretch[gw].v_emit = vloc;
+        if (DC == 2 && tr == emit_r && lane == 0) A.dc_stretch[gw].v_emit = vloc;
         f32x2_t x[16];
         // local DC: the frames of a warm-up tick belong to the emit range of the warp below, which stores them in the tail
         // with ITS state (warp 0's warm-up frames precede n0: copies of the old tail)
-        w2_p0<S, DC, CS16>(A, wsm, lut2, tick_start, lane, cur, x, vloc, DC != 2 || t >= t_emit || gw == 0);
+        w2_p0<S, DC, CS16>(A, wsm, lut2, tick_start, lane, cur, x, vloc, DC != 2 || tr >= emit_r || gw == 0, active, fast);
         if (use_tma) {
             // every lane has consumed its chunks (the conversions in w2_p0 depend on them): the buffer may be refilled
             __syncwarp();
-            staged = (t + 1 < t_end) && w2_tick_fast(A, tick_start + W2_T0);
-            if (staged && lane == 0)
-                w2_tma_load_tick(rawbuf, &A.raw_map, (int)((tick_start + W2_T0 - A.n0) >> 5), &raw_bar[warp]);
+            staged = (unsigned)(tr + 1 - fast_lo) < fast_len;     // (fast_hi <= n_ticks: never beyond the warp's last tick)
+            if (staged && lane == 0) w2_tma_load_tick(rawbuf, &A.raw_map, row0 + 16 * (tr + 1), &raw_bar[warp]);
         }
         bool arb_due = true;
         if constexpr (P::reg0) {
@@ -1115,7 +1122,7 @@ __global__ void __launch_bounds__(W2_MAX_WARPS * 32, 1) fused_front2_kernel(cons
         if (arb_due) {
             // the new flat entries are the last stage's outputs of this run: absolute decimated index
             const long long kA = ((tick_start + W2_T0) >> S) - P::flat_new;
-            if (t >= t_emit) w2_arb<S>(A, flat, sbank, kA, o_cur, lane);
+            if (tr >= emit_r) w2_arb<S>(A, flat, sbank, kA, o_cur, lane);
             __syncwarp();
             float2 h = make_float2(0.f, 0.f);
             const int ssh = P::quad ? A.arb_skew_sh : 31;

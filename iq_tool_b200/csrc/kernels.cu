@@ -907,8 +907,10 @@ __device__ __forceinline__ float agc_step_at(AgcState& s, float pk, unsigned cnt
 }
 __global__ void __launch_bounds__(AGC_SCAN_THREADS) agc_digital_scan_kernel(const uint32_t* __restrict__ seg_start, unsigned nseg,
                                                                             const float* __restrict__ seg_peak, PostParams p,
-                                                                            AgcState* __restrict__ st, float* __restrict__ seg_gain)
+                                                                            AgcState* __restrict__ st, float* __restrict__ seg_gain,
+                                                                            const int* __restrict__ skip_flag)
 {
+    if (skip_flag && *skip_flag) return;        // the grid-wide quiet test (below) already advanced the state over this table
     __shared__ unsigned s_cnt[AGC_SCAN_TILE];
     __shared__ float s_pk[AGC_SCAN_TILE];
     __shared__ float s_gain[AGC_SCAN_TILE];
@@ -1155,24 +1157,6 @@ __global__ void __launch_bounds__(AGC_SCAN_THREADS) agc_digital_scan_kernel(cons
 // walks its block sample by sample).  Both are accurate to ~1 ulp of double, so rounding them to float
 // gives the correctly rounded logf/expf result (checked against libm on 2e7 arguments; the rounding can
 // differ only when the exact value lies within 1e-15 of a float rounding boundary).
-__device__ __forceinline__ double agc_log_pos(float yf)
-{
-    const double y = (double)yf;
-    long long b = __double_as_longlong(y);
-    int e = (int)((b >> 52) & 0x7ff) - 1023;
-    double m = __longlong_as_double((b & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
-    if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
-    const double d = m + 1.0;
-    double r = (double)__frcp_rn((float)d);
-    r = r * fma(-d, r, 2.0);
-    r = r * fma(-d, r, 2.0);
-    const double s = (m - 1.0) * r, z = s * s;
-    double p = 1.0 / 23.0;
-    p = fma(p, z, 1.0 / 21.0); p = fma(p, z, 1.0 / 19.0); p = fma(p, z, 1.0 / 17.0); p = fma(p, z, 1.0 / 15.0);
-    p = fma(p, z, 1.0 / 13.0); p = fma(p, z, 1.0 / 11.0); p = fma(p, z, 1.0 / 9.0);  p = fma(p, z, 1.0 / 7.0);
-    p = fma(p, z, 1.0 / 5.0);  p = fma(p, z, 1.0 / 3.0);  p = fma(p, z, 1.0);
-    return fma((double)e, 0.6931471805599453, 2.0 * s * p);
-}
 __device__ __forceinline__ double agc_exp_small(double t)   // |t| <= 0.5 (t = -alpha/2 * log(y2'), alpha <= 1e-2)
 {
     double p = 1.0 / 6227020800.0;
@@ -1186,25 +1170,65 @@ __device__ __forceinline__ double agc_exp_small(double t)   // |t| <= 0.5 (t = -
 __constant__ AgcLogEntry agc_log_tab_c[AGC_LOG_N];
 __constant__ double agc_coef_c[AGC_NCOEF] = AGC_COEF_LIST;
 
-__device__ __forceinline__ float2 agc_rms_step(float2 v, size_t i, const PostParams& p, const float* __restrict__ lut,
-                                               const AgcLogEntry* __restrict__ ltab,
-                                               float alpha, double oma, float mha, float& g, float& y2p)
+// The recurrence's loop-carried state: g, y2' and y2' once more as a double (its exact value: the next step needs it
+// widened, and widening right after the rounding keeps that conversion off the critical path).
+struct AgcRec { float g, y2p; double y2pd; };
+
+// exact float -> double by integer arithmetic for a NORMAL float (any sign): 2 dependent ALU steps instead of a trip through
+// the conversion unit (F2F: ~19 cycles on B200, tools/ubench/dlat.cu); the callers check normality themselves
+__device__ __forceinline__ double agc_normal_f2d(unsigned bits)
 {
-    if (p.nco_enable) v = nco_mix(v, p.nco_theta0 + (uint32_t)i * p.nco_dtheta, p.nco_sign, lut);
-    const float yr = __fmul_rn(v.x, g), yi = __fmul_rn(v.y, g);
-    const float y2 = __fadd_rn(__fmul_rn(yr, yr), __fmul_rn(yi, yi));
-    y2p = (float)(oma * (double)y2p + (double)__fmul_rn(alpha, y2));
-    if (y2p > 1e-6f) {
-        // logf/expf evaluated in double and rounded once: matches a correctly rounded libm
-        // (agc_math.h: table log + Estrin polynomials, ~12 dependent double operations instead of ~35)
-        const float lf = (float)agc_log_fast(y2p, ltab, agc_coef_c);
+    const unsigned mag = bits & 0x7fffffffu;
+    return __hiloint2double((int)(((mag >> 3) + 0x38000000u) | (bits & 0x80000000u)), (int)(mag << 29));
+}
+
+// generic step (any operand: zero / subnormal / huge): the rare fall-back of agc_rms_step, kept out of line
+__device__ __noinline__ AgcRec agc_rms_step_slow(float ay2, float mha, double oma, const AgcLogEntry* __restrict__ ltab, AgcRec r)
+{
+    const float y2n = (float)fma(oma, r.y2pd, (double)ay2);
+    float gn = r.g;
+    if (y2n > 1e-6f) {
+        const float lf = (float)agc_log_fast(y2n, ltab, agc_coef_c);
         const float tt = __fmul_rn(mha, lf);
         float ex;
         if (fabsf(tt) <= 0.125f) ex = (float)agc_exp_tiny((double)tt, agc_coef_c);
         else ex = (fabsf(tt) <= 0.5f) ? (float)agc_exp_small((double)tt) : (float)exp((double)tt);
-        g = __fmul_rn(g, ex);
+        gn = __fmul_rn(gn, ex);
     }
-    if (g > 1e6f) g = 1e6f;
+    if (gn > 1e6f) gn = 1e6f;
+    r.g = gn; r.y2p = y2n; r.y2pd = (double)y2n;
+    return r;
+}
+
+// One sample of liquid's agc_crcf_execute (reference src/agc.c:92-100).  The recurrence is ONE dependent chain per block
+// of the stream, so the step is written for latency: straight-line code for the operand ranges that occur (everything
+// normal, y2' > 1e-6, |t| <= 0.125), conversions by integer arithmetic where they are exact, the three range checks folded
+// into one predicate that is tested once at the end and sends the rare other cases through agc_rms_step_slow.
+__device__ __forceinline__ float2 agc_rms_step(float2 v, size_t i, const PostParams& p, const float* __restrict__ lut,
+                                               const AgcLogEntry* __restrict__ ltab,
+                                               float alpha, double oma, float mha, AgcRec& r)
+{
+    if (p.nco_enable) v = nco_mix(v, p.nco_theta0 + (uint32_t)i * p.nco_dtheta, p.nco_sign, lut);
+    const float yr = __fmul_rn(v.x, r.g), yi = __fmul_rn(v.y, r.g);
+    const float y2 = __fadd_rn(__fmul_rn(yr, yr), __fmul_rn(yi, yi));
+    const float ay2 = __fmul_rn(alpha, y2);
+    const unsigned ab = __float_as_uint(ay2);
+    const bool ok_a = (ab - 0x00800000u) < 0x7f000000u;                      // positive normal
+    const float y2n = (float)fma(oma, r.y2pd, agc_normal_f2d(ab));            // (1 - alpha) y2' + alpha y2, rounded to float
+    const unsigned yb = __float_as_uint(y2n);
+    // logf(y2n), agc_math.h
+    const float lf = (float)agc_log_fast(y2n, ltab, agc_coef_c);
+    const float tt = __fmul_rn(mha, lf);
+    const unsigned tb = __float_as_uint(tt);
+    const bool ok_t = ((tb & 0x7fffffffu) - 0x00800000u) <= (0x3e000000u - 0x00800000u);   // 2^-126 <= |t| <= 0.125
+    const float ex = (float)agc_exp_tiny(agc_normal_f2d(tb), agc_coef_c);
+    float gn = __fmul_rn(r.g, ex);
+    if (gn > 1e6f) gn = 1e6f;
+    if (ok_a && ok_t && y2n > 1e-6f) {
+        r.g = gn; r.y2p = y2n; r.y2pd = agc_normal_f2d(yb);
+    } else {
+        r = agc_rms_step_slow(ay2, mha, oma, ltab, r);
+    }
     return make_float2(yr, yi);
 }
 
@@ -1223,6 +1247,7 @@ __device__ __forceinline__ bool agc_rms_block(const float2* __restrict__ x, size
     const float alpha = p.agc_alpha;
     const double oma = 1.0 - (double)alpha;
     const float mha = __fmul_rn(-0.5f, alpha);
+    AgcRec r{g, y2p, (double)y2p};
     size_t i = i0;
     float2 nx[8];
     if (i + 8 <= i1) {
@@ -1234,9 +1259,9 @@ __device__ __forceinline__ bool agc_rms_block(const float2* __restrict__ x, size
             float2* c = ck + ((i - i0) / AGC_CK);
             if (compare) {
                 const float2 o = *c;
-                if (__float_as_uint(o.x) == __float_as_uint(g) && __float_as_uint(o.y) == __float_as_uint(y2p)) return true;
+                if (__float_as_uint(o.x) == __float_as_uint(r.g) && __float_as_uint(o.y) == __float_as_uint(r.y2p)) return true;
             }
-            *c = make_float2(g, y2p);
+            *c = make_float2(r.g, r.y2p);
         }
         float2 v[8];
 #pragma unroll
@@ -1246,11 +1271,12 @@ __device__ __forceinline__ bool agc_rms_block(const float2* __restrict__ x, size
             for (int k = 0; k < 8; k++) nx[k] = x[i + 8 + k];
         }
 #pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = agc_rms_step(v[k], i + k, p, lut, ltab, alpha, oma, mha, g, y2p);
+        for (int k = 0; k < 8; k++) v[k] = agc_rms_step(v[k], i + k, p, lut, ltab, alpha, oma, mha, r);
 #pragma unroll
         for (int k = 0; k < 8; k++) y[i + k] = v[k];
     }
-    for (; i < i1; i++) y[i] = agc_rms_step(x[i], i, p, lut, ltab, alpha, oma, mha, g, y2p);
+    for (; i < i1; i++) y[i] = agc_rms_step(x[i], i, p, lut, ltab, alpha, oma, mha, r);
+    g = r.g; y2p = r.y2p;
     return false;
 }
 
@@ -1445,11 +1471,101 @@ cudaError_t launch_agc_peaks(const float2* x, size_t n, const PostParams& p, con
     agc_peaks_kernel<<<grid_tiles(n), 256, 0, st>>>(x, n, p, seg_start, (unsigned)nseg, seg_peak, aligned16(x));
     return cudaGetLastError();
 }
+// ---------------------------------------------------------------------------------------------
+// Grid-wide quiet test for a STATE-ONLY advance over a long chunk table (a time shard advancing over the chunks of the
+// shards below it).  Once the digital AGC is locked (agc.c:165-218) a chunk changes the state only through a
+// ratchet (peak * gain > 1), a creep step (weak for more than 4 s after the latest strong chunk) or by being strong
+// (last_strong <- its time).  Every chunk's time follows from the closed-form table (samples before it), so whether ANY
+// event happens in the table is a parallel question: part b (AGC_QUIET_PART chunks, one CTA) reports an internal event, the
+// time of its latest strong chunk and the time of the last weak chunk in front of its first strong one; a single warp then
+// walks the parts.  Quiet table: seen += total, last_strong <- latest strong time, and the one-CTA scan kernel is skipped
+// (it used to walk the 458 752 chunks of seven lower shards in 1.03 ms on rank 7 of an 8-GPU run: the whole scaling loss of
+// the cfg5 row in profiles/r02h_scale.md).  Any event, or a state that is not locked yet: the scan kernel does the work.
+// ---------------------------------------------------------------------------------------------
+constexpr int AGC_QUIET_PART = 4096, AGC_QUIET_THREADS = 256, AGC_QUIET_PER = AGC_QUIET_PART / AGC_QUIET_THREADS;
+struct AgcQuietPart { int event; int pad; double last_strong, weak_before; };
+
+__global__ void __launch_bounds__(AGC_QUIET_THREADS) agc_quiet_parts_kernel(const uint32_t* __restrict__ seg_start, unsigned nseg,
+                                                                            const float* __restrict__ seg_peak, PostParams p,
+                                                                            const AgcState* __restrict__ st, AgcQuietPart* __restrict__ parts)
+{
+    __shared__ double s_last[AGC_QUIET_THREADS], s_weak[AGC_QUIET_THREADS];
+    __shared__ int s_event;
+    const unsigned t = threadIdx.x;
+    const AgcState s0 = *st;
+    const float strong_thr = __fmul_rn(p.agc_target, 0.75f);
+    const unsigned i0 = min(nseg, blockIdx.x * AGC_QUIET_PART + t * AGC_QUIET_PER), i1 = min(nseg, i0 + AGC_QUIET_PER);
+    if (t == 0) s_event = 0;
+    bool event = false;
+    double local_last = -1.0, weak_before = -1.0;
+    const uint32_t base = __ldg(seg_start);
+    for (unsigned i = i0; i < i1; i++) {
+        const uint32_t a = __ldg(seg_start + i), b = __ldg(seg_start + i + 1);
+        if (b == a) continue;                                          // agc_apply returns on an empty chunk (agc.c:89)
+        const float opk = __fmul_rn(__ldg(seg_peak + i), s0.gain);
+        const double now = (double)(s0.seen + (unsigned long long)(uint32_t)(a - base)) / p.target_rate;
+        if (opk > 1.0f) event = true;
+        else if (opk > strong_thr) local_last = now;
+        else if (local_last >= 0.0) { if (now - local_last > (double)4.0f) event = true; }
+        else weak_before = now;
+    }
+    s_last[t] = local_last; s_weak[t] = weak_before;
+    __syncthreads();
+    if (event) s_event = 1;
+    // latest strong chunk of the part in front of this thread's range (serial look-back is fine: 256 entries in shared memory,
+    // and almost always the very first neighbour is strong)
+    double before = -1.0;
+    for (int k = (int)t - 1; k >= 0 && before < 0.0; k--) before = s_last[k];
+    if (before >= 0.0 && weak_before >= 0.0 && weak_before - before > (double)4.0f) s_event = 1;
+    __syncthreads();
+    if (t == 0) {
+        double last = -1.0, weak = -1.0;
+        bool seen_strong = false;
+        for (int k = 0; k < AGC_QUIET_THREADS; k++) {
+            if (!seen_strong && s_weak[k] > weak) weak = s_weak[k];    // weak chunks in front of the part's first strong one
+            if (s_last[k] >= 0.0) { seen_strong = true; last = s_last[k]; }
+        }
+        parts[blockIdx.x] = AgcQuietPart{s_event, 0, last, weak};
+    }
+}
+
+__global__ void agc_quiet_finish_kernel(const AgcQuietPart* __restrict__ parts, unsigned nparts, const uint32_t* __restrict__ seg_start,
+                                        unsigned nseg, AgcState* __restrict__ st, int* __restrict__ quiet_flag)
+{
+    if (threadIdx.x) return;
+    AgcState s = *st;
+    bool event = !s.locked;
+    double before = s.last_strong;
+    for (unsigned b = 0; b < nparts && !event; b++) {
+        const AgcQuietPart q = parts[b];
+        if (q.event) event = true;
+        else if (q.weak_before >= 0.0 && q.weak_before - before > (double)4.0f) event = true;
+        if (q.last_strong > before) before = q.last_strong;
+    }
+    if (!event) {
+        s.seen += (unsigned long long)(uint32_t)(seg_start[nseg] - seg_start[0]);
+        s.last_strong = before;
+        *st = s;
+    }
+    *quiet_flag = event ? 0 : 1;
+}
+
+size_t agc_quiet_workspace_bytes(size_t nseg) { return ((nseg + AGC_QUIET_PART - 1) / AGC_QUIET_PART + 1) * sizeof(AgcQuietPart) + 16; }
+
 cudaError_t launch_agc_digital_scan(const uint32_t* seg_start, size_t nseg, const float* seg_peak,
-                                    const PostParams& p, AgcState* state, float* seg_gain, cudaStream_t st)
+                                    const PostParams& p, AgcState* state, float* seg_gain, cudaStream_t st, void* quiet_ws)
 {
     if (nseg == 0) return cudaSuccess;
-    agc_digital_scan_kernel<<<1, AGC_SCAN_THREADS, 0, st>>>(seg_start, (unsigned)nseg, seg_peak, p, state, seg_gain);
+    const int* skip = nullptr;
+    if (!seg_gain && quiet_ws && nseg >= 1024) {
+        int* flag = reinterpret_cast<int*>(quiet_ws);
+        AgcQuietPart* parts = reinterpret_cast<AgcQuietPart*>(reinterpret_cast<char*>(quiet_ws) + 16);
+        const unsigned nparts = (unsigned)((nseg + AGC_QUIET_PART - 1) / AGC_QUIET_PART);
+        agc_quiet_parts_kernel<<<nparts, AGC_QUIET_THREADS, 0, st>>>(seg_start, (unsigned)nseg, seg_peak, p, state, parts);
+        agc_quiet_finish_kernel<<<1, 32, 0, st>>>(parts, nparts, seg_start, (unsigned)nseg, state, flag);
+        skip = flag;
+    }
+    agc_digital_scan_kernel<<<1, AGC_SCAN_THREADS, 0, st>>>(seg_start, (unsigned)nseg, seg_peak, p, state, seg_gain, skip);
     return cudaGetLastError();
 }
 // co-resident thread budget of the cooperative RMS-AGC kernel on the current device

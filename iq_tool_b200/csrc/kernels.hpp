@@ -110,8 +110,11 @@ struct PostParams {
 // segment table: seg_start[0..nseg] (prefix offsets into the n samples of this call)
 cudaError_t launch_agc_peaks(const float2* x, size_t n, const PostParams& p, const uint32_t* seg_start,
                              size_t nseg, float* seg_peak, cudaStream_t st);
+// quiet_ws (optional, agc_quiet_workspace_bytes(nseg) device bytes): a state-only advance (seg_gain == nullptr) over a long
+// table first asks, grid-wide, whether anything happens in it at all
+size_t agc_quiet_workspace_bytes(size_t nseg);
 cudaError_t launch_agc_digital_scan(const uint32_t* seg_start, size_t nseg, const float* seg_peak,
-                                    const PostParams& p, AgcState* state, float* seg_gain, cudaStream_t st);
+                                    const PostParams& p, AgcState* state, float* seg_gain, cudaStream_t st, void* quiet_ws = nullptr);
 // rms AGC (liquid agc_crcf): the sequential recurrence evaluated time-parallel to its exact fixed point
 // (after NCO if enabled -> writes mixed+scaled cf32 to y); ws: agc_rms_workspace_bytes(n, alpha) device bytes
 size_t agc_rms_workspace_bytes(size_t n, float alpha);

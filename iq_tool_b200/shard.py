@@ -136,6 +136,29 @@ def exchange_agc_state(peaks: np.ndarray, counts: np.ndarray, target: float, tar
     return state
 
 
+def lower_shard_pieces(shards: List[Shard], rank: int, m: int, base_ptr: int, lock_frames: int):
+    """The scan calls that advance rank `rank`'s digital-AGC state over the shards below it: [device pointer, first frame,
+    frames] per call.  `base_ptr` is the gathered peak buffer (float32, rank r's live chunks at element r*m)."""
+    pieces = []
+    for r in range(rank):
+        sh_r = shards[r]
+        if not sh_r.frames:
+            continue
+        ptr, first, frames = base_ptr + 4 * r * m, sh_r.start, sh_r.frames
+        if sh_r.start < lock_frames < sh_r.start + sh_r.frames and (lock_frames - sh_r.start) % CHUNK_SAMPLES == 0:
+            head = lock_frames - sh_r.start
+            pieces.append([ptr, first, head])
+            pieces.append([ptr + 4 * (head // CHUNK_SAMPLES), first + head, frames - head])
+            continue
+        last = pieces[-1] if pieces else None
+        if (last is not None and last[1] >= lock_frames and last[2] % CHUNK_SAMPLES == 0 and
+                last[1] + last[2] == first and last[0] + 4 * (last[2] // CHUNK_SAMPLES) == ptr):
+            last[2] += frames
+        else:
+            pieces.append([ptr, first, frames])
+    return pieces
+
+
 class ShardedChain:
     """One rank's chain of a time-sharded run.  `process_device` reads the rank's frames
     [shard.lead, shard.start + shard.frames) from device memory and writes the converted output
@@ -155,6 +178,15 @@ class ShardedChain:
         self.chain = gpu.Chain(cfg, device, **opts)
         self.agc_target = cfg.agc_target_level_arg if cfg.agc_target_level_arg > 0 else 0.9   # agc.c:108-110, constants.h:184
         self.target_rate = float(np.float32(cfg.target_rate_hz))
+        # input frames (whole chunks) after which the digital AGC is certainly locked: more than 2 s of output samples
+        # (agc.c:145-149) plus two chunks of slack
+        lock_out = int(2.0 * self.target_rate) + 2
+        k = 0
+        if self.digital_agc:
+            step = max(1, int(lock_out / max(cfg.ratio, 1e-9)) // CHUNK_SAMPLES)
+            while self._probe.resampler_outputs_after(k * CHUNK_SAMPLES) <= lock_out:
+                k += step if self._probe.resampler_outputs_after((k + step) * CHUNK_SAMPLES) <= lock_out else 1
+        self.lock_frames = (k + 2) * CHUNK_SAMPLES
 
     def plan(self, total_frames: int, world: int) -> List[Shard]:
         shards = plan_shards(self._probe, total_frames, world, self.halo)
@@ -221,21 +253,13 @@ class ShardedChain:
             mark()                                            # all-gather done (includes waiting for the slowest rank)
             if not shard.read_frames:
                 return 0
-            # lower shards, in rank order.  The first one holds the scan-to-lock transition (a tile walk); the others are
-            # usually quiet at the locked gain and, when their tables are full (sizes == m) and whole chunks, contiguous in
-            # the gathered buffer: ONE scan launch covers all of them (the quiet test is a parallel pass over the table).
-            lower = [r for r in range(shard.rank) if shards[r].frames]
-            while lower:
-                r0 = lower[0]
-                run = [r0]
-                if r0 != 0:
-                    while (len(run) < len(lower) and lower[len(run)] == run[-1] + 1 and sizes[run[-1]] == m and
-                           shards[run[-1]].frames % CHUNK_SAMPLES == 0 and
-                           shards[run[-1]].start + shards[run[-1]].frames == shards[lower[len(run)]].start):
-                        run.append(lower[len(run)])
-                ch.agc_advance_device(gathered.data_ptr() + 4 * r0 * m, shards[r0].start,
-                                      sum(shards[r].frames for r in run), stream)
-                lower = lower[len(run):]
+            # Lower shards, in rank order, as few scan launches as possible: pieces of the gathered buffer that are contiguous
+            # in memory AND in the capture (full tables of whole chunks) go in ONE call — a locked, quiet stretch is then
+            # settled by the grid-wide quiet test in a few microseconds however long it is.  The head of the capture (until the
+            # AGC locks, 2 s of output samples, agc.c:145-149) is a piece of its own: it needs the sequential tile walk.
+            pieces = lower_shard_pieces(shards, shard.rank, m, gathered.data_ptr(), self.lock_frames)
+            for ptr, first, frames in pieces:
+                ch.agc_advance_device(ptr, first, frames, stream)
             mark()                                            # state advanced over the lower shards
             produced = ch.process_device_finish(shard.skip_chunks, dev_out_ptr, out_capacity_bytes, stream)
             mark()                                            # own scan + scale + convert

@@ -250,34 +250,82 @@ def test_shard_stitch_at_2_pow_28_frames(gpu, workloads):
     total = 1 << 28
     dev = torch.device("cuda", 0)
     raw = synth_torch(wl, total, dev)
-    h = total // 2                                    # a loud stretch so that the AGC ratchets inside a later shard
+    h = (total // 8) * 6 + 100 * CHUNK                # a loud stretch: the AGC ratchets inside shard 6
     raw[2 * h: 2 * (h + 8 * CHUNK)] = torch.clamp(raw[2 * h: 2 * (h + 8 * CHUNK)].to(torch.int32) * 3, -32768, 32767).to(torch.int16)
     single_chain = gpu.Chain(cfg, 0, subtrain_frames=1 << 30)
     out1 = torch.zeros(single_chain.out_capacity_frames(total) * cfg.out_bytes, dtype=torch.uint8, device=dev)
     n1 = single_chain.process_device(raw.data_ptr(), total, out1.data_ptr(), out1.numel())
     torch.cuda.synchronize()
+    from iq_tool_b200.shard import lower_shard_pieces
     sc = ShardedChain(cfg, 0, shard_frames_hint=total // 8 + (1 << 20))
     shards = sc.plan(total, 8)
+    m = max((sh.frames + CHUNK - 1) // CHUNK for sh in shards)
+    gathered = torch.zeros(8 * m, dtype=torch.float32, device=dev)        # the all-gather's receive buffer: rank r at r * m
     stitched = torch.zeros_like(out1)
-    live, pos = [], 0
+    pos, calls = 0, []
+    assert shards[3].start < sc.lock_frames < shards[3].start + shards[3].frames     # the lock falls inside shard 3
     for sh in shards:
         ch = sc.chain
         ch.seek(sh.lead)
         out = torch.zeros(ch.out_capacity_frames(sh.read_frames) * cfg.out_bytes, dtype=torch.uint8, device=dev)
         ch.process_device_begin(raw.data_ptr() + sh.lead * 4, sh.read_frames)
         nlive = (sh.frames + CHUNK - 1) // CHUNK
-        mine = torch.zeros(max(nlive, 1), dtype=torch.float32, device=dev)
-        assert ch.pending_chunk_peaks_device(sh.skip_chunks, mine.data_ptr(), mine.numel()) == nlive
-        for q, buf in zip(shards, live):
-            if q.frames:
-                ch.agc_advance_device(buf.data_ptr(), q.start, q.frames)
-        live.append(mine)
+        mine = gathered[sh.rank * m: sh.rank * m + m]
+        assert ch.pending_chunk_peaks_device(sh.skip_chunks, mine.data_ptr(), m) == nlive
+        # the pieces the NCCL path advances over (ShardedChain._finish_device_exchange): the head of the capture up to the
+        # lock on its own, contiguous locked stretches merged into one call (settled by the grid-wide quiet test when
+        # nothing happens in them: ranks 5 and 6; rank 7's stretch holds the ratchet and takes the tile walk)
+        pieces = lower_shard_pieces(shards, sh.rank, m, gathered.data_ptr(), sc.lock_frames)
+        calls.append(len(pieces))
+        for ptr, first, frames in pieces:
+            ch.agc_advance_device(ptr, first, frames)
         produced = ch.process_device_finish(sh.skip_chunks, out.data_ptr(), out.numel())
         torch.cuda.synchronize()
         assert produced - sh.drop == sh.out_frames
         k = sh.out_frames * cfg.out_bytes
         stitched[pos: pos + k] = out[sh.drop * cfg.out_bytes: produced * cfg.out_bytes]
         pos += k
+    assert calls == [0, 1, 2, 3, 5, 5, 5, 5]             # three pre-lock shards, the split one, then ONE merged call
     assert pos == n1 * cfg.out_bytes
     assert torch.equal(stitched[:pos], out1[:pos])
     assert single_chain.info().agc_locked == 1
+
+
+@pytest.mark.gpu
+def test_state_only_advance_quiet_test_equals_the_state_machine(gpu):
+    """iqgpu_chain_agc_advance_device over long chunk tables: the grid-wide quiet test (locked AGC, nothing happens -> the
+    state moves on in one step) and its fall-back (any ratchet / creep / not yet locked -> the sequential scan) must both
+    leave exactly the state of the host state machine (src/agc.c:105-222 on the sample clock).  Tables: quiet; one ratchet;
+    a weak stretch longer than 4 s (creep) that straddles several 4096-chunk parts; a weak stretch just short of 4 s;
+    weak chunks in front of the first strong one; an unlocked start."""
+    import torch
+    rate, chunk = 65536.0, 64                             # 4 s = 4096 chunks
+    cfg = ChainConfig(input_format="cf32", output_format="cf32", input_rate_hz=rate, target_rate_hz=rate,
+                      no_resample=True, agc_enable=True, agc_profile=AGC_DIGITAL)
+    nch = 20000
+    rng = np.random.default_rng(9)
+    base = (0.40 + 0.04 * rng.random(nch)).astype(np.float32)          # strong at gain 2.0 (0.8 .. 0.88 > 0.675), no ratchet
+    tables = {"quiet": base.copy()}
+    t = base.copy(); t[12345] = 0.51; tables["ratchet"] = t             # 0.51 * 2.0 > 1
+    t = base.copy(); t[3000:3000 + 4200] = 0.05; tables["creep"] = t    # weak for > 4 s: creeps
+    t = base.copy(); t[8000:8000 + 4090] = 0.05; tables["almost"] = t   # weak for < 4 s: nothing happens
+    t = base.copy(); t[:5000] = 0.05; tables["weak_first"] = t          # weak from the start, last strong 0.5 s before the table
+    start = gpu.agc_initial_state()
+    start.locked, start.gain, start.peak_memory, start.samples_seen, start.last_strong_s = 1, 2.0, 0.45, 10 * 65536, 9.5
+    cases = [(k, v, start) for k, v in tables.items()] + [("unlocked", base.copy(), gpu.agc_initial_state())]
+    counts = np.full(nch, chunk, dtype=np.uint32)
+    for name, peaks, st0 in cases:
+        ch = gpu.Chain(cfg, 0, chunk_frames=chunk)
+        ch.seek(0)
+        ch.set_agc_state(st0)
+        d = torch.from_numpy(peaks).cuda()
+        ch.agc_advance_device(d.data_ptr(), 0, nch * chunk)
+        got = ch.get_agc_state().as_tuple()
+        ref = gpu.agc_initial_state()
+        ref.locked, ref.gain, ref.peak_memory, ref.samples_seen, ref.last_strong_s = st0.locked, st0.gain, st0.peak_memory, st0.samples_seen, st0.last_strong_s
+        gpu.agc_digital_advance(ref, 0.9, rate, peaks, counts)
+        want = ref.as_tuple()
+        assert got[0] == want[0] and got[3] == want[3], (name, got, want)
+        assert got[1] == pytest.approx(want[1], rel=1e-6) and got[2] == pytest.approx(want[2], rel=1e-6), (name, got, want)
+        assert got[4] == pytest.approx(want[4], abs=1e-9), (name, got, want)
+    # the quiet and the almost tables left the gain alone; ratchet lowered it, creep raised it
