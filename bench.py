@@ -426,6 +426,9 @@ def main():
     ap.add_argument("--sharded-capture", default="cfg5",
                     help="second workload measured in the same run and reported as `sharded_capture` (BASELINE.json configs[4], the "
                          "multi-GPU configuration: time shards + the AGC peak all-gather); '' = off")
+    ap.add_argument("--stage-leg", default="k1",
+                    help="N = 1: a stage workload measured in the same run and reported as `stage_convert_shift` (k1: the "
+                         "stand-alone convert + NCO shift pass, north_star's >= 60 % of HBM target); '' = off")
     ap.add_argument("--no-pcie-probe", action="store_true")
     ap.add_argument("--train-chunks", type=int, default=2048, help="file workloads: reference chunks per chain call")
     args = ap.parse_args()
@@ -582,6 +585,26 @@ def main():
                    "note": "efficiency at N = value(N) / (N * value(1)) of THIS object across the per-N lines"}
         del run2
 
+    # ---- north_star's other stage target in the driver's record: the stand-alone convert + NCO shift pass (k1) against HBM ----
+    stage = None
+    if args.stage_leg and world == 1 and args.stage_leg != args.workload:
+        run3 = WorkloadRun(args.stage_leg, args, world, rank, local_rank, dev, stream)
+        k3 = 10
+        ms3, _, _, _ = run3.timed(k3, 3)
+        kt3 = run3.chain.kernel_times(reset=True)
+        bps3 = class_bytes_per_sample(run3.cfg, run3.chain.info())
+        if kt3:
+            d3 = max(kt3.items(), key=lambda kv: kv[1][0])[0]
+            per3 = kt3[d3][0] / max(1, kt3[d3][1])
+            hbm3, src3, _ = load_peaks()
+            ach3 = bps3.get(d3, 0.0) * run3.n * k3 / max(1, kt3[d3][1]) / (per3 / 1e3) / 1e9 if per3 > 0 else 0.0
+            stage = {"workload": f"{run3.wl.name}: {run3.wl.description}", "value": run3.n * k3 / (ms3 / 1e3) / 1e6, "unit": UNIT,
+                     "steps": k3, "ms_per_step": ms3 / k3, "frames_per_step": run3.n,
+                     "roofline": {"bound": "hbm", "kernel": d3, "achieved": ach3, "peak": hbm3, "unit": "GB/s",
+                                  "frac": ach3 / hbm3, "peak_source": src3, "launch_ms": per3,
+                                  "algorithmic_bytes_per_input_frame": bps3.get(d3, 0.0)}}
+        del run3
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -611,9 +634,10 @@ def main():
                     "algorithmic_bytes_per_input_frame": bps.get(dom, 0.0),
                     "share_of_step": dom_ms / (ms if world == 1 else sum(v[0] for v in ktimes.values()))}
         if dom == "fused_front" and dc_local_state(cfg, chain.info()):
-            roofline["note"] = ("launch_ms spans the front kernel, the DC stretch scan and the closed-form DC correction pass over "
-                                "the resampled stream; that pass's own read + write (16 r bytes per input frame) is NOT counted "
-                                "as algorithmic traffic (SURVEY 8(d): input + 8 r)")
+            roofline["note"] = ("launch_ms spans the front kernel, the DC stretch scan and the closed-form DC correction of the cf32 "
+                                "tail; the correction of the resampled stream is added by the FIR behind the resampler while it "
+                                "stages its tiles when there is one (cfg2), else by a read-modify-write pass that is inside "
+                                "launch_ms and NOT counted as algorithmic traffic (SURVEY 8(d): input + 8 r)")
     flops = chain_flops_per_sample(cfg, run.info)
     fp32_peak_nominal = 148 * 128 * 2 * 1.965e9 / 1e12
     try:
@@ -657,7 +681,7 @@ def main():
                    "fused_front": int(chain.info().fused_front),
                    "chunk_frames": 16384},
         "roofline": roofline, "fp32": fp32, "cpu_baseline": cpu, "e2e": e2e, "sustained": sustained,
-        "sharded_capture": sharded,
+        "sharded_capture": sharded, "stage_convert_shift": stage,
         "gpu_launches": int(launches_per_step) * args.steps, "clocks": clocks,
         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items()},
     }

@@ -307,6 +307,7 @@ struct iqgpu_chain {
     PreParams pre_params(uint64_t N0) const;
     int prepare_dc(int slot, const void* d_rawp, uint64_t N0, size_t n, cudaStream_t st);
     bool fir_wrote_output = false;    // this sub-train's FIR epilogue converted and stored the final output
+    DcFold dc_fold{};                 // the front's closed-form DC term, when the FIR behind it adds it on the fly
     // long post-resample FIRs are evaluated by the FFT block filter kernel (overlap-save, same causal convolution): the
     // time-domain kernel runs at 85 % of FMA peak, so beyond a few hundred taps only fewer FLOPs help
     bool fir_via_fft = false;
@@ -767,7 +768,13 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
         CK(s_rs.begin((size_t)(O1 - O0), st, &y_rs));
         if (dc_prepared) CK(cudaStreamWaitEvent(st, ev_pre[dc_slot], 0));   // the slot's table was built on `aux`
         span_begin(IQGPU_KCLASS_FUSED_FRONT, st);
-        CK(fused_launch(fused, d_rawp, (int64_t)N0, n, pp, d_dc_carry, (int64_t)O0, (size_t)(O1 - O0), y_rs, &launches, dc_slot, st));
+        // a time-domain FIR right behind the resampler adds the front's closed-form DC term while it stages its tiles
+        // (no extra pass over the resampled stream); whoever else reads the stream needs it in memory
+        const bool fold_ok = post_filter && filter_is_fir(filt) && !fir_via_fft && !record_taps &&
+                             fir_can_fold_dc(fir_taps_padded, filt.impl == IQGPU_FILTER_IMPL_FIR_ASYM, !h_fir_taps.empty());
+        dc_fold.corr = nullptr;
+        CK(fused_launch(fused, d_rawp, (int64_t)N0, n, pp, d_dc_carry, (int64_t)O0, (size_t)(O1 - O0), y_rs, &launches, dc_slot, st,
+                        fold_ok ? &dc_fold : nullptr));
         span_end(st);
         { int rc_iq = iq_run_probes(d_rawp, nullptr, N0, chunks, n_chunks, dc_slot, st); if (rc_iq) return rc_iq; }
         if (dc.enable) { CK(cudaEventRecord(ev_front[dc_slot], st)); front_recorded[dc_slot] = true; }
@@ -945,9 +952,18 @@ int iqgpu_chain::run_subtrain(const void* d_rawp, size_t n, const uint32_t* chun
                                fir_can_convert_out(cfg.output_format, fir_taps_padded, cplx);
             float2* y = nullptr;
             CK(s_f.begin(post_n, st, &y));
+            const bool folding = use_fused && dc_fold.corr != nullptr;
             CK(launch_fir(post_src, post_n, d_fir_taps, fir_taps_padded, cplx, y, st, h_fir_taps.data(),
-                          fir_wrote_output ? cfg.output_format : 0, fir_wrote_output ? d_outp : nullptr));
+                          fir_wrote_output ? cfg.output_format : 0, fir_wrote_output ? d_outp : nullptr,
+                          folding ? &dc_fold : nullptr));
             launches++;
+            if (folding) {
+                // the newest samples stay behind as the next call's filter history: they get the term in memory now
+                const size_t keep = std::min(post_n, s_rs.hist);
+                CK(fused_dc_correct_range(dc_fold, const_cast<float2*>(post_src), post_n - keep, keep, st));
+                if (keep) launches++;
+                dc_fold.corr = nullptr;
+            }
             s_f.commit(post_n);
             post_src = y;
         } else {
@@ -1040,8 +1056,18 @@ int iqgpu_chain::run_back(void* d_outp, size_t skip_chunks, size_t* out_frames, 
                 const std::vector<float> ones(skip_chunks, 1.0f);
                 CK(cudaMemcpyAsync(d_seg_gain, ones.data(), skip_chunks * sizeof(float), cudaMemcpyHostToDevice, st));
             }
+            {
+                const size_t qneed = agc_quiet_workspace_bytes(n_chunks);
+                if (qneed > agc_quiet_bytes) {
+                    CK(cudaStreamSynchronize(st));
+                    cudaFree(d_agc_quiet);
+                    d_agc_quiet = nullptr; agc_quiet_bytes = 0;
+                    CK(cudaMalloc(&d_agc_quiet, qneed * 2));
+                    agc_quiet_bytes = qneed * 2;
+                }
+            }
             CK(launch_agc_digital_scan(d_seg_start + skip_chunks, n_chunks - skip_chunks, d_seg_peak + skip_chunks, qp, d_agc,
-                                       d_seg_gain + skip_chunks, st));
+                                       d_seg_gain + skip_chunks, st, d_agc_quiet));
             CK(launch_post(post_src, post_n, qp, d_seg_start, n_chunks, d_seg_gain, 0, tap2, d_outp, st));
             launches += 2;
         } else if (agc_mode == 2) {

@@ -4,6 +4,7 @@
 #include <cstdint>
 
 #include "../../include/iqgpu.h"
+#include "kernels.hpp"
 
 namespace iqgpu {
 
@@ -232,5 +233,27 @@ __device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b)
 // h * {x.re, x.im} + {acc.re, acc.im}
 __device__ __forceinline__ f32x2_t fma2s(float h, f32x2_t x, f32x2_t acc) { return fma2(pk2(h, h), x, acc); }
 
+// The closed-form DC term of the warp-streaming front for output sample `o` (absolute index), which belongs to stretch
+// w = (nk - B0) / L_full (nk = the input frame its polyphase window ends at).  ONE definition, used by the in-memory pass
+// (w2_dc_correct_kernel) and by consumers that add the term while they load the stream (fir_param_kernel): same bits.
+__device__ __forceinline__ long long dc_fold_frame(unsigned long long o, uint32_t step, int S)
+{
+    return (long long)(((unsigned long long)o * step) >> 24) << S;
+}
+// Pp = o * step (the caller may carry it from sample to sample), since = nk - (first frame of stretch w's warm-up): below
+// 2^31 for any stretch a launch can make (fused_launch_v2 checks)
+__device__ __forceinline__ float2 dc_fold_add_at(float2 v, unsigned long long Pp, int since, float lnc, const W2DcCorr& c,
+                                                 const float* __restrict__ sG)
+{
+    const float e = expf(lnc * (float)since) * sG[(unsigned)(Pp >> 16) & 0xffu];
+    v.x = fmaf(c.c_out.x, e, v.x);
+    v.y = fmaf(c.c_out.y, e, v.y);
+    return v;
+}
+__device__ __forceinline__ float2 dc_fold_add(float2 v, unsigned long long o, uint32_t step, long long nk, long long w,
+                                              const W2DcGeom& g, float lnc, const W2DcCorr& c, const float* __restrict__ sG)
+{
+    return dc_fold_add_at(v, o * step, (int)(nk - (g.B0 + w * g.L_full - g.warm_frames)), lnc, c, sG);
+}
 
 }  // namespace iqgpu

@@ -446,7 +446,7 @@ static bool v2_setup(FusedFront* f, const ResamplerDesc& r, bool nco)
     // cs16 kernels: a 2 KiB raw tick buffer per warp in front of everything else, 1 KiB aligned (up to 1 KiB of slack)
     const size_t fixed = (size_t)W2_BANK_F2 * sizeof(float2) + (nco ? 1024 * sizeof(float2) : 0) + (cs16 ? 1024 : 0);
     const size_t per_warp = (size_t)f->v2_warp_f2 * sizeof(float2) + (cs16 ? (size_t)W2_RAW_TICK_BYTES : 0);
-    const size_t avail = 227 * 1024 - 2048;      // static shared memory (barriers) and the driver's reserve stay clear
+    const size_t avail = 227 * 1024 - 256;       // 227 KiB per block is static + dynamic: the barriers (168 bytes) stay clear
     int warps = (int)((avail - fixed) / per_warp);
     if (warps > W2_MAX_WARPS) warps = W2_MAX_WARPS;
     if (warps < 4) return false;
@@ -555,11 +555,12 @@ FusedFront* fused_create(int format, const ResamplerDesc& r, bool nco, const flo
         // four-output variant: rows of 16 floats, rotated / chunk-permuted for this rate (fused_front2.cuh)
         f->arb_b2 = (int)((2ull * r.step) >> 24);
         f->arb_b3 = (int)((3ull * r.step) >> 24);
-        f->arb_quad_ok = f->v2_S <= 2 &&        // W2Plan<S>::quad
-                         ((f->arb_b2 == 2 && (f->arb_b3 == 3 || f->arb_b3 == 4)) || (f->arb_b2 == 3 && (f->arb_b3 == 4 || f->arb_b3 == 5)));
+        f->arb_quad_ok = ((f->arb_b2 == 2 && (f->arb_b3 == 3 || f->arb_b3 == 4)) || (f->arb_b2 == 3 && (f->arb_b3 == 4 || f->arb_b3 == 5)));
         if (f->arb_quad_ok) {
             f->arb_tz = (int)w2_pick_qbank_tz(r.step);
-            f->arb_skew_sh = getenv("IQGPU_ARB_SKEW") ? atoi(getenv("IQGPU_ARB_SKEW")) : w2_pick_flat_skew(r.step);
+            f->arb_skew_sh = 31;
+            if (f->v2_S <= 2)       // W2Plan<S>::quad_skew: only the shallow plans have room for a skewed level
+                f->arb_skew_sh = getenv("IQGPU_ARB_SKEW") ? atoi(getenv("IQGPU_ARB_SKEW")) : w2_pick_flat_skew(r.step);
             std::vector<float> q((size_t)W2_BANK_F2 * 2, 0.f);
             for (unsigned idx = 0; idx < 256; idx++)
                 for (unsigned j = 0; j < 4; j++)
@@ -748,8 +749,9 @@ static cudaError_t launch_v2_s(const FusedFront* f, const Fused2Args& A, int gri
 
 static cudaError_t fused_launch_v2(FusedFront* f, const void* raw, int64_t n0, size_t n, const PreParams& pre,
                                    double2* d_dc_carry, int64_t O0, size_t n_out, float2* y, uint32_t* launches, int dc_slot,
-                                   cudaStream_t st)
+                                   cudaStream_t st, DcFold* fold)
 {
+    if (fold) fold->corr = nullptr;
     Fused2Args A{};
     A.raw = raw; A.n0 = n0; A.N1 = n0 + (long long)n;
     A.tail_in = f->d_tail[f->tail_cur];
@@ -820,6 +822,7 @@ static cudaError_t fused_launch_v2(FusedFront* f, const void* raw, int64_t n0, s
         geo.n_stretch = (int)warps_needed;
         geo.B0 = A.sup_first * sup_frames;
         geo.L_full = per * sup_frames;
+        if (geo.L_full + (long long)f->v2_warm_sup * sup_frames >= (1LL << 31)) return cudaErrorInvalidValue;   // dc_fold_add: int
         geo.L_last = (A.sup_last - (A.sup_first + (warps_needed - 1) * per) + 1) * sup_frames;
         geo.warm_frames = (long long)f->v2_warm_sup * sup_frames;
         geo.pad_frames = (A.sup_last + 1) * sup_frames - A.N1;
@@ -892,9 +895,12 @@ static cudaError_t fused_launch_v2(FusedFront* f, const void* raw, int64_t n0, s
     if (launches) *launches += 1;
     if (dc_local && e == cudaSuccess) {
         w2_dc_scan_kernel<<<1, 1024, 0, st>>>(f->d_dc_stretch, geo, f->d_dc_corr, d_dc_carry);
-        const long long work = (long long)n_out + f->H_tail;
+        // a consumer that adds the term to the resampled stream itself leaves only the cf32 tail to this pass
+        const long long O1c = fold ? A.O0 : A.O1;
+        if (fold) *fold = DcFold{f->d_dc_corr, f->d_dc_G, geo, A.O0, A.step, f->v2_S};
+        const long long work = (O1c - A.O0) + f->H_tail;
         const int cgrid = (int)std::min<long long>((work + 255) / 256, 148LL * 16);
-        w2_dc_correct_kernel<<<std::max(cgrid, 1), 256, 0, st>>>(y, A.O0, A.O1, A.step, f->v2_S, geo, f->d_dc_corr, f->d_dc_G,
+        w2_dc_correct_kernel<<<std::max(cgrid, 1), 256, 0, st>>>(y, A.O0, O1c, A.step, f->v2_S, geo, f->d_dc_corr, f->d_dc_G,
                                                                f->d_tail[f->tail_cur ^ 1], A.N1 - f->H_tail, A.n0, A.N1);
         e = cudaGetLastError();
         if (launches) *launches += 2;
@@ -903,12 +909,24 @@ static cudaError_t fused_launch_v2(FusedFront* f, const void* raw, int64_t n0, s
     return e;
 }
 
-cudaError_t fused_launch(FusedFront* f, const void* raw, int64_t n0, size_t n, const PreParams& pre, double2* d_dc_carry,
-                         int64_t O0, size_t n_out, float2* y, uint32_t* launches, int dc_slot, cudaStream_t st)
+// the closed-form term, in memory, for the samples [first, first + count) of the launch `fold` describes
+cudaError_t fused_dc_correct_range(const DcFold& fold, float2* y, size_t first, size_t count, cudaStream_t st)
 {
+    if (!fold.corr || count == 0) return cudaSuccess;
+    const long long Oa = fold.O0 + (long long)first;
+    const int cgrid = (int)std::min<size_t>((count + 255) / 256, (size_t)148 * 16);
+    w2_dc_correct_kernel<<<std::max(cgrid, 1), 256, 0, st>>>(y + first, Oa, Oa + (long long)count, fold.step, fold.S, fold.geo,
+                                                           fold.corr, fold.G, nullptr, 0, 0, 0);
+    return cudaGetLastError();
+}
+
+cudaError_t fused_launch(FusedFront* f, const void* raw, int64_t n0, size_t n, const PreParams& pre, double2* d_dc_carry,
+                         int64_t O0, size_t n_out, float2* y, uint32_t* launches, int dc_slot, cudaStream_t st, DcFold* fold)
+{
+    if (fold) fold->corr = nullptr;
     if (n == 0) return cudaSuccess;
     if (dc_slot < 0 || dc_slot > 1) dc_slot = 0;
-    if (f->v2) return fused_launch_v2(f, raw, n0, n, pre, d_dc_carry, O0, n_out, y, launches, dc_slot, st);
+    if (f->v2) return fused_launch_v2(f, raw, n0, n, pre, d_dc_carry, O0, n_out, y, launches, dc_slot, st, fold);
     const FusedPlan& P = f->plan;
     FusedArgs A{};
     A.plan = P;

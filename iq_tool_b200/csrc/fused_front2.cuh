@@ -107,14 +107,32 @@ struct W2Plan {
     __host__ __device__ static constexpr int Hh(int d) { return ((2 * m(d) - 1 + R(d) - 1) / R(d)) * R(d); }   // history entries per plane
     __host__ __device__ static constexpr int entries(int d) { return Hh(d) + out(d); }
     __host__ __device__ static constexpr int phys(int d, int p) { return p + PAD(d) * (p / R(d)); }
-    __host__ __device__ static constexpr int plane_size(int d) { return (phys(d, entries(d)) + 3) & ~1; }
+    // A level whose producer needs two runs per consumer run (both capped: ratio(d - 1) == 2) is written by lane PAIRS per
+    // padded group, which puts two lanes of every quarter (R = 4: STS.128) or three of every half warp (R = 2: STS.64) on a
+    // bank group another lane already uses (profiles/r02i_fused_front2_full_cfg2.md: 12 of 228 LSU wavefronts per tick).
+    // Those lanes store their O entry first and their E entry second (w2_stage_store); that is conflict free when the O
+    // plane starts 8 (mod 16) entries after the E plane, which is what the extra padding here arranges.
+    __host__ __device__ static constexpr bool pair_fed(int d)
+    {
+        return d >= 1 && d < S && (2 * out(d) / out(d - 1) == 2) && (R(d) == 4 || R(d) == 2);
+    }
+    __host__ __device__ static constexpr int plane_size(int d)
+    {
+        int n = (phys(d, entries(d)) + 3) & ~1;
+        if (pair_fed(d)) while (n % 16 != 8) n += 2;
+        return n;
+    }
     // first stage straight from the lane's registers (neighbour entries by warp shuffle): cascades whose first
     // stage has semi-length 3, i.e. S >= 3.  Level 0 then keeps only an 8-entry history instead of its planes.
     static constexpr bool reg0 = (S >= 3) || (S == 2 && W2_REG0_M5_DEF);     // S == 2: first stage of semi-length 5
     // ... and the second one as well when it also has semi-length 3 (S >= 4): the lane's 8 first-stage outputs are 4 (E, O)
     // pairs of level 1, the inputs of its own 4 second-stage outputs; older entries come from the two lanes below
     static constexpr bool reg1 = W2_REG1_DEF && (S >= 4);
-    __host__ __device__ static constexpr int level_size(int d) { return ((d == 0 && reg0) || (d == 1 && reg1)) ? 16 : 2 * plane_size(d); }
+    // (a register stage keeps only the hand-over history of its last lanes: 8 entries at semi-length 3, 14 at 5)
+    __host__ __device__ static constexpr int level_size(int d)
+    {
+        return ((d == 0 && reg0) || (d == 1 && reg1)) ? (m(d) == 3 ? 8 : 16) : 2 * plane_size(d);
+    }
     __host__ __device__ static constexpr int e_off(int d)
     {
         int o = 0;
@@ -133,12 +151,13 @@ struct W2Plan {
     // + 8: the four-output polyphase variant reads up to 6 entries beyond the newest one (they meet zero taps; the slack is
     // zeroed once and never written, so the products are exact zeros)
     // (+ 1/8 on top: room for the skew of the four-output variant, 2 entries per 16)
-    // The four-output variant exists for the shallow cascades, where the polyphase stage is most of the kernel (S <= 2: one
-    // output per lane spends 60 % of cfg1's LSU wavefronts there); deeper cascades keep the smaller level — on S = 4 the extra
-    // 220 bytes per warp would cost the CTA its 20th warp
-    static constexpr bool quad = (S <= 2);
+    // The skewed level exists for the shallow cascades, where the polyphase stage is most of the kernel (S <= 2: one output
+    // per lane spends 60 % of cfg1's LSU wavefronts there); deeper cascades take the four-output variant on the plain level
+    // (+ 64 bytes per warp: S = 4 keeps its 20 warps, the 220 bytes of the skew room would cost the 20th)
+    static constexpr bool quad = true;
+    static constexpr bool quad_skew = (S <= 2);
     static constexpr int flat_lin = W2_ARB_HIST + flat_new + (quad ? 8 : 0);
-    static constexpr int flat_size = quad ? ((flat_lin + flat_lin / 8 + 2 + 1) & ~1) : ((flat_lin + 3) & ~1);
+    static constexpr int flat_size = quad_skew ? ((flat_lin + flat_lin / 8 + 2 + 1) & ~1) : ((flat_lin + 3) & ~1);
     static constexpr int warp_f2 = flat_off + flat_size;                 // float2 per warp
     __host__ __device__ static constexpr int period(int d) { return nat(d) >= CAP ? 1 : CAP / nat(d); }   // stage d runs every `period` ticks
     // runs of stage d per run of stage d+1 (1: every run feeds one consumer run; 2: the consumer waits for two)
@@ -266,6 +285,8 @@ __device__ __forceinline__ void w2_load_quad(int fmt, const void* __restrict__ r
 
 // raw frames of one tick and one lane (cs16 fast path): four 16-byte chunks
 struct W2Raw { uint4 q[4]; };
+struct W2True { static constexpr bool value = true; };
+struct W2False { static constexpr bool value = false; };
 
 // ------------------------------------------------------------------------------------------------
 // P0: one tick (512 frames) of the pre-processor chain into level 0 (or the flat level when S == 0)
@@ -333,7 +354,7 @@ __device__ __forceinline__ void w2_p0(const Fused2Args& A, float2* __restrict__ 
             for (int s = 0; s < 5; s++) {
                 const int dist = 1 << s;
                 const f32x2_t q = __shfl_up_sync(0xffffffffu, pr, dist);
-                if (lane >= dist) pr = fma2s(A.dc.w[s], q, pr);
+                pr = fma2s((lane >= dist) ? A.dc.w[s] : 0.f, q, pr);        // (+ 0 * q: pr unchanged; q is finite)
             }
             f32x2_t e = __shfl_up_sync(0xffffffffu, pr, 1);
             if (lane == 0) e = 0ull;
@@ -416,7 +437,7 @@ __device__ __forceinline__ void w2_stage_store(float2* __restrict__ wsm, int lan
         // (4-way conflict, 48 excess wavefronts per tick on cfg1).  Every lane starts with a different chunk instead — chunk
         // (j + rot) & 3 in instruction j, rot = (lane >> 1) & 3 — which covers all eight groups; the rotation of the register
         // chunks is a two-level select.
-        if (!P::quad) skew_sh = 31;
+        if (!P::quad_skew) skew_sh = 31;
         float2* f = wsm + P::flat_off + w2_flat_phys(W2_ARB_HIST + R * lane, skew_sh);
         const unsigned rot = (skew_sh == 31) ? (((unsigned)lane >> 1) & 3u) : 0u;      // a skewed level is conflict free as it is
         const bool r1 = rot & 1u, r2 = rot & 2u;
@@ -435,7 +456,7 @@ __device__ __forceinline__ void w2_stage_store(float2* __restrict__ wsm, int lan
         for (int j = 0; j < 4; j++)
             *reinterpret_cast<ulonglong2*>(f + 2 * (((unsigned)j + rot) & 3u)) = make_ulonglong2(b[2 * j], b[2 * j + 1]);
     } else if constexpr (D + 1 == S) {
-        if (!P::quad) skew_sh = 31;
+        if (!P::quad_skew) skew_sh = 31;
         float2* f = wsm + P::flat_off + w2_flat_phys(W2_ARB_HIST + R * lane, skew_sh);
         if (R >= 2) {
 #pragma unroll
@@ -471,7 +492,19 @@ __device__ __forceinline__ void w2_stage_store(float2* __restrict__ wsm, int lan
         const int ph0 = p0 + PN * (p0 / RN);
         float2* nE = wsm + P::e_off(D + 1) + ph0;
         float2* nO = wsm + P::o_off(D + 1) + ph0;
-        if (R2 >= 2 && PN == 2) {
+        if constexpr (R2 == 2 && PN == 2 && P::pair_fed(D + 1)) {
+            // lanes 1, 9, 17, 25 would share a bank group with lanes 6, 14, ...: they store O first, E second (plane_size)
+            const bool sw = (lane & 7) == 1;
+            float2* pa = sw ? nO : nE;
+            float2* pb = sw ? nE : nO;
+            *reinterpret_cast<ulonglong2*>(pa) = make_ulonglong2(sw ? v[1] : v[0], sw ? v[3] : v[2]);
+            *reinterpret_cast<ulonglong2*>(pb) = make_ulonglong2(sw ? v[0] : v[1], sw ? v[2] : v[3]);
+        } else if constexpr (R2 == 1 && PN == 1 && P::pair_fed(D + 1)) {
+            const unsigned l15 = (unsigned)lane & 15u;
+            const bool sw = (l15 == 11u) || (l15 == 13u) || (l15 == 15u);
+            *reinterpret_cast<f32x2_t*>(sw ? nO : nE) = sw ? v[1] : v[0];
+            *reinterpret_cast<f32x2_t*>(sw ? nE : nO) = sw ? v[0] : v[1];
+        } else if (R2 >= 2 && PN == 2) {
 #pragma unroll
             for (int i = 0; i < R2; i += 2) {
                 *reinterpret_cast<ulonglong2*>(nE + i) = make_ulonglong2(v[2 * i], v[2 * i + 2]);
@@ -496,6 +529,14 @@ __device__ __forceinline__ void w2_stage_store(float2* __restrict__ wsm, int lan
 // ------------------------------------------------------------------------------------------------
 // the same for a first stage of semi-length 5 (S == 2): 9 older E entries (8 from the lane below, 1 from the lane below
 // that) and 5 older O entries; lanes 0 and 1 take theirs from the 112-byte history lanes 31 and 30 left one tick earlier
+// p ? a : b on both halves of a packed pair (two SELs, no moves)
+__device__ __forceinline__ f32x2_t w2_sel(bool p, f32x2_t a, f32x2_t b)
+{
+    const unsigned lo = p ? (unsigned)a : (unsigned)b;
+    const unsigned hi = p ? (unsigned)(a >> 32) : (unsigned)(b >> 32);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
 template <int S>
 __device__ __forceinline__ void w2_stage0_reg_m5(const Fused2Args& A, float2* __restrict__ wsm, int lane, const f32x2_t (&x)[16],
                                                  f32x2_t (&v)[8])
@@ -554,15 +595,21 @@ __device__ __forceinline__ void w2_stage0_reg(const Fused2Args& A, float2* __res
     else {
     static_assert(P::m(0) == 3 && P::R(0) == 8, "register first stage: semi-length 3, 8 outputs per lane");
     f32x2_t ent[13], oc[8];
-#pragma unroll
-    for (int k = 0; k < 5; k++) ent[k] = __shfl_up_sync(0xffffffffu, x[6 + 2 * k], 1);      // E[q0-5 .. q0-1]
-#pragma unroll
-    for (int k = 0; k < 3; k++) oc[k] = __shfl_up_sync(0xffffffffu, x[11 + 2 * k], 1);      // O[q0-3 .. q0-1]
     ulonglong2* hist = reinterpret_cast<ulonglong2*>(wsm + P::e_off(0));                    // level-0 planes are unused
-    if (lane == 0) {
+    {
+        // every lane reads the history (one broadcast wavefront per load, as a load by lane 0 alone would cost) and lane 0
+        // keeps it through a select: the predicated form cost four register moves per entry (profiles/r02i: 71 of 658
+        // instructions per tick were moves)
         const ulonglong2 h0 = hist[0], h1 = hist[1], h2 = hist[2], h3 = hist[3];
-        ent[0] = h0.x; ent[1] = h0.y; ent[2] = h1.x; ent[3] = h1.y; ent[4] = h2.x;
-        oc[0] = h2.y; oc[1] = h3.x; oc[2] = h3.y;
+        const bool l0 = lane == 0;
+        ent[0] = w2_sel(l0, h0.x, __shfl_up_sync(0xffffffffu, x[6], 1));                    // E[q0-5 .. q0-1]
+        ent[1] = w2_sel(l0, h0.y, __shfl_up_sync(0xffffffffu, x[8], 1));
+        ent[2] = w2_sel(l0, h1.x, __shfl_up_sync(0xffffffffu, x[10], 1));
+        ent[3] = w2_sel(l0, h1.y, __shfl_up_sync(0xffffffffu, x[12], 1));
+        ent[4] = w2_sel(l0, h2.x, __shfl_up_sync(0xffffffffu, x[14], 1));
+        oc[0] = w2_sel(l0, h2.y, __shfl_up_sync(0xffffffffu, x[11], 1));                    // O[q0-3 .. q0-1]
+        oc[1] = w2_sel(l0, h3.x, __shfl_up_sync(0xffffffffu, x[13], 1));
+        oc[2] = w2_sel(l0, h3.y, __shfl_up_sync(0xffffffffu, x[15], 1));
     }
     __syncwarp();
     if (lane == 31) {
@@ -601,19 +648,21 @@ __device__ __forceinline__ void w2_stage1_reg(const Fused2Args& A, float2* __res
     using P = W2Plan<S>;
     static_assert(P::m(1) == 3 && P::R(1) == 4, "register second stage: semi-length 3, 4 outputs per lane");
     f32x2_t ent[9], oc[4];
-    ent[0] = __shfl_up_sync(0xffffffffu, v[6], 2);                                          // E1[q0-5]
-#pragma unroll
-    for (int k = 0; k < 4; k++) ent[1 + k] = __shfl_up_sync(0xffffffffu, v[2 * k], 1);      // E1[q0-4 .. q0-1]
-#pragma unroll
-    for (int k = 0; k < 3; k++) oc[k] = __shfl_up_sync(0xffffffffu, v[3 + 2 * k], 1);       // O1[q0-3 .. q0-1]
     ulonglong2* hist = reinterpret_cast<ulonglong2*>(wsm + P::e_off(1));                    // level-1 planes are unused
     // history: [0..3] = lane 31's E1[0..3], [4..6] = lane 31's O1[1..3], [7] = lane 30's E1[3]
-    if (lane == 0) {
-        const ulonglong2 h0 = hist[0], h1 = hist[1], h2 = hist[2], h3 = hist[3];
-        ent[1] = h0.x; ent[2] = h0.y; ent[3] = h1.x; ent[4] = h1.y;
-        oc[0] = h2.x; oc[1] = h2.y; oc[2] = h3.x; ent[0] = h3.y;
+    {
+        const ulonglong2 h0 = hist[0], h1 = hist[1], h2 = hist[2], h3 = hist[3];            // broadcast loads, selects (w2_stage0_reg)
+        const bool l0 = lane == 0, l1 = lane == 1;
+        // E1[q0-5]: lane 0 takes lane 30's E1[3], lane 1 lane 31's E1[3] of the last tick
+        ent[0] = w2_sel(l0, h3.y, w2_sel(l1, h1.y, __shfl_up_sync(0xffffffffu, v[6], 2)));
+        ent[1] = w2_sel(l0, h0.x, __shfl_up_sync(0xffffffffu, v[0], 1));                    // E1[q0-4 .. q0-1]
+        ent[2] = w2_sel(l0, h0.y, __shfl_up_sync(0xffffffffu, v[2], 1));
+        ent[3] = w2_sel(l0, h1.x, __shfl_up_sync(0xffffffffu, v[4], 1));
+        ent[4] = w2_sel(l0, h1.y, __shfl_up_sync(0xffffffffu, v[6], 1));
+        oc[0] = w2_sel(l0, h2.x, __shfl_up_sync(0xffffffffu, v[3], 1));                     // O1[q0-3 .. q0-1]
+        oc[1] = w2_sel(l0, h2.y, __shfl_up_sync(0xffffffffu, v[5], 1));
+        oc[2] = w2_sel(l0, h3.x, __shfl_up_sync(0xffffffffu, v[7], 1));
     }
-    if (lane == 1) ent[0] = reinterpret_cast<const f32x2_t*>(hist)[3];                     // lane 31's E1[3] of the last tick
     __syncwarp();
     if (lane == 31) {
         hist[0] = make_ulonglong2(v[0], v[2]);
@@ -817,7 +866,7 @@ __host__ static inline int w2_pick_flat_skew(uint32_t step)
     return best;
 }
 
-template <int B2, int B3>
+template <int B2, int B3, bool SKEW>
 __device__ __forceinline__ void w2_arb_quad(const Fused2Args& A, const float2* __restrict__ flat, const float2* __restrict__ sbank,
                                             long long kA, long long oa, long long ob, int lane)
 {
@@ -833,10 +882,16 @@ __device__ __forceinline__ void w2_arb_quad(const Fused2Args& A, const float2* _
         const bool e2 = ((long long)(P2 >> 24) - k0) != B2;
         const bool e3 = ((long long)(P3 >> 24) - k0) != B3;
         const f32x2_t* __restrict__ w = reinterpret_cast<const f32x2_t*>(flat);
-        const int e0 = rel + (W2_ARB_HIST - 13), ssh = A.arb_skew_sh;
+        const int e0 = rel + (W2_ARB_HIST - 13);
         f32x2_t u[NU];
+        if constexpr (SKEW) {
+            const int ssh = A.arb_skew_sh;
 #pragma unroll
-        for (int j = 0; j < NU; j++) u[j] = w[w2_flat_phys(e0 + j, ssh)];
+            for (int j = 0; j < NU; j++) u[j] = w[w2_flat_phys(e0 + j, ssh)];
+        } else {                                            // plain level: one base register, immediate offsets
+#pragma unroll
+            for (int j = 0; j < NU; j++) u[j] = w[e0 + j];
+        }
         f32x2_t s[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -898,11 +953,11 @@ __device__ __forceinline__ void w2_arb(const Fused2Args& A, const float2* __rest
     if (ob > A.O1) ob = A.O1;
     if (P::quad && A.arb_pairs == 2) {
         if (A.arb_b2 == 2) {
-            if (A.arb_b3 == 3) w2_arb_quad<2, 3>(A, flat, sbank, kA, oa, ob, lane);
-            else w2_arb_quad<2, 4>(A, flat, sbank, kA, oa, ob, lane);
+            if (A.arb_b3 == 3) w2_arb_quad<2, 3, P::quad_skew>(A, flat, sbank, kA, oa, ob, lane);
+            else w2_arb_quad<2, 4, P::quad_skew>(A, flat, sbank, kA, oa, ob, lane);
         } else {
-            if (A.arb_b3 == 4) w2_arb_quad<3, 4>(A, flat, sbank, kA, oa, ob, lane);
-            else w2_arb_quad<3, 5>(A, flat, sbank, kA, oa, ob, lane);
+            if (A.arb_b3 == 4) w2_arb_quad<3, 4, P::quad_skew>(A, flat, sbank, kA, oa, ob, lane);
+            else w2_arb_quad<3, 5, P::quad_skew>(A, flat, sbank, kA, oa, ob, lane);
         }
         return;
     }
@@ -1066,9 +1121,12 @@ __global__ void __launch_bounds__(W2_MAX_WARPS * 32, 1) fused_front2_kernel(cons
     const unsigned raw_row = w2_smem_u32(rawbuf) + 128u * (unsigned)(lane >> 1);
     const unsigned raw_sw = (unsigned)(lane >> 1) & 7u, raw_c0 = 4u * (unsigned)(lane & 1);
     long long t = t_begin;
-    for (int tr = 0; tr < n_ticks; tr++, t++) {
+    // The body exists twice: ticks of the fast range (nearly all of them) run a copy in which `fast` and `active` are
+    // compile-time true, i.e. without the range tests, the tail handling and the zero-fill of the general copy.
+    auto tick = [&](auto fast_c, int tr) {
+        constexpr bool FAST = decltype(fast_c)::value;
         const long long tick_start = t * W2_T0;
-        const bool fast = (unsigned)(tr - fast_lo) < fast_len, active = (unsigned)(tr - act_lo) < act_len;
+        const bool fast = FAST, active = FAST || ((unsigned)(tr - act_lo) < act_len);
         W2Raw cur;
         if (CS16) {
             if (staged) {
@@ -1125,12 +1183,16 @@ __global__ void __launch_bounds__(W2_MAX_WARPS * 32, 1) fused_front2_kernel(cons
             if (tr >= emit_r) w2_arb<S>(A, flat, sbank, kA, o_cur, lane);
             __syncwarp();
             float2 h = make_float2(0.f, 0.f);
-            const int ssh = P::quad ? A.arb_skew_sh : 31;
+            const int ssh = P::quad_skew ? A.arb_skew_sh : 31;
             if (lane < W2_ARB_HIST) h = flat[w2_flat_phys(lane + P::flat_new, ssh)];
             __syncwarp();
             if (lane < W2_ARB_HIST) flat[w2_flat_phys(lane, ssh)] = h;
             __syncwarp();
         }
+    };
+    for (int tr = 0; tr < n_ticks; tr++, t++) {
+        if ((unsigned)(tr - fast_lo) < fast_len) tick(W2True{}, tr);
+        else tick(W2False{}, tr);
     }
     if (DC == 2 && lane == 0) A.dc_stretch[gw].v_end = vloc;
 }
@@ -1144,12 +1206,7 @@ __global__ void __launch_bounds__(W2_MAX_WARPS * 32, 1) fused_front2_kernel(cons
 // 256 row gains G are computed once on the host in double from the actual taps).  V0_w follows from the records the
 // warps left: v(B_w+1) = a_w v(B_w) + (v_end_w - a_w v_emit_w), a_w = c^L_w — an affine scan over a few thousand stretches.
 // ------------------------------------------------------------------------------------------------
-struct W2DcCorr { float2 c_out, c_pre; };      // -a V0 Atot (cascade output) and -a V0 (cascade input, for the cf32 tail)
-struct W2DcGeom {
-    int n_stretch;
-    long long B0, L_full, L_last, warm_frames, pad_frames;     // pad: zero frames between N1 and the end of the last tick
-    double lnc, alpha, atot;
-};
+// (W2DcCorr, W2DcGeom: kernels.hpp)
 
 __global__ void __launch_bounds__(1024) w2_dc_scan_kernel(const W2DcStretch* __restrict__ rec, W2DcGeom g,
                                                           W2DcCorr* __restrict__ corr, double2* __restrict__ carry)
@@ -1214,15 +1271,10 @@ __global__ void __launch_bounds__(256) w2_dc_correct_kernel(float2* __restrict__
     const long long n_tail = (N1 > t_lo) ? (N1 - t_lo) : 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_out + n_tail; i += stride) {
         if (i < n_out) {
-            const unsigned long long Pp = (unsigned long long)(O0 + i) * step;
-            const long long nk = (long long)(Pp >> 24) << S;
+            const long long nk = dc_fold_frame((unsigned long long)(O0 + i), step, S);
             const long long w = (nk - g.B0) / g.L_full;
             if (w <= 0) continue;
-            const W2DcCorr c = corr[w];
-            const float e = expf(lnc * (float)(nk - (g.B0 + w * g.L_full - g.warm_frames))) * sG[(unsigned)(Pp >> 16) & 0xffu];
-            float2 v = y[i];
-            v.x = fmaf(c.c_out.x, e, v.x); v.y = fmaf(c.c_out.y, e, v.y);
-            y[i] = v;
+            y[i] = dc_fold_add(y[i], (unsigned long long)(O0 + i), step, nk, w, g, lnc, corr[w], sG);
         } else {
             const long long n = t_lo + (i - n_out);
             const long long w = (n - g.B0) / g.L_full;

@@ -655,15 +655,23 @@ struct FirTaps { float h[FIR_PARAM_TAPS]; };
 // OUTFMT != 0: the filter is the last cf32 stage of the chain (no post shift, no AGC): the epilogue converts to the
 // output sample format (sample_convert.c:213-306, same code as the post kernel) and writes the final stream, so the
 // filtered cf32 stream is never stored.
-template <bool CPLX, int OUTFMT>
+// FOLD: the samples x[0 .. n) lack the fused front's closed-form DC term (DcFold, kernels.hpp); it is added while the tile
+// is staged (the history below x[0] is complete).  A thread's samples are 128 apart and a stretch spans thousands of
+// outputs, so the stretch index costs one 64-bit division per thread and tile, then comparisons.
+template <bool CPLX, int OUTFMT, bool FOLD>
 __global__ void __launch_bounds__(FIR_THREADS) fir_param_kernel(const float2* __restrict__ x, size_t n, unsigned ntaps,
                                                                 float2* __restrict__ y, void* __restrict__ out_conv, bool vec_out,
-                                                                const __grid_constant__ FirTaps T)
+                                                                const __grid_constant__ FirTaps T, const __grid_constant__ DcFold F)
 {
     constexpr int WIN = FIR_TILE + FIR_TC;
     __shared__ __align__(16) f32x2_t sx[WIN + WIN / 8 + 8];
+    __shared__ float sG[FOLD ? 256 : 1];
     const int t = threadIdx.x;
     const long long tile0 = (long long)blockIdx.x * FIR_TILE;
+    if (FOLD) {
+        for (int i = t; i < 256; i += FIR_THREADS) sG[i] = F.G[i];
+    }
+    const float lnc = FOLD ? (float)F.geo.lnc : 0.f;
     f32x2_t acc[FIR_R];
 #pragma unroll
     for (int r = 0; r < FIR_R; r++) acc[r] = 0ull;
@@ -671,9 +679,26 @@ __global__ void __launch_bounds__(FIR_THREADS) fir_param_kernel(const float2* __
         const int tc = (ntaps - c0 < (unsigned)FIR_TC) ? (int)(ntaps - c0) : FIR_TC;
         const long long wbase = tile0 - (long long)(ntaps - 1) + c0;
         __syncthreads();
-        for (int j = t; j < FIR_TILE + tc - 1; j += FIR_THREADS) {
+        // per thread: the sample's o * step carried from sample to sample, the stretch it is in (w), that stretch's record
+        // and first warm-up frame; all 64-bit work happens once per thread and tile
+        long long w = -1, w_end = 0, w_from = 0;
+        W2DcCorr cw{};
+        unsigned long long Pp = FOLD ? (unsigned long long)(F.O0 + wbase + t) * F.step : 0ull;
+        const unsigned long long dPp = (unsigned long long)FIR_THREADS * F.step;
+        for (int j = t; j < FIR_TILE + tc - 1; j += FIR_THREADS, Pp += dPp) {
             const long long g = wbase + j;
-            sx[fir_pad(j)] = (g < (long long)n) ? *reinterpret_cast<const f32x2_t*>(x + g) : 0ull;
+            f32x2_t v = (g < (long long)n) ? *reinterpret_cast<const f32x2_t*>(x + g) : 0ull;
+            if (FOLD && g >= 0 && g < (long long)n) {
+                const long long nk = (long long)(Pp >> 24) << F.S;
+                if (w < 0 || nk >= w_end) {
+                    if (w < 0) { w = (nk - F.geo.B0) / F.geo.L_full; w_end = F.geo.B0 + (w + 1) * F.geo.L_full; }
+                    while (nk >= w_end) { w++; w_end += F.geo.L_full; }
+                    w_from = w_end - F.geo.L_full - F.geo.warm_frames;
+                    if (w > 0) cw = F.corr[w];
+                }
+                if (w > 0) v = pk2(dc_fold_add_at(unpk2(v), Pp, (int)(nk - w_from), lnc, cw, sG));
+            }
+            sx[fir_pad(j)] = v;
         }
         __syncthreads();
         f32x2_t win[FIR_R];
@@ -716,6 +741,12 @@ __global__ void __launch_bounds__(FIR_THREADS) fir_param_kernel(const float2* __
     }
 }
 
+bool fir_can_fold_dc(unsigned ntaps_padded, int complex_taps, bool have_host_taps)
+{
+    const unsigned nfloats = ntaps_padded * (complex_taps ? 2u : 1u);
+    return have_host_taps && nfloats <= FIR_PARAM_TAPS && !getenv("IQGPU_FIR_SMEM_TAPS") && !getenv("IQGPU_NO_DC_FOLD");
+}
+
 bool fir_can_convert_out(int out_format, unsigned ntaps_padded, int complex_taps)
 {
     const unsigned nfloats = ntaps_padded * (complex_taps ? 2u : 1u);
@@ -724,25 +755,29 @@ bool fir_can_convert_out(int out_format, unsigned ntaps_padded, int complex_taps
 }
 
 cudaError_t launch_fir(const float2* x, size_t n, const float* hrev, unsigned ntaps_padded, int complex_taps,
-                       float2* y, cudaStream_t st, const float* hrev_host, int out_format, void* out_conv)
+                       float2* y, cudaStream_t st, const float* hrev_host, int out_format, void* out_conv, const DcFold* fold)
 {
     if (n == 0) return cudaSuccess;
     const int grid = (int)((n + FIR_TILE - 1) / FIR_TILE);
     const unsigned nfloats = ntaps_padded * (complex_taps ? 2u : 1u);
     if (out_conv && !(hrev_host && fir_can_convert_out(out_format, ntaps_padded, complex_taps))) return cudaErrorInvalidValue;
+    const bool folding = fold && fold->corr;
+    if (folding && !fir_can_fold_dc(ntaps_padded, complex_taps, hrev_host != nullptr)) return cudaErrorInvalidValue;
     if (hrev_host && nfloats <= FIR_PARAM_TAPS && !getenv("IQGPU_FIR_SMEM_TAPS")) {
         static thread_local FirTaps T;      // 16 KB: copied into the launch's parameter buffer
         memcpy(T.h, hrev_host, nfloats * sizeof(float));
         const bool vo = (reinterpret_cast<size_t>(out_conv) & 15) == 0;
-#define FIR_GO(C, F) fir_param_kernel<C, F><<<grid, FIR_THREADS, 0, st>>>(x, n, ntaps_padded, y, out_conv, vo, T)
-#define FIR_FMT(C)                                                          \
-        do {                                                                \
-            if (!out_conv) FIR_GO(C, 0);                                    \
-            else if (out_format == IQGPU_FMT_CS16) FIR_GO(C, IQGPU_FMT_CS16); \
-            else if (out_format == IQGPU_FMT_CU8) FIR_GO(C, IQGPU_FMT_CU8); \
-            else FIR_GO(C, IQGPU_FMT_CS8);                                  \
+        const DcFold F = folding ? *fold : DcFold{};
+#define FIR_GO(C, O, D) fir_param_kernel<C, O, D><<<grid, FIR_THREADS, 0, st>>>(x, n, ntaps_padded, y, out_conv, vo, T, F)
+#define FIR_FMT(C, D)                                                          \
+        do {                                                                   \
+            if (!out_conv) FIR_GO(C, 0, D);                                    \
+            else if (out_format == IQGPU_FMT_CS16) FIR_GO(C, IQGPU_FMT_CS16, D); \
+            else if (out_format == IQGPU_FMT_CU8) FIR_GO(C, IQGPU_FMT_CU8, D); \
+            else FIR_GO(C, IQGPU_FMT_CS8, D);                                  \
         } while (0)
-        if (complex_taps) FIR_FMT(true); else FIR_FMT(false);
+        if (complex_taps) { if (folding) FIR_FMT(true, true); else FIR_FMT(true, false); }
+        else              { if (folding) FIR_FMT(false, true); else FIR_FMT(false, false); }
 #undef FIR_FMT
 #undef FIR_GO
         return cudaGetLastError();
@@ -1487,8 +1522,10 @@ struct AgcQuietPart { int event; int pad; double last_strong, weak_before; };
 
 __global__ void __launch_bounds__(AGC_QUIET_THREADS) agc_quiet_parts_kernel(const uint32_t* __restrict__ seg_start, unsigned nseg,
                                                                             const float* __restrict__ seg_peak, PostParams p,
-                                                                            const AgcState* __restrict__ st, AgcQuietPart* __restrict__ parts)
+                                                                            const AgcState* __restrict__ st, AgcQuietPart* __restrict__ parts,
+                                                                            float* __restrict__ seg_gain, const int* __restrict__ done_flag)
 {
+    if (done_flag && *done_flag) return;        // an earlier test already settled the whole table
     __shared__ double s_last[AGC_QUIET_THREADS], s_weak[AGC_QUIET_THREADS];
     __shared__ int s_event;
     const unsigned t = threadIdx.x;
@@ -1501,6 +1538,8 @@ __global__ void __launch_bounds__(AGC_QUIET_THREADS) agc_quiet_parts_kernel(cons
     const uint32_t base = __ldg(seg_start);
     for (unsigned i = i0; i < i1; i++) {
         const uint32_t a = __ldg(seg_start + i), b = __ldg(seg_start + i + 1);
+        // the gains of a quiet table (the scan kernel rewrites every entry if the table is not quiet after all)
+        if (seg_gain) seg_gain[i] = (b == a) ? 1.0f : s0.gain;
         if (b == a) continue;                                          // agc_apply returns on an empty chunk (agc.c:89)
         const float opk = __fmul_rn(__ldg(seg_peak + i), s0.gain);
         const double now = (double)(s0.seen + (unsigned long long)(uint32_t)(a - base)) / p.target_rate;
@@ -1530,9 +1569,11 @@ __global__ void __launch_bounds__(AGC_QUIET_THREADS) agc_quiet_parts_kernel(cons
 }
 
 __global__ void agc_quiet_finish_kernel(const AgcQuietPart* __restrict__ parts, unsigned nparts, const uint32_t* __restrict__ seg_start,
-                                        unsigned nseg, AgcState* __restrict__ st, int* __restrict__ quiet_flag)
+                                        unsigned nseg, AgcState* __restrict__ st, int* __restrict__ quiet_flag,
+                                        const int* __restrict__ done_flag)
 {
     if (threadIdx.x) return;
+    if (done_flag && *done_flag) { *quiet_flag = 1; return; }
     AgcState s = *st;
     bool event = !s.locked;
     double before = s.last_strong;
@@ -1550,22 +1591,41 @@ __global__ void agc_quiet_finish_kernel(const AgcQuietPart* __restrict__ parts, 
     *quiet_flag = event ? 0 : 1;
 }
 
-size_t agc_quiet_workspace_bytes(size_t nseg) { return ((nseg + AGC_QUIET_PART - 1) / AGC_QUIET_PART + 1) * sizeof(AgcQuietPart) + 16; }
+size_t agc_quiet_workspace_bytes(size_t nseg) { return ((nseg + AGC_QUIET_PART - 1) / AGC_QUIET_PART + 2) * sizeof(AgcQuietPart) + 32; }
 
+// A table that is not quiet as a whole is usually not quiet because of its HEAD: a stream starts with the AGC's scanning
+// phase and its lock (2 s of signal, agc.c:117-160), after which nothing happens for a long time.  So the table is asked
+// twice: as a whole, and — if that fails — again behind a head of AGC_HEAD chunks that the scan kernel walks first.  All of
+// it is queued unconditionally; flags in device memory turn the kernels that have nothing left to do into no-ops.
+constexpr size_t AGC_HEAD = 8192;
 cudaError_t launch_agc_digital_scan(const uint32_t* seg_start, size_t nseg, const float* seg_peak,
                                     const PostParams& p, AgcState* state, float* seg_gain, cudaStream_t st, void* quiet_ws)
 {
     if (nseg == 0) return cudaSuccess;
-    const int* skip = nullptr;
-    if (!seg_gain && quiet_ws && nseg >= 1024) {
-        int* flag = reinterpret_cast<int*>(quiet_ws);
-        AgcQuietPart* parts = reinterpret_cast<AgcQuietPart*>(reinterpret_cast<char*>(quiet_ws) + 16);
-        const unsigned nparts = (unsigned)((nseg + AGC_QUIET_PART - 1) / AGC_QUIET_PART);
-        agc_quiet_parts_kernel<<<nparts, AGC_QUIET_THREADS, 0, st>>>(seg_start, (unsigned)nseg, seg_peak, p, state, parts);
-        agc_quiet_finish_kernel<<<1, 32, 0, st>>>(parts, nparts, seg_start, (unsigned)nseg, state, flag);
-        skip = flag;
+    if (!(quiet_ws && nseg >= 1024)) {
+        agc_digital_scan_kernel<<<1, AGC_SCAN_THREADS, 0, st>>>(seg_start, (unsigned)nseg, seg_peak, p, state, seg_gain, nullptr);
+        return cudaGetLastError();
     }
-    agc_digital_scan_kernel<<<1, AGC_SCAN_THREADS, 0, st>>>(seg_start, (unsigned)nseg, seg_peak, p, state, seg_gain, skip);
+    // (with gains too: a locked AGC in which nothing happens applies its one gain to every non-empty chunk)
+    int* flag_all = reinterpret_cast<int*>(quiet_ws);
+    int* flag_rest = flag_all + 4;
+    AgcQuietPart* parts = reinterpret_cast<AgcQuietPart*>(reinterpret_cast<char*>(quiet_ws) + 32);
+    const unsigned nparts = (unsigned)((nseg + AGC_QUIET_PART - 1) / AGC_QUIET_PART);
+    agc_quiet_parts_kernel<<<nparts, AGC_QUIET_THREADS, 0, st>>>(seg_start, (unsigned)nseg, seg_peak, p, state, parts, seg_gain, nullptr);
+    agc_quiet_finish_kernel<<<1, 32, 0, st>>>(parts, nparts, seg_start, (unsigned)nseg, state, flag_all, nullptr);
+    // (a state-only advance comes in pieces that the caller already cut at the lock point, iq_tool_b200/shard.py)
+    const size_t head = (seg_gain && nseg >= 3 * AGC_HEAD) ? AGC_HEAD : nseg;
+    agc_digital_scan_kernel<<<1, AGC_SCAN_THREADS, 0, st>>>(seg_start, (unsigned)head, seg_peak, p, state, seg_gain, flag_all);
+    if (head < nseg) {
+        const size_t rest = nseg - head;
+        const unsigned rparts = (unsigned)((rest + AGC_QUIET_PART - 1) / AGC_QUIET_PART);
+        float* rest_gain = seg_gain ? seg_gain + head : nullptr;
+        agc_quiet_parts_kernel<<<rparts, AGC_QUIET_THREADS, 0, st>>>(seg_start + head, (unsigned)rest, seg_peak + head, p, state, parts,
+                                                                     rest_gain, flag_all);
+        agc_quiet_finish_kernel<<<1, 32, 0, st>>>(parts, rparts, seg_start + head, (unsigned)rest, state, flag_rest, flag_all);
+        agc_digital_scan_kernel<<<1, AGC_SCAN_THREADS, 0, st>>>(seg_start + head, (unsigned)rest, seg_peak + head, p, state, rest_gain,
+                                                                flag_rest);
+    }
     return cudaGetLastError();
 }
 // co-resident thread budget of the cooperative RMS-AGC kernel on the current device

@@ -67,10 +67,14 @@ cudaError_t launch_arb(const float2* x, int64_t a0, const float* bank, uint32_t 
 // travel as kernel parameters and are read as constant-bank FFMA operands.
 // out_conv (optional, only when fir_can_convert_out() says so): the filter is the chain's last cf32 stage; the epilogue
 // converts to `out_format` and writes the final output there instead of the cf32 stream y.
+// fold (optional, only when fir_can_fold_dc() says so): the samples [0, n) still lack the fused front's closed-form DC
+// term (DcFold below); the filter adds it while it stages its tiles, so the stream is not read and written once more.
+struct DcFold;
 cudaError_t launch_fir(const float2* x, size_t n, const float* hrev, unsigned ntaps_padded,
                        int complex_taps, float2* y, cudaStream_t st, const float* hrev_host = nullptr,
-                       int out_format = 0, void* out_conv = nullptr);
+                       int out_format = 0, void* out_conv = nullptr, const DcFold* fold = nullptr);
 bool fir_can_convert_out(int out_format, unsigned ntaps_padded, int complex_taps);
+bool fir_can_fold_dc(unsigned ntaps_padded, int complex_taps, bool have_host_taps);
 
 // ---- K4: FFT block filter (overlap-save form of liquid's fftfilt) --------------------------
 // For each block b in [0,nblocks): window = x[(b-1)*B .. (b+1)*B), y[b*B .. (b+1)*B) =
@@ -147,6 +151,23 @@ struct ResamplerDesc {
     float zeta;
     uint32_t step;
 };
+// Local DC state of the warp-streaming front (fused_front2.cuh): every warp ran its stretch of the stream from v = 0, the
+// term it could not know is a decaying exponential per stretch that is added afterwards in closed form.
+struct W2DcCorr { float2 c_out, c_pre; };      // -a V0 Atot (cascade output) and -a V0 (cascade input, for the cf32 tail)
+struct W2DcGeom {
+    int n_stretch;
+    long long B0, L_full, L_last, warm_frames, pad_frames;     // pad: zero frames between N1 and the end of the last tick
+    double lnc, alpha, atot;
+};
+// what a consumer of the resampled stream needs to add that term itself to sample i (absolute output index O0 + i)
+struct DcFold {
+    const W2DcCorr* corr;      // device: one record per stretch
+    const float* G;            // device: 256 polyphase row gains
+    W2DcGeom geo;
+    long long O0;
+    uint32_t step;
+    int S;
+};
 struct FusedFront;
 bool fused_supported(int format, const ResamplerDesc& r);
 FusedFront* fused_create(int format, const ResamplerDesc& r, bool nco, const float* d_bank, int num_sms, std::string& err);
@@ -159,8 +180,13 @@ const double2* fused_dc_state_at(const FusedFront* f, int slot, int64_t n0, int6
 // (updated to the state at n0+n).  *launches is incremented by the kernels launched.
 // dc_slot (0/1): DC table slot; if fused_prepare_dc() filled it (possibly on another stream, ordered by
 // the caller) the launch uses it, otherwise the pre-pass runs inline on `st`.
+// fold (optional): when the launch used the local DC state, the closed-form term is NOT added to y; *fold describes it
+// (fold->corr != nullptr) for a consumer that adds it on the fly, and fused_dc_correct_range() adds it in memory to the part
+// of y that stays behind as somebody's history.  The cf32 tail of the pre-processed stream is corrected in any case.
 cudaError_t fused_launch(FusedFront* f, const void* raw, int64_t n0, size_t n, const PreParams& pre, double2* d_dc_carry,
-                         int64_t O0, size_t n_out, float2* y, uint32_t* launches, int dc_slot, cudaStream_t st);
+                         int64_t O0, size_t n_out, float2* y, uint32_t* launches, int dc_slot, cudaStream_t st,
+                         DcFold* fold = nullptr);
+cudaError_t fused_dc_correct_range(const DcFold& fold, float2* y, size_t first, size_t count, cudaStream_t st);
 cudaError_t fused_prepare_dc(FusedFront* f, int slot, const void* raw, int64_t n0, size_t n, const PreParams& pre,
                              double2* d_dc_carry, uint32_t* launches, cudaStream_t st);
 

@@ -524,23 +524,12 @@ def test_iq_optimizer_pass_matches_reference(gpu, workloads):
     assert gr < 20.0 and gm == np.float32(0.01) and gp == np.float32(-0.02)
 
 
-def test_digital_agc_chunk_table_scan_equals_the_sequential_state_machine(gpu):
-    """G2 (agc.c:105-222) over thousands of chunks in ONE train: the GPU evaluates the per-chunk state
-    machine with a parallel scan over the chunk table (event-free stretches in one step, chunks with a lock
-    transition / ratchet / creep replayed sequentially); the oracle walks the chunks one by one on the
-    sample clock.  The amplitude schedule covers scanning with a rising peak memory, the lock, long
-    event-free locked stretches (several scan tiles), isolated and back-to-back ratchets, 'strong'
-    refreshes, and long creep phases."""
+def _digital_agc_schedule(gpu, amps, pieces_list, seed=77):
+    """Runs the per-chunk amplitude schedule `amps` through the digital AGC on the GPU (one train and ragged trains) and
+    through the oracle chunk by chunk on the sample clock; returns the oracle's per-chunk gains."""
     from oracle import loader
     rate, chunk = 512.0, 64                      # one chunk = 0.125 s: lock after 17 chunks, creep after 32 weak ones
-    rng = np.random.Generator(np.random.PCG64(77))
-    amps = [0.05, 0.1, 0.2, 0.15, 0.4] + [0.3] * 30                 # scan, lock at chunk 17
-    amps += [0.5, 0.45, 0.44]                                        # ratchet(s)
-    amps += [0.42] * 2500                                            # strong, event free: > one 2048-chunk tile
-    amps += [0.03] * 300                                             # weak: creep starts after 32 chunks
-    amps += [0.9, 0.95, 1.0, 0.2]                                    # ratchets back to back
-    amps += list(rng.choice([0.02, 0.3, 0.45, 0.7], size=1500, p=[0.5, 0.3, 0.15, 0.05]))   # mixed
-    amps += [0.25] * 2200 + [0.6] + [0.01] * 100
+    rng = np.random.Generator(np.random.PCG64(seed))
     amps = np.asarray(amps, dtype=np.float32)
     nchunks = amps.size
     ph = rng.uniform(0, 2 * np.pi, size=nchunks * chunk)
@@ -560,7 +549,8 @@ def test_digital_agc_chunk_table_scan_equals_the_sequential_state_machine(gpu):
         getattr(lib, pfx + "set_fake_clock")(0, 0.0)
     oi = o.info()
     sizes = np.full(nchunks, chunk, dtype=np.uint32)
-    for pieces in (1, 7):                                            # one train, and ragged trains (state carried)
+    gain_r = np.abs(ref[::chunk]) / amps
+    for pieces in pieces_list:                                       # one train, and ragged trains (state carried)
         g = gpu.Chain(cfg, 0)
         outs, edges = [], np.linspace(0, nchunks, pieces + 1).astype(int)
         for a, b in zip(edges[:-1], edges[1:]):
@@ -571,11 +561,50 @@ def test_digital_agc_chunk_table_scan_equals_the_sequential_state_machine(gpu):
         assert (gi.agc_locked, gi.agc_samples_seen) == (oi.agc_locked, oi.agc_samples_seen)
         assert gi.agc_gain == pytest.approx(oi.agc_gain, rel=3e-7) and gi.agc_peak_memory == pytest.approx(oi.agc_peak_memory, rel=3e-7)
         gain_g = np.abs(out[::chunk]) / amps
-        gain_r = np.abs(ref[::chunk]) / amps
         assert np.allclose(gain_g, gain_r, rtol=1e-6, atol=0)
         assert np.allclose(out, ref, rtol=1e-6, atol=1e-9)
+    return gain_r
+
+
+def test_digital_agc_chunk_table_scan_equals_the_sequential_state_machine(gpu):
+    """G2 (agc.c:105-222) over thousands of chunks in ONE train: the GPU evaluates the per-chunk state
+    machine with a parallel scan over the chunk table (event-free stretches in one step, chunks with a lock
+    transition / ratchet / creep replayed sequentially); the oracle walks the chunks one by one on the
+    sample clock.  The amplitude schedule covers scanning with a rising peak memory, the lock, long
+    event-free locked stretches (several scan tiles), isolated and back-to-back ratchets, 'strong'
+    refreshes, and long creep phases."""
+    rng = np.random.Generator(np.random.PCG64(77))
+    amps = [0.05, 0.1, 0.2, 0.15, 0.4] + [0.3] * 30                 # scan, lock at chunk 17
+    amps += [0.5, 0.45, 0.44]                                        # ratchet(s)
+    amps += [0.42] * 2500                                            # strong, event free: > one 2048-chunk tile
+    amps += [0.03] * 300                                             # weak: creep starts after 32 chunks
+    amps += [0.9, 0.95, 1.0, 0.2]                                    # ratchets back to back
+    amps += list(rng.choice([0.02, 0.3, 0.45, 0.7], size=1500, p=[0.5, 0.3, 0.15, 0.05]))   # mixed
+    amps += [0.25] * 2200 + [0.6] + [0.01] * 100
+    # a ratchet, then 3000 strong chunks in which nothing happens: with ragged trains two whole trains lie inside that
+    # stretch — the grid-wide quiet test answers for them and writes their (single) gain, the scan kernel is skipped
+    amps += [0.5] * 40 + [0.45] * 3000
+    gain_r = _digital_agc_schedule(gpu, amps, (1, 7))
     # the schedule really exercised every branch
     assert gain_r[40] < gain_r[30] and gain_r[2500 + 38 + 290] > gain_r[2500 + 38 + 10]
+
+
+@pytest.mark.parametrize("tail", ["quiet", "ratchet_and_creep"])
+def test_digital_agc_long_table_is_asked_again_behind_its_head(tail, gpu):
+    """A train of more than 3 x 8192 chunks that starts with the scanning phase and the lock is not quiet as a whole; the
+    scan kernel then walks only a head of 8192 chunks and the rest of the table is asked again with the state behind the
+    head (launch_agc_digital_scan).  `quiet`: nothing happens behind the head — gains come from the quiet test, the scan of
+    the rest is skipped.  `ratchet_and_creep`: events behind the head — the scan kernel takes the rest after all.  One
+    train (head + rest), and three trains (the later ones are quiet / not quiet as a whole)."""
+    amps = [0.05, 0.1, 0.2, 0.15, 0.4] + [0.3] * 30 + [0.5, 0.45, 0.44] + [0.42] * 9000
+    if tail == "quiet":
+        amps += [0.44] * 17000
+    else:
+        amps += [0.44] * 6000 + [0.6, 0.55] + [0.5] * 5000 + [0.02] * 200 + [0.5] * 5800
+    gain_r = _digital_agc_schedule(gpu, amps, (1, 3), seed=78)
+    if tail != "quiet":
+        k = 38 + 9000 + 6000
+        assert gain_r[k + 3] < gain_r[k - 3] and gain_r[k + 2 + 5000 + 190] > gain_r[k + 2 + 5000 + 10]    # ratchet, creep
 
 
 @pytest.mark.parametrize("out_fmt", ["cs16", "cu8", "cs8"])
@@ -664,6 +693,33 @@ def test_fused_dc_local_state_equals_the_table_pre_pass(gpu, workloads, monkeypa
     assert rel_rms_fullscale(b, t) <= 1e-7 and np.abs(b - t).max() <= 2e-6
     # the blocker did its job in both: the 0.2 offset is gone from the settled part of the stream
     assert abs(a[a.size // 2:].mean()) < 2e-3
+
+
+def test_fir_adds_the_fronts_dc_term_while_staging_its_tiles(gpu, workloads, monkeypatch):
+    """cfg2 as specified (DC offset, local DC state in the fused front, 255-tap FIR behind the resampler): the FIR adds the
+    front's closed-form DC term to the samples it stages instead of a separate read-modify-write pass over the resampled
+    stream (the newest taps-1 samples, the next call's history, get it in memory afterwards).  Same bytes as with the
+    separate pass (IQGPU_NO_DC_FOLD=1), one call or ragged calls that are shorter than, equal to and longer than the
+    filter history, cs16 output (FIR epilogue conversion) and cf32 output (post kernel behind the FIR)."""
+    import dataclasses
+    wl = workloads["cfg2"]
+    n = (1 << 22) + 7777
+    raw = synth_numpy(wl, n)
+    cuts = [0, 1 << 20, (1 << 20) + 3000, (1 << 20) + 3000 + 16384, 3 << 20, n]
+    for out_fmt in ("cs16", "cf32"):
+        cfg = dataclasses.replace(wl.config, output_format=out_fmt)
+        def run(split):
+            if not split:
+                return gpu.Chain(cfg, 0, subtrain_frames=1 << 20).process(raw)          # several sub-trains in one call
+            g = gpu.Chain(cfg, 0, subtrain_frames=1 << 22)
+            return np.concatenate([g.process(raw[2 * lo:2 * hi], chunk_frames=[hi - lo]) for lo, hi in zip(cuts[:-1], cuts[1:])])
+        a, a_split = run(False), run(True)
+        monkeypatch.setenv("IQGPU_NO_DC_FOLD", "1")
+        b, b_split = run(False), run(True)
+        monkeypatch.delenv("IQGPU_NO_DC_FOLD")
+        view = (lambda v: v.view(np.uint32)) if out_fmt == "cf32" else (lambda v: v)
+        assert a.size == b.size and np.array_equal(view(a), view(b))
+        assert a_split.size == b_split.size and np.array_equal(view(a_split), view(b_split))
 
 
 def test_long_post_resample_fir_runs_on_the_fft_block_kernel(gpu, workloads, monkeypatch):
