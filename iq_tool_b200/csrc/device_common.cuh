@@ -245,7 +245,9 @@ __device__ __forceinline__ long long dc_fold_frame(unsigned long long o, uint32_
 __device__ __forceinline__ float2 dc_fold_add_at(float2 v, unsigned long long Pp, int since, float lnc, const W2DcCorr& c,
                                                  const float* __restrict__ sG)
 {
-    const float e = expf(lnc * (float)since) * sG[(unsigned)(Pp >> 16) & 0xffu];
+    // (ex2.approx: 2^-22 relative on a term that is itself a small correction; the full expf cost the FIR 15 instructions
+    // per staged sample, profiles/r02m_fir_fold_cfg2.md)
+    const float e = __expf(lnc * (float)since) * sG[(unsigned)(Pp >> 16) & 0xffu];
     v.x = fmaf(c.c_out.x, e, v.x);
     v.y = fmaf(c.c_out.y, e, v.y);
     return v;
