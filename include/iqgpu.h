@@ -276,7 +276,7 @@ typedef struct {
     uint64_t trains;          /* chain calls made */
 } iqgpu_rawfile_stats;
 int         iqgpu_rawfile_run(const iqgpu_chain_config *cfg, int device, const char *in_path, const char *out_path,
-                              size_t train_chunks /* reference chunks per chain call, 0 = 256 */,
+                              size_t train_chunks /* reference chunks per chain call, 0 = 64 */,
                               iqgpu_rawfile_stats *stats /* optional */);
 const char *iqgpu_rawfile_last_error(void);
 

@@ -380,9 +380,14 @@ __device__ __forceinline__ void w2_p0(const Fused2Args& A, float2* __restrict__ 
 #pragma unroll
             for (int k = 0; k < 16; k++) {
                 const float2 sc2 = lut2[w2_lut_slot(((th + (1u << 21)) >> 22) & 0x3ffu, A.lut_sh, A.lut_mask)];   // {sign*sin, cos}
+                // (v.x c - v.y s, v.x s + v.y c) with every product and every sum rounded on its own (liquid's complex
+                // multiply): the products as two packed multiplies — {v.x, v.y} * c and {v.y, v.x} * {-s, s}, whose swap
+                // and sign are operand modifiers of FMUL2 — the sums as SCALAR adds: ptxas 12.9 contracts a packed
+                // mul.rn.f32x2 into a packed add or fma that consumes it (one rounding instead of two), never into add.rn.f32
                 const float2 v = unpk2(x[k]);
-                x[k] = pk2(__fsub_rn(__fmul_rn(v.x, sc2.y), __fmul_rn(v.y, sc2.x)),
-                           __fadd_rn(__fmul_rn(v.x, sc2.x), __fmul_rn(v.y, sc2.y)));
+                const float2 t1 = unpk2(mul2(x[k], pk2(sc2.y, sc2.y)));
+                const float2 t2 = unpk2(mul2(pk2(v.y, v.x), pk2(-sc2.x, sc2.x)));
+                x[k] = pk2(__fadd_rn(t1.x, t2.x), __fadd_rn(t1.y, t2.y));
                 th += p.nco_dtheta;
             }
         }

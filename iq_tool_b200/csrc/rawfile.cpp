@@ -113,7 +113,7 @@ int iqgpu_rawfile_run(const iqgpu_chain_config* cfg, int device, const char* in_
 int iqio::run_stream(iqgpu_chain* chain, const iqgpu_chain_config* cfg, FILE* fin, uint64_t in_limit_bytes, FILE* fout,
                      size_t train_chunks, iqgpu_rawfile_stats* stats, std::string& err)
 {
-    if (train_chunks == 0) train_chunks = 256;
+    if (train_chunks == 0) train_chunks = 64;      // 1 Mi frames per train: measured best on B200 (profiles/r02_bench_lines.jsonl, file:cfg2)
     const size_t in_bps = iqgpu_get_bytes_per_sample(cfg->input_format), out_bps = iqgpu_get_bytes_per_sample(cfg->output_format);
     if (!in_bps || !out_bps) { err = "unhandled sample format"; return IQGPU_EINVAL; }
     int rc = IQGPU_OK;

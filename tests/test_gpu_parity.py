@@ -361,6 +361,22 @@ def test_fused_front_equals_stage_by_stage_path(name, n, gpu, workloads):
         assert max_lsb(ya, yb) <= 1
 
 
+@pytest.mark.parametrize("rate", [744187.5, 2.4e6, 9.0e6])
+def test_fused_front_gain_that_is_not_a_power_of_two(rate, gpu):
+    """sample_convert.c:136-141 rounds (x / 32768) * gain once per component before anything else sees it.  The packed
+    conversion in the fused front feeds packed adds of the first halfband stage; ptxas 12.9 contracts mul.rn.f32x2 +
+    add.rn.f32x2 into FFMA2 when it can (it does not for the scalar forms), which would skip that rounding.  With a gain of
+    0.7 the product is inexact, so a contraction shows as a bit difference from the stage-by-stage kernels (S = 4, 3, 1)."""
+    cfg = ChainConfig(input_format="cs16", output_format="cf32", input_rate_hz=20e6, target_rate_hz=rate, gain=0.7)
+    rng = np.random.Generator(np.random.PCG64(5))
+    raw = rng.integers(-32768, 32768, size=2 * ((1 << 21) + 777), dtype=np.int16)
+    a = gpu.Chain(cfg, 0, fused=1)
+    b = gpu.Chain(cfg, 0, fused=0)
+    ya, yb = a.process(raw), b.process(raw)
+    assert a.info().fused_front == 1 and b.info().fused_front == 0
+    assert ya.size == yb.size and np.array_equal(ya.view(np.uint32), yb.view(np.uint32))
+
+
 @pytest.mark.parametrize("name,n", [("cfg1", (1 << 22) + 4097), ("cfg5", (1 << 23) + 11)])
 def test_fused_front_parity_vs_oracle(name, n, gpu, workloads):
     wl = workloads[name]

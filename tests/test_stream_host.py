@@ -68,7 +68,7 @@ def test_rawfile_stream_cuts_trains_and_drops_a_torn_frame(stub, frames, train_c
     assert np.array_equal(out, raw.reshape(-1, 2)[::2].reshape(-1))
     assert (st.frames_in, st.frames_out, st.bytes_written) == (frames, (frames + 1) // 2, out.size * 2)
     calls, largest = last_run(stub)
-    per_train = (train_chunks or 256) * CHUNK
+    per_train = (train_chunks or 64) * CHUNK
     assert largest <= per_train and calls == -(-frames // per_train)      # an empty last train makes no chain call
     assert st.trains >= calls
 
