@@ -492,17 +492,14 @@ int iqgpu_chain::init_device()
         const unsigned blk = fir_via_fft ? fir_fft_block : filt.block;
         if (!fftfilt_supported(blk)) return fail(IQGPU_EINVAL, "FFT filter block size not supported by the GPU FFT kernel");
         const unsigned nfft = 2 * blk;
-        std::vector<float2> tw(nfft), hpad(nfft, make_float2(0.f, 0.f));
-        for (unsigned k = 0; k < nfft; k++) {
-            double a = -2.0 * M_PI * (double)k / (double)nfft;
-            tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
-        }
+        std::vector<float2> tw(fft_twiddle_entries(nfft)), hpad(nfft, make_float2(0.f, 0.f));
+        fft_fill_twiddles(nfft, tw.data());
         for (size_t i = 0; i < filt.taps.size(); i++) hpad[i] = make_float2(filt.taps[i].real(), filt.taps[i].imag());
         float2* d_h = nullptr;
-        CK(cudaMalloc(&d_fft_tw, nfft * sizeof(float2)));
+        CK(cudaMalloc(&d_fft_tw, tw.size() * sizeof(float2)));
         CK(cudaMalloc(&d_fft_H, nfft * sizeof(float2)));
         CK(cudaMalloc(&d_h, nfft * sizeof(float2)));
-        CK(cudaMemcpy(d_fft_tw, tw.data(), nfft * sizeof(float2), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_fft_tw, tw.data(), tw.size() * sizeof(float2), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(d_h, hpad.data(), nfft * sizeof(float2), cudaMemcpyHostToDevice));
         CK(launch_fft_forward(d_h, nfft, d_fft_tw, d_fft_H, stream));
         CK(cudaStreamSynchronize(stream));

@@ -15,6 +15,7 @@
 // split: radix-2 DIF stages over a global scratch down to 16384-point sub-blocks, the shared
 // memory kernel on each sub-block, radix-2 DIT stages back up.
 #include <cstdio>
+#include <cmath>
 #include <cstdlib>
 
 #include "fft_core.cuh"
@@ -151,8 +152,38 @@ static cudaError_t launch_smem(const float2* src, float2* dst, unsigned M, unsig
 }
 
 // v2 (radix-16 register butterflies, fft_filter2.cuh) serves every transform that fits one CTA
-static bool use_v2(unsigned nfft) { return nfft >= 64 && nfft <= fft2::MAX_POINTS && !getenv("IQGPU_FFT_V1"); }
+static bool v2_capable(unsigned nfft) { return nfft >= 64 && nfft <= fft2::MAX_POINTS; }
+static bool use_v2(unsigned nfft) { return v2_capable(nfft) && !getenv("IQGPU_FFT_V1"); }
 static size_t v2_smem_bytes(unsigned nfft) { return (size_t)(fft2::pad(nfft) + 8) * sizeof(float2); }
+
+size_t fft_twiddle_entries(unsigned nfft)
+{
+    size_t n = nfft;
+    if (v2_capable(nfft)) {      // (whatever IQGPU_FFT_V1 says now: the kernel choice is made at launch time)
+        const fft2::Plan P = fft2::make_plan(nfft);
+        unsigned L = nfft;
+        for (unsigned k = 0; k < P.n16; k++, L >>= 4) n += 4 * (size_t)(L >> 4);
+    }
+    return n;
+}
+void fft_fill_twiddles(unsigned nfft, float2* host)
+{
+    for (unsigned k = 0; k < nfft; k++) {
+        const double a = -2.0 * M_PI * (double)k / (double)nfft;
+        host[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+    if (!v2_capable(nfft)) return;
+    // compact records {W_L^j, W_L^2j, W_L^4j, W_L^8j}, j < L/16, for the radix-16 passes L = nfft, nfft/16, ...:
+    // copies of natural entries (same floats)
+    const fft2::Plan P = fft2::make_plan(nfft);
+    float2* rec = host + nfft;
+    unsigned L = nfft;
+    for (unsigned k = 0; k < P.n16; k++, L >>= 4) {
+        const unsigned s = L >> 4, tws = nfft / L;
+        for (unsigned j = 0; j < s; j++)
+            for (unsigned p = 1; p <= 8; p <<= 1) *rec++ = host[(size_t)p * j * tws];
+    }
+}
 
 cudaError_t launch_fft_forward(const float2* in, unsigned nfft, const float2* twiddle, float2* out, cudaStream_t st)
 {

@@ -22,14 +22,29 @@
 #include <cuda_runtime.h>
 
 #include "fft_core.cuh"
+#include "device_common.cuh"
 
 namespace iqgpu {
 namespace fft2 {
 
-using fftcore::cadd;
-using fftcore::cmul;
-using fftcore::cmulc;
-using fftcore::csub;
+// Complex arithmetic on packed {re, im} pairs (add/sub/mul/fma.f32x2 -> FADD2 / FMUL2 / FFMA2): a complex add is one
+// instruction instead of two, a complex multiply two instead of four — the swap of the halves and the sign of one half
+// that the cross terms need are operand modifiers of the packed instructions (ptxas folds the mov.b64 re-packs into them).
+// The radix-16 network is two thirds additions; the scalar form spent 66 % of its issue slots on FP instructions at
+// 35 % FMA-pipe utilisation (profiles/r01f_fftfilt2_full_cfg3.md).  Rounding differs from the scalar form in the last
+// bit of some products (fma contraction); H is produced by the same network, the parity bars are those of the oracle.
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return unpk2(add2(pk2(a), pk2(b))); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return unpk2(add2(pk2(a), pk2(-b.x, -b.y))); }
+// a * w = {a.x w.x - a.y w.y, a.y w.x + a.x w.y} = {a.x, a.y} * w.x + {a.y, a.x} * {-w.y, w.y}
+__device__ __forceinline__ float2 cmul(float2 a, float2 w)
+{
+    return unpk2(fma2(pk2(a), pk2(w.x, w.x), mul2(pk2(a.y, a.x), pk2(-w.y, w.y))));
+}
+// a * conj(w) = {a.x w.x + a.y w.y, a.y w.x - a.x w.y}
+__device__ __forceinline__ float2 cmulc(float2 a, float2 w)
+{
+    return unpk2(fma2(pk2(a), pk2(w.x, w.x), mul2(pk2(a.y, a.x), pk2(w.y, -w.y))));
+}
 using fftcore::mulmj;
 using fftcore::mulpj;
 
@@ -89,10 +104,35 @@ __device__ __forceinline__ void dft16(float2 (&u)[16])
 
 // twiddles W_L^(j p), p = 1..R-1, from the table tw[k] = exp(-2 pi i k / NT): the powers of two are read,
 // the others are products
+// Radix-16 passes read their four table twiddles from COMPACT records behind the natural table (tw + NT): the record of
+// butterfly offset j of the pass with sub-length L is {W_L^j, W_L^2j, W_L^4j, W_L^8j} (32 bytes), records of one pass are
+// contiguous in j, passes follow each other from L = NT downwards.  In the natural table the four entries of one lane are
+// j NT/L, 2j NT/L, ... entries apart from the next lane's: at L = 1024 of a 16384-point transform every lane of every load
+// touches its own 128-byte line — 128 L1 wavefronts per warp and load instruction, more LSU traffic than the pass's own
+// shared-memory round trip (profiles/r02p_fftfilt2_full_cfg3.md: LSU data pipe 71 %, issue 34 %).
+__host__ __device__ inline unsigned compact_offset(unsigned NT, unsigned L)      // in records; L = NT >> (4 k)
+{
+    unsigned off = 0;
+    for (unsigned l = NT; l > L; l >>= 4) off += l >> 4;
+    return off;
+}
 template <int R>
-__device__ __forceinline__ void pass_twiddles(const float2* __restrict__ tw, unsigned j, unsigned tws, float2 (&w)[R])
+__device__ __forceinline__ void pass_twiddles(const float2* __restrict__ tw, unsigned j, unsigned tws, float2 (&w)[R],
+                                              unsigned NT = 0, unsigned L = 0)
 {
     w[0] = make_float2(1.f, 0.f);
+    if constexpr (R == 16) {
+        if (NT) {
+            const float4* rec = reinterpret_cast<const float4*>(tw + NT) + 2 * (size_t)(compact_offset(NT, L) + j);
+            const float4 a = __ldg(rec), b = __ldg(rec + 1);
+            w[1] = make_float2(a.x, a.y); w[2] = make_float2(a.z, a.w); w[4] = make_float2(b.x, b.y); w[8] = make_float2(b.z, b.w);
+            w[3] = cmul(w[1], w[2]);
+            w[5] = cmul(w[1], w[4]); w[6] = cmul(w[2], w[4]); w[7] = cmul(w[3], w[4]);
+#pragma unroll
+            for (int p = 1; p < 8; p++) w[8 + p] = cmul(w[p], w[8]);
+            return;
+        }
+    }
     if (R >= 2) w[1] = __ldg(tw + j * tws);
     if (R >= 4) { w[2] = __ldg(tw + 2 * j * tws); w[3] = cmul(w[1], w[2]); }
     if (R >= 16) {
@@ -134,7 +174,7 @@ __device__ __forceinline__ void smem_pass_impl(float2* __restrict__ buf, unsigne
         float2 u[R], w[R];
 #pragma unroll
         for (int q = 0; q < R; q++) u[q] = buf[pad_at<LINEAR>(p0, base, q, s, stride)];
-        pass_twiddles<R>(tw, j, tws, w);
+        pass_twiddles<R>(tw, j, tws, w, NT, L);
         if (INV) {
 #pragma unroll
             for (int p = 1; p < R; p++) u[p] = cmulc(u[p], w[p]);
@@ -167,7 +207,7 @@ __device__ __forceinline__ void first_pass_from_global(const float2* __restrict_
         float2 u[R], w[R];
 #pragma unroll
         for (int q = 0; q < R; q++) u[q] = x[t + q * s];
-        pass_twiddles<R>(tw, t, tws, w);
+        pass_twiddles<R>(tw, t, tws, w, NT, N);
         dft_r<R, false>(u);
 #pragma unroll
         for (int p = 1; p < R; p++) u[p] = cmul(u[p], w[p]);
@@ -199,7 +239,7 @@ __device__ __forceinline__ void last_pass_to_global(float2* __restrict__ buf, fl
 #pragma unroll
             for (int q = 0; q < R; q++) u[q] = buf[pad(t + q * s)];
         }
-        pass_twiddles<R>(tw, t, tws, w);
+        pass_twiddles<R>(tw, t, tws, w, NT, N);
 #pragma unroll
         for (int p = 1; p < R; p++) u[p] = cmulc(u[p], w[p]);
         dft_r<R, true>(u);

@@ -88,6 +88,10 @@ size_t fftfilt_scratch_bytes(size_t nblocks, unsigned B);
 cudaError_t launch_fft_forward(const float2* in, unsigned nfft, const float2* twiddle, float2* out,
                                cudaStream_t st);
 bool fftfilt_supported(unsigned B);
+// twiddle table of an nfft-point transform as the FFT kernels expect it: exp(-2 pi i k / nfft), k < nfft, followed by the
+// compact per-pass records of the radix-16 kernel (fft_filter2.cuh); float2 entries in total / filled on the host
+size_t fft_twiddle_entries(unsigned nfft);
+void fft_fill_twiddles(unsigned nfft, float2* host);
 
 // ---- K5: post-processor ([NCO] + AGC + convert) ---------------------------------------------
 struct AgcState {           // lives in device memory

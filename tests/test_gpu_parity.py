@@ -642,7 +642,7 @@ def test_fir_epilogue_conversion_equals_the_post_kernel(out_fmt, gpu, workloads,
 
 
 @pytest.mark.parametrize("S", [0, 1, 2, 3, 4, 5, 6])
-def test_fused_front_every_cascade_depth(S, gpu):
+def test_fused_front_every_cascade_depth(S, gpu, monkeypatch):
     """Every compiled cascade plan of the warp-streaming fused front (S = 0..6 halfband stages: register first stage
     for S >= 3, deep stages on 128 / 64 outputs per run) against the stage-by-stage kernels: same FMA order -> same
     bits; against the oracle: the north_star bar; ragged calls (incl. an empty one) == one call."""
@@ -683,6 +683,37 @@ def test_fused_front_every_cascade_depth(S, gpu):
         pos += m
     many = np.concatenate(parts)
     assert many.size == ya.size and np.array_equal(many.view(np.uint32), ya.view(np.uint32))
+    # the polyphase stage with two and with four outputs per lane (picked by timing on long calls, forced here): same bits
+    for mode in ("1", "2"):
+        monkeypatch.setenv("IQGPU_ARB_PAIRS", mode)
+        ym = gpu.Chain(cfg, 0, fused=1).process(raw)
+        monkeypatch.delenv("IQGPU_ARB_PAIRS")
+        assert ym.size == ya.size and np.array_equal(ym.view(np.uint32), ya.view(np.uint32))
+
+
+@pytest.mark.parametrize("S", [1, 4, 6])
+@pytest.mark.parametrize("rate", [0.505, 0.55, 0.66, 0.7, 0.8, 0.97])
+def test_polyphase_variants_are_bit_identical_at_every_rate_class(S, rate, gpu, monkeypatch):
+    """The four-output polyphase variant has a compiled form per (floor(2/rate), floor(3/rate)) = (3,5), (3,4), (2,4),
+    (2,3); rates outside them fall back to two outputs per lane.  Every variant, shallow (skewed level, S = 1) and deep
+    (plain level, S = 4, 6) cascades, DC blocker on (local DC state: the closed-form term uses the same row gains): the same
+    bits as one output per lane."""
+    rng = np.random.Generator(np.random.PCG64(int(1000 * rate) + S))
+    fs = 8e6
+    n = (1 << 19) + (3000 << S) + 13
+    raw = rng.integers(-20000, 20000, size=2 * n, dtype=np.int16)
+    cfg = ChainConfig(input_format="cs16", output_format="cf32", input_rate_hz=fs, target_rate_hz=fs * rate / (1 << S),
+                      dc_block=True)
+    outs = []
+    for mode in ("0", "1", "2"):
+        monkeypatch.setenv("IQGPU_ARB_PAIRS", mode)
+        g = gpu.Chain(cfg, 0, fused=1)
+        outs.append(g.process(raw))
+        assert g.info().fused_front == 1 and g.info().num_halfband == S
+        monkeypatch.delenv("IQGPU_ARB_PAIRS")
+    assert outs[0].size == outs[1].size == outs[2].size
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+    assert np.array_equal(outs[0].view(np.uint32), outs[2].view(np.uint32))
 
 
 def test_fused_dc_local_state_equals_the_table_pre_pass(gpu, workloads, monkeypatch):
