@@ -14,6 +14,7 @@
 // same digit-reversed order, conjugate-transposed network back (fft_core.cuh).  2n > 16384 is
 // split: radix-2 DIF stages over a global scratch down to 16384-point sub-blocks, the shared
 // memory kernel on each sub-block, radix-2 DIT stages back up.
+#include <algorithm>
 #include <cstdio>
 #include <cmath>
 #include <cstdlib>
@@ -217,7 +218,17 @@ cudaError_t launch_fftfilt(const float2* x, size_t nblocks, unsigned B, const fl
                                               (int)(fft2::SMEM_F2 * sizeof(float2)));
         if (ea != cudaSuccess) return ea;
         if (launches) *launches += 1;
-        fft2::fftfilt2_kernel<<<(unsigned)nblocks, fft2::THREADS, v2_smem_bytes(N), st>>>(x, y, N, twiddle, H, scale);
+        // CTAs resident at a time: the L2 prefetch distance of the kernel (0 = off)
+        static int wave = -1;
+        if (wave < 0) {
+            int dev = 0, sms = 0, per_sm = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fft2::fftfilt2_kernel, fft2::THREADS, v2_smem_bytes(fft2::MAX_POINTS));
+            wave = getenv("IQGPU_FFT_NO_PREFETCH") ? 0 : std::max(1, sms * std::max(1, per_sm));
+        }
+        const unsigned w = (N == fft2::MAX_POINTS) ? (unsigned)wave : 0u;     // smaller transforms run several CTAs per SM
+        fft2::fftfilt2_kernel<<<(unsigned)nblocks, fft2::THREADS, v2_smem_bytes(N), st>>>(x, y, N, twiddle, H, scale, w);
         return cudaGetLastError();
     }
     if (N <= FFT_SMEM_MAX) {

@@ -116,15 +116,33 @@ __host__ __device__ inline unsigned compact_offset(unsigned NT, unsigned L)     
     for (unsigned l = NT; l > L; l >>= 4) off += l >> 4;
     return off;
 }
+// records of the INNER radix-16 passes (L < NT: at most 64 + 4 of them) are staged in shared memory once per CTA: a pass
+// between two barriers has nothing to hide a global-memory round trip behind (one CTA per SM at 16384 points)
+constexpr unsigned INNER_RECORDS = 72;
+__device__ __forceinline__ void stage_inner_twiddles(const float2* __restrict__ tw, unsigned NT, float4* __restrict__ twi, unsigned tid)
+{
+    const unsigned first = NT >> 4;                                  // records of the L = NT pass come first
+    const Plan P = make_plan(NT);
+    unsigned n = 0, l = NT >> 4;
+    for (unsigned k = 1; k < P.n16; k++, l >>= 4) n += l >> 4;       // records of the other radix-16 passes: L = NT/16, NT/256, ...
+    const float4* src = reinterpret_cast<const float4*>(tw + NT) + 2 * (size_t)first;
+    for (unsigned i = tid; i < 2 * n && i < 2 * INNER_RECORDS; i += THREADS) twi[i] = __ldg(src + i);
+}
 template <int R>
 __device__ __forceinline__ void pass_twiddles(const float2* __restrict__ tw, unsigned j, unsigned tws, float2 (&w)[R],
-                                              unsigned NT = 0, unsigned L = 0)
+                                              unsigned NT = 0, unsigned L = 0, const float4* __restrict__ twi = nullptr)
 {
     w[0] = make_float2(1.f, 0.f);
     if constexpr (R == 16) {
         if (NT) {
-            const float4* rec = reinterpret_cast<const float4*>(tw + NT) + 2 * (size_t)(compact_offset(NT, L) + j);
-            const float4 a = __ldg(rec), b = __ldg(rec + 1);
+            float4 a, b;
+            if (twi && L < NT) {
+                const float4* rec = twi + 2 * (compact_offset(NT, L) - (NT >> 4) + j);
+                a = rec[0]; b = rec[1];
+            } else {
+                const float4* rec = reinterpret_cast<const float4*>(tw + NT) + 2 * (size_t)(compact_offset(NT, L) + j);
+                a = __ldg(rec); b = __ldg(rec + 1);
+            }
             w[1] = make_float2(a.x, a.y); w[2] = make_float2(a.z, a.w); w[4] = make_float2(b.x, b.y); w[8] = make_float2(b.z, b.w);
             w[3] = cmul(w[1], w[2]);
             w[5] = cmul(w[1], w[4]); w[6] = cmul(w[2], w[4]); w[7] = cmul(w[3], w[4]);
@@ -166,7 +184,7 @@ __device__ __forceinline__ unsigned pad_stride(unsigned s) { return s >= 64 ? s 
 // forward (DIF): u <- DFT_R(u), u[p] *= W_L^(j p).   inverse (DIT): u[p] *= conj(W_L^(j p)), u <- IDFT_R(u).
 template <int R, bool INV, bool LINEAR>
 __device__ __forceinline__ void smem_pass_impl(float2* __restrict__ buf, unsigned N, unsigned L, const float2* __restrict__ tw,
-                                               unsigned NT, unsigned tid)
+                                               unsigned NT, unsigned tid, const float4* __restrict__ twi)
 {
     const unsigned s = L / R, tws = NT / L, stride = pad_stride(s);
     for (unsigned t = tid; t < N / R; t += THREADS) {
@@ -174,7 +192,7 @@ __device__ __forceinline__ void smem_pass_impl(float2* __restrict__ buf, unsigne
         float2 u[R], w[R];
 #pragma unroll
         for (int q = 0; q < R; q++) u[q] = buf[pad_at<LINEAR>(p0, base, q, s, stride)];
-        pass_twiddles<R>(tw, j, tws, w, NT, L);
+        pass_twiddles<R>(tw, j, tws, w, NT, L, twi);
         if (INV) {
 #pragma unroll
             for (int p = 1; p < R; p++) u[p] = cmulc(u[p], w[p]);
@@ -190,10 +208,10 @@ __device__ __forceinline__ void smem_pass_impl(float2* __restrict__ buf, unsigne
 }
 template <int R, bool INV>
 __device__ __forceinline__ void smem_pass(float2* __restrict__ buf, unsigned N, unsigned L, const float2* __restrict__ tw,
-                                          unsigned NT, unsigned tid)
+                                          unsigned NT, unsigned tid, const float4* __restrict__ twi)
 {
-    if (pad_linear(L, L / R)) smem_pass_impl<R, INV, true>(buf, N, L, tw, NT, tid);
-    else smem_pass_impl<R, INV, false>(buf, N, L, tw, NT, tid);
+    if (pad_linear(L, L / R)) smem_pass_impl<R, INV, true>(buf, N, L, tw, NT, tid, twi);
+    else smem_pass_impl<R, INV, false>(buf, N, L, tw, NT, tid, twi);
 }
 
 // first forward pass (L = N) with its inputs read from global memory
@@ -270,7 +288,7 @@ __device__ __forceinline__ void middle_pass(float2* __restrict__ buf, unsigned N
 // passes between the first/last (L = N) pass and the middle: sub-lengths go N/R0, ... down to 4 (exclusive)
 template <bool INV>
 __device__ __forceinline__ void inner_passes(float2* __restrict__ buf, const Plan& P, unsigned L_after_first, const float2* __restrict__ tw,
-                                             unsigned tid)
+                                             unsigned tid, const float4* __restrict__ twi)
 {
     // radices in forward order after the first pass
     unsigned n16 = P.n16, n4 = P.n4, n2 = P.n2;
@@ -278,25 +296,39 @@ __device__ __forceinline__ void inner_passes(float2* __restrict__ buf, const Pla
     if (n16) n16--; else if (n4) n4--; else if (n2) n2--;
     if (!INV) {
         unsigned L = L_after_first;
-        for (unsigned i = 0; i < n16; i++, L >>= 4) { smem_pass<16, false>(buf, P.N, L, tw, P.N, tid); __syncthreads(); }
-        for (unsigned i = 0; i < n4; i++, L >>= 2) { smem_pass<4, false>(buf, P.N, L, tw, P.N, tid); __syncthreads(); }
-        for (unsigned i = 0; i < n2; i++, L >>= 1) { smem_pass<2, false>(buf, P.N, L, tw, P.N, tid); __syncthreads(); }
+        for (unsigned i = 0; i < n16; i++, L >>= 4) { smem_pass<16, false>(buf, P.N, L, tw, P.N, tid, twi); __syncthreads(); }
+        for (unsigned i = 0; i < n4; i++, L >>= 2) { smem_pass<4, false>(buf, P.N, L, tw, P.N, tid, twi); __syncthreads(); }
+        for (unsigned i = 0; i < n2; i++, L >>= 1) { smem_pass<2, false>(buf, P.N, L, tw, P.N, tid, twi); __syncthreads(); }
     } else {
         // reverse order, starting just above the middle radix-4: radix-2 passes first, then radix-4, then radix-16
         unsigned L = 4;
-        for (unsigned i = 0; i < n2; i++) { L <<= 1; smem_pass<2, true>(buf, P.N, L, tw, P.N, tid); __syncthreads(); }
-        for (unsigned i = 0; i < n4; i++) { L <<= 2; smem_pass<4, true>(buf, P.N, L, tw, P.N, tid); __syncthreads(); }
-        for (unsigned i = 0; i < n16; i++) { L <<= 4; smem_pass<16, true>(buf, P.N, L, tw, P.N, tid); __syncthreads(); }
+        for (unsigned i = 0; i < n2; i++) { L <<= 1; smem_pass<2, true>(buf, P.N, L, tw, P.N, tid, twi); __syncthreads(); }
+        for (unsigned i = 0; i < n4; i++) { L <<= 2; smem_pass<4, true>(buf, P.N, L, tw, P.N, tid, twi); __syncthreads(); }
+        for (unsigned i = 0; i < n16; i++) { L <<= 4; smem_pass<16, true>(buf, P.N, L, tw, P.N, tid, twi); __syncthreads(); }
     }
 }
 
 // One CTA = one block of the filter.  x points at block 0's first sample (history below).
 __global__ void __launch_bounds__(THREADS) fftfilt2_kernel(const float2* __restrict__ x, float2* __restrict__ y, unsigned N,
-                                                           const float2* __restrict__ tw, const float2* __restrict__ H, float scale)
+                                                           const float2* __restrict__ tw, const float2* __restrict__ H, float scale,
+                                                           unsigned wave)
 {
     extern __shared__ __align__(16) float2 fbuf[];
+    __shared__ float4 twi[2 * INNER_RECORDS];
     const unsigned tid = threadIdx.x, B = N >> 1;
     const Plan P = make_plan(N);
+    stage_inner_twiddles(tw, N, twi, tid);          // (read after the first pass's barrier)
+    {
+        // One CTA per SM (16384 points fill the shared memory) leaves nothing to overlap the first pass's DRAM round trip
+        // with: pull the new half of the window of the block this SM will most likely run next — one wave of CTAs ahead —
+        // into L2 now (the other half is this wave's input and already there)
+        const unsigned long long nb = (unsigned long long)blockIdx.x + wave;
+        if (wave && nb < gridDim.x) {
+            const char* p = reinterpret_cast<const char*>(x + (nb - 0) * (unsigned long long)B);
+            for (unsigned o = tid * 128u; o < B * (unsigned)sizeof(float2); o += THREADS * 128u)
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(p + o));
+        }
+    }
     const float2* w = x + ((long long)blockIdx.x - 1) * (long long)B;
     float2* out = y + (size_t)blockIdx.x * B;
     unsigned L;
@@ -304,10 +336,10 @@ __global__ void __launch_bounds__(THREADS) fftfilt2_kernel(const float2* __restr
     else if (P.n4) { first_pass_from_global<4>(w, fbuf, N, tw, N, tid); L = N >> 2; }
     else { first_pass_from_global<2>(w, fbuf, N, tw, N, tid); L = N >> 1; }
     __syncthreads();
-    inner_passes<false>(fbuf, P, L, tw, tid);
+    inner_passes<false>(fbuf, P, L, tw, tid, twi);
     middle_pass(fbuf, N, H, tid);
     __syncthreads();
-    inner_passes<true>(fbuf, P, L, tw, tid);
+    inner_passes<true>(fbuf, P, L, tw, tid, twi);
     if (P.n16) last_pass_to_global<16>(fbuf, out, N, tw, N, scale, tid);
     else if (P.n4) last_pass_to_global<4>(fbuf, out, N, tw, N, scale, tid);
     else last_pass_to_global<2>(fbuf, out, N, tw, N, scale, tid);
@@ -318,14 +350,16 @@ __global__ void __launch_bounds__(THREADS) fft2_forward_kernel(const float2* __r
                                                                const float2* __restrict__ tw)
 {
     extern __shared__ __align__(16) float2 fbuf[];
+    __shared__ float4 twi[2 * INNER_RECORDS];
     const unsigned tid = threadIdx.x;
     const Plan P = make_plan(N);
+    stage_inner_twiddles(tw, N, twi, tid);
     unsigned L;
     if (P.n16) { first_pass_from_global<16>(in, fbuf, N, tw, N, tid); L = N >> 4; }
     else if (P.n4) { first_pass_from_global<4>(in, fbuf, N, tw, N, tid); L = N >> 2; }
     else { first_pass_from_global<2>(in, fbuf, N, tw, N, tid); L = N >> 1; }
     __syncthreads();
-    inner_passes<false>(fbuf, P, L, tw, tid);
+    inner_passes<false>(fbuf, P, L, tw, tid, twi);
     for (unsigned t = tid; t < N / 4; t += THREADS) {
         float2 a = fbuf[pad(4 * t)], b = fbuf[pad(4 * t + 1)], c = fbuf[pad(4 * t + 2)], d = fbuf[pad(4 * t + 3)];
         dft4<false>(a, b, c, d);
