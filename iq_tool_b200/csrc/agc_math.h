@@ -79,8 +79,11 @@ static inline void agc_log_table(AgcLogEntry (&tab)[AGC_LOG_N])
      1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 3628800.0, 1.0, -1.0}                        /* 13..17     */
 constexpr int AGC_NCOEF = 18;
 
-// log(x) in double for a positive normal float x (caller guarantees x > 1e-6); K = AGC_COEF_LIST
-AGC_HD double agc_log_fast(float x, const AgcLogEntry* __restrict__ tab, const double* __restrict__ K)
+// log(x) in double for a positive normal float x (caller guarantees x > 1e-6); K = AGC_COEF_LIST.
+// Device form: TAB is the table's 32-bit shared-window address (a generic pointer makes the compiler rebuild the window
+// base — S2UR + ULEA, in program order in front of the load — in every step of the serial chain).
+template <typename TAB>
+AGC_HD double agc_log_fast(float x, TAB tab, const double* __restrict__ K)
 {
     const uint32_t ix = agc_f2u(x);
     const uint32_t tmp = ix - AGC_LOG_OFF;
@@ -88,7 +91,15 @@ AGC_HD double agc_log_fast(float x, const AgcLogEntry* __restrict__ tab, const d
     const int k = (int)tmp >> 23;                              // arithmetic shift
     const uint32_t iz = ix - (tmp & 0xff800000u);
     const double z = agc_pos_float_to_double(iz);
-    const AgcLogEntry e = tab[i];
+    AgcLogEntry e;
+#if defined(__CUDA_ARCH__)
+    if constexpr (sizeof(TAB) == 4) {
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(e.invc), "=d"(e.logc) : "r"((uint32_t)tab + 16u * (uint32_t)i));
+    } else
+#endif
+    {
+        e = reinterpret_cast<const AgcLogEntry*>((uintptr_t)tab)[i];
+    }
     const double r = fma(z, e.invc, K[17]);
     const double y0 = fma((double)k, K[0], e.logc);
     const double r2 = r * r;

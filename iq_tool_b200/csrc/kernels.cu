@@ -1240,7 +1240,7 @@ __device__ __noinline__ AgcRec agc_rms_step_slow(float ay2, float mha, double om
 // normal, y2' > 1e-6, |t| <= 0.125), conversions by integer arithmetic where they are exact, the three range checks folded
 // into one predicate that is tested once at the end and sends the rare other cases through agc_rms_step_slow.
 __device__ __forceinline__ float2 agc_rms_step(float2 v, size_t i, const PostParams& p, const float* __restrict__ lut,
-                                               const AgcLogEntry* __restrict__ ltab,
+                                               const AgcLogEntry* __restrict__ ltab, uint32_t ltab_s,
                                                float alpha, double oma, float mha, AgcRec& r)
 {
     if (p.nco_enable) v = nco_mix(v, p.nco_theta0 + (uint32_t)i * p.nco_dtheta, p.nco_sign, lut);
@@ -1251,8 +1251,8 @@ __device__ __forceinline__ float2 agc_rms_step(float2 v, size_t i, const PostPar
     const bool ok_a = (ab - 0x00800000u) < 0x7f000000u;                      // positive normal
     const float y2n = (float)fma(oma, r.y2pd, agc_normal_f2d(ab));            // (1 - alpha) y2' + alpha y2, rounded to float
     const unsigned yb = __float_as_uint(y2n);
-    // logf(y2n), agc_math.h
-    const float lf = (float)agc_log_fast(y2n, ltab, agc_coef_c);
+    // logf(y2n), agc_math.h (table through its shared-window address)
+    const float lf = (float)agc_log_fast(y2n, ltab_s, agc_coef_c);
     const float tt = __fmul_rn(mha, lf);
     const unsigned tb = __float_as_uint(tt);
     const bool ok_t = ((tb & 0x7fffffffu) - 0x00800000u) <= (0x3e000000u - 0x00800000u);   // 2^-126 <= |t| <= 0.125
@@ -1274,21 +1274,47 @@ __device__ __forceinline__ float2 agc_rms_step(float2 v, size_t i, const PostPar
 // that is run AGAIN (its start state changed) stops as soon as its state equals the one its previous run had at the same
 // sample: from there on the two trajectories are the same bits, so the outputs and the end state already in memory stand.
 // Returns true when the run stopped that way.
+__device__ __forceinline__ void ld_global_nc_256(const float2* p, float2& a, float2& b, float2& c, float2& d)
+{
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(b.x), "=f"(b.y), "=f"(c.x), "=f"(c.y), "=f"(d.x), "=f"(d.y) : "l"(p));
+}
+__device__ __forceinline__ void st_global_256(float2* p, float2 a, float2 b, float2 c, float2 d)
+{
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :: "l"(p), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y), "f"(d.x), "f"(d.y) : "memory");
+}
 constexpr int AGC_CK = 256;
 __device__ __forceinline__ bool agc_rms_block(const float2* __restrict__ x, size_t i0, size_t i1, const PostParams& p,
                                               const float* __restrict__ lut, const AgcLogEntry* __restrict__ ltab,
-                                              float& g, float& y2p, float2* __restrict__ y, float2* __restrict__ ck, bool compare)
+                                              float& g, float& y2p, float2* __restrict__ y, float2* __restrict__ ck, bool compare,
+                                              uint32_t opaque_zero)
 {
     const float alpha = p.agc_alpha;
     const double oma = 1.0 - (double)alpha;
     const float mha = __fmul_rn(-0.5f, alpha);
     AgcRec r{g, y2p, (double)y2p};
+    // the table's shared-window address in a plain register: `opaque_zero` (a run-time 0 the compiler cannot see through)
+    // keeps ptxas from re-deriving it as CTA-window base + offset — S2UR + ULEA in front of the load in every step
+    uint32_t ltab_s = (uint32_t)__cvta_generic_to_shared(ltab) + opaque_zero;
     size_t i = i0;
     float2 nx[8];
-    if (i + 8 <= i1) {
+    // A lane's samples are contiguous and the lanes of a warp are a whole block apart, so every global access of the warp
+    // touches 32 different sectors.  As 64-bit accesses that was 64 LSU wavefronts per sample and warp, issued in bursts of
+    // eight loads / eight stores — and the step's one shared-memory load (the log table, ON the dependent chain) queued
+    // behind them: 190 cycles of the 660 per sample (profiles/r02i_agc_rms_full_cfg4.md, short-scoreboard samples at the
+    // DFMA behind the LDS).  256-bit accesses (LDG.E.256 / STG.E.256, sm_100) need four instructions per group of eight.
+    const bool wide = (((reinterpret_cast<size_t>(x + i0) | reinterpret_cast<size_t>(y + i0)) & 31) == 0);
+    auto load8 = [&](size_t at) {
+        if (wide) {
+            ld_global_nc_256(x + at, nx[0], nx[1], nx[2], nx[3]);
+            ld_global_nc_256(x + at + 4, nx[4], nx[5], nx[6], nx[7]);
+        } else {
 #pragma unroll
-        for (int k = 0; k < 8; k++) nx[k] = x[i + k];
-    }
+            for (int k = 0; k < 8; k++) nx[k] = x[at + k];
+        }
+    };
+    if (i + 8 <= i1) load8(i);
     for (; i + 8 <= i1; i += 8) {
         if (((i - i0) & (AGC_CK - 1)) == 0) {
             float2* c = ck + ((i - i0) / AGC_CK);
@@ -1301,16 +1327,18 @@ __device__ __forceinline__ bool agc_rms_block(const float2* __restrict__ x, size
         float2 v[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) v[k] = nx[k];
-        if (i + 16 <= i1) {
+        if (i + 16 <= i1) load8(i + 8);
 #pragma unroll
-            for (int k = 0; k < 8; k++) nx[k] = x[i + 8 + k];
+        for (int k = 0; k < 8; k++) v[k] = agc_rms_step(v[k], i + k, p, lut, ltab, ltab_s, alpha, oma, mha, r);
+        if (wide) {
+            st_global_256(y + i, v[0], v[1], v[2], v[3]);
+            st_global_256(y + i + 4, v[4], v[5], v[6], v[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) y[i + k] = v[k];
         }
-#pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = agc_rms_step(v[k], i + k, p, lut, ltab, alpha, oma, mha, r);
-#pragma unroll
-        for (int k = 0; k < 8; k++) y[i + k] = v[k];
     }
-    for (; i < i1; i++) y[i] = agc_rms_step(x[i], i, p, lut, ltab, alpha, oma, mha, r);
+    for (; i < i1; i++) y[i] = agc_rms_step(x[i], i, p, lut, ltab, ltab_s, alpha, oma, mha, r);
     g = r.g; y2p = r.y2p;
     return false;
 }
@@ -1339,7 +1367,7 @@ __global__ void __launch_bounds__(AGC_RMS_THREADS) agc_rms_parallel_kernel(const
     for (unsigned it = 0; it <= nblocks; it++) {
         if (active && run) {
             float g = start.x, y2p = start.y;
-            const bool merged = agc_rms_block(x, i0, i1, p, lut, ltab, g, y2p, y, ck, it > 0);
+            const bool merged = agc_rms_block(x, i0, i1, p, lut, ltab, g, y2p, y, ck, it > 0, (uint32_t)(B >> 48));
             if (!merged) fin[b] = make_float2(g, y2p);
         }
         grid.sync();
@@ -1650,9 +1678,10 @@ static void agc_rms_plan(size_t n, float alpha, size_t& B, unsigned& nblocks)
     // blocks of ~20 time constants the second sweep already starts every block within ~e^-20 of the truth, so two
     // or three full sweeps plus a short tail of partial ones reach the fixed point; shorter blocks need one full
     // sweep per block length of convergence (measured: 25 sweeps at 493 samples, alpha = 1e-2).
-    static const double tc = getenv("IQGPU_AGC_BLOCK_TC") ? atof(getenv("IQGPU_AGC_BLOCK_TC")) : 40.0;
+    static const double tc = getenv("IQGPU_AGC_BLOCK_TC") ? atof(getenv("IQGPU_AGC_BLOCK_TC")) : 30.0;     // measured on cfg4: 40 -> 3.65 ms, 30 -> 3.51, 20 -> 3.79, 10 -> 4.82
     const size_t floorB = (size_t)std::min(65536.0, std::max(256.0, tc / std::max((double)alpha, 1e-6)));
     if (B < floorB) B = floorB;
+    B = (B + 3) & ~(size_t)3;           // whole 32-byte groups per block: the 256-bit accesses of agc_rms_block stay aligned
     nblocks = (unsigned)((n + B - 1) / B);
 }
 size_t agc_rms_workspace_bytes(size_t n, float alpha)
