@@ -1630,7 +1630,9 @@ cudaError_t launch_agc_digital_scan(const uint32_t* seg_start, size_t nseg, cons
                                     const PostParams& p, AgcState* state, float* seg_gain, cudaStream_t st, void* quiet_ws)
 {
     if (nseg == 0) return cudaSuccess;
-    if (!(quiet_ws && nseg >= 1024)) {
+    // the test itself costs two launches (~25 us): worth it for a state-only advance (its tables are long and mostly quiet)
+    // and for tables the one-CTA scan would need more than a few tiles for (cfg1's 7324 chunks: 18 us of scan)
+    if (!(quiet_ws && nseg >= (seg_gain ? 2 * AGC_HEAD : 1024))) {
         agc_digital_scan_kernel<<<1, AGC_SCAN_THREADS, 0, st>>>(seg_start, (unsigned)nseg, seg_peak, p, state, seg_gain, nullptr);
         return cudaGetLastError();
     }
