@@ -893,6 +893,9 @@ __device__ __forceinline__ void w2_arb_quad(const Fused2Args& A, const float2* _
             const int ssh = A.arb_skew_sh;
 #pragma unroll
             for (int j = 0; j < NU; j++) u[j] = w[w2_flat_phys(e0 + j, ssh)];
+            // (two thresholds on one base register instead of a shift and an add per load, and a separate loop for
+            // ssh == 31, measured SLOWER: cfg1 0.437 -> 0.469 ms, session r2y — the selects cost what the shifts did and
+            // the second copy of the loop cost registers)
         } else {                                            // plain level: one base register, immediate offsets
 #pragma unroll
             for (int j = 0; j < NU; j++) u[j] = w[e0 + j];
