@@ -747,14 +747,17 @@ def test_fir_adds_the_fronts_dc_term_while_staging_its_tiles(gpu, workloads, mon
     front's closed-form DC term to the samples it stages instead of a separate read-modify-write pass over the resampled
     stream (the newest taps-1 samples, the next call's history, get it in memory afterwards).  Same bytes as with the
     separate pass (IQGPU_NO_DC_FOLD=1), one call or ragged calls that are shorter than, equal to and longer than the
-    filter history, cs16 output (FIR epilogue conversion) and cf32 output (post kernel behind the FIR)."""
+    filter history, cs16 output (FIR epilogue conversion), cf32 output (post kernel behind the FIR) and an asymmetric pass
+    range (complex taps)."""
     import dataclasses
     wl = workloads["cfg2"]
     n = (1 << 22) + 7777
     raw = synth_numpy(wl, n)
     cuts = [0, 1 << 20, (1 << 20) + 3000, (1 << 20) + 3000 + 16384, 3 << 20, n]
-    for out_fmt in ("cs16", "cf32"):
-        cfg = dataclasses.replace(wl.config, output_format=out_fmt)
+    from iq_tool_b200.configs import pass_range
+    variants = [("cs16", wl.config.filters), ("cf32", wl.config.filters), ("cu8", [pass_range(20e3, 180e3)])]   # last: complex taps
+    for out_fmt, filters in variants:
+        cfg = dataclasses.replace(wl.config, output_format=out_fmt, filters=filters)
         def run(split):
             if not split:
                 return gpu.Chain(cfg, 0, subtrain_frames=1 << 20).process(raw)          # several sub-trains in one call
