@@ -380,7 +380,7 @@ struct FusedFront {
     // large enough times both on its own data — the kernel is idempotent — and the choice sticks.
     int arb_pairs = -1;
     uint32_t lut_dtheta = 0;            // NCO table swizzle chosen for this phase increment
-    unsigned lut_sh = 4, lut_mask = 0;
+    unsigned lut_sh = 4, lut_mask = 0, lut_rot_sh = 4, lut_rot_c = 0;
     bool lut_picked = false;
 };
 
@@ -768,9 +768,14 @@ static cudaError_t fused_launch_v2(FusedFront* f, const void* raw, int64_t n0, s
     if (pre.nco_enable) {
         if (f->lut_dtheta != pre.nco_dtheta || !f->lut_picked) {
             w2_pick_lut_swizzle(pre.nco_dtheta, f->lut_sh, f->lut_mask);
+            f->lut_rot_c = 0;
+            if (!getenv("IQGPU_LUT_NO_ROT") && (pre.format == IQGPU_FMT_CS16 || pre.format == IQGPU_FMT_SC16Q11)) w2_pick_lut_rotation(pre.nco_dtheta, f->lut_sh, f->lut_mask, f->lut_rot_sh, f->lut_rot_c);
+            if (getenv("IQGPU_VERBOSE"))
+                fprintf(stderr, "iqgpu: NCO table layout: fold sh %u mask %u, rotation sh %u c %u\n", f->lut_sh, f->lut_mask, f->lut_rot_sh, f->lut_rot_c);
             f->lut_dtheta = pre.nco_dtheta; f->lut_picked = true;
         }
         A.lut_sh = f->lut_sh; A.lut_mask = f->lut_mask;
+        A.lut_rot_sh = f->lut_rot_sh; A.lut_rot_c = f->lut_rot_c;
     }
     memcpy(A.taps, f->v2_taps, sizeof(A.taps));
     const long long sup_frames = (long long)f->v2_sup * W2_T0;

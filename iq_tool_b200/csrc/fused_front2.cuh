@@ -54,6 +54,50 @@ constexpr int W2_ARB_HIST = 16;     // >= 13 decimated samples of look-back
 // Which fold (none, or index bits sh..sh+3 with sh = 4, 5, 6) is best depends on the phase increment, so the
 // host simulates the half-warp access pattern for the actual increment and picks one (w2_pick_lut_swizzle).
 __host__ __device__ constexpr unsigned w2_lut_slot(unsigned idx, unsigned sh, unsigned mask) { return idx ^ ((idx >> sh) & mask); }
+// Second family, for increments at which no XOR fold gets below two-way conflicts (cfg5: lanes 26.67 entries apart,
+// 2.2 wavefronts per half warp after the best fold, 1.6 here): the entries of every row of 16 are ROTATED by a multiple of
+// a higher index field, slot = row | ((idx + c (idx >> sh)) mod 16) — a permutation of the table for any c.
+__host__ __device__ constexpr unsigned w2_lut_slot_rot(unsigned idx, unsigned sh, unsigned c)
+{
+    return (idx & ~15u) | ((idx + c * (idx >> sh)) & 15u);
+}
+template <typename SLOT>
+__host__ static inline double w2_lut_cost(uint32_t dtheta, SLOT slot)
+{
+    double cost = 0;
+    for (uint32_t trial = 0; trial < 64; trial++) {
+        const uint32_t th0 = trial * 0x9e3779b9u;          // arbitrary start phases
+        for (int half = 0; half < 2; half++) {
+            int hits[16] = {0};
+            unsigned seen_idx[16];
+            int deg = 0;
+            for (int l = 0; l < 16; l++) {
+                const uint32_t th = th0 + (uint32_t)((half * 16 + l) * 16) * dtheta;
+                const unsigned idx = ((th + (1u << 21)) >> 22) & 0x3ffu;
+                seen_idx[l] = idx;
+                bool dup = false;                          // identical addresses broadcast
+                for (int m = 0; m < l; m++) dup |= (seen_idx[m] == idx);
+                if (dup) continue;
+                const unsigned b = slot(idx) & 15u;
+                if (++hits[b] > deg) deg = hits[b];
+            }
+            cost += deg;
+        }
+    }
+    return cost;
+}
+// rotation (c != 0) only when it beats the best fold by 10 %: it costs one more instruction per look-up
+__host__ static inline void w2_pick_lut_rotation(uint32_t dtheta, unsigned xor_sh, unsigned xor_mask, unsigned& rot_sh, unsigned& rot_c)
+{
+    const double base = w2_lut_cost(dtheta, [&](unsigned i) { return w2_lut_slot(i, xor_sh, xor_mask); });
+    double best = base * 0.9;
+    rot_sh = 4; rot_c = 0;
+    for (unsigned sh = 3; sh <= 7; sh++)
+        for (unsigned c = 1; c < 16; c++) {
+            const double k = w2_lut_cost(dtheta, [&](unsigned i) { return w2_lut_slot_rot(i, sh, c); });
+            if (k < best - 1e-9) { best = k; rot_sh = sh; rot_c = c; }
+        }
+}
 __host__ static inline void w2_pick_lut_swizzle(uint32_t dtheta, unsigned& sh, unsigned& mask)
 {
     const unsigned cand_sh[4] = {4, 4, 5, 6}, cand_mask[4] = {0, 15, 15, 15};
@@ -199,6 +243,7 @@ struct Fused2Args {
     uint32_t step;
     float zeta;
     unsigned lut_sh, lut_mask;          // NCO table swizzle (w2_lut_slot)
+    unsigned lut_rot_sh, lut_rot_c;     // lut_rot_c != 0: the rotation family instead (w2_lut_slot_rot)
     int arb_pairs;                      // polyphase stage: one output per lane (0), two (1) or four (2); same bits, picked by timing
     int arb_tz, arb_b2, arb_b3;         // four-output variant: row rotation of the bank image; floor(2/rate), floor(3/rate)
     // skew of the polyphase input level: entry e sits at e + 2 * (e >> arb_skew_sh) (31: none).  The four-output variant's
@@ -377,9 +422,13 @@ __device__ __forceinline__ void w2_p0(const Fused2Args& A, float2* __restrict__ 
         }
         if (p.nco_enable) {  // liquid LIQUID_NCO: 32-bit phase, 1024-entry table, nearest entry
             uint32_t th = p.nco_theta0 + (uint32_t)(a0 - A.n0) * p.nco_dtheta;
+            // one loop per table layout (the choice is uniform: a branch around the loop, not a select per look-up)
+            auto mix = [&](auto rot_c) {
 #pragma unroll
             for (int k = 0; k < 16; k++) {
-                const float2 sc2 = lut2[w2_lut_slot(((th + (1u << 21)) >> 22) & 0x3ffu, A.lut_sh, A.lut_mask)];   // {sign*sin, cos}
+                const unsigned li = ((th + (1u << 21)) >> 22) & 0x3ffu;
+                const float2 sc2 = lut2[decltype(rot_c)::value ? w2_lut_slot_rot(li, A.lut_rot_sh, A.lut_rot_c)
+                                                               : w2_lut_slot(li, A.lut_sh, A.lut_mask)];   // {sign*sin, cos}
                 // (v.x c - v.y s, v.x s + v.y c) with every product and every sum rounded on its own (liquid's complex
                 // multiply): the products as two packed multiplies — {v.x, v.y} * c and {v.y, v.x} * {-s, s}, whose swap
                 // and sign are operand modifiers of FMUL2 — the sums as SCALAR adds: ptxas 12.9 contracts a packed
@@ -390,6 +439,10 @@ __device__ __forceinline__ void w2_p0(const Fused2Args& A, float2* __restrict__ 
                 x[k] = pk2(__fadd_rn(t1.x, t2.x), __fadd_rn(t1.y, t2.y));
                 th += p.nco_dtheta;
             }
+            };
+            // (the second copy of the loop exists in the cs16 kernels only: on the cu8 / table-DC kernel of cfg4 it cost 8 %
+            // of the kernel whichever copy ran — session r3b; the host never picks a rotation for other formats)
+            if (CS16 && A.lut_rot_c) mix(W2True{}); else mix(W2False{});
         }
     }
     if (!fast) {
@@ -1074,7 +1127,7 @@ __global__ void __launch_bounds__(W2_MAX_WARPS * 32, 1) fused_front2_kernel(cons
     if (tid == 0) w2_tma_load(sbank, A.bank_image, W2_BANK_F2 * sizeof(float2), &tma_bar);
     if (A.pre.nco_enable)
         for (int i = tid; i < 1024; i += blockDim.x)
-            lut2[w2_lut_slot((unsigned)i, A.lut_sh, A.lut_mask)] = make_float2(A.pre.nco_table[i] * A.pre.nco_sign, A.pre.nco_table[(i + 256) & 1023]);
+            lut2[A.lut_rot_c ? w2_lut_slot_rot((unsigned)i, A.lut_rot_sh, A.lut_rot_c) : w2_lut_slot((unsigned)i, A.lut_sh, A.lut_mask)] = make_float2(A.pre.nco_table[i] * A.pre.nco_sign, A.pre.nco_table[(i + 256) & 1023]);
     for (int i = lane; i < P::warp_f2; i += 32) wsm[i] = make_float2(0.f, 0.f);
     w2_mbar_wait(&tma_bar, 0);
     __syncthreads();
