@@ -513,6 +513,15 @@ __device__ __forceinline__ void w2_stage_store(float2* __restrict__ wsm, int lan
 #pragma unroll
         for (int j = 0; j < 4; j++)
             *reinterpret_cast<ulonglong2*>(f + 2 * (((unsigned)j + rot) & 3u)) = make_ulonglong2(b[2 * j], b[2 * j + 1]);
+    } else if constexpr (D + 1 == S && R == 4) {
+        // 32 contiguous bytes per lane: two STS.128 in lane order put the 8 lanes of a quarter warp on four bank groups
+        // (8 wavefronts instead of 4 per instruction, profiles/r03e_fused_front2_full_cfg3.md); lanes 4..7 of every eight
+        // store their second chunk first
+        if (!P::quad_skew) skew_sh = 31;
+        float2* f = wsm + P::flat_off + w2_flat_phys(W2_ARB_HIST + R * lane, skew_sh);
+        const bool rot = (skew_sh == 31) && (((unsigned)lane >> 2) & 1u);
+        *reinterpret_cast<ulonglong2*>(f + (rot ? 2 : 0)) = make_ulonglong2(rot ? v[2] : v[0], rot ? v[3] : v[1]);
+        *reinterpret_cast<ulonglong2*>(f + (rot ? 0 : 2)) = make_ulonglong2(rot ? v[0] : v[2], rot ? v[1] : v[3]);
     } else if constexpr (D + 1 == S) {
         if (!P::quad_skew) skew_sh = 31;
         float2* f = wsm + P::flat_off + w2_flat_phys(W2_ARB_HIST + R * lane, skew_sh);
